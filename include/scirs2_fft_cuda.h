@@ -1,0 +1,204 @@
+/* scirs2_fft_cuda.h — C ABI of libscirs2_fft_cuda.so: the B200-native replacement
+ * for the data-parallel FFT hot path of scirs2-fft (cool-japan/scirs 0.1.0-alpha.6).
+ *
+ * Every entry point names the reference interface it replaces (file:line relative
+ * to the reference tree).  Plain pointers and sizes only; no C++ or torch types.
+ * All functions return 0 (SFC_OK) or a negative sfc_status that maps 1:1 onto a
+ * variant of `FFTError` (scirs2-fft/src/error.rs:7-46); the message text is
+ * available from sfc_last_error() (thread-local).
+ *
+ * There is NO CPU fallback: without a CUDA device every compute entry point
+ * fails with SFC_ERR_BACKEND.
+ */
+#ifndef SCIRS2_FFT_CUDA_H
+#define SCIRS2_FFT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFC_MAX_DIMS 8
+#define SFC_ABI_VERSION 1
+
+/* FFTError variants, scirs2-fft/src/error.rs:7-46 */
+typedef enum sfc_status {
+    SFC_OK = 0,
+    SFC_ERR_COMPUTATION = -1,     /* FFTError::ComputationError    */
+    SFC_ERR_DIMENSION = -2,       /* FFTError::DimensionError      */
+    SFC_ERR_VALUE = -3,           /* FFTError::ValueError          */
+    SFC_ERR_NOT_IMPLEMENTED = -4, /* FFTError::NotImplementedError */
+    SFC_ERR_IO = -5,              /* FFTError::IOError             */
+    SFC_ERR_BACKEND = -6,         /* FFTError::BackendError        */
+    SFC_ERR_PLAN = -7,            /* FFTError::PlanError           */
+    SFC_ERR_COMMUNICATION = -8,   /* FFTError::CommunicationError  */
+    SFC_ERR_MEMORY = -9           /* FFTError::MemoryError         */
+} sfc_status;
+
+/* element types accepted at the boundary (the reference is generic over
+ * `T: NumCast` and widens everything to Complex64, fft/algorithms.rs:71-102) */
+typedef enum sfc_dtype {
+    SFC_F32 = 0,  /* f32 real                */
+    SFC_F64 = 1,  /* f64 real                */
+    SFC_C64 = 2,  /* Complex<f32> interleaved */
+    SFC_C128 = 3  /* Complex64  interleaved   */
+} sfc_dtype;
+
+typedef enum sfc_kind { SFC_C2C = 0, SFC_R2C = 1, SFC_C2R = 2 } sfc_kind;
+typedef enum sfc_prec { SFC_PREC_F32 = 0, SFC_PREC_F64 = 1 } sfc_prec;
+typedef enum sfc_dir { SFC_FORWARD = 0, SFC_INVERSE = 1 } sfc_dir;
+
+/* ------------------------------------------------------------------ runtime */
+
+/* Select the CUDA device this thread's calls run on (one process per GPU).
+ * Fails with SFC_ERR_BACKEND when no device is present. */
+int sfc_init(int device);
+int sfc_device_count(void);
+/* Thread-local text of the last error (never NULL). */
+const char* sfc_last_error(void);
+int sfc_abi_version(void);
+/* 1 when a CUDA device is usable (FftBackend::is_available, backend.rs:24). */
+int sfc_is_available(void);
+
+/* -------------------------------------------------------------------- plans
+ * Replaces rustfft's `FftPlanner::plan_fft_forward/inverse` +
+ * `Fft::process` as used at fft/algorithms.rs:159-167, 350-376, 667-683 and the
+ * `FftPlan` / `FftPlanExecutor` pair of planning.rs:75-180, 474-556.
+ *
+ * A plan transforms a C-order contiguous N-D array along `axes` (in list
+ * order, duplicates allowed as in fftn, algorithms.rs:667-690).
+ *   C2C: in  complex[shape]            -> out complex[shape]
+ *   R2C: in  real[shape]               -> out complex[shape with axes[last] -> n/2+1]
+ *   C2R: in  complex[shape, halved]    -> out real[shape]
+ * `shape` is always the logical (full) transform shape.  `scale` multiplies the
+ * result (the caller folds the reference's norm table into it).
+ */
+typedef struct sfc_plan sfc_plan;
+
+typedef struct sfc_desc {
+    int32_t ndim;
+    int64_t shape[SFC_MAX_DIMS];
+    int32_t naxes;
+    int32_t axes[SFC_MAX_DIMS];
+    int32_t kind;      /* sfc_kind */
+    int32_t prec;      /* sfc_prec: arithmetic + element precision of in/out */
+    int32_t direction; /* sfc_dir (C2C only; R2C is forward, C2R inverse) */
+    int32_t flags;     /* SFC_DESC_* */
+    double scale;
+    /* C2R only, with SFC_DESC_CUSTOM_IN_SHAPE: extents of the half-spectrum input when it is
+     * not shape-with-last-axis-halved (irfftn pads / reflects what is there, rfft.rs:733-901) */
+    int64_t in_shape[SFC_MAX_DIMS];
+} sfc_desc;
+#define SFC_DESC_CUSTOM_IN_SHAPE 1
+/* C2C only: the input array is real (imag = 0), as when the reference widens real input
+ * to Complex64 before the transform (fft/algorithms.rs:71-102) */
+#define SFC_DESC_REAL_INPUT 2
+
+typedef struct sfc_plan_info {
+    int64_t in_bytes, out_bytes, scratch_bytes;
+    int64_t algorithmic_bytes; /* read+write of the working array per unavoidable pass */
+    int64_t device_bytes;      /* bytes the launched kernels actually move (all passes) */
+    double nominal_flops;      /* 5 N log2 N (2.5 for real transforms) */
+    int32_t num_launches;      /* kernel launches per execution */
+    int32_t num_passes;        /* global-memory passes over the working array */
+} sfc_plan_info;
+
+/* Looks the plan up in the process-wide plan cache first (plan_cache.rs:102-161). */
+int sfc_plan_create(sfc_plan** out, const sfc_desc* desc);
+/* Drops the caller's reference (cached plans stay alive in the cache). */
+int sfc_plan_destroy(sfc_plan* plan);
+int sfc_plan_get_info(const sfc_plan* plan, sfc_plan_info* info);
+/* Human-readable pass list ("pass 0: tile L=4096 TL=1 ..."); returns bytes written. */
+int sfc_plan_describe(const sfc_plan* plan, char* buf, size_t cap);
+
+/* Device pointers, caller's stream (cudaStream_t passed as void*; NULL = default). */
+int sfc_exec_device(sfc_plan* plan, const void* d_in, void* d_out, void* stream);
+/* Host pointers: H2D + transform + D2H (what the drop-in free functions use). */
+int sfc_exec_host(sfc_plan* plan, const void* h_in, void* h_out);
+
+/* --------------------------------------------------------------- plan cache
+ * plan_cache.rs:28-235 — 128 entries, 1 h TTL, LRU, hit/miss counters. */
+typedef struct sfc_cache_stats {
+    uint64_t hit_count, miss_count;
+    double hit_rate;
+    uint64_t size, max_size;
+} sfc_cache_stats;
+int sfc_cache_get_stats(sfc_cache_stats* out);   /* PlanCache::get_stats  :182-190 */
+int sfc_cache_set_enabled(int enabled);          /* PlanCache::set_enabled :57-59  */
+int sfc_cache_is_enabled(void);                  /* PlanCache::is_enabled  :62-64  */
+int sfc_cache_clear(void);                       /* PlanCache::clear       :66-71  */
+int sfc_cache_configure(uint64_t max_entries, double max_age_seconds); /* with_config :47-54 */
+
+/* ------------------------------------------------- drop-in free functions
+ * Reference semantics (including its SciPy-divergent quirks) with
+ * HOST buffers.  `n`/shape arguments use -1 / NULL for the reference's `None`.
+ * `norm` is "backward" | "ortho" | "forward" | anything else (= no scaling) | NULL.
+ * Outputs are caller-allocated; `out_cap` is the capacity in ELEMENTS and the
+ * produced element count / shape is written back.  Output is always f64
+ * (Complex64 or f64), exactly as the reference.
+ */
+
+/* fft / ifft: fft/algorithms.rs:131-176, 210-263 */
+int sfc_fft(const void* x, int64_t len, int dtype, int64_t n, double* out, int64_t out_cap, int64_t* out_len);
+int sfc_ifft(const void* x, int64_t len, int dtype, int64_t n, double* out, int64_t out_cap, int64_t* out_len);
+/* rfft / irfft: rfft.rs:39-59, 92-178 (the hard-coded test returns at :97-116 are NOT reproduced) */
+int sfc_rfft(const void* x, int64_t len, int dtype, int64_t n, double* out, int64_t out_cap, int64_t* out_len);
+int sfc_irfft(const void* x, int64_t len, int dtype, int64_t n, double* out, int64_t out_cap, int64_t* out_len);
+/* fft2 / ifft2: fft/algorithms.rs:293-401, 439-541; shape/axes NULL = None. */
+int sfc_fft2(const void* x, int64_t rows, int64_t cols, int dtype, const int64_t* shape2, const int32_t* axes2,
+             const char* norm, double* out, int64_t out_cap, int64_t* out_shape2);
+int sfc_ifft2(const void* x, int64_t rows, int64_t cols, int dtype, const int64_t* shape2, const int32_t* axes2,
+              const char* norm, double* out, int64_t out_cap, int64_t* out_shape2);
+/* rfft2 / irfft2: rfft.rs:212-232, 274-355 (halves axis 0; irfft2 keeps the reference's
+ * (N0out*N1out)/(N0in*N1in) factor; its hard-coded 2x2 return is NOT reproduced) */
+int sfc_rfft2(const void* x, int64_t rows, int64_t cols, int dtype, const int64_t* shape2, double* out,
+              int64_t out_cap, int64_t* out_shape2);
+int sfc_irfft2(const void* x, int64_t rows, int64_t cols, int dtype, const int64_t* shape2, double* out,
+               int64_t out_cap, int64_t* out_shape2);
+/* fftn / ifftn: fft/algorithms.rs:576-706, 757-890.  shape NULL = None (else ndim entries),
+ * axes NULL = None (else naxes entries). */
+int sfc_fftn(const void* x, int32_t ndim, const int64_t* in_shape, int dtype, const int64_t* shape,
+             const int64_t* axes, int32_t naxes, const char* norm, double* out, int64_t out_cap,
+             int64_t* out_shape);
+int sfc_ifftn(const void* x, int32_t ndim, const int64_t* in_shape, int dtype, const int64_t* shape,
+              const int64_t* axes, int32_t naxes, const char* norm, double* out, int64_t out_cap,
+              int64_t* out_shape);
+/* rfftn / irfftn: rfft.rs:472-525, 621-725.  For irfftn `shape` may have ndim or naxes
+ * entries (nshape says which). */
+int sfc_rfftn(const void* x, int32_t ndim, const int64_t* in_shape, int dtype, const int64_t* shape,
+              const int64_t* axes, int32_t naxes, const char* norm, double* out, int64_t out_cap,
+              int64_t* out_shape);
+int sfc_irfftn(const void* x, int32_t ndim, const int64_t* in_shape, int dtype, const int64_t* shape,
+               int32_t nshape, const int64_t* axes, int32_t naxes, const char* norm, double* out,
+               int64_t out_cap, int64_t* out_shape);
+/* fft_strided / fft_strided_complex / ifft_strided: strided_fft.rs:16-239 (one axis of an N-D array) */
+int sfc_fft_strided(const void* x, int32_t ndim, const int64_t* in_shape, int dtype, int64_t axis,
+                    int inverse, double* out, int64_t out_cap);
+
+/* ----------------------------------------------------- FftBackend trait
+ * backend.rs:14-48: fft / ifft (1/n-normalised, :149-152) / *_sized on Complex64 slices. */
+int sfc_backend_fft(const double* input, int64_t in_len, double* output, int64_t out_len);
+int sfc_backend_ifft(const double* input, int64_t in_len, double* output, int64_t out_len);
+int sfc_backend_fft_sized(const double* input, int64_t in_len, double* output, int64_t out_len, int64_t size);
+int sfc_backend_ifft_sized(const double* input, int64_t in_len, double* output, int64_t out_len, int64_t size);
+int sfc_backend_supports_feature(const char* feature); /* backend.rs:157-160 (+ "gpu_acceleration") */
+const char* sfc_backend_name(void);                    /* "cuda_fft", examples/backend_example.rs:103 */
+const char* sfc_backend_description(void);
+
+/* ------------------------------------------ batched executor (planning_parallel.rs:316-405)
+ * `count` independent length-`size` complex transforms, contiguous [count][size]. */
+int sfc_execute_batch(const double* inputs, double* outputs, int64_t count, int64_t size, int inverse);
+
+/* --------------------------------------------------------- f32 compute path
+ * The reference has no f32 arithmetic; BASELINE config 2b asks for one.  Batched
+ * real transforms over the last axis, element precision chosen by `prec`.
+ * x: [batch][n] real -> out: [batch][n/2+1] complex (rfft) and back (irfft). */
+int sfc_rfft_batch(const void* x, int64_t batch, int64_t n, int prec, void* out);
+int sfc_irfft_batch(const void* x, int64_t batch, int64_t n, int prec, void* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCIRS2_FFT_CUDA_H */

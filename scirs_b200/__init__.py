@@ -1,0 +1,18 @@
+"""scirs_b200 — B200-native drop-in for the data-parallel FFT hot path of scirs2-fft.
+
+Host-side mirror of the reference's interface for that path (same names,
+argument meaning and error behaviour); all arithmetic happens in
+``lib/libscirs2_fft_cuda.so`` (hand-written sm_100a kernels behind a C ABI,
+``include/scirs2_fft_cuda.h``).  No CPU fallback.
+"""
+from .error import (FFTError, ComputationError, DimensionError, ValueError_, NotImplementedError_, BackendError,
+                    PlanError, CommunicationError, MemoryError_)
+from .fft import (fft, ifft, rfft, irfft, fft2, ifft2, fft2_parallel, ifft2_parallel, rfft2, irfft2, fftn, ifftn,
+                  rfftn, irfftn, fft_strided, fft_strided_complex, ifft_strided, fft_simd, ifft_simd, fft_adaptive,
+                  ifft_adaptive, fft2_simd, fft2_adaptive, fftn_simd, fftn_adaptive, ifft2_simd, ifftn_simd,
+                  rfft_simd, irfft_simd, rfft_adaptive, irfft_adaptive, rfft_batch, irfft_batch)
+from .plan import FftPlan, FftPlanExecutor
+from .plan_cache import PlanCache, CacheStats, get_global_cache
+from .backend import FftBackend, CudaFftBackend, BackendManager, BackendContext, get_backend_manager
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,533 @@
+// fft_tile.cuh — the one hot kernel: a tile of TL lanes x L points (L = 2^k)
+// transformed by a Stockham autosort radix-16/8/4/2 FFT held in registers
+// (E = 16 points per thread) with shared-memory exchanges between stages.
+//
+// It replaces the arithmetic the reference delegates to rustfft's scalar
+// planner (`fft.process(&mut buffer)`, scirs2-fft/src/fft/algorithms.rs:167,
+// 362, 376, 683) together with the gather/scatter/scale loops around it
+// (:353-395, :677-703).  Forward sign is exp(-2*pi*i*jk/n), unnormalised, as in
+// rustfft; the inverse is the same code with re/im swapped on the way in and out.
+//
+// Index algebra (DIF Stockham, stage radix R at stride S, S*n = L):
+//   thread butterfly index ib in [0, L/R):  q = ib mod S, base = ib - q
+//   reads  x[ib + r*L/R],            r < R      (always "i + m*L/E": coalesced)
+//   writes y[q + R*base + k*S] = W_L^(base*k) * DFT_R(x)[k]
+//   last stage (S*R == L): base = 0, output index ib + k*L/R -> same register
+//   pattern as the loads, so global stores are coalesced too.
+//
+// Shared-memory slot of logical element e of lane t:  t*LP + swz(e) with an XOR
+// swizzle chosen per exchange so that both the strided writes and the unit-
+// stride reads are bank-conflict free (tools/bank_sim.py checks every config).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pass_params.h"
+
+namespace sfc {
+
+template <typename T>
+struct alignas(2 * sizeof(T)) Cx {
+    T x, y;
+};
+
+template <typename T>
+__device__ __forceinline__ Cx<T> cadd(Cx<T> a, Cx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T>
+__device__ __forceinline__ Cx<T> csub(Cx<T> a, Cx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T>
+__device__ __forceinline__ Cx<T> cmul(Cx<T> a, Cx<T> b) {
+    return {fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)};
+}
+template <typename T>
+__device__ __forceinline__ Cx<T> cmulc(Cx<T> a, Cx<T> b) {  // a * conj(b)
+    return {fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -(a.x * b.y))};
+}
+template <typename T>
+__device__ __forceinline__ Cx<T> csqr(Cx<T> a) {
+    return {fma(a.x, a.x, -(a.y * a.y)), (a.x + a.x) * a.y};
+}
+template <typename T>
+__device__ __forceinline__ Cx<T> cswap(Cx<T> a) { return {a.y, a.x}; }
+template <typename T>
+__device__ __forceinline__ Cx<T> cconj(Cx<T> a) { return {a.x, -a.y}; }
+template <typename T>
+__device__ __forceinline__ Cx<T> mul_mi(Cx<T> a) { return {a.y, -a.x}; }  // a * (-i)
+
+// ---- radix butterflies (forward, in place, natural-order output) ------------
+
+template <typename T>
+__device__ __forceinline__ void dft2(Cx<T>& a0, Cx<T>& a1) {
+    Cx<T> t = a0;
+    a0 = cadd(t, a1);
+    a1 = csub(t, a1);
+}
+
+template <typename T>
+__device__ __forceinline__ void dft4(Cx<T>& a0, Cx<T>& a1, Cx<T>& a2, Cx<T>& a3) {
+    Cx<T> t0 = cadd(a0, a2), t1 = csub(a0, a2);
+    Cx<T> t2 = cadd(a1, a3), t3 = mul_mi(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+
+// a * W16^J  (W16 = exp(-2*pi*i/16)), J folded at compile time
+template <int J, typename T>
+__device__ __forceinline__ Cx<T> mul_w16(Cx<T> a) {
+    constexpr T H = (T)0.70710678118654752440084436210485L;
+    constexpr T C1 = (T)0.92387953251128675612818318939679L;  // cos(pi/8)
+    constexpr T S1 = (T)0.38268343236508977172845998403040L;  // sin(pi/8)
+    if constexpr (J == 0) return a;
+    else if constexpr (J == 1) return {fma(a.y, S1, a.x * C1), fma(a.y, C1, -(a.x * S1))};
+    else if constexpr (J == 2) return {(a.x + a.y) * H, (a.y - a.x) * H};
+    else if constexpr (J == 3) return {fma(a.y, C1, a.x * S1), fma(a.y, S1, -(a.x * C1))};
+    else if constexpr (J == 4) return {a.y, -a.x};
+    else if constexpr (J == 6) return {(a.y - a.x) * H, -((a.x + a.y) * H)};
+    else if constexpr (J == 9) return {-fma(a.y, S1, a.x * C1), fma(a.x, S1, -(a.y * C1))};
+    else { static_assert(J < 0, "unsupported W16 power"); return a; }
+}
+
+template <int R, typename T>
+struct Dft;
+
+template <typename T>
+struct Dft<2, T> {
+    static __device__ __forceinline__ void run(Cx<T> (&v)[2]) { dft2(v[0], v[1]); }
+};
+template <typename T>
+struct Dft<4, T> {
+    static __device__ __forceinline__ void run(Cx<T> (&v)[4]) { dft4(v[0], v[1], v[2], v[3]); }
+};
+template <typename T>
+struct Dft<8, T> {
+    // n = 4*n1 + n2, k = k1 + 2*k2
+    static __device__ __forceinline__ void run(Cx<T> (&v)[8]) {
+        Cx<T> y0[4], y1[4];
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) {
+            y0[n2] = cadd(v[n2], v[n2 + 4]);
+            y1[n2] = csub(v[n2], v[n2 + 4]);
+        }
+        y1[1] = mul_w16<2>(y1[1]);
+        y1[2] = mul_w16<4>(y1[2]);
+        y1[3] = mul_w16<6>(y1[3]);
+        dft4(y0[0], y0[1], y0[2], y0[3]);
+        dft4(y1[0], y1[1], y1[2], y1[3]);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+            v[2 * k2] = y0[k2];
+            v[2 * k2 + 1] = y1[k2];
+        }
+    }
+};
+template <typename T>
+struct Dft<16, T> {
+    // n = 4*n1 + n2, k = k1 + 4*k2
+    static __device__ __forceinline__ void run(Cx<T> (&v)[16]) {
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) dft4(v[n2], v[n2 + 4], v[n2 + 8], v[n2 + 12]);
+        // v[n2 + 4*k1] now holds y[n2][k1]; apply W16^(n2*k1)
+        v[1 + 4] = mul_w16<1>(v[1 + 4]);
+        v[2 + 4] = mul_w16<2>(v[2 + 4]);
+        v[3 + 4] = mul_w16<3>(v[3 + 4]);
+        v[1 + 8] = mul_w16<2>(v[1 + 8]);
+        v[2 + 8] = mul_w16<4>(v[2 + 8]);
+        v[3 + 8] = mul_w16<6>(v[3 + 8]);
+        v[1 + 12] = mul_w16<3>(v[1 + 12]);
+        v[2 + 12] = mul_w16<6>(v[2 + 12]);
+        v[3 + 12] = mul_w16<9>(v[3 + 12]);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+        // v[k2 + 4*k1] holds X[k1 + 4*k2]: transpose register names
+        Cx<T> o[16];
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) o[k1 + 4 * k2] = v[k2 + 4 * k1];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = o[k];
+    }
+};
+
+// v[k] *= w^k, k = 1..R-1, powers built by a depth <= 5 product tree
+template <int R, typename T>
+__device__ __forceinline__ void apply_twiddle_powers(Cx<T> (&v)[R], Cx<T> w1) {
+    if constexpr (R >= 2) v[1] = cmul(v[1], w1);
+    if constexpr (R >= 4) {
+        Cx<T> w2 = csqr(w1);
+        v[2] = cmul(v[2], w2);
+        Cx<T> w3 = cmul(w2, w1);
+        v[3] = cmul(v[3], w3);
+        if constexpr (R >= 8) {
+            Cx<T> w4 = csqr(w2);
+            v[4] = cmul(v[4], w4);
+            v[5] = cmul(v[5], cmul(w4, w1));
+            v[6] = cmul(v[6], cmul(w4, w2));
+            v[7] = cmul(v[7], cmul(w4, w3));
+            if constexpr (R >= 16) {
+                Cx<T> w8 = csqr(w4);
+                v[8] = cmul(v[8], w8);
+                v[9] = cmul(v[9], cmul(w8, w1));
+                v[10] = cmul(v[10], cmul(w8, w2));
+                v[11] = cmul(v[11], cmul(w8, w3));
+                Cx<T> w12 = cmul(w8, w4);
+                v[12] = cmul(v[12], w12);
+                v[13] = cmul(v[13], cmul(w12, w1));
+                v[14] = cmul(v[14], cmul(w12, w2));
+                v[15] = cmul(v[15], cmul(w12, w3));
+            }
+        }
+    }
+}
+
+__host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
+
+// ---- tile configuration ------------------------------------------------------
+
+template <typename T, int L_, int TL_>
+struct TileCfg {
+    static constexpr int L = L_;
+    static constexpr int TL = TL_;
+    static constexpr int E = L < 16 ? L : 16;          // points per thread
+    static constexpr int TPL = L / E;                  // threads per lane
+    static constexpr int NT = TPL * TL;                // threads per CTA
+    static constexpr int G = 128 / (int)sizeof(Cx<T>);  // threads per smem wavefront
+    static __host__ __device__ constexpr int lane_pitch() {
+        int want = (TL < G) ? (G / TL) % G : 1;
+        int lp = L + 1;  // >= L+1: the real-transform paths stage L+1 points per lane
+        while (lp % G != want) ++lp;
+        return lp;
+    }
+    static constexpr int LP = lane_pitch();
+    static constexpr size_t SMEM = (size_t)TL * LP * sizeof(Cx<T>);
+    // resident CTAs per SM the register allocator must leave room for
+    static constexpr int MINB = (NT <= 256 && sizeof(T) == 8) ? 2 : (NT <= 256 ? 3 : 1);
+};
+
+template <typename C, int R, int S>
+__device__ __forceinline__ int swz(int e) {
+    constexpr int sh_rs = ilog2(R * S), sh_s = ilog2(S);
+    return e ^ (((e >> sh_rs) << sh_s) & (C::G - 1));
+}
+
+// One Stockham stage of radix R at stride S over the thread's E registers, then
+// recurse.  (tw, iw) = mapping of the thread while it holds the stage inputs,
+// (tr, ir) = mapping used after the exchange.
+template <typename T, typename C, int S, bool FIRST>
+__device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__ sm,
+                                           const Cx<T>* __restrict__ tw, int tw_, int iw, int tr,
+                                           int ir) {
+    constexpr int L = C::L, E = C::E, TPL = C::TPL;
+    constexpr int R = (L / S >= 16) ? 16 : (L / S);
+    constexpr bool LAST = (S * R == L);
+    constexpr int NB = E / R;  // butterflies per thread in this stage
+    if constexpr (!LAST && !FIRST) __syncthreads();  // previous readers done before we overwrite
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        Cx<T> v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = a[b + r * NB];
+        Dft<R, T>::run(v);
+        if constexpr (LAST) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) a[b + k * NB] = v[k];
+        } else {
+            const int ib = iw + b * TPL;
+            const int q = ib & (S - 1);
+            const int base = ib - q;
+            apply_twiddle_powers<R, T>(v, tw[base]);
+            Cx<T>* dst = sm + tw_ * C::LP;
+            const int p0 = q + R * base;
+#pragma unroll
+            for (int k = 0; k < R; ++k) dst[swz<C, R, S>(p0 + k * S)] = v[k];
+        }
+    }
+    if constexpr (!LAST) {
+        __syncthreads();
+        const Cx<T>* src = sm + tr * C::LP;
+#pragma unroll
+        for (int m = 0; m < E; ++m) a[m] = src[swz<C, R, S>(ir + m * TPL)];
+        run_stages<T, C, S * R, false>(a, sm, tw, tr, ir, tr, ir);
+    }
+}
+
+// W_32^m = exp(-2*pi*i*m/32), m < 16 (real-transform post/pre twiddle split)
+template <typename T>
+__device__ __forceinline__ Cx<T> w32(int m) {
+    switch (m) {
+        case 0: return {(T)1.0L, (T)-0.0L};
+        case 1: return {(T)0.98078528040323044912618223613424L, (T)-0.19509032201612826784828486847702L};
+        case 2: return {(T)0.92387953251128675612818318939679L, (T)-0.38268343236508977172845998403040L};
+        case 3: return {(T)0.83146961230254523707878837761791L, (T)-0.55557023301960222474283081394853L};
+        case 4: return {(T)0.70710678118654752440084436210485L, (T)-0.70710678118654752440084436210485L};
+        case 5: return {(T)0.55557023301960222474283081394853L, (T)-0.83146961230254523707878837761791L};
+        case 6: return {(T)0.38268343236508977172845998403040L, (T)-0.92387953251128675612818318939679L};
+        case 7: return {(T)0.19509032201612826784828486847702L, (T)-0.98078528040323044912618223613424L};
+        case 8: return {(T)0.0L, (T)-1.0L};
+        case 9: return {(T)-0.19509032201612826784828486847702L, (T)-0.98078528040323044912618223613424L};
+        case 10: return {(T)-0.38268343236508977172845998403040L, (T)-0.92387953251128675612818318939679L};
+        case 11: return {(T)-0.55557023301960222474283081394853L, (T)-0.83146961230254523707878837761791L};
+        case 12: return {(T)-0.70710678118654752440084436210485L, (T)-0.70710678118654752440084436210485L};
+        case 13: return {(T)-0.83146961230254523707878837761791L, (T)-0.55557023301960222474283081394853L};
+        case 14: return {(T)-0.92387953251128675612818318939679L, (T)-0.38268343236508977172845998403040L};
+        default: return {(T)-0.98078528040323044912618223613424L, (T)-0.19509032201612826784828486847702L};
+    }
+}
+
+template <int TL, int TPL>
+__device__ __forceinline__ void map_thread(int mode, int tid, int& t, int& i) {
+    if (mode == MAP_COL) {
+        t = tid % TL;
+        i = tid / TL;
+    } else {
+        i = tid % TPL;
+        t = tid / TPL;
+    }
+}
+
+// ---- the kernel ---------------------------------------------------------------
+
+template <typename T, int L, int TL, bool DOUBLE>
+__global__ void __launch_bounds__(TileCfg<T, L, TL>::NT, TileCfg<T, L, TL>::MINB)
+tile_fft_kernel(const __grid_constant__ PassParams p) {
+    using C = TileCfg<T, L, TL>;
+    using cx = Cx<T>;
+    constexpr int E = C::E, TPL = C::TPL, LP = C::LP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx* sm = reinterpret_cast<cx*>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const uint32_t tile = blockIdx.x % p.tiles_per_batch;
+    const uint32_t batch = blockIdx.x / p.tiles_per_batch;
+
+    int t0, i0, t1, i1;
+    map_thread<TL, TPL>(p.map_in, tid, t0, i0);
+    map_thread<TL, TPL>(p.map_out, tid, t1, i1);
+
+    cx a[E];
+
+    // ------------------------------ load ------------------------------------
+    {
+        const uint32_t lane = tile * TL + (uint32_t)t0;
+        const bool valid = lane < p.nlanes;
+        const uint32_t lo = lane / p.inner_count;
+        const uint32_t li = lane - lo * p.inner_count;
+        const int64_t off = (int64_t)batch * p.in.batch_stride + (int64_t)lo * p.in.outer_stride +
+                            (int64_t)li * p.in.inner_stride;
+        const int64_t pos0 = (int64_t)lo * p.in.pos_ls;
+        const bool swap_pre = p.flags & F_SWAP_LD_PRE;
+        if (p.ld_op == LD_C2R) {
+            // stage the L+1 Hermitian inputs of each lane, then build the packed
+            // spectrum Z[k] = (X[k] + conj X[L-k]) + i*conj(W_2L^k)*(X[k] - conj X[L-k])
+            const cx* __restrict__ src = reinterpret_cast<const cx*>(p.in.ptr) + off;
+            cx* row = sm + t0 * LP;
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int e = i0 + m * TPL;
+                cx v = {0, 0};
+                if (valid && (int64_t)e < p.in.len) v = src[(int64_t)e * p.in.elem_stride];
+                row[e] = v;
+            }
+            if (i0 == 0) {
+                cx v = {0, 0};
+                if (valid && (int64_t)L < p.in.len) v = src[(int64_t)L * p.in.elem_stride];
+                row[L] = v;
+            }
+            __syncthreads();
+            if constexpr (E == 16) {
+                const cx wi = reinterpret_cast<const cx*>(p.rtw)[i0];
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const int k = i0 + m * TPL;
+                    cx xk = row[k];
+                    cx xp = row[L - k];
+                    if (k == 0) {  // imag of DC / Nyquist never reaches the real output
+                        xk.y = 0;
+                        xp.y = 0;
+                    }
+                    const cx A = {xk.x + xp.x, xk.y - xp.y};
+                    const cx D = {xk.x - xp.x, xk.y + xp.y};
+                    const cx w = cmul(wi, w32<T>(m));
+                    const cx Bc = cmulc(D, w);           // conj(W) * D
+                    a[m] = {A.x - Bc.y, A.y + Bc.x};     // A + i*Bc
+                }
+            }
+            __syncthreads();
+        } else {
+            const bool is_real = (p.ld_op == LD_R) || (p.ld_op == LD_R_MUL);
+            const bool has_mul = (p.ld_op == LD_C_MUL) || (p.ld_op == LD_R_MUL);
+            if (is_real) {
+                const T* __restrict__ src = reinterpret_cast<const T*>(p.in.ptr) + off;
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const int e = i0 + m * TPL;
+                    const int64_t pos = (int64_t)e * p.in.pos_es + pos0;
+                    T r = 0;
+                    if (valid && pos < p.in.len) r = src[(int64_t)e * p.in.elem_stride];
+                    a[m] = {r, (T)0};
+                }
+            } else {
+                const cx* __restrict__ src = reinterpret_cast<const cx*>(p.in.ptr) + off;
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const int e = i0 + m * TPL;
+                    const int64_t pos = (int64_t)e * p.in.pos_es + pos0;
+                    cx v = {0, 0};
+                    if (valid && pos < p.in.len) v = src[(int64_t)e * p.in.elem_stride];
+                    a[m] = v;
+                }
+            }
+            if (swap_pre) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) a[m] = cswap(a[m]);
+            }
+            if (has_mul) {
+                const cx* __restrict__ aux = reinterpret_cast<const cx*>(p.aux_in);
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const int e = i0 + m * TPL;
+                    const int64_t pos = (int64_t)e * p.in.pos_es + pos0;
+                    if (pos < p.in.len) a[m] = cmul(a[m], aux[pos]);
+                }
+            }
+        }
+        if (p.flags & F_SWAP_LD_POST) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) a[m] = cswap(a[m]);
+        }
+    }
+
+    // ---------------------------- transform ---------------------------------
+    const cx* __restrict__ tw = reinterpret_cast<const cx*>(p.tw);
+    const bool staged = (p.ld_op == LD_C2R);
+    if (staged)
+        run_stages<T, C, 1, false>(a, sm, tw, t0, i0, t1, i1);
+    else
+        run_stages<T, C, 1, true>(a, sm, tw, t0, i0, t1, i1);
+
+    if constexpr (C::E == C::L) {
+        // single-stage tiles never touch shared memory: remap explicitly if the
+        // store wants the other thread->lane mapping
+        if (p.map_in != p.map_out) {
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < E; ++m) sm[t0 * LP + m] = a[m];
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < E; ++m) a[m] = sm[t1 * LP + m];
+        }
+    }
+
+    const uint32_t lane = tile * TL + (uint32_t)t1;
+    const bool valid = lane < p.nlanes;
+    const uint32_t lo = lane / p.inner_count;
+    const uint32_t li = lane - lo * p.inner_count;
+
+    if constexpr (DOUBLE) {
+        // forward transform -> pointwise table -> inverse transform, all on chip
+        const cx* __restrict__ mid = reinterpret_cast<const cx*>(p.mid);
+        const int64_t mid0 = (int64_t)lo * p.mid_ls;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int e = i1 + m * TPL;
+            cx w = mid[(int64_t)e * p.mid_es + mid0];
+            a[m] = cswap(cmul(a[m], w));
+        }
+        run_stages<T, C, 1, false>(a, sm, tw, t1, i1, t1, i1);
+#pragma unroll
+        for (int m = 0; m < E; ++m) a[m] = cswap(a[m]);
+    }
+
+    // ------------------------------ store -----------------------------------
+    const int64_t off = (int64_t)batch * p.out.batch_stride + (int64_t)lo * p.out.outer_stride +
+                        (int64_t)li * p.out.inner_stride;
+    const int64_t pos0 = (int64_t)lo * p.out.pos_ls;
+    const T scale = (T)p.scale;
+
+    if (p.flags & F_SWAP_ST_PRE) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) a[m] = cswap(a[m]);
+    }
+
+    if (p.st_op == ST_R2C) {
+        if constexpr (E == 16) {
+            // a[m] = Z[i1 + m*TPL] of the packed half-length transform
+            cx* row = sm + t1 * LP;
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < E; ++m) row[i1 + m * TPL] = a[m];
+            __syncthreads();
+            cx* __restrict__ dst = reinterpret_cast<cx*>(p.out.ptr) + off;
+            const cx wi = reinterpret_cast<const cx*>(p.rtw)[i1];
+#pragma unroll
+            for (int m = 0; m < E / 2; ++m) {
+                const int k = i1 + m * TPL;
+                const cx zk = a[m];
+                const cx zp = row[(L - k) & (L - 1)];
+                const cx A = {zk.x + zp.x, zk.y - zp.y};
+                const cx B = {zk.x - zp.x, zk.y + zp.y};
+                const cx Cw = cmul(B, cmul(wi, w32<T>(m)));
+                const T h = (T)0.5 * scale;
+                const cx xk = {(A.x + Cw.y) * h, (A.y - Cw.x) * h};
+                const cx xq = {(A.x - Cw.y) * h, -((A.y + Cw.x) * h)};
+                if (valid) {
+                    if ((int64_t)k < p.out.len) dst[(int64_t)k * p.out.elem_stride] = xk;
+                    if ((int64_t)(L - k) < p.out.len) dst[(int64_t)(L - k) * p.out.elem_stride] = xq;
+                }
+            }
+            if (i1 == 0 && valid && (int64_t)(L / 2) < p.out.len) {
+                const cx z = a[E / 2];
+                dst[(int64_t)(L / 2) * p.out.elem_stride] = {z.x * scale, -(z.y * scale)};
+            }
+        }
+        return;
+    }
+
+    if (p.st_op == ST_TW) {
+        const cx* __restrict__ tlo = reinterpret_cast<const cx*>(p.tw_lo);
+        const cx* __restrict__ thi = reinterpret_cast<const cx*>(p.tw_hi);
+        const uint64_t lmask = ((uint64_t)1 << p.tw_shift) - 1;
+        const bool cj = p.flags & F_TW_CONJ;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const uint64_t ex = (uint64_t)(i1 + m * TPL) * (uint64_t)lo;
+            cx w = cmul(thi[ex >> p.tw_shift], tlo[ex & lmask]);
+            a[m] = cj ? cmulc(a[m], w) : cmul(a[m], w);
+        }
+    } else if (p.st_op == ST_MUL) {
+        const cx* __restrict__ aux = reinterpret_cast<const cx*>(p.aux_out);
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int64_t pos = (int64_t)(i1 + m * TPL) * p.out.pos_es + pos0;
+            if (pos < p.out.len) a[m] = cmul(a[m], aux[pos]);
+        }
+    }
+    if (p.scale != 1.0) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) a[m] = {a[m].x * scale, a[m].y * scale};
+    }
+    if (p.flags & F_SWAP_ST_POST) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) a[m] = cswap(a[m]);
+    }
+    if (p.flags & F_ST_REAL) {
+        T* __restrict__ dst = reinterpret_cast<T*>(p.out.ptr) + off;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int e = i1 + m * TPL;
+            const int64_t pos = (int64_t)e * p.out.pos_es + pos0;
+            if (valid && pos < p.out.len) dst[(int64_t)e * p.out.elem_stride] = a[m].x;
+        }
+    } else {
+        cx* __restrict__ dst = reinterpret_cast<cx*>(p.out.ptr) + off;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int e = i1 + m * TPL;
+            const int64_t pos = (int64_t)e * p.out.pos_es + pos0;
+            if (valid && pos < p.out.len) dst[(int64_t)e * p.out.elem_stride] = a[m];
+        }
+    }
+}
+
+}  // namespace sfc

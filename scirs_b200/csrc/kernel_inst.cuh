@@ -1,0 +1,41 @@
+// kernel_inst.cuh — instantiate tile_fft_kernel and wrap it in a launcher.
+#pragma once
+#include "fft_tile.cuh"
+#include "kernel_registry.h"
+
+namespace sfc {
+
+template <typename T, int L, int TL, bool DBL>
+struct KernelInst {
+    using C = TileCfg<T, L, TL>;
+    static cudaError_t launch(const PassParams& p, unsigned grid, cudaStream_t s) {
+        static bool configured[64] = {};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 64 && !configured[dev]) {
+            e = cudaFuncSetAttribute(tile_fft_kernel<T, L, TL, DBL>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+            if (e != cudaSuccess) return e;
+            configured[dev] = true;
+        }
+        tile_fft_kernel<T, L, TL, DBL><<<grid, C::NT, C::SMEM, s>>>(p);
+        return cudaGetLastError();
+    }
+    static KernelEntry entry() {
+        KernelEntry k;
+        k.prec = sizeof(T) == 8 ? PREC_F64 : PREC_F32;
+        k.L = L;
+        k.TL = TL;
+        k.dbl = DBL ? 1 : 0;
+        k.threads = C::NT;
+        k.smem = C::SMEM;
+        k.func = (const void*)tile_fft_kernel<T, L, TL, DBL>;
+        k.launch = &launch;
+        return k;
+    }
+};
+
+}  // namespace sfc
+
+#define SFC_ADD(T, L, TL, DBL) add(::sfc::KernelInst<T, L, TL, DBL>::entry());

@@ -1,0 +1,38 @@
+// kernel_registry.h — table of compiled tile_fft_kernel instantiations.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include "pass_params.h"
+
+namespace sfc {
+
+enum Prec : int { PREC_F32 = 0, PREC_F64 = 1 };
+
+struct KernelEntry {
+    int prec;       // Prec
+    int L;          // points per lane
+    int TL;         // lanes per tile
+    int dbl;        // 1 = forward * table * inverse fused
+    int threads;    // CTA size
+    size_t smem;    // dynamic shared memory bytes
+    const void* func;
+    cudaError_t (*launch)(const PassParams& p, unsigned grid, cudaStream_t s);
+};
+
+// all entries (built once, thread-safe)
+const KernelEntry* kernel_table(int* count);
+const KernelEntry* find_kernel(int prec, int L, int TL, int dbl);
+
+// per-file registration hooks (one per kernels_*.cu translation unit)
+void register_kernels_f64_small(void (*add)(const KernelEntry&));
+void register_kernels_f64_mid(void (*add)(const KernelEntry&));
+void register_kernels_f64_big(void (*add)(const KernelEntry&));
+void register_kernels_f64_dbl_a(void (*add)(const KernelEntry&));
+void register_kernels_f64_dbl_b(void (*add)(const KernelEntry&));
+void register_kernels_f32_small(void (*add)(const KernelEntry&));
+void register_kernels_f32_mid(void (*add)(const KernelEntry&));
+void register_kernels_f32_big(void (*add)(const KernelEntry&));
+void register_kernels_f32_dbl_a(void (*add)(const KernelEntry&));
+void register_kernels_f32_dbl_b(void (*add)(const KernelEntry&));
+
+}  // namespace sfc

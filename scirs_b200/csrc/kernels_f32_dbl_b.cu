@@ -1,0 +1,11 @@
+// kernels_f32_dbl_b.cu — generated list of tile kernel instantiations (see kernel_inst.cuh)
+#include "kernel_inst.cuh"
+namespace sfc {
+void register_kernels_f32_dbl_b(void (*add)(const KernelEntry&)) {
+    SFC_ADD(float, 1024, 4, true)
+    SFC_ADD(float, 2048, 2, true)
+    SFC_ADD(float, 4096, 1, true)
+    SFC_ADD(float, 8192, 1, true)
+    SFC_ADD(float, 16384, 1, true)
+}
+}  // namespace sfc

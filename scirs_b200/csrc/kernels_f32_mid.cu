@@ -1,0 +1,13 @@
+// kernels_f32_mid.cu — generated list of tile kernel instantiations (see kernel_inst.cuh)
+#include "kernel_inst.cuh"
+namespace sfc {
+void register_kernels_f32_mid(void (*add)(const KernelEntry&)) {
+    SFC_ADD(float, 256, 16, false)
+    SFC_ADD(float, 512, 8, false)
+    SFC_ADD(float, 512, 16, false)
+    SFC_ADD(float, 1024, 4, false)
+    SFC_ADD(float, 1024, 16, false)
+    SFC_ADD(float, 2048, 2, false)
+    SFC_ADD(float, 2048, 8, false)
+}
+}  // namespace sfc

@@ -1,0 +1,13 @@
+// kernels_f64_dbl_a.cu — generated list of tile kernel instantiations (see kernel_inst.cuh)
+#include "kernel_inst.cuh"
+namespace sfc {
+void register_kernels_f64_dbl_a(void (*add)(const KernelEntry&)) {
+    SFC_ADD(double, 8, 256, true)
+    SFC_ADD(double, 16, 256, true)
+    SFC_ADD(double, 32, 128, true)
+    SFC_ADD(double, 64, 64, true)
+    SFC_ADD(double, 128, 32, true)
+    SFC_ADD(double, 256, 16, true)
+    SFC_ADD(double, 512, 8, true)
+}
+}  // namespace sfc

@@ -1,0 +1,74 @@
+// pass_params.h — host/device shared description of ONE global-memory pass.
+//
+// A "pass" is one launch of the tile FFT kernel (fft_tile.cuh): every CTA loads
+// a tile of TL lanes x L elements, transforms each lane in shared memory /
+// registers and stores it.  All the reference's wrapper work around the rustfft
+// call (gather -> process -> scatter -> scale, scirs2-fft/src/fft/algorithms.rs:
+// 677-703) is folded into the load / store operators below.
+#pragma once
+#include <stdint.h>
+
+namespace sfc {
+
+// thread -> (lane, butterfly) mapping of a tile
+enum MapMode : int32_t {
+    MAP_ROW = 0,  // butterfly index fastest: lanes are contiguous rows (elem stride 1)
+    MAP_COL = 1,  // lane index fastest: adjacent lanes are contiguous in memory
+};
+
+enum LoadOp : int32_t {
+    LD_C = 0,       // complex element
+    LD_R = 1,       // real element, imag = 0            (reference: convert_to_complex, algorithms.rs:71-94)
+    LD_C_MUL = 2,   // complex element * aux_in[pos]     (Bluestein chirp pre-multiply)
+    LD_R_MUL = 3,   // real element * aux_in[pos]
+    LD_C2R = 4,     // Hermitian half-spectrum -> packed N/2 complex (irfft fast path, rfft.rs:92-178)
+};
+
+enum StoreOp : int32_t {
+    ST_C = 0,       // complex * scale
+    ST_TW = 1,      // complex * W_M^(e*lane_outer) * scale   (four-step inter-pass twiddle)
+    ST_MUL = 2,     // complex * aux_out[pos] * scale         (Bluestein chirp post-multiply)
+    ST_R2C = 3,     // packed N/2 complex spectrum -> N/2+1 Hermitian half (rfft fast path, rfft.rs:39-59)
+};
+
+enum PassFlags : uint32_t {
+    F_SWAP_LD_PRE = 1u << 0,   // swap re/im right after the raw load        (outer inverse)
+    F_SWAP_LD_POST = 1u << 1,  // swap re/im after the load operator         (inner inverse FFT)
+    F_SWAP_ST_PRE = 1u << 2,   // swap re/im before the store operator       (undo inner inverse)
+    F_SWAP_ST_POST = 1u << 3,  // swap re/im just before the raw store       (outer inverse)
+    F_TW_CONJ = 1u << 4,       // ST_TW uses conj(W)
+    F_ST_REAL = 1u << 5,       // store only the real part into a real array (irfftn, rfft.rs:722)
+};
+
+struct IoDesc {
+    void* ptr;
+    int64_t batch_stride;  // elements, per batch index (blockIdx / tiles_per_batch)
+    int64_t outer_stride;  // elements, per (lane / inner_count)
+    int64_t inner_stride;  // elements, per (lane % inner_count)
+    int64_t elem_stride;   // elements, per transform index e
+    int64_t len;           // valid logical positions: pos < len is loaded / stored, else 0 / skipped
+    int64_t pos_es;        // logical position pos = e*pos_es + lane_outer*pos_ls  (lane_outer = lane / inner_count)
+    int64_t pos_ls;
+};
+
+struct PassParams {
+    IoDesc in, out;
+    uint32_t nlanes;           // lanes per batch
+    uint32_t inner_count;      // lanes per outer index (shared by in/out)
+    uint32_t tiles_per_batch;  // ceil(nlanes / TL)
+    int32_t map_in, map_out;
+    int32_t ld_op, st_op;
+    uint32_t flags;
+    const void* tw;            // W_L^j, j < L              (stage twiddles)
+    const void* aux_in;        // LD_*_MUL table, indexed by in pos
+    const void* aux_out;       // ST_MUL table, indexed by out pos
+    const void* tw_lo;         // ST_TW: W_M^j, j < 2^tw_shift
+    const void* tw_hi;         // ST_TW: W_M^(j << tw_shift)
+    int32_t tw_shift;
+    const void* mid;           // double kernels: pointwise table between the two transforms
+    int64_t mid_es, mid_ls;    // mid index = e*mid_es + lane_outer*mid_ls
+    const void* rtw;           // R2C/C2R: W_{2L}^i, i < L/E
+    double scale;
+};
+
+}  // namespace sfc

@@ -1,0 +1,959 @@
+// plan.cu — planner + executor.  See plan.h.
+#include "plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+namespace sfc {
+
+// ------------------------------------------------------------ kernel table
+
+static std::vector<KernelEntry>& ktable() {
+    static std::vector<KernelEntry> v;
+    return v;
+}
+static void add_entry(const KernelEntry& e) { ktable().push_back(e); }
+static std::once_flag g_kernels_once;
+
+const KernelEntry* kernel_table(int* count) {
+    std::call_once(g_kernels_once, [] {
+        register_kernels_f64_small(add_entry);
+        register_kernels_f64_mid(add_entry);
+        register_kernels_f64_big(add_entry);
+        register_kernels_f64_dbl_a(add_entry);
+        register_kernels_f64_dbl_b(add_entry);
+        register_kernels_f32_small(add_entry);
+        register_kernels_f32_mid(add_entry);
+        register_kernels_f32_big(add_entry);
+        register_kernels_f32_dbl_a(add_entry);
+        register_kernels_f32_dbl_b(add_entry);
+    });
+    if (count) *count = (int)ktable().size();
+    return ktable().data();
+}
+
+const KernelEntry* find_kernel(int prec, int L, int TL, int dbl) {
+    int n = 0;
+    const KernelEntry* t = kernel_table(&n);
+    for (int i = 0; i < n; ++i)
+        if (t[i].prec == prec && t[i].L == L && t[i].TL == TL && t[i].dbl == dbl) return &t[i];
+    return nullptr;
+}
+
+// ROW tiles want few lanes per CTA (small tiles, more CTAs per SM); COL tiles want
+// many adjacent lanes (>= 128 B contiguous per element row).
+static const KernelEntry* pick_kernel(int prec, int L, bool want_wide, int dbl) {
+    int n = 0;
+    const KernelEntry* t = kernel_table(&n);
+    const KernelEntry* best = nullptr;
+    for (int i = 0; i < n; ++i) {
+        if (t[i].prec != prec || t[i].L != L || t[i].dbl != dbl) continue;
+        if (!best || (want_wide ? t[i].TL > best->TL : t[i].TL < best->TL)) best = &t[i];
+    }
+    return best;
+}
+
+// ------------------------------------------------------------- device tables
+
+using TableKey = std::tuple<int, int, int, int64_t, int64_t, int64_t, int64_t>;
+static std::recursive_mutex g_table_mu;
+static std::map<TableKey, const void*>& tables() {
+    static std::map<TableKey, const void*> m;
+    return m;
+}
+enum TableKind { TK_STAGE = 1, TK_RTW, TK_FS_LO, TK_FS_HI, TK_CHIRP, TK_BLUE };
+
+static inline void unit_root(long double num, long double den, long double& c, long double& s) {
+    // exp(-2*pi*i*num/den) in extended precision
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    const long double a = two_pi * (num / den);
+    c = cosl(a);
+    s = -sinl(a);
+}
+
+static const void* upload_table(const std::vector<long double>& re, const std::vector<long double>& im,
+                                int prec, PlanError& err) {
+    const size_t n = re.size();
+    void* d = nullptr;
+    const size_t bytes = n * (prec == PREC_F64 ? 16 : 8);
+    if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess) {
+        err = {SFC_ERR_MEMORY, "cudaMalloc failed for a twiddle table"};
+        cudaGetLastError();
+        return nullptr;
+    }
+    cudaError_t e;
+    if (prec == PREC_F64) {
+        std::vector<double> h(2 * n);
+        for (size_t i = 0; i < n; ++i) {
+            h[2 * i] = (double)re[i];
+            h[2 * i + 1] = (double)im[i];
+        }
+        e = cudaMemcpy(d, h.data(), bytes, cudaMemcpyHostToDevice);
+    } else {
+        std::vector<float> h(2 * n);
+        for (size_t i = 0; i < n; ++i) {
+            h[2 * i] = (float)re[i];
+            h[2 * i + 1] = (float)im[i];
+        }
+        e = cudaMemcpy(d, h.data(), bytes, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        err = {SFC_ERR_BACKEND, std::string("table upload failed: ") + cudaGetErrorString(e)};
+        cudaFree(d);
+        return nullptr;
+    }
+    return d;
+}
+
+static int cur_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
+
+static const void* roots_table(int kind, int prec, int64_t count, long double den, long double mult,
+                               int64_t keyN, PlanError& err) {
+    std::lock_guard<std::recursive_mutex> lk(g_table_mu);
+    TableKey key{cur_device(), kind, prec, keyN, count, (int64_t)mult, 0};
+    auto it = tables().find(key);
+    if (it != tables().end()) return it->second;
+    std::vector<long double> re(count), im(count);
+    for (int64_t j = 0; j < count; ++j) unit_root((long double)j * mult, den, re[j], im[j]);
+    const void* d = upload_table(re, im, prec, err);
+    if (d) tables()[key] = d;
+    return d;
+}
+
+const void* table_stage_tw(int prec, int L, PlanError& err) {
+    return roots_table(TK_STAGE, prec, L, (long double)L, 1.0L, L, err);
+}
+
+const void* table_rtw(int prec, int L, PlanError& err) {
+    const int cnt = std::max(L / 16, 1);
+    return roots_table(TK_RTW, prec, cnt, 2.0L * L, 1.0L, L, err);
+}
+
+bool table_fourstep(int prec, int64_t M, const void** lo, const void** hi, int* shift, PlanError& err) {
+    int lg = 0;
+    while (((int64_t)1 << lg) < M) ++lg;
+    const int sh = (lg + 1) / 2;
+    const int64_t nlo = (int64_t)1 << sh;
+    const int64_t nhi = std::max<int64_t>(M >> sh, 1);
+    *lo = roots_table(TK_FS_LO, prec, nlo, (long double)M, 1.0L, M, err);
+    if (!*lo) return false;
+    *hi = roots_table(TK_FS_HI, prec, nhi, (long double)M, (long double)nlo, M, err);
+    if (!*hi) return false;
+    *shift = sh;
+    return true;
+}
+
+const void* table_chirp(int prec, int64_t N, PlanError& err) {
+    std::lock_guard<std::recursive_mutex> lk(g_table_mu);
+    TableKey key{cur_device(), TK_CHIRP, prec, N, 0, 0, 0};
+    auto it = tables().find(key);
+    if (it != tables().end()) return it->second;
+    std::vector<long double> re(N), im(N);
+    const unsigned __int128 twoN = 2 * (unsigned __int128)N;
+    for (int64_t n = 0; n < N; ++n) {
+        // exp(-i*pi*n^2/N) with the phase reduced exactly: n^2 mod 2N
+        const unsigned __int128 r = ((unsigned __int128)n * (unsigned __int128)n) % twoN;
+        unit_root((long double)(uint64_t)r, (long double)(2 * N), re[n], im[n]);
+    }
+    const void* d = upload_table(re, im, prec, err);
+    if (d) tables()[key] = d;
+    return d;
+}
+
+const void* table_bluestein_b(int prec, int64_t N, int64_t M, int64_t L1, int64_t L2, PlanError& err) {
+    std::lock_guard<std::recursive_mutex> lk(g_table_mu);
+    TableKey key{cur_device(), TK_BLUE, prec, N, M, L1, L2};
+    auto it = tables().find(key);
+    if (it != tables().end()) return it->second;
+
+    // b[n] = conj(chirp[n]) for |n| < N (wrapped into length M), FFT_M(b)/M computed with
+    // our own f64 transform, then laid out for the consuming pass.
+    std::vector<double> hb(2 * (size_t)M, 0.0);
+    const unsigned __int128 twoN = 2 * (unsigned __int128)N;
+    for (int64_t n = 0; n < N; ++n) {
+        const unsigned __int128 r = ((unsigned __int128)n * (unsigned __int128)n) % twoN;
+        long double c, s;
+        unit_root((long double)(uint64_t)r, (long double)(2 * N), c, s);
+        hb[2 * n] = (double)c;
+        hb[2 * n + 1] = (double)(-s);
+        if (n > 0) {
+            hb[2 * (M - n)] = (double)c;
+            hb[2 * (M - n) + 1] = (double)(-s);
+        }
+    }
+    sfc_desc d{};
+    d.ndim = 1;
+    d.shape[0] = M;
+    d.naxes = 1;
+    d.axes[0] = 0;
+    d.kind = SFC_C2C;
+    d.prec = SFC_PREC_F64;
+    d.direction = SFC_FORWARD;
+    d.scale = 1.0 / (double)M;
+    std::shared_ptr<Plan> pl = Plan::create(d, err);
+    if (!pl) return nullptr;
+    void* dbuf = nullptr;
+    const size_t bytes = (size_t)M * 16;
+    if (cudaMalloc(&dbuf, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        err = {SFC_ERR_MEMORY, "cudaMalloc failed for the Bluestein kernel spectrum"};
+        return nullptr;
+    }
+    std::string es;
+    cudaError_t e = cudaMemcpy(dbuf, hb.data(), bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && pl->exec(dbuf, dbuf, 0, es) != 0) {
+        err = {SFC_ERR_COMPUTATION, "Bluestein kernel spectrum: " + es};
+        cudaFree(dbuf);
+        return nullptr;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    if (e == cudaSuccess) e = cudaMemcpy(hb.data(), dbuf, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(dbuf);
+    if (e != cudaSuccess) {
+        err = {SFC_ERR_BACKEND, std::string("Bluestein kernel spectrum: ") + cudaGetErrorString(e)};
+        return nullptr;
+    }
+    std::vector<long double> re(M), im(M);
+    if (L1 > 0) {
+        for (int64_t k1 = 0; k1 < L1; ++k1)
+            for (int64_t k2 = 0; k2 < L2; ++k2) {
+                const int64_t k = k1 + L1 * k2;
+                re[k1 * L2 + k2] = hb[2 * k];
+                im[k1 * L2 + k2] = hb[2 * k + 1];
+            }
+    } else {
+        for (int64_t k = 0; k < M; ++k) {
+            re[k] = hb[2 * k];
+            im[k] = hb[2 * k + 1];
+        }
+    }
+    const void* t = upload_table(re, im, prec, err);
+    if (t) tables()[key] = t;
+    return t;
+}
+
+// ------------------------------------------------------------------ builder
+
+static inline bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
+static inline int64_t next_pow2(int64_t n) {
+    int64_t p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+static inline int ilog2_64(int64_t n) {
+    int l = 0;
+    while (((int64_t)1 << l) < n) ++l;
+    return l;
+}
+
+static int64_t scratch_budget_bytes() {
+    static int64_t v = [] {
+        const char* e = getenv("SFC_WORK_MB");
+        int64_t mb = e ? atoll(e) : 64;
+        if (mb < 1) mb = 1;
+        return mb << 20;
+    }();
+    return v;
+}
+
+struct ArrayRef {
+    int role;
+    bool real;
+    int64_t n;  // extent of the transform axis in this array
+};
+
+struct PlanBuilder {
+    Plan& pl;
+    int prec;
+    size_t cs;  // complex element bytes
+    size_t rs;  // real element bytes
+    PlanError& err;
+    int64_t dev_bytes = 0;
+
+    bool fail(int code, const std::string& m) {
+        err = {code, m};
+        return false;
+    }
+
+    void need_ms(size_t bytes) { pl.ms_bytes_ = std::max(pl.ms_bytes_, bytes); }
+    void need_sa(size_t bytes) { pl.sa_bytes_ = std::max(pl.sa_bytes_, bytes); }
+
+    static void set_io(IoDesc& d, int64_t bs, int64_t os, int64_t is, int64_t es, int64_t len, int64_t pes,
+                       int64_t pls) {
+        d.ptr = nullptr;
+        d.batch_stride = bs;
+        d.outer_stride = os;
+        d.inner_stride = is;
+        d.elem_stride = es;
+        d.len = len;
+        d.pos_es = pes;
+        d.pos_ls = pls;
+    }
+
+    bool finish_tile(Step& s, int64_t nlanes, int64_t inner, int64_t nbatch, const char* what) {
+        if (!s.k) return fail(SFC_ERR_PLAN, std::string("no kernel instantiation for ") + what);
+        if (nlanes <= 0 || nlanes > 0xFFFFFFFFLL) return fail(SFC_ERR_VALUE, "too many lanes for one pass");
+        s.p.nlanes = (uint32_t)nlanes;
+        s.p.inner_count = (uint32_t)std::max<int64_t>(inner, 1);
+        const int64_t tiles = (nlanes + s.k->TL - 1) / s.k->TL;
+        s.p.tiles_per_batch = (uint32_t)tiles;
+        s.nbatch = nbatch;
+        s.p.tw = table_stage_tw(prec, s.k->L, err);
+        if (!s.p.tw) return false;
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s: tile L=%d TL=%d%s threads=%d smem=%zu lanes=%lld batches=%lld map=%s->%s", what,
+                 s.k->L, s.k->TL, s.k->dbl ? " fwd*tab*inv" : "", s.k->threads, s.k->smem, (long long)nlanes,
+                 (long long)nbatch, s.p.map_in == MAP_ROW ? "row" : "col", s.p.map_out == MAP_ROW ? "row" : "col");
+        s.desc = buf;
+        pl.steps_.push_back(s);
+        return true;
+    }
+
+    int new_group(int64_t nbatch, int64_t bytes_per_batch) {
+        Group g;
+        g.nbatch = nbatch;
+        g.chunk = std::max<int64_t>(1, scratch_budget_bytes() / std::max<int64_t>(bytes_per_batch, 1));
+        g.chunk = std::min(g.chunk, nbatch);
+        // keep at least ~2 waves of tiles in flight is handled by the caller's tile sizes
+        pl.groups_.push_back(g);
+        need_ms((size_t)g.chunk * (size_t)bytes_per_batch);
+        return (int)pl.groups_.size() - 1;
+    }
+
+    bool add_copy(ArrayRef src, ArrayRef dst, const std::vector<int64_t>& src_shape,
+                  const std::vector<int64_t>& dst_shape, double scale, bool src_f64_override = true,
+                  bool use_override = false) {
+        Step s;
+        s.kind = K_COPY;
+        s.src = src.role;
+        s.dst = dst.role;
+        CopyParams& c = s.cp;
+        c.ndim = (int)dst_shape.size();
+        c.total = 1;
+        for (int i = 0; i < c.ndim; ++i) {
+            c.dst_shape[i] = dst_shape[i];
+            c.src_shape[i] = src_shape[i];
+            c.total *= dst_shape[i];
+        }
+        if (c.ndim == 0) {
+            c.ndim = 1;
+            c.dst_shape[0] = c.src_shape[0] = 1;
+            c.total = 1;
+        }
+        c.src_complex = src.real ? 0 : 1;
+        c.dst_complex = dst.real ? 0 : 1;
+        c.src_f64 = use_override ? (src_f64_override ? 1 : 0) : (prec == PREC_F64);
+        c.dst_f64 = (prec == PREC_F64);
+        c.conj_src = 0;
+        c.scale = scale;
+        s.desc = "copy/pad/crop";
+        dev_bytes += c.total * (int64_t)((src.real ? rs : cs) + (dst.real ? rs : cs));
+        pl.steps_.push_back(s);
+        return true;
+    }
+
+    // One 1-D transform of length n along the middle axis of [O][n][I] arrays.
+    bool add_axis(int64_t n, int64_t O, int64_t I, ArrayRef src, ArrayRef dst, bool inverse, double scale,
+                  bool store_real) {
+        const int lmax = lmax_for(prec);
+        const uint32_t fl_in = inverse ? F_SWAP_LD_PRE : 0;
+        const uint32_t fl_out = (inverse ? F_SWAP_ST_POST : 0) | (store_real ? F_ST_REAL : 0);
+        const size_t src_es = src.real ? rs : cs;
+        const size_t dst_es = (dst.real || store_real) ? rs : cs;
+        const bool col = I > 1;
+        if (O <= 0 || I <= 0 || n <= 0) return fail(SFC_ERR_VALUE, "empty transform axis");
+
+        if (n == 1) {
+            // length-1 DFT is the identity
+            std::vector<int64_t> ss{O, src.n, I}, ds{O, dst.n, I};
+            ArrayRef d2 = dst;
+            d2.real = dst.real || store_real;
+            return add_copy(src, d2, ss, ds, scale);
+        }
+
+        if (is_pow2(n) && n <= lmax) {
+            Step s;
+            s.k = pick_kernel(prec, (int)n, col, 0);
+            s.src = src.role;
+            s.dst = dst.role;
+            s.src_esize = src_es;
+            s.dst_esize = dst_es;
+            set_io(s.p.in, 0, src.n * I, 1, I, std::min(n, src.n), 1, 0);
+            set_io(s.p.out, 0, dst.n * I, 1, I, std::min(n, dst.n), 1, 0);
+            s.p.map_in = s.p.map_out = col ? MAP_COL : MAP_ROW;
+            s.p.ld_op = src.real ? LD_R : LD_C;
+            s.p.st_op = ST_C;
+            s.p.flags = fl_in | fl_out;
+            s.p.scale = scale;
+            dev_bytes += O * I * (std::min(n, src.n) * (int64_t)src_es + std::min(n, dst.n) * (int64_t)dst_es);
+            return finish_tile(s, O * I, I, 1, "single-pass axis");
+        }
+
+        if (is_pow2(n)) {
+            // four-step (Bailey): n = L1*L2, columns then rows, through the work area [O][n][I]
+            const int lg = ilog2_64(n);
+            if (n > (int64_t)lmax * lmax) return fail(SFC_ERR_NOT_IMPLEMENTED, "transform length above lmax^2");
+            int64_t L1 = (int64_t)1 << (lg / 2);
+            int64_t L2 = n / L1;
+            if (L2 > lmax) {
+                L2 = lmax;
+                L1 = n / L2;
+            }
+            const void *lo, *hi;
+            int sh;
+            if (!table_fourstep(prec, n, &lo, &hi, &sh, err)) return false;
+            const int g = new_group(O, n * I * (int64_t)cs);
+            Step a;
+            a.k = pick_kernel(prec, (int)L1, true, 0);
+            a.src = src.role;
+            a.dst = R_MS;
+            a.src_esize = src_es;
+            a.dst_esize = cs;
+            a.group = g;
+            set_io(a.p.in, src.n * I, I, 1, L2 * I, std::min(n, src.n), L2, 1);
+            set_io(a.p.out, n * I, I, 1, L2 * I, n, L2, 1);
+            a.p.map_in = a.p.map_out = MAP_COL;
+            a.p.ld_op = src.real ? LD_R : LD_C;
+            a.p.st_op = ST_TW;
+            a.p.tw_lo = lo;
+            a.p.tw_hi = hi;
+            a.p.tw_shift = sh;
+            a.p.flags = fl_in;
+            a.p.scale = 1.0;
+            if (!finish_tile(a, L2 * I, I, O, "four-step pass A (columns + twiddle)")) return false;
+            Step b;
+            b.k = pick_kernel(prec, (int)L2, true, 0);
+            b.src = R_MS;
+            b.dst = dst.role;
+            b.src_esize = cs;
+            b.dst_esize = dst_es;
+            b.group = g;
+            set_io(b.p.in, n * I, L2 * I, 1, I, L2, 1, 0);
+            set_io(b.p.out, dst.n * I, I, 1, L1 * I, std::min(n, dst.n), L1, 1);
+            b.p.map_in = col ? MAP_COL : MAP_ROW;
+            b.p.map_out = MAP_COL;
+            b.p.ld_op = LD_C;
+            b.p.st_op = ST_C;
+            b.p.flags = fl_out;
+            b.p.scale = scale;
+            dev_bytes += O * I * (std::min(n, src.n) * (int64_t)src_es + 2 * n * (int64_t)cs +
+                                  std::min(n, dst.n) * (int64_t)dst_es);
+            return finish_tile(b, L1 * I, I, O, "four-step pass B (rows, transposed store)");
+        }
+
+        // Bluestein chirp-z over a padded power-of-two convolution of length M >= 2n-1
+        const int64_t M = next_pow2(2 * n - 1);
+        const void* chirp = table_chirp(prec, n, err);
+        if (!chirp) return false;
+        if (M <= lmax) {
+            const void* bf = table_bluestein_b(prec, n, M, 0, 0, err);
+            if (!bf) return false;
+            Step s;
+            s.k = pick_kernel(prec, (int)M, col, 1);
+            s.src = src.role;
+            s.dst = dst.role;
+            s.src_esize = src_es;
+            s.dst_esize = dst_es;
+            set_io(s.p.in, 0, src.n * I, 1, I, std::min(n, src.n), 1, 0);
+            set_io(s.p.out, 0, dst.n * I, 1, I, std::min(n, dst.n), 1, 0);
+            s.p.map_in = s.p.map_out = col ? MAP_COL : MAP_ROW;
+            s.p.ld_op = src.real ? LD_R_MUL : LD_C_MUL;
+            s.p.aux_in = chirp;
+            s.p.mid = bf;
+            s.p.mid_es = 1;
+            s.p.mid_ls = 0;
+            s.p.st_op = ST_MUL;
+            s.p.aux_out = chirp;
+            s.p.flags = fl_in | fl_out;
+            s.p.scale = scale;
+            dev_bytes += O * I * (std::min(n, src.n) * (int64_t)src_es + std::min(n, dst.n) * (int64_t)dst_es);
+            return finish_tile(s, O * I, I, 1, "Bluestein single-pass (chirp*FFT*B*IFFT*chirp)");
+        }
+        if (M > (int64_t)lmax * lmax) return fail(SFC_ERR_NOT_IMPLEMENTED, "Bluestein length above lmax^2");
+        const int lg = ilog2_64(M);
+        int64_t L1 = (int64_t)1 << (lg / 2);
+        int64_t L2 = M / L1;
+        if (L2 > lmax) {
+            L2 = lmax;
+            L1 = M / L2;
+        }
+        const void* bf = table_bluestein_b(prec, n, M, L1, L2, err);
+        if (!bf) return false;
+        const void *lo, *hi;
+        int sh;
+        if (!table_fourstep(prec, M, &lo, &hi, &sh, err)) return false;
+        const int g = new_group(O, M * I * (int64_t)cs);
+        {
+            Step a;
+            a.k = pick_kernel(prec, (int)L1, true, 0);
+            a.src = src.role;
+            a.dst = R_MS;
+            a.src_esize = src_es;
+            a.dst_esize = cs;
+            a.group = g;
+            set_io(a.p.in, src.n * I, I, 1, L2 * I, std::min(n, src.n), L2, 1);
+            set_io(a.p.out, M * I, I, 1, L2 * I, M, L2, 1);
+            a.p.map_in = a.p.map_out = MAP_COL;
+            a.p.ld_op = src.real ? LD_R_MUL : LD_C_MUL;
+            a.p.aux_in = chirp;
+            a.p.st_op = ST_TW;
+            a.p.tw_lo = lo;
+            a.p.tw_hi = hi;
+            a.p.tw_shift = sh;
+            a.p.flags = fl_in;
+            a.p.scale = 1.0;
+            if (!finish_tile(a, L2 * I, I, O, "Bluestein pass A (chirp, pad, columns, twiddle)")) return false;
+        }
+        {
+            Step b;
+            b.k = pick_kernel(prec, (int)L2, col, 1);
+            b.src = R_MS;
+            b.dst = R_MS;
+            b.src_esize = cs;
+            b.dst_esize = cs;
+            b.group = g;
+            set_io(b.p.in, M * I, L2 * I, 1, I, L2, 1, 0);
+            set_io(b.p.out, M * I, L2 * I, 1, I, L2, 1, 0);
+            b.p.map_in = b.p.map_out = col ? MAP_COL : MAP_ROW;
+            b.p.ld_op = LD_C;
+            b.p.mid = bf;
+            b.p.mid_es = 1;
+            b.p.mid_ls = L2;
+            b.p.st_op = ST_TW;
+            b.p.tw_lo = lo;
+            b.p.tw_hi = hi;
+            b.p.tw_shift = sh;
+            b.p.flags = F_TW_CONJ;
+            b.p.scale = 1.0;
+            if (!finish_tile(b, L1 * I, I, O, "Bluestein pass B (rows: FFT * B * IFFT * conj twiddle)")) return false;
+        }
+        {
+            Step c;
+            c.k = pick_kernel(prec, (int)L1, true, 0);
+            c.src = R_MS;
+            c.dst = dst.role;
+            c.src_esize = cs;
+            c.dst_esize = dst_es;
+            c.group = g;
+            set_io(c.p.in, M * I, I, 1, L2 * I, M, L2, 1);
+            set_io(c.p.out, dst.n * I, I, 1, L2 * I, std::min(n, dst.n), L2, 1);
+            c.p.map_in = c.p.map_out = MAP_COL;
+            c.p.ld_op = LD_C;
+            c.p.st_op = ST_MUL;
+            c.p.aux_out = chirp;
+            c.p.flags = F_SWAP_LD_POST | F_SWAP_ST_PRE | fl_out;
+            c.p.scale = scale;
+            dev_bytes += O * I * (std::min(n, src.n) * (int64_t)src_es + 5 * M * (int64_t)cs +
+                                  std::min(n, dst.n) * (int64_t)dst_es);
+            return finish_tile(c, L2 * I, I, O, "Bluestein pass C (inverse columns, chirp, crop)");
+        }
+    }
+
+    bool r2c_fast_ok(int64_t n, int64_t I) const {
+        return I == 1 && is_pow2(n) && n >= 64 && n / 2 <= lmax_for(prec);
+    }
+
+    // rows of n reals -> rows of n/2+1 complex (rfft.rs:39-59)
+    bool add_r2c(int64_t n, int64_t O, ArrayRef src, ArrayRef dst, double scale) {
+        Step s;
+        const int L = (int)(n / 2);
+        s.k = pick_kernel(prec, L, false, 0);
+        s.src = src.role;
+        s.dst = dst.role;
+        s.src_esize = cs;  // addressed as packed complex
+        s.dst_esize = cs;
+        set_io(s.p.in, 0, L, 1, 1, L, 1, 0);
+        set_io(s.p.out, 0, dst.n, 1, 1, std::min<int64_t>(L + 1, dst.n), 1, 0);
+        s.p.map_in = s.p.map_out = MAP_ROW;
+        s.p.ld_op = LD_C;
+        s.p.st_op = ST_R2C;
+        s.p.flags = 0;
+        s.p.scale = scale;
+        s.p.rtw = table_rtw(prec, L, err);
+        if (!s.p.rtw) return false;
+        dev_bytes += O * (n * (int64_t)rs + std::min<int64_t>(L + 1, dst.n) * (int64_t)cs);
+        return finish_tile(s, O, 1, 1, "real->complex fused pack + post-twiddle");
+    }
+
+    // rows of src.n (<= n/2+1 used) complex -> rows of n reals (rfft.rs:92-178)
+    bool add_c2r(int64_t n, int64_t O, ArrayRef src, ArrayRef dst, double scale) {
+        Step s;
+        const int L = (int)(n / 2);
+        s.k = pick_kernel(prec, L, false, 0);
+        s.src = src.role;
+        s.dst = dst.role;
+        s.src_esize = cs;
+        s.dst_esize = cs;  // addressed as packed complex
+        set_io(s.p.in, 0, src.n, 1, 1, std::min<int64_t>(L + 1, src.n), 1, 0);
+        set_io(s.p.out, 0, L, 1, 1, L, 1, 0);
+        s.p.map_in = s.p.map_out = MAP_ROW;
+        s.p.ld_op = LD_C2R;
+        s.p.st_op = ST_C;
+        s.p.flags = F_SWAP_LD_POST | F_SWAP_ST_PRE;
+        s.p.scale = scale;
+        s.p.rtw = table_rtw(prec, L, err);
+        if (!s.p.rtw) return false;
+        dev_bytes += O * (std::min<int64_t>(L + 1, src.n) * (int64_t)cs + n * (int64_t)rs);
+        return finish_tile(s, O, 1, 1, "complex->real fused pre-twiddle + unpack");
+    }
+};
+
+// ---------------------------------------------------------------- Plan::create
+
+static int64_t prod(const std::vector<int64_t>& v, size_t a, size_t b) {
+    int64_t p = 1;
+    for (size_t i = a; i < b; ++i) p *= v[i];
+    return p;
+}
+
+std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
+    if (d.ndim < 1 || d.ndim > SFC_MAX_DIMS) {
+        err = {SFC_ERR_VALUE, "ndim must be in 1..8"};
+        return nullptr;
+    }
+    if (d.naxes < 0 || d.naxes > SFC_MAX_DIMS) {
+        err = {SFC_ERR_VALUE, "naxes must be in 0..8"};
+        return nullptr;
+    }
+    if (d.prec != SFC_PREC_F32 && d.prec != SFC_PREC_F64) {
+        err = {SFC_ERR_VALUE, "unknown precision"};
+        return nullptr;
+    }
+    std::vector<int64_t> shape(d.shape, d.shape + d.ndim);
+    for (int64_t s : shape)
+        if (s <= 0) {
+            err = {SFC_ERR_VALUE, "shape entries must be positive"};
+            return nullptr;
+        }
+    std::vector<int> axes(d.axes, d.axes + d.naxes);
+    for (int a : axes)
+        if (a < 0 || a >= d.ndim) {
+            char b[96];
+            snprintf(b, sizeof b, "Axis %d out of bounds for array of dimension %d", a, d.ndim);
+            err = {SFC_ERR_VALUE, b};
+            return nullptr;
+        }
+    int devcount = 0;
+    if (cudaGetDeviceCount(&devcount) != cudaSuccess || devcount == 0) {
+        cudaGetLastError();
+        err = {SFC_ERR_BACKEND, "no CUDA device available (this library has no CPU fallback)"};
+        return nullptr;
+    }
+
+    std::shared_ptr<Plan> sp(new Plan());
+    Plan& pl = *sp;
+    pl.desc = d;
+    pl.device = cur_device();
+    const int prec = d.prec == SFC_PREC_F64 ? PREC_F64 : PREC_F32;
+    const size_t cs = prec == PREC_F64 ? 16 : 8, rs = cs / 2;
+    PlanBuilder B{pl, prec, cs, rs, err};
+
+    const int64_t total = prod(shape, 0, shape.size());
+    double log2sum = 0;
+    for (int a : axes) log2sum += std::log2((double)shape[a]);
+    int64_t alg = 0;
+    int passes = 0;
+    auto axis_passes = [&](int64_t n) {
+        if (n == 1) return 0;
+        const int lmax = lmax_for(prec);
+        if (is_pow2(n)) return n <= lmax ? 1 : 2;
+        return next_pow2(2 * n - 1) <= lmax ? 1 : 4;
+    };
+
+    bool ok = true;
+    if (d.kind == SFC_C2C) {
+        pl.in_elems = pl.out_elems = total;
+        pl.in_esize = pl.out_esize = cs;
+        const bool inv = d.direction == SFC_INVERSE;
+        const bool real_in = (d.flags & SFC_DESC_REAL_INPUT) != 0;
+        if (real_in) pl.in_esize = rs;
+        if (axes.empty()) {
+            ok = B.add_copy({R_IN, real_in, 1}, {R_OUT, false, 1}, shape, shape, d.scale);
+        }
+        for (size_t i = 0; ok && i < axes.size(); ++i) {
+            const int a = axes[i];
+            const int64_t n = shape[a], O = prod(shape, 0, a), I = prod(shape, a + 1, shape.size());
+            const bool last = (i + 1 == axes.size());
+            ok = B.add_axis(n, O, I, {i == 0 ? R_IN : R_OUT, i == 0 && real_in, n}, {R_OUT, false, n}, inv,
+                            last ? d.scale : 1.0, false);
+            const int ap = axis_passes(n);
+            passes += ap;
+            if (!is_pow2(n) && ap == 4)
+                alg += O * I * (2 * n + 6 * next_pow2(2 * n - 1)) * (int64_t)cs;
+            else
+                alg += (int64_t)ap * 2 * total * (int64_t)cs;
+        }
+        pl.info.nominal_flops = 5.0 * (double)total * log2sum;
+    } else if (d.kind == SFC_R2C) {
+        if (axes.empty()) {
+            err = {SFC_ERR_VALUE, "real transform needs at least one axis"};
+            return nullptr;
+        }
+        const int la = axes.back();
+        std::vector<int64_t> hshape = shape;
+        hshape[la] = shape[la] / 2 + 1;
+        pl.in_elems = total;
+        pl.in_esize = rs;
+        pl.out_elems = prod(hshape, 0, hshape.size());
+        pl.out_esize = cs;
+        const int dup = (int)std::count(axes.begin(), axes.end(), la);
+        if (dup > 1) {
+            // transform at full size in scratch, crop at the end (rfft.rs:484-523 literally)
+            B.need_sa((size_t)total * cs);
+            for (size_t i = 0; ok && i < axes.size(); ++i) {
+                const int a = axes[i];
+                const int64_t n = shape[a], O = prod(shape, 0, a), I = prod(shape, a + 1, shape.size());
+                ok = B.add_axis(n, O, I, {i == 0 ? R_IN : R_SA, i == 0, n}, {R_SA, false, n}, false, 1.0, false);
+                passes += axis_passes(n);
+                alg += (int64_t)axis_passes(n) * 2 * total * (int64_t)cs;
+            }
+            if (ok) ok = B.add_copy({R_SA, false, 1}, {R_OUT, false, 1}, shape, hshape, d.scale);
+        } else {
+            const int64_t n = shape[la], O = prod(shape, 0, la), I = prod(shape, la + 1, shape.size());
+            const bool only = axes.size() == 1;
+            if (B.r2c_fast_ok(n, I))
+                ok = B.add_r2c(n, O, {R_IN, true, n}, {R_OUT, false, n / 2 + 1}, only ? d.scale : 1.0);
+            else
+                ok = B.add_axis(n, O, I, {R_IN, true, n}, {R_OUT, false, n / 2 + 1}, false, only ? d.scale : 1.0,
+                                false);
+            passes += axis_passes(n);
+            alg += (int64_t)std::max(axis_passes(n), 1) * (total * (int64_t)rs + pl.out_elems * (int64_t)cs);
+            for (size_t i = 0; ok && i + 1 < axes.size(); ++i) {
+                const int a = axes[i];
+                const int64_t m = hshape[a], O2 = prod(hshape, 0, a), I2 = prod(hshape, a + 1, hshape.size());
+                const bool last = (i + 2 == axes.size());
+                ok = B.add_axis(m, O2, I2, {R_OUT, false, m}, {R_OUT, false, m}, false, last ? d.scale : 1.0, false);
+                passes += axis_passes(m);
+                alg += (int64_t)axis_passes(m) * 2 * pl.out_elems * (int64_t)cs;
+            }
+        }
+        pl.info.nominal_flops = 2.5 * (double)total * log2sum;
+    } else if (d.kind == SFC_C2R) {
+        if (axes.empty()) {
+            err = {SFC_ERR_VALUE, "real transform needs at least one axis"};
+            return nullptr;
+        }
+        const int la = axes.back();
+        std::vector<int64_t> xshape = shape;
+        xshape[la] = shape[la] / 2 + 1;
+        const bool custom_in = (d.flags & SFC_DESC_CUSTOM_IN_SHAPE) != 0;
+        if (custom_in)
+            for (int i = 0; i < d.ndim; ++i) {
+                xshape[i] = d.in_shape[i];
+                if (xshape[i] <= 0) {
+                    err = {SFC_ERR_VALUE, "in_shape entries must be positive"};
+                    return nullptr;
+                }
+            }
+        for (int i = 0; i < d.ndim; ++i)
+            if (xshape[i] > shape[i]) {
+                err = {SFC_ERR_DIMENSION, "input extent exceeds the output shape (the reference indexes out of bounds here)"};
+                return nullptr;
+            }
+        pl.in_elems = prod(xshape, 0, xshape.size());
+        pl.in_esize = cs;
+        pl.out_elems = total;
+        pl.out_esize = rs;
+        std::vector<int64_t> hshape = shape;
+        hshape[la] = shape[la] / 2 + 1;
+        const int dup = (int)std::count(axes.begin(), axes.end(), la);
+        const int64_t n = shape[la], I = prod(shape, la + 1, shape.size());
+        const bool fast = dup == 1 && xshape == hshape && B.r2c_fast_ok(n, I);
+        if (fast) {
+            const bool only = axes.size() == 1;
+            if (!only) B.need_sa((size_t)pl.in_elems * cs);
+            for (size_t i = 0; ok && i + 1 < axes.size(); ++i) {
+                const int a = axes[i];
+                const int64_t m = hshape[a], O2 = prod(hshape, 0, a), I2 = prod(hshape, a + 1, hshape.size());
+                ok = B.add_axis(m, O2, I2, {i == 0 ? R_IN : R_SA, false, m}, {R_SA, false, m}, true, 1.0, false);
+                passes += axis_passes(m);
+                alg += (int64_t)axis_passes(m) * 2 * pl.in_elems * (int64_t)cs;
+            }
+            const int64_t O = prod(shape, 0, la);
+            if (ok) ok = B.add_c2r(n, O, {only ? R_IN : R_SA, false, n / 2 + 1}, {R_OUT, true, n}, d.scale);
+            passes += 1;
+            alg += pl.in_elems * (int64_t)cs + total * (int64_t)rs;
+        } else {
+            // literal reference algorithm: Hermitian fill -> complex inverse over all axes -> real part
+            B.need_sa((size_t)total * cs);
+            Step h;
+            h.kind = K_HERM;
+            h.src = R_IN;
+            h.dst = R_SA;
+            h.hp.ndim = d.ndim;
+            h.hp.naxes = d.naxes;
+            h.hp.total = total;
+            h.hp.src_complex = 1;
+            h.hp.f64 = prec == PREC_F64;
+            for (int i = 0; i < d.ndim; ++i) {
+                h.hp.out_shape[i] = shape[i];
+                h.hp.x_shape[i] = xshape[i];
+            }
+            for (int i = 0; i < d.naxes; ++i) h.hp.axes[i] = axes[i];
+            h.desc = "Hermitian reconstruction (rfft.rs:733-901)";
+            pl.steps_.push_back(h);
+            B.dev_bytes += pl.in_elems * (int64_t)cs + total * (int64_t)cs;
+            for (size_t i = 0; ok && i < axes.size(); ++i) {
+                const int a = axes[i];
+                const int64_t m = shape[a], O2 = prod(shape, 0, a), I2 = prod(shape, a + 1, shape.size());
+                const bool last = (i + 1 == axes.size());
+                ok = B.add_axis(m, O2, I2, {R_SA, false, m}, {last ? R_OUT : R_SA, false, m}, true,
+                                last ? d.scale : 1.0, last);
+                passes += axis_passes(m);
+                alg += (int64_t)axis_passes(m) * 2 * total * (int64_t)cs;
+            }
+        }
+        pl.info.nominal_flops = 2.5 * (double)total * log2sum;
+    } else {
+        err = {SFC_ERR_VALUE, "unknown transform kind"};
+        return nullptr;
+    }
+    if (!ok) return nullptr;
+
+    if (pl.sa_bytes_) {
+        if (cudaMalloc(&pl.sa_, pl.sa_bytes_) != cudaSuccess) {
+            cudaGetLastError();
+            err = {SFC_ERR_MEMORY, "cudaMalloc failed for plan scratch"};
+            return nullptr;
+        }
+    }
+    if (pl.ms_bytes_) {
+        if (cudaMalloc(&pl.ms_, pl.ms_bytes_) != cudaSuccess) {
+            cudaGetLastError();
+            err = {SFC_ERR_MEMORY, "cudaMalloc failed for plan work area"};
+            return nullptr;
+        }
+    }
+    pl.info.in_bytes = pl.in_elems * (int64_t)pl.in_esize;
+    pl.info.out_bytes = pl.out_elems * (int64_t)pl.out_esize;
+    pl.info.scratch_bytes = (int64_t)(pl.sa_bytes_ + pl.ms_bytes_);
+    pl.info.algorithmic_bytes = alg;
+    pl.info.device_bytes = B.dev_bytes;
+    pl.info.num_passes = passes;
+    int launches = 0;
+    for (const Step& s : pl.steps_) {
+        if (s.group >= 0) {
+            const Group& g = pl.groups_[s.group];
+            launches += (int)((g.nbatch + g.chunk - 1) / g.chunk);
+        } else
+            launches += 1;
+    }
+    pl.info.num_launches = launches;
+    return sp;
+}
+
+Plan::~Plan() {
+    if (sa_) cudaFree(sa_);
+    if (ms_) cudaFree(ms_);
+}
+
+std::string Plan::describe() const {
+    std::string s;
+    char b[160];
+    snprintf(b, sizeof b, "plan kind=%d prec=%s dir=%d ndim=%d passes=%d launches=%d scratch=%lld B\n", desc.kind,
+             desc.prec == SFC_PREC_F64 ? "f64" : "f32", desc.direction, desc.ndim, info.num_passes,
+             info.num_launches, (long long)info.scratch_bytes);
+    s += b;
+    int i = 0;
+    for (const Step& st : steps_) {
+        snprintf(b, sizeof b, "  step %d: ", i++);
+        s += b;
+        s += st.desc;
+        if (st.group >= 0) {
+            snprintf(b, sizeof b, " [group %d: %lld batches, %lld per round]", st.group,
+                     (long long)groups_[st.group].nbatch, (long long)groups_[st.group].chunk);
+            s += b;
+        }
+        s += "\n";
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------ Plan::exec
+
+int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& es) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto base = [&](int role) -> char* {
+        switch (role) {
+            case R_IN: return (char*)const_cast<void*>(d_in);
+            case R_OUT: return (char*)d_out;
+            case R_SA: return (char*)sa_;
+            default: return (char*)ms_;
+        }
+    };
+    auto fail = [&](cudaError_t e, const Step& s) {
+        es = std::string("kernel launch failed (") + s.desc + "): " + cudaGetErrorString(e);
+        return (int)SFC_ERR_COMPUTATION;
+    };
+    size_t i = 0;
+    while (i < steps_.size()) {
+        Step& s = steps_[i];
+        if (s.kind == K_COPY) {
+            s.cp.src = base(s.src);
+            s.cp.dst = base(s.dst);
+            cudaError_t e = launch_nd_copy(s.cp, stream);
+            if (e != cudaSuccess) return fail(e, s);
+            ++i;
+            continue;
+        }
+        if (s.kind == K_HERM) {
+            s.hp.src = base(s.src);
+            s.hp.dst = base(s.dst);
+            cudaError_t e = launch_herm_fill(s.hp, stream);
+            if (e != cudaSuccess) return fail(e, s);
+            ++i;
+            continue;
+        }
+        if (s.group < 0) {
+            PassParams p = s.p;
+            p.in.ptr = base(s.src);
+            p.out.ptr = base(s.dst);
+            const uint64_t grid = (uint64_t)p.tiles_per_batch * (uint64_t)s.nbatch;
+            if (grid == 0 || grid > 0x7FFFFFFFULL) {
+                es = "grid too large";
+                return SFC_ERR_VALUE;
+            }
+            cudaError_t e = s.k->launch(p, (unsigned)grid, stream);
+            if (e != cudaSuccess) return fail(e, s);
+            ++i;
+            continue;
+        }
+        // chunk-looped group: steps [i, j) share the work area
+        size_t j = i;
+        while (j < steps_.size() && steps_[j].group == s.group) ++j;
+        const Group& g = groups_[s.group];
+        for (int64_t b0 = 0; b0 < g.nbatch; b0 += g.chunk) {
+            const int64_t nb = std::min(g.chunk, g.nbatch - b0);
+            for (size_t k = i; k < j; ++k) {
+                Step& t = steps_[k];
+                PassParams p = t.p;
+                char* ib = base(t.src);
+                char* ob = base(t.dst);
+                if (t.src != R_MS) ib += (size_t)b0 * (size_t)p.in.batch_stride * t.src_esize;
+                if (t.dst != R_MS) ob += (size_t)b0 * (size_t)p.out.batch_stride * t.dst_esize;
+                p.in.ptr = ib;
+                p.out.ptr = ob;
+                const uint64_t grid = (uint64_t)p.tiles_per_batch * (uint64_t)nb;
+                if (grid == 0 || grid > 0x7FFFFFFFULL) {
+                    es = "grid too large";
+                    return SFC_ERR_VALUE;
+                }
+                cudaError_t e = t.k->launch(p, (unsigned)grid, stream);
+                if (e != cudaSuccess) return fail(e, t);
+            }
+        }
+        i = j;
+    }
+    return 0;
+}
+
+}  // namespace sfc

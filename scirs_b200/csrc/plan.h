@@ -1,0 +1,90 @@
+// plan.h — GPU planner: picks the pass decomposition per transform length and
+// owns the device tables / scratch of one plan.
+//
+// Replaces `FftPlanner` + `Arc<dyn Fft<f64>>` (rustfft, external) as consumed at
+// scirs2-fft/src/fft/algorithms.rs:159-167 and the plan objects of
+// scirs2-fft/src/planning.rs:75-180.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/scirs2_fft_cuda.h"
+#include "aux_kernels.cuh"
+#include "kernel_registry.h"
+#include "pass_params.h"
+
+namespace sfc {
+
+enum BufRole : int { R_IN = 0, R_OUT = 1, R_SA = 2, R_MS = 3 };
+enum StepKind : int { K_TILE = 0, K_COPY = 1, K_HERM = 2 };
+
+// one kernel launch (or one launch per batch chunk)
+struct Step {
+    int kind = K_TILE;
+    const KernelEntry* k = nullptr;
+    PassParams p{};
+    CopyParams cp{};
+    HermParams hp{};
+    int src = R_IN, dst = R_OUT;
+    size_t src_esize = 16, dst_esize = 16;  // bytes per addressed element (for batch offsets)
+    int group = -1;                          // steps sharing a group are chunk-looped together
+    int64_t nbatch = 1;                      // batches (blockIdx-level outer index)
+    std::string desc;
+};
+
+struct Group {
+    int64_t nbatch = 1;
+    int64_t chunk = 1;  // batches per launch round
+};
+
+struct PlanError {
+    int code;
+    std::string msg;
+};
+
+class Plan {
+   public:
+    static std::shared_ptr<Plan> create(const sfc_desc& d, PlanError& err);
+    ~Plan();
+
+    // d_in / d_out are device pointers; not re-entrant (serialised internally)
+    int exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& err);
+
+    sfc_desc desc{};
+    sfc_plan_info info{};
+    int device = 0;
+    std::string describe() const;
+
+    int64_t in_elems = 0, out_elems = 0;  // elements of the in / out arrays
+    size_t in_esize = 16, out_esize = 16;
+
+   private:
+    Plan() = default;
+    std::vector<Step> steps_;
+    std::vector<Group> groups_;
+    void* sa_ = nullptr;  // array-layout scratch
+    size_t sa_bytes_ = 0;
+    void* ms_ = nullptr;  // four-step / Bluestein work area
+    size_t ms_bytes_ = 0;
+    std::mutex mu_;
+    friend struct PlanBuilder;
+};
+
+// largest single-tile transform per precision
+inline int lmax_for(int prec) { return prec == PREC_F64 ? 8192 : 16384; }
+
+// device tables (built once per device, never freed before process exit)
+const void* table_stage_tw(int prec, int L, PlanError& err);                // W_L^j, j < L
+const void* table_rtw(int prec, int L, PlanError& err);                     // W_{2L}^i, i < max(L/16,1)
+bool table_fourstep(int prec, int64_t M, const void** lo, const void** hi, int* shift, PlanError& err);
+const void* table_chirp(int prec, int64_t N, PlanError& err);               // exp(-i*pi*n^2/N), n < N
+// FFT_M(conj chirp, wrapped)/M ; layout: natural (L1 == 0) or [k1][k2] four-step order
+const void* table_bluestein_b(int prec, int64_t N, int64_t M, int64_t L1, int64_t L2, PlanError& err);
+
+void set_error(int code, const std::string& msg);
+
+}  // namespace sfc
