@@ -185,11 +185,11 @@ __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x
 
 // ---- tile configuration ------------------------------------------------------
 
-template <typename T, int L_, int TL_>
+template <typename T, int L_, int TL_, int EMAX_ = 16>
 struct TileCfg {
     static constexpr int L = L_;
     static constexpr int TL = TL_;
-    static constexpr int E = L < 16 ? L : 16;          // points per thread
+    static constexpr int E = L < EMAX_ ? L : EMAX_;    // points per thread (= largest radix)
     static constexpr int TPL = L / E;                  // threads per lane
     static constexpr int NT = TPL * TL;                // threads per CTA
     static constexpr int G = 128 / (int)sizeof(Cx<T>);  // threads per smem wavefront
@@ -202,7 +202,8 @@ struct TileCfg {
     static constexpr int LP = lane_pitch();
     static constexpr size_t SMEM = (size_t)TL * LP * sizeof(Cx<T>);
     // resident CTAs per SM the register allocator must leave room for
-    static constexpr int MINB = (NT <= 256 && sizeof(T) == 8) ? 2 : (NT <= 256 ? 3 : 1);
+    static constexpr int MINB =
+        (E <= 8) ? (NT <= 512 ? (sizeof(T) == 8 ? 2 : 3) : 1) : ((NT <= 256 && sizeof(T) == 8) ? 2 : (NT <= 256 ? 3 : 1));
 };
 
 template <typename C, int R, int S>
@@ -219,7 +220,7 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
                                            const Cx<T>* __restrict__ tw, int tw_, int iw, int tr,
                                            int ir) {
     constexpr int L = C::L, E = C::E, TPL = C::TPL;
-    constexpr int R = (L / S >= 16) ? 16 : (L / S);
+    constexpr int R = (L / S >= E) ? E : (L / S);
     constexpr bool LAST = (S * R == L);
     constexpr int NB = E / R;  // butterflies per thread in this stage
     if constexpr (!LAST && !FIRST) __syncthreads();  // previous readers done before we overwrite
@@ -288,10 +289,10 @@ __device__ __forceinline__ void map_thread(int mode, int tid, int& t, int& i) {
 
 // ---- the kernel ---------------------------------------------------------------
 
-template <typename T, int L, int TL, bool DOUBLE>
-__global__ void __launch_bounds__(TileCfg<T, L, TL>::NT, TileCfg<T, L, TL>::MINB)
+template <typename T, int L, int TL, bool DOUBLE, int EMAX = 16>
+__global__ void __launch_bounds__(TileCfg<T, L, TL, EMAX>::NT, TileCfg<T, L, TL, EMAX>::MINB)
 tile_fft_kernel(const __grid_constant__ PassParams p) {
-    using C = TileCfg<T, L, TL>;
+    using C = TileCfg<T, L, TL, EMAX>;
     using cx = Cx<T>;
     constexpr int E = C::E, TPL = C::TPL, LP = C::LP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -306,6 +307,16 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
     map_thread<TL, TPL>(p.map_out, tid, t1, i1);
 
     cx a[E];
+
+    // Pull the input block of a tile that a later CTA will transform into L2 now, so its
+    // loads find the data on chip (one bulk-prefetch instruction, no registers or smem).
+    if (p.pf_bytes != 0 && tid == 0) {
+        const uint64_t nt = (uint64_t)blockIdx.x + p.pf_ahead;
+        if (nt < gridDim.x) {
+            const char* src = reinterpret_cast<const char*>(p.in.ptr) + nt * (uint64_t)p.pf_stride_bytes;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(p.pf_bytes) : "memory");
+        }
+    }
 
     // ------------------------------ load ------------------------------------
     {
@@ -335,7 +346,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
                 row[L] = v;
             }
             __syncthreads();
-            if constexpr (E == 16) {
+            if constexpr (E >= 8) {
                 const cx wi = reinterpret_cast<const cx*>(p.rtw)[i0];
 #pragma unroll
                 for (int m = 0; m < E; ++m) {
@@ -348,7 +359,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
                     }
                     const cx A = {xk.x + xp.x, xk.y - xp.y};
                     const cx D = {xk.x - xp.x, xk.y + xp.y};
-                    const cx w = cmul(wi, w32<T>(m));
+                    const cx w = cmul(wi, w32<T>(m * (16 / E)));
                     const cx Bc = cmulc(D, w);           // conj(W) * D
                     a[m] = {A.x - Bc.y, A.y + Bc.x};     // A + i*Bc
                 }
@@ -451,7 +462,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
     }
 
     if (p.st_op == ST_R2C) {
-        if constexpr (E == 16) {
+        if constexpr (E >= 8) {
             // a[m] = Z[i1 + m*TPL] of the packed half-length transform
             cx* row = sm + t1 * LP;
             __syncthreads();
@@ -467,7 +478,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
                 const cx zp = row[(L - k) & (L - 1)];
                 const cx A = {zk.x + zp.x, zk.y - zp.y};
                 const cx B = {zk.x - zp.x, zk.y + zp.y};
-                const cx Cw = cmul(B, cmul(wi, w32<T>(m)));
+                const cx Cw = cmul(B, cmul(wi, w32<T>(m * (16 / E))));
                 const T h = (T)0.5 * scale;
                 const cx xk = {(A.x + Cw.y) * h, (A.y - Cw.x) * h};
                 const cx xq = {(A.x - Cw.y) * h, -((A.y + Cw.x) * h)};

@@ -5,21 +5,21 @@
 
 namespace sfc {
 
-template <typename T, int L, int TL, bool DBL>
+template <typename T, int L, int TL, bool DBL, int EMAX = 16>
 struct KernelInst {
-    using C = TileCfg<T, L, TL>;
+    using C = TileCfg<T, L, TL, EMAX>;
     static cudaError_t launch(const PassParams& p, unsigned grid, cudaStream_t s) {
         static bool configured[64] = {};
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
         if (dev < 64 && !configured[dev]) {
-            e = cudaFuncSetAttribute(tile_fft_kernel<T, L, TL, DBL>,
+            e = cudaFuncSetAttribute(tile_fft_kernel<T, L, TL, DBL, EMAX>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
             if (e != cudaSuccess) return e;
             configured[dev] = true;
         }
-        tile_fft_kernel<T, L, TL, DBL><<<grid, C::NT, C::SMEM, s>>>(p);
+        tile_fft_kernel<T, L, TL, DBL, EMAX><<<grid, C::NT, C::SMEM, s>>>(p);
         return cudaGetLastError();
     }
     static KernelEntry entry() {
@@ -27,10 +27,11 @@ struct KernelInst {
         k.prec = sizeof(T) == 8 ? PREC_F64 : PREC_F32;
         k.L = L;
         k.TL = TL;
+        k.E = C::E;
         k.dbl = DBL ? 1 : 0;
         k.threads = C::NT;
         k.smem = C::SMEM;
-        k.func = (const void*)tile_fft_kernel<T, L, TL, DBL>;
+        k.func = (const void*)tile_fft_kernel<T, L, TL, DBL, EMAX>;
         k.launch = &launch;
         return k;
     }
@@ -39,3 +40,4 @@ struct KernelInst {
 }  // namespace sfc
 
 #define SFC_ADD(T, L, TL, DBL) add(::sfc::KernelInst<T, L, TL, DBL>::entry());
+#define SFC_ADD_E(T, L, TL, DBL, E) add(::sfc::KernelInst<T, L, TL, DBL, E>::entry());

@@ -12,6 +12,7 @@ struct KernelEntry {
     int prec;       // Prec
     int L;          // points per lane
     int TL;         // lanes per tile
+    int E;          // points per thread (largest radix)
     int dbl;        // 1 = forward * table * inverse fused
     int threads;    // CTA size
     size_t smem;    // dynamic shared memory bytes
@@ -34,5 +35,6 @@ void register_kernels_f32_mid(void (*add)(const KernelEntry&));
 void register_kernels_f32_big(void (*add)(const KernelEntry&));
 void register_kernels_f32_dbl_a(void (*add)(const KernelEntry&));
 void register_kernels_f32_dbl_b(void (*add)(const KernelEntry&));
+void register_kernels_e8(void (*add)(const KernelEntry&));
 
 }  // namespace sfc

@@ -1,0 +1,115 @@
+"""CPU: the C-ABI library loads, exports every symbol the header declares, and fails loudly
+(no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "scirs2_fft_cuda.h")
+
+
+@pytest.fixture(scope="module")
+def lib(build_artifacts):
+    from scirs_b200 import _lib
+
+    return _lib.load()
+
+
+def header_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(sfc_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_are_exported(lib):
+    syms = header_symbols()
+    assert len(syms) >= 35
+    out = subprocess.run(["nm", "-D", "--defined-only", lib._name], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\b(sfc_[a-z0-9_]+)\b", out))
+    missing = [s for s in syms if s not in exported]
+    assert not missing, f"header declares symbols the library does not export: {missing}"
+    # nothing but the C ABI leaks out of the shared object
+    leaked = [l for l in out.splitlines() if " T " in l and "sfc_" not in l]
+    assert not leaked, leaked
+
+
+def test_python_binding_covers_header(lib):
+    from scirs_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == header_symbols()
+    assert lib.sfc_abi_version() == 1
+
+
+def test_struct_layouts_match_header(lib):
+    from scirs_b200 import _lib
+
+    # sfc_desc: int32 ndim (+pad) | int64 shape[8] | int32 naxes, axes[8], kind, prec, direction, flags (+pad) | double | int64[8]
+    assert C.sizeof(_lib.sfc_desc) == 8 + 64 + 4 * 13 + 4 + 8 + 64
+    assert C.sizeof(_lib.sfc_plan_info) == 8 * 5 + 8 + 4 * 2
+    assert C.sizeof(_lib.sfc_cache_stats) == 40
+
+
+def test_sm100a_only(lib):
+    out = subprocess.run(["cuobjdump", "-lelf", lib._name], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_uses_bulk_async_and_fp64_pipe_not_tensor_cores(lib):
+    # FFT is bandwidth-bound: no tcgen05/HMMA in the product (north_star), DFMA present
+    out = subprocess.run(["cuobjdump", "-sass", lib._name], capture_output=True, text=True).stdout
+    assert "DFMA" in out
+    assert not re.search(r"\b(UTC\w*MMA|HMMA|DMMA)\b", out)
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="CPU-only behaviour")
+def test_no_cpu_fallback(lib):
+    import scirs_b200 as sb
+
+    assert lib.sfc_device_count() == 0 and lib.sfc_is_available() == 0
+    assert lib.sfc_init(0) == -6
+    for call in (lambda: sb.fft(np.ones(8)), lambda: sb.rfft(np.ones(8)), lambda: sb.fft2(np.ones((4, 4))),
+                 lambda: sb.fftn(np.ones((2, 2, 2))), lambda: sb.irfftn(np.ones((2, 2, 2)) + 0j),
+                 lambda: sb.FftPlan([8], [0]), lambda: sb.rfft_batch(np.ones((2, 64)))):
+        with pytest.raises(sb.BackendError) as e:
+            call()
+        assert "no CPU fallback" in str(e.value)
+    b = sb.CudaFftBackend()
+    assert b.name() == "cuda_fft" and not b.is_available()
+    assert b.supports_feature("1d_fft") and b.supports_feature("gpu_acceleration") and not b.supports_feature("x")
+
+
+def test_cache_controls_work_without_gpu(lib):
+    import scirs_b200 as sb
+
+    c = sb.get_global_cache()
+    c.configure(128, 3600.0)
+    s = c.get_stats()
+    assert (s.hit_count, s.miss_count, s.size, s.max_size, s.hit_rate) == (0, 0, 0, 128, 0.0)
+    c.set_enabled(False)
+    assert not c.is_enabled()
+    c.set_enabled(True)
+    assert c.is_enabled()
+    c.clear()
+
+
+def test_argument_validation_precedes_device_use(lib):
+    import scirs_b200 as sb
+
+    m = sb.get_backend_manager()
+    assert m.get_backend_name() == "cuda_fft" and "cuda_fft" in m.list_backends()
+    with pytest.raises(sb.ValueError_):
+        m.register_backend("cuda_fft", sb.CudaFftBackend())  # backend.rs:184-194
+    with pytest.raises(sb.ValueError_):
+        m.set_backend("nope")  # backend.rs:203-224
+    # size check of fft_sized comes before any device work (backend.rs:96-100)
+    x = np.zeros(8, dtype=np.complex128)
+    with pytest.raises(sb.ValueError_) as e:
+        sb.CudaFftBackend().fft_sized(x, np.zeros(4, dtype=np.complex128), 8)
+    assert str(e.value) == "Input and output sizes must match the specified size"
+    with pytest.raises(sb.NotImplementedError_):
+        sb.ifft2_simd(np.ones((2, 2)))  # simd_fft.rs:99-111
