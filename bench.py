@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline FFT metric on B200, one JSON line on rank 0.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+  (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+  default workload  c2c_f64_65536x4096   BASELINE configs[1] geometry (65,536 signals x 4096), f64 c2c
+                                          (the transform the metric — 5 N log2 N — is quoted on)
+  other workloads   rfft_f64 / irfft_f64 / rfft_f32 / irfft_f32 (configs[1] as written),
+                    fft2_8192 (configs[2]), fft_2p20 (configs[0], batch 64), fftn_512 (configs[4], 1 GPU),
+                    bluestein_1000003 (configs[3], batch 32)
+  The non-default workloads are also timed briefly and reported under "others".
+N > 1 shards the batch across ranks with no data-path collective (weak scaling: every rank owns
+65,536 signals); "others.fftn_512_slab" adds the slab-decomposed 3-D transform with its all-to-all.
+
+value      = whole-job GFLOP/s (5 N log2 N per transform), inputs resident in HBM, CUDA events on
+             the launching stream, barrier + synchronize on both sides, max over ranks.
+e2e        = same metric through the C-ABI host call (sfc_exec_host) with pinned HOST buffers:
+             H2D + kernels + D2H inside the timed region.
+roofline   = algorithmic bytes per launch / mean kernel time vs MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline / --impl reference = oracle/rustfft_port.c (a port: the Rust reference cannot be
+             built here) timed on this box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+WORKLOADS = {
+    # name: (shape, axes, kind, prec, forward, description)
+    "c2c_f64_65536x4096": ([65536, 4096], [1], "c2c", "f64", True, "batched c2c f64, 65,536 signals x 4096 (BASELINE configs[1] geometry)"),
+    "rfft_f64": ([65536, 4096], [1], "r2c", "f64", True, "batched rfft f64, 65,536 x 4096 (configs[1])"),
+    "irfft_f64": ([65536, 4096], [1], "c2r", "f64", False, "batched irfft f64, 65,536 x 4096 (configs[1])"),
+    "rfft_f32": ([65536, 4096], [1], "r2c", "f32", True, "batched rfft f32, 65,536 x 4096 (configs[1])"),
+    "irfft_f32": ([65536, 4096], [1], "c2r", "f32", False, "batched irfft f32, 65,536 x 4096 (configs[1])"),
+    "fft2_8192": ([8192, 8192], [1, 0], "c2c", "f64", True, "fft2 c128 8192 x 8192 (configs[2])"),
+    "fft_2p20": ([64, 1 << 20], [1], "c2c", "f64", True, "fft c128 2^20, batch 64 (configs[0] steady state)"),
+    "fftn_512": ([512, 512, 512], [0, 1, 2], "c2c", "f64", True, "fftn c128 512^3 on one GPU (configs[4])"),
+    "bluestein_1000003": ([32, 1000003], [1], "c2c", "f64", True, "fft c128 N=1,000,003 (prime, Bluestein), batch 32 (configs[3])"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [t.strip() for t in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def flops_of(shape, axes, kind):
+    total = 1
+    for s in shape:
+        total *= s
+    lg = sum(math.log2(shape[a]) for a in axes)
+    return (5.0 if kind == "c2c" else 2.5) * total * lg
+
+
+# ------------------------------------------------------------------ CPU port timing (baseline / reference arm)
+
+
+def load_port():
+    import ctypes as C
+
+    path = os.path.join(ROOT, "oracle", "librustfft_port.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    lib = C.CDLL(path)
+    lib.rfp_ref_rfft_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+    lib.rfp_ref_irfft_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+    lib.rfp_ref_fft.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+    lib.rfp_ref_fftn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
+    lib.rfp_ref_c2c_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int]
+    return lib
+
+
+def cpu_port_run(workload: str, threads: int, budget_s: float, steps: int = 1):
+    """Time the reference call pattern (oracle/rustfft_port.c) on a bounded sample; returns
+    (GFLOP/s, sample description, seconds per step)."""
+    import ctypes as C
+
+    import numpy as np
+
+    lib = load_port()
+    shape, axes, kind, prec, fwd, _ = WORKLOADS[workload]
+    rng = np.random.default_rng(2)
+    if workload in ("c2c_f64_65536x4096", "rfft_f64", "irfft_f64", "rfft_f32", "irfft_f32", "fft_2p20", "bluestein_1000003"):
+        n = shape[1]
+        # per-row cost estimate -> rows that fit the budget
+        per_row = {4096: 2.5e-4, 1 << 20: 0.12, 1000003: 0.9}.get(n, 1e-3)
+        rows = int(max(threads, min(shape[0], budget_s * threads / per_row)))
+        rows = max(threads, (rows // threads) * threads)
+        if kind == "r2c":
+            x = rng.standard_normal((rows, n))
+            out = np.empty((rows, n // 2 + 1), dtype=np.complex128)
+            fn = lambda: lib.rfp_ref_rfft_rows(x.ctypes.data, rows, n, out.ctypes.data, threads)
+        elif kind == "c2r":
+            x = (rng.standard_normal((rows, n // 2 + 1)) + 1j * rng.standard_normal((rows, n // 2 + 1)))
+            out = np.empty((rows, n), dtype=np.float64)
+            fn = lambda: lib.rfp_ref_irfft_rows(x.ctypes.data, rows, n, out.ctypes.data, threads)
+        else:
+            x = rng.standard_normal((rows, n)) + 1j * rng.standard_normal((rows, n))
+            out = np.empty_like(x)
+            fn = lambda: lib.rfp_ref_c2c_rows(x.ctypes.data, rows, n, out.ctypes.data, threads, 0)
+        fl = flops_of([rows, n], [1], kind)
+        sample = f"{rows} of {shape[0]} signals x {n} ({'loop of fft(&row, Some(n))' if kind == 'c2c' else 'loop of ' + ('rfft' if kind == 'r2c' else 'irfft') + '(&row)'}; reference call pattern, {threads} thread(s))"
+    else:
+        # N-D: reduced cube through the fftn lanes pattern (single-threaded like the reference)
+        sub = [256, 256] if workload == "fft2_8192" else [128, 128, 128]
+        if workload == "fft2_8192":
+            sub = [2048, 2048]
+        x = rng.standard_normal(sub) + 1j * rng.standard_normal(sub)
+        shp = (C.c_int64 * len(sub))(*sub)
+        ax = (C.c_int32 * len(axes))(*axes)
+        fn = lambda: lib.rfp_ref_fftn(x.ctypes.data, len(sub), shp, ax, len(axes), 0)
+        fl = flops_of(sub, axes, "c2c")
+        threads = 1
+        sample = f"{'x'.join(map(str, sub))} sub-problem of {'x'.join(map(str, shape))} through the fftn lane loop (1 thread, as the reference)"
+    fn()  # warm
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / steps
+    return fl / dt / 1e9, sample, dt, threads
+
+
+# ------------------------------------------------------------------ GPU arm
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import scirs_b200 as sb
+    from scirs_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    lib = _lib.load()
+    if lib.sfc_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    sb.error.check(lib.sfc_init(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    hbm, hbm_src = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def alloc(workload):
+        shape, axes, kind, prec, fwd, desc = WORKLOADS[workload]
+        rt = torch.float64 if prec == "f64" else torch.float32
+        total = 1
+        for s in shape:
+            total *= s
+        half = total // shape[axes[-1]] * (shape[axes[-1]] // 2 + 1)
+        n_in = {"c2c": 2 * total, "r2c": total, "c2r": 2 * half}[kind]
+        n_out = {"c2c": 2 * total, "r2c": 2 * half, "c2r": total}[kind]
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        din = torch.randn(n_in, dtype=rt, device=dev, generator=g)
+        dout = torch.empty(n_out, dtype=rt, device=dev)
+        scale = 1.0 / shape[axes[-1]] if kind == "c2r" else 1.0
+        plan = sb.FftPlan(shape, axes, kind, prec, fwd, scale)
+        return plan, din, dout
+
+    def time_workload(workload, steps, warmup, sample_clocks=False):
+        plan, din, dout = alloc(workload)
+        stream = torch.cuda.current_stream()
+        for _ in range(warmup):
+            plan.execute_device(din, dout, stream.cuda_stream)
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_all0.record(stream)
+        for e0, e1 in evs:
+            e0.record(stream)
+            plan.execute_device(din, dout, stream.cuda_stream)
+            e1.record(stream)
+        t_all1.record(stream)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        total_ms = t_all0.elapsed_time(t_all1)
+        per = [a.elapsed_time(b) for a, b in evs]
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        info = plan.info
+        del din, dout
+        return {"ms_per_step": total_ms / steps, "kernel_ms": sum(per) / len(per), "info": info, "plan": plan,
+                "clocks": clocks}
+
+    def summarize(workload, r):
+        shape, axes, kind, prec, fwd, desc = WORKLOADS[workload]
+        fl = flops_of(shape, axes, kind)
+        ms = r["ms_per_step"]
+        alg = r["info"]["algorithmic_bytes"]
+        return {"what": desc, "gflops": fl * world / ms / 1e6, "ms_per_step": ms, "hbm_gbs": alg / r["kernel_ms"] / 1e6,
+                "frac_of_hbm": alg / r["kernel_ms"] / 1e6 / hbm, "launches_per_step": r["info"]["num_launches"],
+                "passes": r["info"]["num_passes"], "dtype": prec}
+
+    # ---------------- headline workload
+    wl = args.workload
+    shape, axes, kind, prec, fwd, desc = WORKLOADS[wl]
+    r = time_workload(wl, args.steps, args.warmup, sample_clocks=True)
+    clocks = r.pop("clocks", None)
+    head = summarize(wl, r)
+    launches = r["info"]["num_launches"] * args.steps
+
+    # roofline of the dominant (here: only) kernel of the step
+    alg = r["info"]["algorithmic_bytes"]
+    traffic = None
+    summ = os.path.join(ROOT, "profiles", "r1_ncu_summary.json")
+    if os.path.exists(summ):
+        try:
+            traffic = json.load(open(summ)).get(wl, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    achieved = alg / r["info"]["num_launches"] / (r["kernel_ms"] / r["info"]["num_launches"]) / 1e6
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
+                "traffic": traffic, "peak_source": hbm_src, "kernel": "sfc::tile_fft_kernel",
+                "algorithmic_bytes_per_launch": alg // r["info"]["num_launches"],
+                "kernel_ms": round(r["kernel_ms"] / r["info"]["num_launches"], 4)}
+
+    # ---------------- e2e through the C ABI with pinned host buffers
+    e2e = None
+    try:
+        import numpy as np
+
+        plan = r["plan"]
+        nin, nout = plan.info["in_bytes"], plan.info["out_bytes"]
+        hin = torch.empty(nin, dtype=torch.uint8).pin_memory()
+        hout = torch.empty(nout, dtype=torch.uint8).pin_memory()
+        rt = np.float64 if prec == "f64" else np.float32
+        hin.numpy().view(rt)[:] = np.random.default_rng(7 + rank).standard_normal(nin // np.dtype(rt).itemsize).astype(rt)
+        import ctypes as C
+
+        e_steps = max(2, min(args.steps, 5))
+        for _ in range(1):
+            sb.error.check(lib.sfc_exec_host(plan._h, C.c_void_p(hin.data_ptr()), C.c_void_p(hout.data_ptr())))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            sb.error.check(lib.sfc_exec_host(plan._h, C.c_void_p(hin.data_ptr()), C.c_void_p(hout.data_ptr())))
+        barrier()
+        dt = (time.perf_counter() - t0) / e_steps
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": round(flops_of(shape, axes, kind) * world / dt / 1e9, 2), "unit": "GFLOP/s",
+               "h2d_bytes_per_step": int(nin), "d2h_bytes_per_step": int(nout), "ms_per_step": round(dt * 1e3, 3),
+               "api": "sfc_exec_host (C ABI, pinned host buffers)", "steps": e_steps}
+        del hin, hout
+    except Exception as ex:  # keep the line printable; say why
+        e2e = {"value": None, "unit": "GFLOP/s", "error": str(ex)[:200]}
+
+    # ---------------- the other BASELINE configs, briefly
+    others = {}
+    if not args.no_others:
+        del r
+        torch.cuda.empty_cache()
+        for name in WORKLOADS:
+            if name == wl:
+                continue
+            try:
+                rr = time_workload(name, 5, 3)
+                others[name] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in summarize(name, rr).items()}
+                del rr
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                others[name] = {"error": str(ex)[:160]}
+        if world > 1:
+            try:
+                from scirs_b200.distributed import bench_slab_fftn
+
+                others["fftn_512_slab"] = bench_slab_fftn(512, steps=5, warmup=3)
+            except Exception as ex:
+                others["fftn_512_slab"] = {"error": str(ex)[:200]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, sample, dt, th = cpu_port_run(wl, 1, 12.0)
+        cpu = {"value": round(v, 3), "unit": "GFLOP/s", "cores": th, "kind": "port", "sample": sample,
+               "seconds": round(dt, 2)}
+
+    if rank == 0:
+        line = {
+            "metric": "batched f64 c2c FFT GFLOP/s (5 N log2 N)" if kind == "c2c" else "batched FFT GFLOP/s (2.5 N log2 N, real)",
+            "value": round(head["gflops"], 2), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(head["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": prec, "data": "synthetic",
+            "config": {"workload": wl, "what": desc, "per_gpu_shape": shape, "axes": axes, "sharding": "batch split, no collective",
+                       "l2": "inputs (>= 2 GB) larger than the 126 MB L2; no flush needed"},
+            "hbm_gbs": round(head["hbm_gbs"] * world, 1), "roofline": roofline, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches, "cpu_baseline": cpu, "others": others,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ reference arm
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    shape, axes, kind, prec, fwd, desc = WORKLOADS[wl]
+    threads = os.cpu_count() or 1
+    # bounded: the whole steps+warmup run stays within a few minutes
+    budget = max(1.0, min(15.0, 150.0 / max(args.steps + args.warmup, 1)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_run(wl, threads, min(budget, 2.0))
+    v, sample, dt, th = cpu_port_run(wl, threads, budget, steps=max(args.steps, 1))
+    line = {
+        "impl": "reference",
+        "metric": "batched f64 c2c FFT GFLOP/s (5 N log2 N)" if kind == "c2c" else "batched FFT GFLOP/s (2.5 N log2 N, real)",
+        "value": round(v, 3), "unit": "GFLOP/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl, "what": desc, "per_gpu_shape": shape, "axes": axes},
+        "cpu_baseline": {"value": round(v, 3), "unit": "GFLOP/s", "cores": th, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 3), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle/rustfft_port.c: restatement of the scirs2-fft call pattern over rustfft's scalar algorithm classes; "
+                "the Rust reference cannot be compiled in this image (no cargo/rustc, rustfft not vendored)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2c_f64_65536x4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-others", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -272,7 +272,7 @@ int rfp_ref_fft(const double* x, int64_t len, int64_t n, int inverse, double* ou
 }
 
 typedef struct {
-    const double* x; double* out; int64_t r0, r1, n; int inverse_real;
+    const double* x; double* out; int64_t r0, r1, n; int inverse_real; /* 0 rfft, 1 irfft, 2 fft, 3 ifft */
 } row_job;
 
 static void rfft_one_row(const double* row, int64_t n, double* out) {
@@ -313,7 +313,9 @@ static void* row_worker(void* arg) {
     row_job* j = (row_job*)arg;
     const int64_t n = j->n, h = n / 2 + 1;
     for (int64_t r = j->r0; r < j->r1; ++r) {
-        if (j->inverse_real)
+        if (j->inverse_real >= 2)
+            rfp_ref_fft(j->x + 2 * r * n, n, n, j->inverse_real == 3, j->out + 2 * r * n);
+        else if (j->inverse_real)
             irfft_one_row(j->x + 2 * r * h, n, j->out + r * n);
         else
             rfft_one_row(j->x + r * n, n, j->out + 2 * r * h);
@@ -335,6 +337,11 @@ static int rows_threaded(const double* x, int64_t rows, int64_t n, double* out, 
     }
     for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
     return 0;
+}
+
+/* loop of fft(&row, Some(n)) / ifft over the rows of a [rows][n] complex batch */
+int rfp_ref_c2c_rows(const double* x, int64_t rows, int64_t n, double* out, int nthreads, int inverse) {
+    return rows_threaded(x, rows, n, out, nthreads, inverse ? 3 : 2);
 }
 
 int rfp_ref_rfft_rows(const double* x, int64_t rows, int64_t n, double* out, int nthreads) {
