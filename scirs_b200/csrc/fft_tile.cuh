@@ -308,16 +308,6 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
 
     cx a[E];
 
-    // Pull the input block of a tile that a later CTA will transform into L2 now, so its
-    // loads find the data on chip (one bulk-prefetch instruction, no registers or smem).
-    if (p.pf_bytes != 0 && tid == 0) {
-        const uint64_t nt = (uint64_t)blockIdx.x + p.pf_ahead;
-        if (nt < gridDim.x) {
-            const char* src = reinterpret_cast<const char*>(p.in.ptr) + nt * (uint64_t)p.pf_stride_bytes;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(p.pf_bytes) : "memory");
-        }
-    }
-
     // ------------------------------ load ------------------------------------
     {
         const uint32_t lane = tile * TL + (uint32_t)t0;

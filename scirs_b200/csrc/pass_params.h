@@ -69,11 +69,6 @@ struct PassParams {
     int64_t mid_es, mid_ls;    // mid index = e*mid_es + lane_outer*mid_ls
     const void* rtw;           // R2C/C2R: W_{2L}^i, i < L/E
     double scale;
-    // L2 prefetch of a later tile's (contiguous) input block: tile t+pf_ahead starts at
-    // in.ptr + (t+pf_ahead)*pf_stride_bytes and spans pf_bytes (0 = off)
-    int64_t pf_stride_bytes;
-    uint32_t pf_bytes;
-    uint32_t pf_ahead;
 };
 
 }  // namespace sfc

@@ -49,11 +49,10 @@ const KernelEntry* find_kernel(int prec, int L, int TL, int dbl) {
 
 // ROW tiles want few lanes per CTA (small tiles, more CTAs per SM); COL tiles want
 // many adjacent lanes (>= 128 B contiguous per element row).
-// prefetch distance in "waves" of resident CTAs (0 disables), env SFC_PREFETCH
-static int prefetch_ahead() {
+static int col_tl_cap() {
     static int v = [] {
-        const char* e = getenv("SFC_PREFETCH");
-        return e ? atoi(e) : 0;  // measured on B200: L2 prefetch lowers throughput (94% -> 75% at L=256)
+        const char* e = getenv("SFC_COL_TL");
+        return e ? atoi(e) : 0;
     }();
     return v;
 }
@@ -74,11 +73,16 @@ static const KernelEntry* pick_kernel(int prec, int L, bool want_wide, int dbl) 
     bool have_e = false;
     for (int i = 0; i < n; ++i)
         if (t[i].prec == prec && t[i].L == L && t[i].dbl == dbl && t[i].E == std::min(want_e, L)) have_e = true;
+    const int cap = (want_wide && col_tl_cap() > 0) ? col_tl_cap() : (1 << 30);
+    const KernelEntry* smallest = nullptr;
     for (int i = 0; i < n; ++i) {
         if (t[i].prec != prec || t[i].L != L || t[i].dbl != dbl) continue;
         if (have_e ? t[i].E != std::min(want_e, L) : t[i].E != std::min(16, L)) continue;
+        if (!smallest || t[i].TL < smallest->TL) smallest = &t[i];
+        if (t[i].TL > cap) continue;
         if (!best || (want_wide ? t[i].TL > best->TL : t[i].TL < best->TL)) best = &t[i];
     }
+    if (!best) best = smallest;
     return best;
 }
 
@@ -282,7 +286,7 @@ static inline int ilog2_64(int64_t n) {
 static int64_t scratch_budget_bytes() {
     static int64_t v = [] {
         const char* e = getenv("SFC_WORK_MB");
-        int64_t mb = e ? atoll(e) : 64;
+        int64_t mb = e ? atoll(e) : 2048;
         if (mb < 1) mb = 1;
         return mb << 20;
     }();
@@ -333,25 +337,6 @@ struct PlanBuilder {
         s.nbatch = nbatch;
         s.p.tw = table_stage_tw(prec, s.k->L, err);
         if (!s.p.tw) return false;
-        // L2 prefetch is possible when a tile's input is one contiguous block: unit element
-        // stride, one lane per outer index, lanes packed back to back, no batch dimension
-        s.p.pf_bytes = 0;
-        {
-            const size_t es = s.src_esize;
-            const int64_t lane_elems = s.p.in.outer_stride;
-            const int ahead = prefetch_ahead();
-            if (ahead > 0 && nbatch == 1 && s.p.inner_count == 1 && s.p.in.elem_stride == 1 &&
-                s.p.map_in == MAP_ROW && lane_elems > 0 && nlanes % s.k->TL == 0) {
-                const int64_t bytes = (int64_t)s.k->TL * lane_elems * (int64_t)es;
-                if (bytes % 16 == 0 && bytes >= 4096 && bytes <= (1 << 20)) {
-                    s.p.pf_bytes = (uint32_t)bytes;
-                    s.p.pf_stride_bytes = bytes;
-                    int occ = (int)std::max<size_t>(1, std::min<size_t>((227 * 1024) / std::max<size_t>(s.k->smem, 1),
-                                                                        2048 / (size_t)s.k->threads));
-                    s.p.pf_ahead = (uint32_t)(148 * occ * ahead);
-                }
-            }
-        }
         char buf[256];
         snprintf(buf, sizeof buf, "%s: tile L=%d TL=%d%s threads=%d smem=%zu lanes=%lld batches=%lld map=%s->%s", what,
                  s.k->L, s.k->TL, s.k->dbl ? " fwd*tab*inv" : "", s.k->threads, s.k->smem, (long long)nlanes,
