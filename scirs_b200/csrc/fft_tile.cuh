@@ -195,7 +195,9 @@ struct TileCfg {
     static constexpr int G = 128 / (int)sizeof(Cx<T>);  // threads per smem wavefront
     static __host__ __device__ constexpr int lane_pitch() {
         int want = (TL < G) ? (G / TL) % G : 1;
-        int lp = L + 1;  // >= L+1: the real-transform paths stage L+1 points per lane
+        // padded exchange layout (one pad slot per E elements) and >= L+1 because the
+        // real-transform paths stage L+1 points per lane
+        int lp = L + (L > E ? L / E : 0) + 1;
         while (lp % G != want) ++lp;
         return lp;
     }
@@ -206,11 +208,29 @@ struct TileCfg {
         (E <= 8) ? (NT <= 512 ? (sizeof(T) == 8 ? 2 : 3) : 1) : ((NT <= 256 && sizeof(T) == 8) ? 2 : (NT <= 256 ? 3 : 1));
 };
 
+// Padded exchange layout: logical element e of a lane lives at slot e + (e >> log2(R*S)) * PADW,
+// PADW = S when S is smaller than a shared-memory wavefront (G slots), else 0.  All offsets a
+// thread needs are then "thread base + compile-time constant", so LDS/STS carry immediates.
 template <typename C, int R, int S>
-__device__ __forceinline__ int swz(int e) {
-    constexpr int sh_rs = ilog2(R * S), sh_s = ilog2(S);
-    return e ^ (((e >> sh_rs) << sh_s) & (C::G - 1));
-}
+struct Xch {
+    static constexpr int BLK = R * S;
+    static constexpr int SH = ilog2(BLK);
+    static constexpr int PADW = (S < C::G) ? S : 0;
+    // slot of the first output (k = 0) of butterfly ib; output k sits k*S slots further
+    static __device__ __forceinline__ int write_base(int ib) {
+        const int q = ib & (S - 1);
+        const int p0 = q + R * (ib - q);
+        return p0 + (p0 >> SH) * PADW;
+    }
+    // thread base of the read pattern e = i + m*TPL
+    static __device__ __forceinline__ int read_base(int i) {
+        if constexpr (C::TPL >= BLK) return i + (i >> SH) * PADW;
+        else return i;
+    }
+    static __host__ __device__ constexpr int read_off(int m) {
+        return (C::TPL >= BLK) ? m * (C::TPL + (C::TPL >> SH) * PADW) : m * C::TPL + ((m * C::TPL) >> SH) * PADW;
+    }
+};
 
 // One Stockham stage of radix R at stride S over the thread's E registers, then
 // recurse.  (tw, iw) = mapping of the thread while it holds the stage inputs,
@@ -235,20 +255,17 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
             for (int k = 0; k < R; ++k) a[b + k * NB] = v[k];
         } else {
             const int ib = iw + b * TPL;
-            const int q = ib & (S - 1);
-            const int base = ib - q;
-            apply_twiddle_powers<R, T>(v, tw[base]);
-            Cx<T>* dst = sm + tw_ * C::LP;
-            const int p0 = q + R * base;
+            apply_twiddle_powers<R, T>(v, tw[ib & ~(S - 1)]);
+            Cx<T>* dst = sm + tw_ * C::LP + Xch<C, R, S>::write_base(ib);
 #pragma unroll
-            for (int k = 0; k < R; ++k) dst[swz<C, R, S>(p0 + k * S)] = v[k];
+            for (int k = 0; k < R; ++k) dst[k * S] = v[k];
         }
     }
     if constexpr (!LAST) {
         __syncthreads();
-        const Cx<T>* src = sm + tr * C::LP;
+        const Cx<T>* src = sm + tr * C::LP + Xch<C, R, S>::read_base(ir);
 #pragma unroll
-        for (int m = 0; m < E; ++m) a[m] = src[swz<C, R, S>(ir + m * TPL)];
+        for (int m = 0; m < E; ++m) a[m] = src[Xch<C, R, S>::read_off(m)];
         run_stages<T, C, S * R, false>(a, sm, tw, tr, ir, tr, ir);
     }
 }
@@ -358,25 +375,54 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         } else {
             const bool is_real = (p.ld_op == LD_R) || (p.ld_op == LD_R_MUL);
             const bool has_mul = (p.ld_op == LD_C_MUL) || (p.ld_op == LD_R_MUL);
+            const bool nomask = p.flags & F_IN_NOMASK;
             if (is_real) {
                 const T* __restrict__ src = reinterpret_cast<const T*>(p.in.ptr) + off;
+                if (nomask) {
+                    if (!valid) {
 #pragma unroll
-                for (int m = 0; m < E; ++m) {
-                    const int e = i0 + m * TPL;
-                    const int64_t pos = (int64_t)e * p.in.pos_es + pos0;
-                    T r = 0;
-                    if (valid && pos < p.in.len) r = src[(int64_t)e * p.in.elem_stride];
-                    a[m] = {r, (T)0};
+                        for (int m = 0; m < E; ++m) a[m] = {(T)0, (T)0};
+                    } else if (p.in.elem_stride == 1) {
+#pragma unroll
+                        for (int m = 0; m < E; ++m) a[m] = {src[i0 + m * TPL], (T)0};
+                    } else {
+                        const int64_t es = p.in.elem_stride;
+#pragma unroll
+                        for (int m = 0; m < E; ++m) a[m] = {src[(int64_t)(i0 + m * TPL) * es], (T)0};
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < E; ++m) {
+                        const int e = i0 + m * TPL;
+                        const int64_t pos = (int64_t)e * p.in.pos_es + pos0;
+                        T r = 0;
+                        if (valid && pos < p.in.len) r = src[(int64_t)e * p.in.elem_stride];
+                        a[m] = {r, (T)0};
+                    }
                 }
             } else {
                 const cx* __restrict__ src = reinterpret_cast<const cx*>(p.in.ptr) + off;
+                if (nomask) {
+                    if (!valid) {
 #pragma unroll
-                for (int m = 0; m < E; ++m) {
-                    const int e = i0 + m * TPL;
-                    const int64_t pos = (int64_t)e * p.in.pos_es + pos0;
-                    cx v = {0, 0};
-                    if (valid && pos < p.in.len) v = src[(int64_t)e * p.in.elem_stride];
-                    a[m] = v;
+                        for (int m = 0; m < E; ++m) a[m] = {(T)0, (T)0};
+                    } else if (p.in.elem_stride == 1) {
+#pragma unroll
+                        for (int m = 0; m < E; ++m) a[m] = src[i0 + m * TPL];
+                    } else {
+                        const int64_t es = p.in.elem_stride;
+#pragma unroll
+                        for (int m = 0; m < E; ++m) a[m] = src[(int64_t)(i0 + m * TPL) * es];
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < E; ++m) {
+                        const int e = i0 + m * TPL;
+                        const int64_t pos = (int64_t)e * p.in.pos_es + pos0;
+                        cx v = {0, 0};
+                        if (valid && pos < p.in.len) v = src[(int64_t)e * p.in.elem_stride];
+                        a[m] = v;
+                    }
                 }
             }
             if (swap_pre) {
@@ -522,11 +568,24 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         }
     } else {
         cx* __restrict__ dst = reinterpret_cast<cx*>(p.out.ptr) + off;
+        if (p.flags & F_OUT_NOMASK) {
+            if (valid) {
+                if (p.out.elem_stride == 1) {
 #pragma unroll
-        for (int m = 0; m < E; ++m) {
-            const int e = i1 + m * TPL;
-            const int64_t pos = (int64_t)e * p.out.pos_es + pos0;
-            if (valid && pos < p.out.len) dst[(int64_t)e * p.out.elem_stride] = a[m];
+                    for (int m = 0; m < E; ++m) dst[i1 + m * TPL] = a[m];
+                } else {
+                    const int64_t es = p.out.elem_stride;
+#pragma unroll
+                    for (int m = 0; m < E; ++m) dst[(int64_t)(i1 + m * TPL) * es] = a[m];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int e = i1 + m * TPL;
+                const int64_t pos = (int64_t)e * p.out.pos_es + pos0;
+                if (valid && pos < p.out.len) dst[(int64_t)e * p.out.elem_stride] = a[m];
+            }
         }
     }
 }

@@ -37,7 +37,9 @@ enum PassFlags : uint32_t {
     F_SWAP_ST_PRE = 1u << 2,   // swap re/im before the store operator       (undo inner inverse)
     F_SWAP_ST_POST = 1u << 3,  // swap re/im just before the raw store       (outer inverse)
     F_TW_CONJ = 1u << 4,       // ST_TW uses conj(W)
-    F_ST_REAL = 1u << 5,       // store only the real part into a real array (irfftn, rfft.rs:722)
+    F_ST_REAL = 1u << 5,
+    F_IN_NOMASK = 1u << 6,     // every (lane, e) position is < in.len: loads need no bounds predicate
+    F_OUT_NOMASK = 1u << 7,    // likewise for stores       // store only the real part into a real array (irfftn, rfft.rs:722)
 };
 
 struct IoDesc {

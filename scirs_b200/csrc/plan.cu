@@ -337,6 +337,14 @@ struct PlanBuilder {
         s.nbatch = nbatch;
         s.p.tw = table_stage_tw(prec, s.k->L, err);
         if (!s.p.tw) return false;
+        {
+            // positions are e*pos_es + lane_outer*pos_ls with e < L and lane_outer < nlanes/inner
+            const int64_t max_lo = (nlanes - 1) / std::max<int64_t>(inner, 1);
+            const int64_t in_max = (int64_t)(s.k->L - 1) * s.p.in.pos_es + max_lo * s.p.in.pos_ls;
+            const int64_t out_max = (int64_t)(s.k->L - 1) * s.p.out.pos_es + max_lo * s.p.out.pos_ls;
+            if (in_max < s.p.in.len && s.p.ld_op != LD_C2R) s.p.flags |= F_IN_NOMASK;
+            if (out_max < s.p.out.len && s.p.st_op != ST_R2C) s.p.flags |= F_OUT_NOMASK;
+        }
         char buf[256];
         snprintf(buf, sizeof buf, "%s: tile L=%d TL=%d%s threads=%d smem=%zu lanes=%lld batches=%lld map=%s->%s", what,
                  s.k->L, s.k->TL, s.k->dbl ? " fwd*tab*inv" : "", s.k->threads, s.k->smem, (long long)nlanes,
