@@ -6,7 +6,7 @@
 // planner (`fft.process(&mut buffer)`, scirs2-fft/src/fft/algorithms.rs:167,
 // 362, 376, 683) together with the gather/scatter/scale loops around it
 // (:353-395, :677-703).  Forward sign is exp(-2*pi*i*jk/n), unnormalised, as in
-// rustfft; the inverse is the same code with re/im swapped on the way in and out.
+// rustfft; the inverse is the same code with the data conjugated on the way in and out.
 //
 // Index algebra (DIF Stockham, stage radix R at stride S, S*n = L):
 //   thread butterfly index ib in [0, L/R):  q = ib mod S, base = ib - q
@@ -47,7 +47,7 @@ __device__ __forceinline__ Cx<T> csqr(Cx<T> a) {
     return {fma(a.x, a.x, -(a.y * a.y)), (a.x + a.x) * a.y};
 }
 template <typename T>
-__device__ __forceinline__ Cx<T> cswap(Cx<T> a) { return {a.y, a.x}; }
+__device__ __forceinline__ Cx<T> cconjf(Cx<T> a) { return {a.x, -a.y}; }
 template <typename T>
 __device__ __forceinline__ Cx<T> cconj(Cx<T> a) { return {a.x, -a.y}; }
 template <typename T>
@@ -306,12 +306,47 @@ __device__ __forceinline__ void map_thread(int mode, int tid, int& t, int& i) {
 
 // ---- the kernel ---------------------------------------------------------------
 
-template <typename T, int L, int TL, bool DOUBLE, int EMAX = 16>
+// Kernel flavours.  The planner picks a FAST flavour whenever every lane of every tile is valid
+// and no bounds mask is needed (PlanBuilder::finish_tile); they carry no predicates, no zero
+// fill and no runtime-selected code on the hot path.
+enum TileMode : int {
+    TM_GENERIC = 0,   // every load / store operator, masks, partial tiles
+    TM_FAST_C2C = 1,  // complex in, complex out, optional table multiplies / twiddles / scale
+    TM_FAST_R2C = 2,  // packed real rows in, N/2+1 Hermitian half out (fused post-twiddle)
+    TM_FAST_C2R = 3,  // N/2+1 Hermitian half in (fused pre-twiddle), packed real rows out
+};
+
+// Z[k] = (X[k] + conj X[L-k]) + i*conj(W_2L^k)*(X[k] - conj X[L-k]) from a staged row
+template <typename T, typename C>
+__device__ __forceinline__ void c2r_pretwiddle(Cx<T> (&a)[C::E], const Cx<T>* row, const Cx<T>* rtw, int i0) {
+    constexpr int E = C::E, TPL = C::TPL, L = C::L;
+    if constexpr (E >= 8) {
+        const Cx<T> wi = rtw[i0];
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int k = i0 + m * TPL;
+            Cx<T> xk = row[k];
+            Cx<T> xp = row[L - k];
+            if (k == 0) {  // imag of DC / Nyquist never reaches the real output
+                xk.y = 0;
+                xp.y = 0;
+            }
+            const Cx<T> A = {xk.x + xp.x, xk.y - xp.y};
+            const Cx<T> D = {xk.x - xp.x, xk.y + xp.y};
+            const Cx<T> w = cmul(wi, w32<T>(m * (16 / E)));
+            const Cx<T> Bc = cmulc(D, w);        // conj(W) * D
+            a[m] = {A.x - Bc.y, A.y + Bc.x};     // A + i*Bc
+        }
+    }
+}
+
+template <typename T, int L, int TL, bool DOUBLE, int EMAX = 16, int MODE = TM_GENERIC>
 __global__ void __launch_bounds__(TileCfg<T, L, TL, EMAX>::NT, TileCfg<T, L, TL, EMAX>::MINB)
 tile_fft_kernel(const __grid_constant__ PassParams p) {
     using C = TileCfg<T, L, TL, EMAX>;
     using cx = Cx<T>;
     constexpr int E = C::E, TPL = C::TPL, LP = C::LP;
+    constexpr bool FAST = MODE != TM_GENERIC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx* sm = reinterpret_cast<cx*>(smem_raw);
 
@@ -324,6 +359,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
     map_thread<TL, TPL>(p.map_out, tid, t1, i1);
 
     cx a[E];
+    bool staged = false;
 
     // ------------------------------ load ------------------------------------
     {
@@ -334,10 +370,33 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         const int64_t off = (int64_t)batch * p.in.batch_stride + (int64_t)lo * p.in.outer_stride +
                             (int64_t)li * p.in.inner_stride;
         const int64_t pos0 = (int64_t)lo * p.in.pos_ls;
-        const bool swap_pre = p.flags & F_SWAP_LD_PRE;
-        if (p.ld_op == LD_C2R) {
-            // stage the L+1 Hermitian inputs of each lane, then build the packed
-            // spectrum Z[k] = (X[k] + conj X[L-k]) + i*conj(W_2L^k)*(X[k] - conj X[L-k])
+        if constexpr (MODE == TM_FAST_C2R) {
+            // stage the L+1 Hermitian inputs of each lane (unit stride), then pre-twiddle
+            const cx* __restrict__ src = reinterpret_cast<const cx*>(p.in.ptr) + off + i0;
+            cx* row = sm + t0 * LP;
+#pragma unroll
+            for (int m = 0; m < E; ++m) row[i0 + m * TPL] = src[m * TPL];
+            if (i0 == 0) row[L] = src[L];
+            __syncthreads();
+            c2r_pretwiddle<T, C>(a, row, reinterpret_cast<const cx*>(p.rtw), i0);
+            staged = true;
+        } else if constexpr (FAST) {
+            const cx* __restrict__ src =
+                reinterpret_cast<const cx*>(p.in.ptr) + off + (int64_t)i0 * p.in.elem_stride;
+            const int64_t step = (int64_t)TPL * p.in.elem_stride;
+#pragma unroll
+            for (int m = 0; m < E; ++m) a[m] = src[m * step];
+            if (p.flags & F_CONJ_LD_PRE) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
+            }
+            if (p.ld_op == LD_C_MUL) {
+                const cx* __restrict__ aux = reinterpret_cast<const cx*>(p.aux_in);
+#pragma unroll
+                for (int m = 0; m < E; ++m)
+                    a[m] = cmul(a[m], aux[(int64_t)(i0 + m * TPL) * p.in.pos_es + pos0]);
+            }
+        } else if (p.ld_op == LD_C2R) {
             const cx* __restrict__ src = reinterpret_cast<const cx*>(p.in.ptr) + off;
             cx* row = sm + t0 * LP;
 #pragma unroll
@@ -353,81 +412,35 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
                 row[L] = v;
             }
             __syncthreads();
-            if constexpr (E >= 8) {
-                const cx wi = reinterpret_cast<const cx*>(p.rtw)[i0];
-#pragma unroll
-                for (int m = 0; m < E; ++m) {
-                    const int k = i0 + m * TPL;
-                    cx xk = row[k];
-                    cx xp = row[L - k];
-                    if (k == 0) {  // imag of DC / Nyquist never reaches the real output
-                        xk.y = 0;
-                        xp.y = 0;
-                    }
-                    const cx A = {xk.x + xp.x, xk.y - xp.y};
-                    const cx D = {xk.x - xp.x, xk.y + xp.y};
-                    const cx w = cmul(wi, w32<T>(m * (16 / E)));
-                    const cx Bc = cmulc(D, w);           // conj(W) * D
-                    a[m] = {A.x - Bc.y, A.y + Bc.x};     // A + i*Bc
-                }
-            }
-            __syncthreads();
+            c2r_pretwiddle<T, C>(a, row, reinterpret_cast<const cx*>(p.rtw), i0);
+            staged = true;
         } else {
             const bool is_real = (p.ld_op == LD_R) || (p.ld_op == LD_R_MUL);
             const bool has_mul = (p.ld_op == LD_C_MUL) || (p.ld_op == LD_R_MUL);
-            const bool nomask = p.flags & F_IN_NOMASK;
             if (is_real) {
                 const T* __restrict__ src = reinterpret_cast<const T*>(p.in.ptr) + off;
-                if (nomask) {
-                    if (!valid) {
 #pragma unroll
-                        for (int m = 0; m < E; ++m) a[m] = {(T)0, (T)0};
-                    } else if (p.in.elem_stride == 1) {
-#pragma unroll
-                        for (int m = 0; m < E; ++m) a[m] = {src[i0 + m * TPL], (T)0};
-                    } else {
-                        const int64_t es = p.in.elem_stride;
-#pragma unroll
-                        for (int m = 0; m < E; ++m) a[m] = {src[(int64_t)(i0 + m * TPL) * es], (T)0};
-                    }
-                } else {
-#pragma unroll
-                    for (int m = 0; m < E; ++m) {
-                        const int e = i0 + m * TPL;
-                        const int64_t pos = (int64_t)e * p.in.pos_es + pos0;
-                        T r = 0;
-                        if (valid && pos < p.in.len) r = src[(int64_t)e * p.in.elem_stride];
-                        a[m] = {r, (T)0};
-                    }
+                for (int m = 0; m < E; ++m) {
+                    const int e = i0 + m * TPL;
+                    const int64_t pos = (int64_t)e * p.in.pos_es + pos0;
+                    T r = 0;
+                    if (valid && pos < p.in.len) r = src[(int64_t)e * p.in.elem_stride];
+                    a[m] = {r, (T)0};
                 }
             } else {
                 const cx* __restrict__ src = reinterpret_cast<const cx*>(p.in.ptr) + off;
-                if (nomask) {
-                    if (!valid) {
 #pragma unroll
-                        for (int m = 0; m < E; ++m) a[m] = {(T)0, (T)0};
-                    } else if (p.in.elem_stride == 1) {
-#pragma unroll
-                        for (int m = 0; m < E; ++m) a[m] = src[i0 + m * TPL];
-                    } else {
-                        const int64_t es = p.in.elem_stride;
-#pragma unroll
-                        for (int m = 0; m < E; ++m) a[m] = src[(int64_t)(i0 + m * TPL) * es];
-                    }
-                } else {
-#pragma unroll
-                    for (int m = 0; m < E; ++m) {
-                        const int e = i0 + m * TPL;
-                        const int64_t pos = (int64_t)e * p.in.pos_es + pos0;
-                        cx v = {0, 0};
-                        if (valid && pos < p.in.len) v = src[(int64_t)e * p.in.elem_stride];
-                        a[m] = v;
-                    }
+                for (int m = 0; m < E; ++m) {
+                    const int e = i0 + m * TPL;
+                    const int64_t pos = (int64_t)e * p.in.pos_es + pos0;
+                    cx v = {0, 0};
+                    if (valid && pos < p.in.len) v = src[(int64_t)e * p.in.elem_stride];
+                    a[m] = v;
                 }
             }
-            if (swap_pre) {
+            if (p.flags & F_CONJ_LD_PRE) {
 #pragma unroll
-                for (int m = 0; m < E; ++m) a[m] = cswap(a[m]);
+                for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
             }
             if (has_mul) {
                 const cx* __restrict__ aux = reinterpret_cast<const cx*>(p.aux_in);
@@ -439,19 +452,24 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
                 }
             }
         }
-        if (p.flags & F_SWAP_LD_POST) {
+        if (MODE == TM_FAST_C2R || (p.flags & F_CONJ_LD_POST)) {
 #pragma unroll
-            for (int m = 0; m < E; ++m) a[m] = cswap(a[m]);
+            for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
         }
     }
 
     // ---------------------------- transform ---------------------------------
     const cx* __restrict__ tw = reinterpret_cast<const cx*>(p.tw);
-    const bool staged = (p.ld_op == LD_C2R);
-    if (staged)
+    if constexpr (MODE == TM_FAST_C2R) {
         run_stages<T, C, 1, false>(a, sm, tw, t0, i0, t1, i1);
-    else
+    } else if constexpr (FAST) {
         run_stages<T, C, 1, true>(a, sm, tw, t0, i0, t1, i1);
+    } else {
+        if (staged)
+            run_stages<T, C, 1, false>(a, sm, tw, t0, i0, t1, i1);
+        else
+            run_stages<T, C, 1, true>(a, sm, tw, t0, i0, t1, i1);
+    }
 
     if constexpr (C::E == C::L) {
         // single-stage tiles never touch shared memory: remap explicitly if the
@@ -467,7 +485,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
     }
 
     const uint32_t lane = tile * TL + (uint32_t)t1;
-    const bool valid = lane < p.nlanes;
+    const bool valid = FAST ? true : (lane < p.nlanes);
     const uint32_t lo = lane / p.inner_count;
     const uint32_t li = lane - lo * p.inner_count;
 
@@ -479,11 +497,11 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         for (int m = 0; m < E; ++m) {
             const int e = i1 + m * TPL;
             cx w = mid[(int64_t)e * p.mid_es + mid0];
-            a[m] = cswap(cmul(a[m], w));
+            a[m] = cconjf(cmul(a[m], w));
         }
         run_stages<T, C, 1, false>(a, sm, tw, t1, i1, t1, i1);
 #pragma unroll
-        for (int m = 0; m < E; ++m) a[m] = cswap(a[m]);
+        for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
     }
 
     // ------------------------------ store -----------------------------------
@@ -492,13 +510,13 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
     const int64_t pos0 = (int64_t)lo * p.out.pos_ls;
     const T scale = (T)p.scale;
 
-    if (p.flags & F_SWAP_ST_PRE) {
+    if (MODE == TM_FAST_C2R || (p.flags & F_CONJ_ST_PRE)) {
 #pragma unroll
-        for (int m = 0; m < E; ++m) a[m] = cswap(a[m]);
+        for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
     }
 
-    if (p.st_op == ST_R2C) {
-        if constexpr (E >= 8) {
+    if (MODE == TM_FAST_R2C || (MODE == TM_GENERIC && p.st_op == ST_R2C)) {
+        if constexpr (E >= 8 && E != L && (MODE == TM_FAST_R2C || MODE == TM_GENERIC)) {
             // a[m] = Z[i1 + m*TPL] of the packed half-length transform
             cx* row = sm + t1 * LP;
             __syncthreads();
@@ -507,6 +525,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
             __syncthreads();
             cx* __restrict__ dst = reinterpret_cast<cx*>(p.out.ptr) + off;
             const cx wi = reinterpret_cast<const cx*>(p.rtw)[i1];
+            const T h = (T)0.5 * scale;
 #pragma unroll
             for (int m = 0; m < E / 2; ++m) {
                 const int k = i1 + m * TPL;
@@ -515,17 +534,24 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
                 const cx A = {zk.x + zp.x, zk.y - zp.y};
                 const cx B = {zk.x - zp.x, zk.y + zp.y};
                 const cx Cw = cmul(B, cmul(wi, w32<T>(m * (16 / E))));
-                const T h = (T)0.5 * scale;
                 const cx xk = {(A.x + Cw.y) * h, (A.y - Cw.x) * h};
                 const cx xq = {(A.x - Cw.y) * h, -((A.y + Cw.x) * h)};
-                if (valid) {
+                if constexpr (MODE == TM_FAST_R2C) {
+                    dst[k] = xk;
+                    dst[L - k] = xq;
+                } else if (valid) {
                     if ((int64_t)k < p.out.len) dst[(int64_t)k * p.out.elem_stride] = xk;
                     if ((int64_t)(L - k) < p.out.len) dst[(int64_t)(L - k) * p.out.elem_stride] = xq;
                 }
             }
-            if (i1 == 0 && valid && (int64_t)(L / 2) < p.out.len) {
+            if (i1 == 0) {
                 const cx z = a[E / 2];
-                dst[(int64_t)(L / 2) * p.out.elem_stride] = {z.x * scale, -(z.y * scale)};
+                const cx v = {z.x * scale, -(z.y * scale)};
+                if constexpr (MODE == TM_FAST_R2C) {
+                    dst[L / 2] = v;
+                } else if (valid && (int64_t)(L / 2) < p.out.len) {
+                    dst[(int64_t)(L / 2) * p.out.elem_stride] = v;
+                }
             }
         }
         return;
@@ -535,30 +561,36 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         const cx* __restrict__ tlo = reinterpret_cast<const cx*>(p.tw_lo);
         const cx* __restrict__ thi = reinterpret_cast<const cx*>(p.tw_hi);
         const uint64_t lmask = ((uint64_t)1 << p.tw_shift) - 1;
-        const bool cj = p.flags & F_TW_CONJ;
+        const T sgn = (p.flags & F_TW_CONJ) ? (T)-1 : (T)1;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const uint64_t ex = (uint64_t)(i1 + m * TPL) * (uint64_t)lo;
             cx w = cmul(thi[ex >> p.tw_shift], tlo[ex & lmask]);
-            a[m] = cj ? cmulc(a[m], w) : cmul(a[m], w);
+            w.y *= sgn;
+            a[m] = cmul(a[m], w);
         }
     } else if (p.st_op == ST_MUL) {
         const cx* __restrict__ aux = reinterpret_cast<const cx*>(p.aux_out);
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int64_t pos = (int64_t)(i1 + m * TPL) * p.out.pos_es + pos0;
-            if (pos < p.out.len) a[m] = cmul(a[m], aux[pos]);
+            if (FAST || pos < p.out.len) a[m] = cmul(a[m], aux[pos]);
         }
     }
     if (p.scale != 1.0) {
 #pragma unroll
         for (int m = 0; m < E; ++m) a[m] = {a[m].x * scale, a[m].y * scale};
     }
-    if (p.flags & F_SWAP_ST_POST) {
+    if (p.flags & F_CONJ_ST_POST) {
 #pragma unroll
-        for (int m = 0; m < E; ++m) a[m] = cswap(a[m]);
+        for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
     }
-    if (p.flags & F_ST_REAL) {
+    if constexpr (FAST) {
+        cx* __restrict__ dst = reinterpret_cast<cx*>(p.out.ptr) + off + (int64_t)i1 * p.out.elem_stride;
+        const int64_t step = (int64_t)TPL * p.out.elem_stride;
+#pragma unroll
+        for (int m = 0; m < E; ++m) dst[m * step] = a[m];
+    } else if (p.flags & F_ST_REAL) {
         T* __restrict__ dst = reinterpret_cast<T*>(p.out.ptr) + off;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
@@ -568,24 +600,11 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         }
     } else {
         cx* __restrict__ dst = reinterpret_cast<cx*>(p.out.ptr) + off;
-        if (p.flags & F_OUT_NOMASK) {
-            if (valid) {
-                if (p.out.elem_stride == 1) {
 #pragma unroll
-                    for (int m = 0; m < E; ++m) dst[i1 + m * TPL] = a[m];
-                } else {
-                    const int64_t es = p.out.elem_stride;
-#pragma unroll
-                    for (int m = 0; m < E; ++m) dst[(int64_t)(i1 + m * TPL) * es] = a[m];
-                }
-            }
-        } else {
-#pragma unroll
-            for (int m = 0; m < E; ++m) {
-                const int e = i1 + m * TPL;
-                const int64_t pos = (int64_t)e * p.out.pos_es + pos0;
-                if (valid && pos < p.out.len) dst[(int64_t)e * p.out.elem_stride] = a[m];
-            }
+        for (int m = 0; m < E; ++m) {
+            const int e = i1 + m * TPL;
+            const int64_t pos = (int64_t)e * p.out.pos_es + pos0;
+            if (valid && pos < p.out.len) dst[(int64_t)e * p.out.elem_stride] = a[m];
         }
     }
 }

@@ -5,7 +5,7 @@
 
 namespace sfc {
 
-template <typename T, int L, int TL, bool DBL, int EMAX = 16>
+template <typename T, int L, int TL, bool DBL, int EMAX = 16, int MODE = 0>
 struct KernelInst {
     using C = TileCfg<T, L, TL, EMAX>;
     static cudaError_t launch(const PassParams& p, unsigned grid, cudaStream_t s) {
@@ -14,12 +14,12 @@ struct KernelInst {
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
         if (dev < 64 && !configured[dev]) {
-            e = cudaFuncSetAttribute(tile_fft_kernel<T, L, TL, DBL, EMAX>,
+            e = cudaFuncSetAttribute(tile_fft_kernel<T, L, TL, DBL, EMAX, MODE>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
             if (e != cudaSuccess) return e;
             configured[dev] = true;
         }
-        tile_fft_kernel<T, L, TL, DBL, EMAX><<<grid, C::NT, C::SMEM, s>>>(p);
+        tile_fft_kernel<T, L, TL, DBL, EMAX, MODE><<<grid, C::NT, C::SMEM, s>>>(p);
         return cudaGetLastError();
     }
     static KernelEntry entry() {
@@ -29,9 +29,10 @@ struct KernelInst {
         k.TL = TL;
         k.E = C::E;
         k.dbl = DBL ? 1 : 0;
+        k.mode = MODE;
         k.threads = C::NT;
         k.smem = C::SMEM;
-        k.func = (const void*)tile_fft_kernel<T, L, TL, DBL, EMAX>;
+        k.func = (const void*)tile_fft_kernel<T, L, TL, DBL, EMAX, MODE>;
         k.launch = &launch;
         return k;
     }
@@ -39,5 +40,12 @@ struct KernelInst {
 
 }  // namespace sfc
 
-#define SFC_ADD(T, L, TL, DBL) add(::sfc::KernelInst<T, L, TL, DBL>::entry());
+// generic + fast complex flavour of one tile shape
+#define SFC_ADD(T, L, TL, DBL)                              \
+    add(::sfc::KernelInst<T, L, TL, DBL, 16, 0>::entry()); \
+    add(::sfc::KernelInst<T, L, TL, DBL, 16, 1>::entry());
+// fused real-transform flavours (row tiles only)
+#define SFC_ADD_REAL(T, L, TL)                                \
+    add(::sfc::KernelInst<T, L, TL, false, 16, 2>::entry()); \
+    add(::sfc::KernelInst<T, L, TL, false, 16, 3>::entry());
 #define SFC_ADD_E(T, L, TL, DBL, E) add(::sfc::KernelInst<T, L, TL, DBL, E>::entry());

@@ -14,6 +14,7 @@ struct KernelEntry {
     int TL;         // lanes per tile
     int E;          // points per thread (largest radix)
     int dbl;        // 1 = forward * table * inverse fused
+    int mode;       // TileMode (0 generic, 1 fast c2c, 2 fast r2c, 3 fast c2r)
     int threads;    // CTA size
     size_t smem;    // dynamic shared memory bytes
     const void* func;
@@ -22,7 +23,7 @@ struct KernelEntry {
 
 // all entries (built once, thread-safe)
 const KernelEntry* kernel_table(int* count);
-const KernelEntry* find_kernel(int prec, int L, int TL, int dbl);
+const KernelEntry* find_kernel(int prec, int L, int TL, int dbl, int mode = 0);
 
 // per-file registration hooks (one per kernels_*.cu translation unit)
 void register_kernels_f64_small(void (*add)(const KernelEntry&));
@@ -36,5 +37,7 @@ void register_kernels_f32_big(void (*add)(const KernelEntry&));
 void register_kernels_f32_dbl_a(void (*add)(const KernelEntry&));
 void register_kernels_f32_dbl_b(void (*add)(const KernelEntry&));
 void register_kernels_e8(void (*add)(const KernelEntry&));
+void register_kernels_f64_real(void (*add)(const KernelEntry&));
+void register_kernels_f32_real(void (*add)(const KernelEntry&));
 
 }  // namespace sfc

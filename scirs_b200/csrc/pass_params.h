@@ -32,10 +32,11 @@ enum StoreOp : int32_t {
 };
 
 enum PassFlags : uint32_t {
-    F_SWAP_LD_PRE = 1u << 0,   // swap re/im right after the raw load        (outer inverse)
-    F_SWAP_LD_POST = 1u << 1,  // swap re/im after the load operator         (inner inverse FFT)
-    F_SWAP_ST_PRE = 1u << 2,   // swap re/im before the store operator       (undo inner inverse)
-    F_SWAP_ST_POST = 1u << 3,  // swap re/im just before the raw store       (outer inverse)
+    // inverse transforms run the forward code on conjugated data: IFFT(x) = conj(FFT(conj(x)))
+    F_CONJ_LD_PRE = 1u << 0,   // conjugate right after the raw load         (outer inverse)
+    F_CONJ_LD_POST = 1u << 1,  // conjugate after the load operator          (inner inverse FFT)
+    F_CONJ_ST_PRE = 1u << 2,   // conjugate before the store operator        (undo inner inverse)
+    F_CONJ_ST_POST = 1u << 3,  // conjugate just before the raw store        (outer inverse)
     F_TW_CONJ = 1u << 4,       // ST_TW uses conj(W)
     F_ST_REAL = 1u << 5,
     F_IN_NOMASK = 1u << 6,     // every (lane, e) position is < in.len: loads need no bounds predicate

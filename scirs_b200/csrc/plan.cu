@@ -34,17 +34,38 @@ const KernelEntry* kernel_table(int* count) {
         register_kernels_f32_dbl_a(add_entry);
         register_kernels_f32_dbl_b(add_entry);
         register_kernels_e8(add_entry);
+        register_kernels_f64_real(add_entry);
+        register_kernels_f32_real(add_entry);
     });
     if (count) *count = (int)ktable().size();
     return ktable().data();
 }
 
-const KernelEntry* find_kernel(int prec, int L, int TL, int dbl) {
+const KernelEntry* find_kernel(int prec, int L, int TL, int dbl, int mode) {
     int n = 0;
     const KernelEntry* t = kernel_table(&n);
     for (int i = 0; i < n; ++i)
-        if (t[i].prec == prec && t[i].L == L && t[i].TL == TL && t[i].dbl == dbl) return &t[i];
+        if (t[i].prec == prec && t[i].L == L && t[i].TL == TL && t[i].dbl == dbl && t[i].mode == mode) return &t[i];
     return nullptr;
+}
+
+// same tile shape, different flavour (nullptr when that flavour is not compiled)
+static const KernelEntry* flavour_of(const KernelEntry* k, int mode) {
+    int n = 0;
+    const KernelEntry* t = kernel_table(&n);
+    for (int i = 0; i < n; ++i)
+        if (t[i].prec == k->prec && t[i].L == k->L && t[i].TL == k->TL && t[i].dbl == k->dbl && t[i].E == k->E &&
+            t[i].mode == mode)
+            return &t[i];
+    return nullptr;
+}
+
+static bool fast_enabled() {
+    static int v = [] {
+        const char* e = getenv("SFC_FAST");
+        return e ? atoi(e) : 1;
+    }();
+    return v != 0;
 }
 
 // ROW tiles want few lanes per CTA (small tiles, more CTAs per SM); COL tiles want
@@ -72,11 +93,12 @@ static const KernelEntry* pick_kernel(int prec, int L, bool want_wide, int dbl) 
     const int want_e = forced_e() ? forced_e() : 16;
     bool have_e = false;
     for (int i = 0; i < n; ++i)
-        if (t[i].prec == prec && t[i].L == L && t[i].dbl == dbl && t[i].E == std::min(want_e, L)) have_e = true;
+        if (t[i].mode == 0 && t[i].prec == prec && t[i].L == L && t[i].dbl == dbl && t[i].E == std::min(want_e, L))
+            have_e = true;
     const int cap = (want_wide && col_tl_cap() > 0) ? col_tl_cap() : (1 << 30);
     const KernelEntry* smallest = nullptr;
     for (int i = 0; i < n; ++i) {
-        if (t[i].prec != prec || t[i].L != L || t[i].dbl != dbl) continue;
+        if (t[i].mode != 0 || t[i].prec != prec || t[i].L != L || t[i].dbl != dbl) continue;
         if (have_e ? t[i].E != std::min(want_e, L) : t[i].E != std::min(16, L)) continue;
         if (!smallest || t[i].TL < smallest->TL) smallest = &t[i];
         if (t[i].TL > cap) continue;
@@ -344,10 +366,33 @@ struct PlanBuilder {
             const int64_t out_max = (int64_t)(s.k->L - 1) * s.p.out.pos_es + max_lo * s.p.out.pos_ls;
             if (in_max < s.p.in.len && s.p.ld_op != LD_C2R) s.p.flags |= F_IN_NOMASK;
             if (out_max < s.p.out.len && s.p.st_op != ST_R2C) s.p.flags |= F_OUT_NOMASK;
+            // pick the predicate-free flavour when nothing needs masking
+            const bool full_tiles = nlanes % s.k->TL == 0;
+            int mode = 0;
+            if (full_tiles && fast_enabled()) {
+                if (s.p.st_op == ST_R2C) {
+                    if (s.p.ld_op == LD_C && in_max < s.p.in.len && s.p.in.elem_stride == 1 &&
+                        s.p.out.elem_stride == 1 && s.p.out.len >= s.k->L + 1 &&
+                        (s.p.flags & ~(uint32_t)(F_IN_NOMASK | F_OUT_NOMASK)) == 0)
+                        mode = 2;
+                } else if (s.p.ld_op == LD_C2R) {
+                    if (s.p.in.elem_stride == 1 && s.p.in.len >= s.k->L + 1 && out_max < s.p.out.len &&
+                        s.p.st_op == ST_C && !(s.p.flags & F_ST_REAL))
+                        mode = 3;
+                } else if ((s.p.flags & F_IN_NOMASK) && (s.p.flags & F_OUT_NOMASK) && !(s.p.flags & F_ST_REAL) &&
+                           (s.p.ld_op == LD_C || s.p.ld_op == LD_C_MUL)) {
+                    mode = 1;
+                }
+            }
+            if (mode) {
+                const KernelEntry* f = flavour_of(s.k, mode);
+                if (f) s.k = f;
+            }
         }
         char buf[256];
-        snprintf(buf, sizeof buf, "%s: tile L=%d TL=%d%s threads=%d smem=%zu lanes=%lld batches=%lld map=%s->%s", what,
-                 s.k->L, s.k->TL, s.k->dbl ? " fwd*tab*inv" : "", s.k->threads, s.k->smem, (long long)nlanes,
+        snprintf(buf, sizeof buf, "%s: tile L=%d TL=%d%s%s threads=%d smem=%zu lanes=%lld batches=%lld map=%s->%s", what,
+                 s.k->L, s.k->TL, s.k->dbl ? " fwd*tab*inv" : "",
+                 s.k->mode == 0 ? " generic" : (s.k->mode == 1 ? " fast" : (s.k->mode == 2 ? " fast-r2c" : " fast-c2r")), s.k->threads, s.k->smem, (long long)nlanes,
                  (long long)nbatch, s.p.map_in == MAP_ROW ? "row" : "col", s.p.map_out == MAP_ROW ? "row" : "col");
         s.desc = buf;
         pl.steps_.push_back(s);
@@ -401,8 +446,8 @@ struct PlanBuilder {
     bool add_axis(int64_t n, int64_t O, int64_t I, ArrayRef src, ArrayRef dst, bool inverse, double scale,
                   bool store_real) {
         const int lmax = lmax_for(prec);
-        const uint32_t fl_in = inverse ? F_SWAP_LD_PRE : 0;
-        const uint32_t fl_out = (inverse ? F_SWAP_ST_POST : 0) | (store_real ? F_ST_REAL : 0);
+        const uint32_t fl_in = inverse ? F_CONJ_LD_PRE : 0;
+        const uint32_t fl_out = (inverse ? F_CONJ_ST_POST : 0) | (store_real ? F_ST_REAL : 0);
         const size_t src_es = src.real ? rs : cs;
         const size_t dst_es = (dst.real || store_real) ? rs : cs;
         const bool col = I > 1;
@@ -586,7 +631,7 @@ struct PlanBuilder {
             c.p.ld_op = LD_C;
             c.p.st_op = ST_MUL;
             c.p.aux_out = chirp;
-            c.p.flags = F_SWAP_LD_POST | F_SWAP_ST_PRE | fl_out;
+            c.p.flags = F_CONJ_LD_POST | F_CONJ_ST_PRE | fl_out;
             c.p.scale = scale;
             dev_bytes += O * I * (std::min(n, src.n) * (int64_t)src_es + 5 * M * (int64_t)cs +
                                   std::min(n, dst.n) * (int64_t)dst_es);
@@ -634,7 +679,7 @@ struct PlanBuilder {
         s.p.map_in = s.p.map_out = MAP_ROW;
         s.p.ld_op = LD_C2R;
         s.p.st_op = ST_C;
-        s.p.flags = F_SWAP_LD_POST | F_SWAP_ST_PRE;
+        s.p.flags = F_CONJ_LD_POST | F_CONJ_ST_PRE;
         s.p.scale = scale;
         s.p.rtw = table_rtw(prec, L, err);
         if (!s.p.rtw) return false;
