@@ -384,8 +384,21 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
             const cx* __restrict__ src =
                 reinterpret_cast<const cx*>(p.in.ptr) + off + (int64_t)i0 * p.in.elem_stride;
             const int64_t step = (int64_t)TPL * p.in.elem_stride;
+            // optional zero padding: element e is real data iff e*pos_es + pos0 < len, i.e. e < elim
+            int elim = L;
+            if (!(p.flags & F_IN_NOMASK)) {
+                const int64_t rem = p.in.len - pos0;
+                elim = rem <= 0 ? 0 : (int)min((uint32_t)L, ((uint32_t)rem + (uint32_t)p.in.pos_es - 1u) / (uint32_t)p.in.pos_es);
 #pragma unroll
-            for (int m = 0; m < E; ++m) a[m] = src[m * step];
+                for (int m = 0; m < E; ++m) {
+                    cx v = {(T)0, (T)0};
+                    if (i0 + m * TPL < elim) v = src[m * step];
+                    a[m] = v;
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < E; ++m) a[m] = src[m * step];
+            }
             if (p.flags & F_CONJ_LD_PRE) {
 #pragma unroll
                 for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
@@ -394,7 +407,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
                 const cx* __restrict__ aux = reinterpret_cast<const cx*>(p.aux_in);
 #pragma unroll
                 for (int m = 0; m < E; ++m)
-                    a[m] = cmul(a[m], aux[(int64_t)(i0 + m * TPL) * p.in.pos_es + pos0]);
+                    if (i0 + m * TPL < elim) a[m] = cmul(a[m], aux[(int64_t)(i0 + m * TPL) * p.in.pos_es + pos0]);
             }
         } else if (p.ld_op == LD_C2R) {
             const cx* __restrict__ src = reinterpret_cast<const cx*>(p.in.ptr) + off;
@@ -558,23 +571,45 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
     }
 
     if (p.st_op == ST_TW) {
+        // four-step twiddle W_M^(e*lo), e = i1 + m*TPL:  w_m = W^(i1*lo) * (W^(TPL*lo))^m.  Two
+        // two-level table lookups per thread, then a depth-4 product tree (no per-element loads).
         const cx* __restrict__ tlo = reinterpret_cast<const cx*>(p.tw_lo);
         const cx* __restrict__ thi = reinterpret_cast<const cx*>(p.tw_hi);
         const uint64_t lmask = ((uint64_t)1 << p.tw_shift) - 1;
         const T sgn = (p.flags & F_TW_CONJ) ? (T)-1 : (T)1;
+        const uint64_t e0 = (uint64_t)i1 * (uint64_t)lo, e1 = (uint64_t)TPL * (uint64_t)lo;
+        cx b = cmul(thi[e0 >> p.tw_shift], tlo[e0 & lmask]);
+        cx s1 = cmul(thi[e1 >> p.tw_shift], tlo[e1 & lmask]);
+        b.y *= sgn;
+        s1.y *= sgn;
+        if constexpr (E == 16) {
+            const cx s2 = csqr(s1), s4 = csqr(s2), s8 = csqr(s4);
+            cx w[8];
+            w[0] = b;
+            w[1] = cmul(b, s1);
+            w[2] = cmul(b, s2);
+            w[3] = cmul(w[1], s2);
 #pragma unroll
-        for (int m = 0; m < E; ++m) {
-            const uint64_t ex = (uint64_t)(i1 + m * TPL) * (uint64_t)lo;
-            cx w = cmul(thi[ex >> p.tw_shift], tlo[ex & lmask]);
-            w.y *= sgn;
-            a[m] = cmul(a[m], w);
+            for (int j = 0; j < 4; ++j) w[4 + j] = cmul(w[j], s4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a[j] = cmul(a[j], w[j]);
+                a[8 + j] = cmul(a[8 + j], cmul(w[j], s8));
+            }
+        } else {
+            cx w = b;
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                a[m] = cmul(a[m], w);
+                w = cmul(w, s1);
+            }
         }
     } else if (p.st_op == ST_MUL) {
         const cx* __restrict__ aux = reinterpret_cast<const cx*>(p.aux_out);
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int64_t pos = (int64_t)(i1 + m * TPL) * p.out.pos_es + pos0;
-            if (FAST || pos < p.out.len) a[m] = cmul(a[m], aux[pos]);
+            if (pos < p.out.len) a[m] = cmul(a[m], aux[pos]);
         }
     }
     if (p.scale != 1.0) {
@@ -588,8 +623,18 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
     if constexpr (FAST) {
         cx* __restrict__ dst = reinterpret_cast<cx*>(p.out.ptr) + off + (int64_t)i1 * p.out.elem_stride;
         const int64_t step = (int64_t)TPL * p.out.elem_stride;
+        if (!(p.flags & F_OUT_NOMASK)) {
+            // optional crop: only positions < len are stored
+            const int64_t rem = p.out.len - pos0;
+            const int elim =
+                rem <= 0 ? 0 : (int)min((uint32_t)L, ((uint32_t)rem + (uint32_t)p.out.pos_es - 1u) / (uint32_t)p.out.pos_es);
 #pragma unroll
-        for (int m = 0; m < E; ++m) dst[m * step] = a[m];
+            for (int m = 0; m < E; ++m)
+                if (i1 + m * TPL < elim) dst[m * step] = a[m];
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; ++m) dst[m * step] = a[m];
+        }
     } else if (p.flags & F_ST_REAL) {
         T* __restrict__ dst = reinterpret_cast<T*>(p.out.ptr) + off;
 #pragma unroll

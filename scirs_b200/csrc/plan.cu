@@ -108,6 +108,21 @@ static const KernelEntry* pick_kernel(int prec, int L, bool want_wide, int dbl) 
     return best;
 }
 
+// Internal column passes of four-step / Bluestein: the widest tile whose exchange buffer still
+// lets two CTAs share an SM (measured: 2^20 four-step 60% -> 77% of HBM peak vs one 128 KiB CTA).
+static const KernelEntry* pick_kernel_two_per_sm(int prec, int L, int dbl) {
+    int n = 0;
+    const KernelEntry* t = kernel_table(&n);
+    const KernelEntry *best = nullptr, *smallest = nullptr;
+    for (int i = 0; i < n; ++i) {
+        if (t[i].mode != 0 || t[i].prec != prec || t[i].L != L || t[i].dbl != dbl || t[i].E != std::min(16, L)) continue;
+        if (!smallest || t[i].TL < smallest->TL) smallest = &t[i];
+        if (t[i].smem > (size_t)100 * 1024) continue;
+        if (!best || t[i].TL > best->TL) best = &t[i];
+    }
+    return best ? best : smallest;
+}
+
 // ------------------------------------------------------------- device tables
 
 using TableKey = std::tuple<int, int, int, int64_t, int64_t, int64_t, int64_t>;
@@ -305,6 +320,15 @@ static inline int ilog2_64(int64_t n) {
     return l;
 }
 
+static int col_single_limit(int prec) {
+    static int v = [] {
+        const char* e = getenv("SFC_COL_SINGLE_MAX");
+        return e ? atoi(e) : 0;
+    }();
+    if (v > 0) return v;
+    return prec == PREC_F64 ? 2048 : 4096;
+}
+
 static int64_t scratch_budget_bytes() {
     static int64_t v = [] {
         const char* e = getenv("SFC_WORK_MB");
@@ -379,9 +403,13 @@ struct PlanBuilder {
                     if (s.p.in.elem_stride == 1 && s.p.in.len >= s.k->L + 1 && out_max < s.p.out.len &&
                         s.p.st_op == ST_C && !(s.p.flags & F_ST_REAL))
                         mode = 3;
-                } else if ((s.p.flags & F_IN_NOMASK) && (s.p.flags & F_OUT_NOMASK) && !(s.p.flags & F_ST_REAL) &&
-                           (s.p.ld_op == LD_C || s.p.ld_op == LD_C_MUL)) {
-                    mode = 1;
+                } else if (!(s.p.flags & F_ST_REAL) && (s.p.ld_op == LD_C || s.p.ld_op == LD_C_MUL)) {
+                    // masks (zero padding on load, crop on store) are handled by a per-thread element
+                    // limit in 32-bit arithmetic
+                    const int64_t lim = (int64_t)1 << 31;
+                    if (s.p.in.len < lim && s.p.out.len < lim && in_max < lim && out_max < lim && s.p.in.pos_es < lim &&
+                        s.p.out.pos_es < lim && s.p.in.pos_es > 0 && s.p.out.pos_es > 0)
+                        mode = 1;
                 }
             }
             if (mode) {
@@ -461,7 +489,11 @@ struct PlanBuilder {
             return add_copy(src, d2, ss, ds, scale);
         }
 
-        if (is_pow2(n) && n <= lmax) {
+        // strided lanes need >= 64..128 B of adjacent lanes per element row; above this length a
+        // whole-column tile no longer fits shared memory with that many lanes, so the axis is
+        // split into two strided sub-passes (four-step) instead
+        const int col_single_max = col_single_limit(prec);
+        if (is_pow2(n) && n <= lmax && !(col && n > col_single_max)) {
             Step s;
             s.k = pick_kernel(prec, (int)n, col, 0);
             s.src = src.role;
@@ -494,7 +526,7 @@ struct PlanBuilder {
             if (!table_fourstep(prec, n, &lo, &hi, &sh, err)) return false;
             const int g = new_group(O, n * I * (int64_t)cs);
             Step a;
-            a.k = pick_kernel(prec, (int)L1, true, 0);
+            a.k = pick_kernel_two_per_sm(prec, (int)L1, 0);
             a.src = src.role;
             a.dst = R_MS;
             a.src_esize = src_es;
@@ -512,7 +544,7 @@ struct PlanBuilder {
             a.p.scale = 1.0;
             if (!finish_tile(a, L2 * I, I, O, "four-step pass A (columns + twiddle)")) return false;
             Step b;
-            b.k = pick_kernel(prec, (int)L2, true, 0);
+            b.k = pick_kernel_two_per_sm(prec, (int)L2, 0);
             b.src = R_MS;
             b.dst = dst.role;
             b.src_esize = cs;
@@ -561,7 +593,9 @@ struct PlanBuilder {
         }
         if (M > (int64_t)lmax * lmax) return fail(SFC_ERR_NOT_IMPLEMENTED, "Bluestein length above lmax^2");
         const int lg = ilog2_64(M);
-        int64_t L1 = (int64_t)1 << (lg / 2);
+        // column passes (A, C) like short lanes (two CTAs per SM with >= 64 B rows); the fused row
+        // pass B takes whatever is left
+        int64_t L1 = std::min<int64_t>((int64_t)1 << (lg / 2), 1024);
         int64_t L2 = M / L1;
         if (L2 > lmax) {
             L2 = lmax;
@@ -575,7 +609,7 @@ struct PlanBuilder {
         const int g = new_group(O, M * I * (int64_t)cs);
         {
             Step a;
-            a.k = pick_kernel(prec, (int)L1, true, 0);
+            a.k = pick_kernel_two_per_sm(prec, (int)L1, 0);
             a.src = src.role;
             a.dst = R_MS;
             a.src_esize = src_es;
@@ -619,7 +653,7 @@ struct PlanBuilder {
         }
         {
             Step c;
-            c.k = pick_kernel(prec, (int)L1, true, 0);
+            c.k = pick_kernel_two_per_sm(prec, (int)L1, 0);
             c.src = R_MS;
             c.dst = dst.role;
             c.src_esize = cs;

@@ -14,6 +14,8 @@ cases = {
     "c2c8192": ([32768, 8192], [1], "c2c", "f64", (1 << 28) * 2, (1 << 28) * 2),
     "fftn512": ([512, 512, 512], [0, 1, 2], "c2c", "f64", 512 ** 3 * 2, 512 ** 3 * 2),
     "fft2_8192": ([8192, 8192], [1, 0], "c2c", "f64", 8192 ** 2 * 2, 8192 ** 2 * 2),
+    "blue1m": ([16, 1000003], [1], "c2c", "f64", 16 * 1000003 * 2, 16 * 1000003 * 2),
+    "fftn1024": ([1024, 1024, 1024], [0, 1, 2], "c2c", "f64", 1024 ** 3 * 2, 1024 ** 3 * 2),
     "fft1m64": ([64, 1 << 20], [1], "c2c", "f64", (64 << 20) * 2, (64 << 20) * 2),
 }
 shape, axes, kind, prec, ni, no = cases[case]
