@@ -90,6 +90,11 @@ typedef struct sfc_desc {
     /* C2R only, with SFC_DESC_CUSTOM_IN_SHAPE: extents of the half-spectrum input when it is
      * not shape-with-last-axis-halved (irfftn pads / reflects what is there, rfft.rs:733-901) */
     int64_t in_shape[SFC_MAX_DIMS];
+    /* C2C only: > 1 splits the LAST listed axis into `scatter_parts` equal blocks and stores block q
+     * through the q-th pointer given to sfc_exec_device_scatter (layout [outer][n/parts][inner]):
+     * the slab transpose of a distributed fftn fused into the FFT store (distributed.rs:232-268) */
+    int32_t scatter_parts;
+    int32_t reserved;
 } sfc_desc;
 #define SFC_DESC_CUSTOM_IN_SHAPE 1
 /* C2C only: the input array is real (imag = 0), as when the reference widens real input
@@ -115,8 +120,24 @@ int sfc_plan_describe(const sfc_plan* plan, char* buf, size_t cap);
 
 /* Device pointers, caller's stream (cudaStream_t passed as void*; NULL = default). */
 int sfc_exec_device(sfc_plan* plan, const void* d_in, void* d_out, void* stream);
+/* Plans created with desc.scatter_parts = P: d_outs[q] receives block q of the last listed axis.
+ * The pointers may be device memory of PEER GPUs (opened with sfc_ipc_open_handle): the kernel then
+ * writes over NVLink and no separate all-to-all is needed. */
+int sfc_exec_device_scatter(sfc_plan* plan, const void* d_in, void* const* d_outs, int32_t nouts, void* stream);
 /* Host pointers: H2D + transform + D2H (what the drop-in free functions use). */
 int sfc_exec_host(sfc_plan* plan, const void* h_in, void* h_out);
+
+/* ------------------------------------------------- peer memory (one process per GPU)
+ * Raw device allocations that can be exported to the other ranks of a node with CUDA IPC; used by
+ * the slab-decomposed fftn to let every rank store its transposed blocks directly into the
+ * destination rank's buffer (replaces `Communicator::all_to_all`, distributed.rs:85-103). */
+#define SFC_IPC_HANDLE_BYTES 64
+int sfc_dev_malloc(void** d_ptr, size_t bytes);
+int sfc_dev_free(void* d_ptr);
+int sfc_ipc_get_handle(const void* d_ptr, void* handle_out);   /* SFC_IPC_HANDLE_BYTES */
+int sfc_ipc_open_handle(const void* handle, void** d_ptr_out); /* maps a peer allocation */
+int sfc_ipc_close_handle(void* d_ptr);
+int sfc_stream_synchronize(void* stream);
 
 /* --------------------------------------------------------------- plan cache
  * plan_cache.rs:28-235 — 128 entries, 1 h TTL, LRU, hit/miss counters. */

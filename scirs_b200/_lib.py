@@ -43,6 +43,8 @@ class sfc_desc(C.Structure):
         ("flags", C.c_int32),
         ("scale", C.c_double),
         ("in_shape", C.c_int64 * SFC_MAX_DIMS),
+        ("scatter_parts", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -89,6 +91,13 @@ SIGNATURES = {
     "sfc_plan_describe": (_int, [_vp, C.c_char_p, C.c_size_t]),
     "sfc_exec_device": (_int, [_vp, _vp, _vp, _vp]),
     "sfc_exec_host": (_int, [_vp, _vp, _vp]),
+    "sfc_exec_device_scatter": (_int, [_vp, _vp, C.POINTER(_vp), _i32, _vp]),
+    "sfc_dev_malloc": (_int, [C.POINTER(_vp), C.c_size_t]),
+    "sfc_dev_free": (_int, [_vp]),
+    "sfc_ipc_get_handle": (_int, [_vp, _vp]),
+    "sfc_ipc_open_handle": (_int, [_vp, C.POINTER(_vp)]),
+    "sfc_ipc_close_handle": (_int, [_vp]),
+    "sfc_stream_synchronize": (_int, [_vp]),
     "sfc_cache_get_stats": (_int, [C.POINTER(sfc_cache_stats)]),
     "sfc_cache_set_enabled": (_int, [_int]),
     "sfc_cache_is_enabled": (_int, []),

@@ -95,6 +95,7 @@ CacheKey make_key(const sfc_desc& d) {
     k.direction = d.kind == SFC_C2C ? d.direction : 0;
     k.flags = d.flags;
     k.scale = d.scale;
+    k.scatter_parts = d.scatter_parts;
     if (d.flags & SFC_DESC_CUSTOM_IN_SHAPE)
         for (int i = 0; i < d.ndim && i < SFC_MAX_DIMS; ++i) k.in_shape[i] = d.in_shape[i];
     int dev = 0;
@@ -225,6 +226,65 @@ extern "C" __attribute__((visibility("default"))) int sfc_exec_device(sfc_plan* 
     std::string es;
     const int rc = plan->p->exec(d_in, d_out, (cudaStream_t)stream, es);
     if (rc != 0) return fail(rc, es);
+    return SFC_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sfc_exec_device_scatter(sfc_plan* plan, const void* d_in,
+                                                                             void* const* d_outs, int32_t nouts,
+                                                                             void* stream) {
+    if (!plan || !d_in || !d_outs || nouts <= 0) return fail(SFC_ERR_VALUE, "null argument");
+    std::string es;
+    const int rc = plan->p->exec(d_in, d_outs[0], (cudaStream_t)stream, es, d_outs, nouts);
+    if (rc != 0) return fail(rc, es);
+    return SFC_OK;
+}
+
+// ------------------------------------------------------------ peer memory
+
+extern "C" __attribute__((visibility("default"))) int sfc_dev_malloc(void** d_ptr, size_t bytes) {
+    if (!d_ptr) return fail(SFC_ERR_VALUE, "null argument");
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 256);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    return SFC_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sfc_dev_free(void* d_ptr) {
+    cudaError_t e = cudaFree(d_ptr);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFree");
+    return SFC_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sfc_ipc_get_handle(const void* d_ptr, void* handle_out) {
+    if (!d_ptr || !handle_out) return fail(SFC_ERR_VALUE, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SFC_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcGetMemHandle");
+    memcpy(handle_out, &h, sizeof h);
+    return SFC_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sfc_ipc_open_handle(const void* handle, void** d_ptr_out) {
+    if (!handle || !d_ptr_out) return fail(SFC_ERR_VALUE, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    cudaError_t e = cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SFC_ERR_COMMUNICATION, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    }
+    return SFC_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sfc_ipc_close_handle(void* d_ptr) {
+    cudaError_t e = cudaIpcCloseMemHandle(d_ptr);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcCloseMemHandle");
+    return SFC_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sfc_stream_synchronize(void* stream) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
     return SFC_OK;
 }
 

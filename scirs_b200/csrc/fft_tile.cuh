@@ -621,6 +621,19 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
     }
     if constexpr (FAST) {
+        if (p.peer_shift >= 0) {
+            // fused transpose: each block of the transform axis is stored straight into its
+            // destination rank's buffer (peer memory over NVLink, or a local send buffer)
+            const int emask = (1 << p.peer_shift) - 1;
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int e = i1 + m * TPL;
+                cx* dst = reinterpret_cast<cx*>(p.peer_out[e >> p.peer_shift]) + off +
+                          (int64_t)(e & emask) * p.out.elem_stride;
+                *dst = a[m];
+            }
+            return;
+        }
         cx* __restrict__ dst = reinterpret_cast<cx*>(p.out.ptr) + off + (int64_t)i1 * p.out.elem_stride;
         const int64_t step = (int64_t)TPL * p.out.elem_stride;
         if (!(p.flags & F_OUT_NOMASK)) {

@@ -72,6 +72,11 @@ struct PassParams {
     int64_t mid_es, mid_ls;    // mid index = e*mid_es + lane_outer*mid_ls
     const void* rtw;           // R2C/C2R: W_{2L}^i, i < L/E
     double scale;
+    // split-axis scatter (slab transpose fused into the store): output element e of the transform
+    // axis goes to peer_out[e >> peer_shift] at element index (e & ((1 << peer_shift) - 1)).
+    // peer_shift < 0 = off.  The pointers may be peer-GPU memory mapped over NVLink.
+    int32_t peer_shift;
+    void* peer_out[16];
 };
 
 }  // namespace sfc

@@ -352,6 +352,7 @@ struct PlanBuilder {
     size_t rs;  // real element bytes
     PlanError& err;
     int64_t dev_bytes = 0;
+    int scatter_parts = 0;  // > 1: the next single-pass axis stores through the scatter table
 
     bool fail(int code, const std::string& m) {
         err = {code, m};
@@ -381,6 +382,7 @@ struct PlanBuilder {
         const int64_t tiles = (nlanes + s.k->TL - 1) / s.k->TL;
         s.p.tiles_per_batch = (uint32_t)tiles;
         s.nbatch = nbatch;
+        if (!s.scatter) s.p.peer_shift = -1;
         s.p.tw = table_stage_tw(prec, s.k->L, err);
         if (!s.p.tw) return false;
         {
@@ -508,6 +510,18 @@ struct PlanBuilder {
             s.p.flags = fl_in | fl_out;
             s.p.scale = scale;
             dev_bytes += O * I * (std::min(n, src.n) * (int64_t)src_es + std::min(n, dst.n) * (int64_t)dst_es);
+            if (scatter_parts > 1) {
+                const int64_t blk = n / scatter_parts;
+                if (n % scatter_parts || !is_pow2(blk) || dst.n != n || store_real)
+                    return fail(SFC_ERR_VALUE, "scatter needs the split axis length / parts to be a power of two");
+                s.scatter = true;
+                s.p.peer_shift = ilog2_64(blk);
+                set_io(s.p.out, 0, blk * I, 1, I, n, 1, 0);
+                if (!finish_tile(s, O * I, I, 1, "single-pass axis + split-axis scatter store")) return false;
+                if (pl.steps_.back().k->mode != 1)
+                    return fail(SFC_ERR_NOT_IMPLEMENTED, "scatter store needs full tiles (lanes % tile lanes == 0)");
+                return true;
+            }
             return finish_tile(s, O * I, I, 1, "single-pass axis");
         }
 
@@ -798,8 +812,21 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
             const int a = axes[i];
             const int64_t n = shape[a], O = prod(shape, 0, a), I = prod(shape, a + 1, shape.size());
             const bool last = (i + 1 == axes.size());
-            ok = B.add_axis(n, O, I, {i == 0 ? R_IN : R_OUT, i == 0 && real_in, n}, {R_OUT, false, n}, inv,
-                            last ? d.scale : 1.0, false);
+            B.scatter_parts = (last && d.scatter_parts > 1) ? d.scatter_parts : 0;
+            if (B.scatter_parts > 16) {
+                err = {SFC_ERR_VALUE, "scatter_parts must be <= 16"};
+                return nullptr;
+            }
+            if (B.scatter_parts && (n > col_single_limit(prec) || !is_pow2(n))) {
+                err = {SFC_ERR_NOT_IMPLEMENTED, "scatter store needs a single-pass power-of-two split axis"};
+                return nullptr;
+            }
+            // with a scatter the intermediate passes must not touch the caller's outputs: use scratch
+            const int mid_role = d.scatter_parts > 1 ? R_SA : R_OUT;
+            if (d.scatter_parts > 1) B.need_sa((size_t)total * cs);
+            ok = B.add_axis(n, O, I, {i == 0 ? R_IN : mid_role, i == 0 && real_in, n}, {last ? R_OUT : mid_role, false, n},
+                            inv, last ? d.scale : 1.0, false);
+            B.scatter_parts = 0;
             const int ap = axis_passes(n);
             passes += ap;
             if (!is_pow2(n) && ap == 4)
@@ -995,7 +1022,7 @@ std::string Plan::describe() const {
 
 // ------------------------------------------------------------------ Plan::exec
 
-int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& es) {
+int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& es, void* const* scatter, int nscatter) {
     std::lock_guard<std::mutex> lk(mu_);
     auto base = [&](int role) -> char* {
         switch (role) {
@@ -1032,6 +1059,13 @@ int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& 
             PassParams p = s.p;
             p.in.ptr = base(s.src);
             p.out.ptr = base(s.dst);
+            if (s.scatter) {
+                if (!scatter || nscatter != desc.scatter_parts) {
+                    es = "this plan stores through a scatter table: use sfc_exec_device_scatter with scatter_parts pointers";
+                    return SFC_ERR_VALUE;
+                }
+                for (int q = 0; q < nscatter; ++q) p.peer_out[q] = scatter[q];
+            }
             const uint64_t grid = (uint64_t)p.tiles_per_batch * (uint64_t)s.nbatch;
             if (grid == 0 || grid > 0x7FFFFFFFULL) {
                 es = "grid too large";

@@ -32,6 +32,7 @@ struct Step {
     int src = R_IN, dst = R_OUT;
     size_t src_esize = 16, dst_esize = 16;  // bytes per addressed element (for batch offsets)
     int group = -1;                          // steps sharing a group are chunk-looped together
+    bool scatter = false;                    // store through the caller's per-block pointer table
     int64_t nbatch = 1;                      // batches (blockIdx-level outer index)
     std::string desc;
 };
@@ -52,7 +53,8 @@ class Plan {
     ~Plan();
 
     // d_in / d_out are device pointers; not re-entrant (serialised internally)
-    int exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& err);
+    int exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& err, void* const* scatter = nullptr,
+             int nscatter = 0);
 
     sfc_desc desc{};
     sfc_plan_info info{};

@@ -28,7 +28,7 @@ class FftPlan:
 
     def __init__(self, shape: Sequence[int], axes: Optional[Sequence[int]] = None, kind: str = "c2c",
                  prec: str = "f64", forward: bool = True, scale: float = 1.0,
-                 in_shape: Optional[Sequence[int]] = None, real_input: bool = False):
+                 in_shape: Optional[Sequence[int]] = None, real_input: bool = False, scatter_parts: int = 0):
         lib = _lib.load()
         shape = [int(s) for s in shape]
         if not 1 <= len(shape) <= _lib.SFC_MAX_DIMS:
@@ -52,6 +52,7 @@ class FftPlan:
                 d.in_shape[i] = int(s)
         if real_input:
             d.flags |= _lib.SFC_DESC_REAL_INPUT
+        d.scatter_parts = int(scatter_parts)
         self._h = C.c_void_p()
         check(lib.sfc_plan_create(C.byref(self._h), C.byref(d)))
         self._lib = lib
