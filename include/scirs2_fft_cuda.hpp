@@ -1,0 +1,222 @@
+// scirs2_fft_cuda.hpp — header-only C++ mirror of the scirs2-fft interface for the hot path, on top
+// of the C ABI (scirs2_fft_cuda.h).  Same names, argument meaning and error behaviour as the Rust
+// reference (scirs2-fft/src/fft/algorithms.rs, rfft.rs, backend.rs, plan_cache.rs); `Option<T>` is
+// std::optional<T>, `FFTResult<T>` is "T or throw FFTError".  No arithmetic happens here.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "scirs2_fft_cuda.h"
+
+namespace scirs2_fft_cuda {
+
+using Complex64 = std::complex<double>;
+
+// FFTError, scirs2-fft/src/error.rs:7-46
+struct FFTError : std::runtime_error {
+    enum Kind { Computation, Dimension, Value, NotImplemented, IO, Backend, Plan, Communication, Memory } kind;
+    FFTError(Kind k, const std::string& m) : std::runtime_error(m), kind(k) {}
+};
+
+inline void check(int rc) {
+    if (rc >= 0) return;
+    static const FFTError::Kind kinds[] = {FFTError::Computation, FFTError::Dimension,      FFTError::Value,
+                                           FFTError::NotImplemented, FFTError::IO,          FFTError::Backend,
+                                           FFTError::Plan,        FFTError::Communication,  FFTError::Memory};
+    const int i = -rc - 1;
+    throw FFTError(i >= 0 && i < 9 ? kinds[i] : FFTError::Computation, sfc_last_error());
+}
+
+namespace detail {
+template <typename T> struct dtype_of;
+template <> struct dtype_of<float> { static constexpr int v = SFC_F32; };
+template <> struct dtype_of<double> { static constexpr int v = SFC_F64; };
+template <> struct dtype_of<std::complex<float>> { static constexpr int v = SFC_C64; };
+template <> struct dtype_of<std::complex<double>> { static constexpr int v = SFC_C128; };
+inline int64_t next_pow2(int64_t n) { int64_t p = 1; while (p < n) p <<= 1; return p; }
+inline int64_t prod(const std::vector<int64_t>& v) { int64_t p = 1; for (auto x : v) p *= x; return p; }
+}  // namespace detail
+
+// fft / ifft — fft/algorithms.rs:131-176, 210-263
+template <typename T>
+std::vector<Complex64> fft(const std::vector<T>& x, std::optional<size_t> n = std::nullopt) {
+    const int64_t cap = n ? (int64_t)*n : detail::next_pow2((int64_t)x.size());
+    std::vector<Complex64> out((size_t)std::max<int64_t>(cap, 1));
+    int64_t len = 0;
+    check(sfc_fft(x.data(), (int64_t)x.size(), detail::dtype_of<T>::v, n ? (int64_t)*n : -1,
+                  reinterpret_cast<double*>(out.data()), (int64_t)out.size(), &len));
+    out.resize((size_t)len);
+    return out;
+}
+template <typename T>
+std::vector<Complex64> ifft(const std::vector<T>& x, std::optional<size_t> n = std::nullopt) {
+    const int64_t cap = n ? (int64_t)*n : detail::next_pow2((int64_t)x.size());
+    std::vector<Complex64> out((size_t)std::max<int64_t>(cap, 1));
+    int64_t len = 0;
+    check(sfc_ifft(x.data(), (int64_t)x.size(), detail::dtype_of<T>::v, n ? (int64_t)*n : -1,
+                   reinterpret_cast<double*>(out.data()), (int64_t)out.size(), &len));
+    out.resize((size_t)len);
+    return out;
+}
+// rfft / irfft — rfft.rs:39-59, 92-178
+template <typename T>
+std::vector<Complex64> rfft(const std::vector<T>& x, std::optional<size_t> n = std::nullopt) {
+    const int64_t nv = n ? (int64_t)*n : (int64_t)x.size();
+    std::vector<Complex64> out((size_t)(nv / 2 + 1));
+    int64_t len = 0;
+    check(sfc_rfft(x.data(), (int64_t)x.size(), detail::dtype_of<T>::v, n ? (int64_t)*n : -1,
+                   reinterpret_cast<double*>(out.data()), (int64_t)out.size(), &len));
+    out.resize((size_t)len);
+    return out;
+}
+template <typename T>
+std::vector<double> irfft(const std::vector<T>& x, std::optional<size_t> n = std::nullopt) {
+    const int64_t nv = n ? (int64_t)*n : 2 * ((int64_t)x.size() - 1);
+    std::vector<double> out((size_t)std::max<int64_t>(nv, 1));
+    int64_t len = 0;
+    check(sfc_irfft(x.data(), (int64_t)x.size(), detail::dtype_of<T>::v, n ? (int64_t)*n : -1, out.data(),
+                    (int64_t)out.size(), &len));
+    out.resize((size_t)len);
+    return out;
+}
+
+// N-D arrays: C-order data + shape (the ndarray `ArrayD` of the reference)
+template <typename T>
+struct ArrayD {
+    std::vector<int64_t> shape;
+    std::vector<T> data;
+};
+
+// fftn / ifftn — fft/algorithms.rs:576-706, 757-890 (overwrite_x and workers are accepted and ignored, :581-582)
+template <typename T>
+ArrayD<Complex64> fftn(const ArrayD<T>& x, const std::optional<std::vector<int64_t>>& shape = std::nullopt,
+                       const std::optional<std::vector<int64_t>>& axes = std::nullopt, const char* norm = nullptr,
+                       bool inverse = false) {
+    if (shape && shape->size() != x.shape.size())
+        throw FFTError(FFTError::Value, "Output shape must have the same number of dimensions as input");
+    ArrayD<Complex64> out;
+    out.shape = shape ? *shape : x.shape;
+    out.data.resize((size_t)std::max<int64_t>(detail::prod(out.shape), 1));
+    std::vector<int64_t> oshape(x.shape.size());
+    auto fn = inverse ? sfc_ifftn : sfc_fftn;
+    check(fn(x.data.data(), (int32_t)x.shape.size(), x.shape.data(), detail::dtype_of<T>::v,
+             shape ? shape->data() : nullptr, axes ? axes->data() : nullptr, axes ? (int32_t)axes->size() : 0, norm,
+             reinterpret_cast<double*>(out.data.data()), (int64_t)out.data.size(), oshape.data()));
+    out.shape = oshape;
+    return out;
+}
+template <typename T>
+ArrayD<Complex64> ifftn(const ArrayD<T>& x, const std::optional<std::vector<int64_t>>& shape = std::nullopt,
+                        const std::optional<std::vector<int64_t>>& axes = std::nullopt, const char* norm = nullptr) {
+    return fftn(x, shape, axes, norm, true);
+}
+// fft2 / ifft2 — fft/algorithms.rs:293-401, 439-541
+template <typename T>
+ArrayD<Complex64> fft2(const ArrayD<T>& x, const std::optional<std::pair<size_t, size_t>>& shape = std::nullopt,
+                       const std::optional<std::pair<int, int>>& axes = std::nullopt, const char* norm = nullptr,
+                       bool inverse = false) {
+    if (x.shape.size() != 2) throw FFTError(FFTError::Dimension, "expected a 2-D array");
+    int64_t sh[2] = {shape ? (int64_t)shape->first : x.shape[0], shape ? (int64_t)shape->second : x.shape[1]};
+    int32_t ax[2] = {axes ? axes->first : 0, axes ? axes->second : 1};
+    ArrayD<Complex64> out;
+    out.shape = {sh[0], sh[1]};
+    out.data.resize((size_t)std::max<int64_t>(sh[0] * sh[1], 1));
+    int64_t os[2];
+    auto fn = inverse ? sfc_ifft2 : sfc_fft2;
+    check(fn(x.data.data(), x.shape[0], x.shape[1], detail::dtype_of<T>::v, shape ? sh : nullptr, axes ? ax : nullptr,
+             norm, reinterpret_cast<double*>(out.data.data()), (int64_t)out.data.size(), os));
+    return out;
+}
+
+// PlanCache — plan_cache.rs:28-235 (the cache itself lives in the library)
+struct CacheStats { uint64_t hit_count, miss_count; double hit_rate; uint64_t size, max_size; };
+class PlanCache {
+   public:
+    void set_enabled(bool e) { check(sfc_cache_set_enabled(e ? 1 : 0)); }
+    bool is_enabled() const { return sfc_cache_is_enabled() != 0; }
+    void clear() { check(sfc_cache_clear()); }
+    CacheStats get_stats() const {
+        sfc_cache_stats s;
+        check(sfc_cache_get_stats(&s));
+        return {s.hit_count, s.miss_count, s.hit_rate, s.size, s.max_size};
+    }
+};
+inline PlanCache& get_global_cache() { static PlanCache c; return c; }
+
+// trait FftBackend — backend.rs:14-48
+class FftBackend {
+   public:
+    virtual ~FftBackend() = default;
+    virtual const char* name() const = 0;
+    virtual const char* description() const = 0;
+    virtual bool is_available() const = 0;
+    virtual void fft(const std::vector<Complex64>& in, std::vector<Complex64>& out) const = 0;
+    virtual void ifft(const std::vector<Complex64>& in, std::vector<Complex64>& out) const = 0;
+    virtual void fft_sized(const std::vector<Complex64>& in, std::vector<Complex64>& out, size_t size) const = 0;
+    virtual void ifft_sized(const std::vector<Complex64>& in, std::vector<Complex64>& out, size_t size) const = 0;
+    virtual bool supports_feature(const std::string& f) const = 0;
+};
+
+class CudaFftBackend final : public FftBackend {
+   public:
+    const char* name() const override { return sfc_backend_name(); }
+    const char* description() const override { return sfc_backend_description(); }
+    bool is_available() const override { return sfc_is_available() != 0; }
+    void fft(const std::vector<Complex64>& in, std::vector<Complex64>& out) const override {
+        fft_sized(in, out, in.size());
+    }
+    void ifft(const std::vector<Complex64>& in, std::vector<Complex64>& out) const override {
+        ifft_sized(in, out, in.size());
+    }
+    void fft_sized(const std::vector<Complex64>& in, std::vector<Complex64>& out, size_t size) const override {
+        check(sfc_backend_fft_sized(reinterpret_cast<const double*>(in.data()), (int64_t)in.size(),
+                                    reinterpret_cast<double*>(out.data()), (int64_t)out.size(), (int64_t)size));
+    }
+    void ifft_sized(const std::vector<Complex64>& in, std::vector<Complex64>& out, size_t size) const override {
+        check(sfc_backend_ifft_sized(reinterpret_cast<const double*>(in.data()), (int64_t)in.size(),
+                                     reinterpret_cast<double*>(out.data()), (int64_t)out.size(), (int64_t)size));
+    }
+    bool supports_feature(const std::string& f) const override { return sfc_backend_supports_feature(f.c_str()) != 0; }
+};
+
+// BackendManager — backend.rs:163-281
+class BackendManager {
+   public:
+    BackendManager() { backends_["cuda_fft"] = std::make_shared<CudaFftBackend>(); }
+    void register_backend(const std::string& name, std::shared_ptr<FftBackend> b) {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (backends_.count(name)) throw FFTError(FFTError::Value, "Backend '" + name + "' already exists");
+        backends_[name] = std::move(b);
+    }
+    void set_backend(const std::string& name) {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = backends_.find(name);
+        if (it == backends_.end()) throw FFTError(FFTError::Value, "Backend '" + name + "' not found");
+        if (!it->second->is_available()) throw FFTError(FFTError::Value, "Backend '" + name + "' is not available");
+        current_ = name;
+    }
+    std::shared_ptr<FftBackend> get_backend() {
+        std::lock_guard<std::mutex> lk(mu_);
+        return backends_.at(current_);
+    }
+    std::string get_backend_name() {
+        std::lock_guard<std::mutex> lk(mu_);
+        return current_;
+    }
+
+   private:
+    std::mutex mu_;
+    std::map<std::string, std::shared_ptr<FftBackend>> backends_;
+    std::string current_ = "cuda_fft";
+};
+inline BackendManager& get_backend_manager() { static BackendManager m; return m; }
+
+}  // namespace scirs2_fft_cuda

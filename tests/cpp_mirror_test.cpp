@@ -1,0 +1,41 @@
+// Exercises include/scirs2_fft_cuda.hpp the way the reference's tests exercise scirs2-fft
+// (doctests of fft/algorithms.rs, rfft.rs:926-966, backend.rs:350-386).  Exit code 0 = pass.
+// Without a CUDA device it checks that every call fails with FFTError::Backend (no CPU fallback).
+#include <cmath>
+#include <cstdio>
+#include "scirs2_fft_cuda.hpp"
+using namespace scirs2_fft_cuda;
+#define REQUIRE(c) do { if (!(c)) { std::printf("FAILED: %s (line %d)\n", #c, __LINE__); return 1; } } while (0)
+int main() {
+    std::vector<double> sig{1.0, 2.0, 3.0, 4.0};
+    if (!sfc_is_available()) {
+        try { fft(sig); } catch (const FFTError& e) { REQUIRE(e.kind == FFTError::Backend); std::puts("no device: BackendError ok"); return 0; }
+        return 1;
+    }
+    auto s = fft(sig);
+    REQUIRE(std::abs(s[0].real() - 10.0) < 1e-10 && std::abs(s[0].imag()) < 1e-10);
+    auto r = ifft(s);
+    for (int i = 0; i < 4; ++i) REQUIRE(std::abs(r[i].real() - sig[i]) < 1e-10 && std::abs(r[i].imag()) < 1e-10);
+    auto sp = rfft(sig);
+    REQUIRE(sp.size() == 3 && std::abs(sp[0].real() - 10.0) < 1e-10);
+    auto back = irfft(sp, 4);
+    for (int i = 0; i < 4; ++i) REQUIRE(std::abs(back[i] - sig[i]) < 1e-10);
+    REQUIRE(fft(std::vector<double>(100, 1.0)).size() == 128);  // next-power-of-two padding quirk
+    ArrayD<double> a{{2, 2}, {1, 2, 3, 4}};
+    REQUIRE(std::abs(fft2(a).data[0].real() - 10.0) < 1e-10);
+    ArrayD<double> v{{2, 2, 2}, {0, 1, 2, 3, 4, 5, 6, 7}};
+    auto rt = ifftn(fftn(v));
+    for (int i = 0; i < 8; ++i) REQUIRE(std::abs(rt.data[i].real() - v.data[i]) < 1e-10);
+    try { fftn(v, std::nullopt, std::vector<int64_t>{3}); return 1; } catch (const FFTError& e) {
+        REQUIRE(e.kind == FFTError::Value && std::string(e.what()) == "Axis 3 out of bounds for array of dimension 3");
+    }
+    auto b = get_backend_manager().get_backend();
+    REQUIRE(std::string(b->name()) == "cuda_fft" && b->supports_feature("gpu_acceleration"));
+    std::vector<Complex64> imp(8, 0.0), out(8);
+    imp[0] = 1.0;
+    b->fft(imp, out);
+    for (auto& c : out) REQUIRE(std::abs(std::abs(c) - 1.0) < 1e-10);
+    try { b->fft_sized(imp, out, 4); return 1; } catch (const FFTError& e) { REQUIRE(e.kind == FFTError::Value); }
+    std::puts("cpp mirror ok");
+    return 0;
+}
