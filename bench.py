@@ -286,10 +286,13 @@ def run_gpu(args):
     # roofline of the dominant (here: only) kernel of the step
     alg = r["info"]["algorithmic_bytes"]
     traffic = None
-    summ = os.path.join(ROOT, "profiles", "r1_ncu_summary.json")
-    if os.path.exists(summ):
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+    summ = os.path.join(ROOT, "profiles", "r1_ncu_full.json")
+    ncu_key = {"c2c_f64_65536x4096": "r1_full_c2c4096#0", "rfft_f64": "r1_full_rfft4096#0",
+               "irfft_f64": "r1_full_irfft4096#0"}.get(wl)
+    if ncu_key and os.path.exists(summ):
         try:
-            traffic = json.load(open(summ)).get(wl, {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(summ)).get(ncu_key, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     achieved = alg / r["info"]["num_launches"] / (r["kernel_ms"] / r["info"]["num_launches"]) / 1e6

@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -44,11 +45,15 @@ struct sfc_plan {
     void* d_in = nullptr;
     void* d_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev;
     ~sfc_plan() {
         if (d_in) cudaFree(d_in);
         if (d_out) cudaFree(d_out);
         if (stream) cudaStreamDestroy(stream);
+        if (s_h2d) cudaStreamDestroy(s_h2d);
+        if (s_d2h) cudaStreamDestroy(s_d2h);
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
     }
 };
 
@@ -299,6 +304,58 @@ static int ensure(void** p, size_t* cap, size_t bytes) {
     return SFC_OK;
 }
 
+// Large batched plans are executed as a 3-stream pipeline over chunks of the outermost
+// (untransformed) dimension: H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1 overlap, so the
+// call costs ~max(H2D, D2H) instead of their sum (PCIe is full duplex).
+static int exec_host_pipelined(sfc_plan* plan, const void* h_in, void* h_out, int nchunks) {
+    Plan& p = *plan->p;
+    const int64_t n0 = p.desc.shape[0];
+    const size_t in_row = (size_t)p.info.in_bytes / (size_t)n0, out_row = (size_t)p.info.out_bytes / (size_t)n0;
+    if (!plan->s_h2d) {
+        cudaError_t e = cudaStreamCreateWithFlags(&plan->s_h2d, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&plan->s_d2h, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+    }
+    if ((int)plan->ev.size() < 2 * nchunks) {
+        const size_t old = plan->ev.size();
+        plan->ev.resize(2 * nchunks);
+        for (size_t i = old; i < plan->ev.size(); ++i) {
+            cudaError_t e = cudaEventCreateWithFlags(&plan->ev[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+        }
+    }
+    const int64_t per = (n0 + nchunks - 1) / nchunks;
+    int ci = 0;
+    for (int64_t r0 = 0; r0 < n0; r0 += per, ++ci) {
+        const int64_t rows = std::min(per, n0 - r0);
+        sfc_desc d = p.desc;
+        d.shape[0] = rows;
+        if (d.flags & SFC_DESC_CUSTOM_IN_SHAPE) d.in_shape[0] = rows;
+        PlanError perr{0, ""};
+        std::shared_ptr<Plan> sub = (rows == n0) ? plan->p : get_or_create_plan(d, perr);
+        if (!sub) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
+        char* din = (char*)plan->d_in + (size_t)r0 * in_row;
+        char* dout = (char*)plan->d_out + (size_t)r0 * out_row;
+        cudaError_t e = cudaMemcpyAsync(din, (const char*)h_in + (size_t)r0 * in_row, (size_t)rows * in_row,
+                                        cudaMemcpyHostToDevice, plan->s_h2d);
+        if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+        cudaEventRecord(plan->ev[2 * ci], plan->s_h2d);
+        cudaStreamWaitEvent(plan->stream, plan->ev[2 * ci], 0);
+        std::string es;
+        int rc = sub->exec(din, dout, plan->stream, es);
+        if (rc != 0) return fail(rc, es);
+        cudaEventRecord(plan->ev[2 * ci + 1], plan->stream);
+        cudaStreamWaitEvent(plan->s_d2h, plan->ev[2 * ci + 1], 0);
+        e = cudaMemcpyAsync((char*)h_out + (size_t)r0 * out_row, dout, (size_t)rows * out_row, cudaMemcpyDeviceToHost,
+                            plan->s_d2h);
+        if (e != cudaSuccess) return cuda_fail(e, "D2H copy");
+    }
+    cudaError_t e = cudaStreamSynchronize(plan->s_d2h);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(plan->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "transform execution");
+    return SFC_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int sfc_exec_host(sfc_plan* plan, const void* h_in, void* h_out) {
     if (!plan || !h_in || !h_out) return fail(SFC_ERR_VALUE, "null argument");
     Plan& p = *plan->p;
@@ -308,6 +365,20 @@ extern "C" __attribute__((visibility("default"))) int sfc_exec_host(sfc_plan* pl
     if (!plan->stream) {
         cudaError_t e = cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+    }
+    // pipeline when dimension 0 is a pure batch dimension and the transfer is big enough to matter
+    {
+        bool batch0 = p.desc.ndim >= 2 && p.desc.shape[0] >= 2 && p.desc.scatter_parts <= 1;
+        for (int i = 0; i < p.desc.naxes; ++i) batch0 = batch0 && p.desc.axes[i] != 0;
+        const int64_t bytes = p.info.in_bytes + p.info.out_bytes;
+        static const int want = [] {
+            const char* e = getenv("SFC_HOST_CHUNKS");
+            return e ? atoi(e) : 8;
+        }();
+        if (batch0 && want > 1 && bytes >= ((int64_t)64 << 20)) {
+            const int nchunks = (int)std::min<int64_t>(want, p.desc.shape[0]);
+            return exec_host_pipelined(plan, h_in, h_out, nchunks);
+        }
     }
     cudaStream_t s = plan->stream;
     cudaError_t e = cudaMemcpyAsync(plan->d_in, h_in, (size_t)p.info.in_bytes, cudaMemcpyHostToDevice, s);
