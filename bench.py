@@ -210,6 +210,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     sb.error.check(lib.sfc_init(local))
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     hbm, hbm_src = peaks()
