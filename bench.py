@@ -240,12 +240,18 @@ def run_gpu(args):
     def time_workload(workload, steps, warmup, sample_clocks=False):
         plan, din, dout = alloc(workload)
         stream = torch.cuda.current_stream()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            # nvidia-smi needs ~0.2 s to start: begin before the warm-up, keep the GPU under the same
+            # load for a moment after the timed steps, and report the median over the whole window
+            sampler.start()
+            t_end = time.time() + 0.6
+            while time.time() < t_end:
+                plan.execute_device(din, dout, stream.cuda_stream)
+                torch.cuda.synchronize()
         for _ in range(warmup):
             plan.execute_device(din, dout, stream.cuda_stream)
         barrier()
-        sampler = ClockSampler(local) if sample_clocks else None
-        if sampler:
-            sampler.start()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -256,7 +262,13 @@ def run_gpu(args):
             e1.record(stream)
         t_all1.record(stream)
         barrier()
-        clocks = sampler.stop() if sampler else None
+        clocks = None
+        if sampler:
+            t_end = time.time() + 0.4
+            while time.time() < t_end:
+                plan.execute_device(din, dout, stream.cuda_stream)
+                torch.cuda.synchronize()
+            clocks = sampler.stop()
         total_ms = t_all0.elapsed_time(t_all1)
         per = [a.elapsed_time(b) for a, b in evs]
         if world > 1:

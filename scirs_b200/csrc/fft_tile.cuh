@@ -235,7 +235,10 @@ struct Xch {
 // One Stockham stage of radix R at stride S over the thread's E registers, then
 // recurse.  (tw, iw) = mapping of the thread while it holds the stage inputs,
 // (tr, ir) = mapping used after the exchange.
-template <typename T, typename C, int S, bool FIRST>
+// MIRROR (real-to-complex transforms whose last stage has two radix-E/2 butterflies per thread):
+// the thread takes butterfly i and its mirror image S_last - i, so that after the last stage the
+// pairs (k, L-k) the Hermitian post-pass combines are both in its own registers.
+template <typename T, typename C, int S, bool FIRST, bool MIRROR = false>
 __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__ sm,
                                            const Cx<T>* __restrict__ tw, int tw_, int iw, int tr,
                                            int ir) {
@@ -264,9 +267,23 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
     if constexpr (!LAST) {
         __syncthreads();
         const Cx<T>* src = sm + tr * C::LP + Xch<C, R, S>::read_base(ir);
+        constexpr int SN = S * R;                                  // stride of the next stage
+        constexpr int RN = (L / SN >= E) ? E : (L / SN);           // its radix
+        if constexpr (MIRROR && SN * RN == L && E / RN == 2) {
+            // butterfly 0 = ir (elements ir + r*SN), butterfly 1 = its mirror (SN - ir, or SN/2 for ir = 0)
+            const Cx<T>* lane = sm + tr * C::LP;
+            const int j2 = ir == 0 ? SN / 2 : SN - ir;
 #pragma unroll
-        for (int m = 0; m < E; ++m) a[m] = src[Xch<C, R, S>::read_off(m)];
-        run_stages<T, C, S * R, false>(a, sm, tw, tr, ir, tr, ir);
+            for (int r = 0; r < RN; ++r) {
+                a[2 * r] = src[Xch<C, R, S>::read_off(2 * r)];
+                const int e = j2 + r * SN;
+                a[2 * r + 1] = lane[e + (e >> Xch<C, R, S>::SH) * Xch<C, R, S>::PADW];
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; ++m) a[m] = src[Xch<C, R, S>::read_off(m)];
+        }
+        run_stages<T, C, S * R, false, MIRROR>(a, sm, tw, tr, ir, tr, ir);
     }
 }
 
@@ -371,7 +388,9 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
                             (int64_t)li * p.in.inner_stride;
         const int64_t pos0 = (int64_t)lo * p.in.pos_ls;
         if constexpr (MODE == TM_FAST_C2R) {
-            // stage the L+1 Hermitian inputs of each lane (unit stride), then pre-twiddle
+            // stage the L+1 Hermitian inputs of each lane (unit stride), then pre-twiddle.
+            // (Measured alternative: every thread loading X[k] and its mirror X[L-k] straight from
+            // global memory, no staging — 71 % -> 67 % of HBM peak, so staging stays.)
             const cx* __restrict__ src = reinterpret_cast<const cx*>(p.in.ptr) + off + i0;
             cx* row = sm + t0 * LP;
 #pragma unroll
@@ -473,7 +492,12 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
 
     // ---------------------------- transform ---------------------------------
     const cx* __restrict__ tw = reinterpret_cast<const cx*>(p.tw);
-    if constexpr (MODE == TM_FAST_C2R) {
+    // last radix 8 with 16 points per thread = two butterflies per thread in the last stage
+    constexpr bool R2C_MIRROR =
+        (MODE == TM_FAST_R2C) && E == 16 && L >= 128 && (ilog2(L) % 4 == 3) && sizeof(T) == 8;  // f32: measured slower
+    if constexpr (R2C_MIRROR) {
+        run_stages<T, C, 1, true, true>(a, sm, tw, t0, i0, t1, i1);
+    } else if constexpr (MODE == TM_FAST_C2R) {
         run_stages<T, C, 1, false>(a, sm, tw, t0, i0, t1, i1);
     } else if constexpr (FAST) {
         run_stages<T, C, 1, true>(a, sm, tw, t0, i0, t1, i1);
@@ -528,7 +552,36 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
     }
 
-    if (MODE == TM_FAST_R2C || (MODE == TM_GENERIC && p.st_op == ST_R2C)) {
+    if constexpr (R2C_MIRROR) {
+        // a[2*kk] = Z[i1 + kk*SL], a[2*kk+1] = Z[j2 + kk*SL] with j2 the mirror butterfly:
+        // Z[L-(i1 + kk*SL)] = a[2*(7-kk)+1] — the whole Hermitian post-pass stays in registers.
+        constexpr int SL = L / 8;
+        cx* __restrict__ dst = reinterpret_cast<cx*>(p.out.ptr) + off;
+        const T h = (T)0.5 * scale;
+        auto emit = [&](cx zk, cx zp, cx w, int k) {
+            const cx A = {zk.x + zp.x, zk.y - zp.y};
+            const cx B = {zk.x - zp.x, zk.y + zp.y};
+            const cx Cw = cmul(B, w);
+            dst[k] = {(A.x + Cw.y) * h, (A.y - Cw.x) * h};
+            dst[L - k] = {(A.x - Cw.y) * h, -((A.y + Cw.x) * h)};
+        };
+        if (i1 != 0) {
+            const cx wi = reinterpret_cast<const cx*>(p.rtw)[i1];
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+                emit(a[2 * kk], a[2 * (7 - kk) + 1], cmul(wi, w32<T>(2 * kk)), i1 + kk * SL);
+        } else {
+            // butterfly 0 pairs kk <-> 8-kk (kk = 0: DC / Nyquist, kk = 4: self), butterfly SL/2 pairs kk <-> 7-kk
+            emit(a[0], a[0], w32<T>(0), 0);
+#pragma unroll
+            for (int kk = 1; kk < 4; ++kk) emit(a[2 * kk], a[2 * (8 - kk)], w32<T>(2 * kk), kk * SL);
+            dst[L / 2] = {a[8].x * scale, -(a[8].y * scale)};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                emit(a[2 * kk + 1], a[2 * (7 - kk) + 1], w32<T>(2 * kk + 1), SL / 2 + kk * SL);
+        }
+        return;
+    } else if (MODE == TM_FAST_R2C || (MODE == TM_GENERIC && p.st_op == ST_R2C)) {
         if constexpr (E >= 8 && E != L && (MODE == TM_FAST_R2C || MODE == TM_GENERIC)) {
             // a[m] = Z[i1 + m*TPL] of the packed half-length transform
             cx* row = sm + t1 * LP;
