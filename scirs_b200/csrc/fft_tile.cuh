@@ -197,7 +197,7 @@ struct TileCfg {
         int want = (TL < G) ? (G / TL) % G : 1;
         // padded exchange layout (one pad slot per E elements) and >= L+1 because the
         // real-transform paths stage L+1 points per lane
-        int lp = L + (L > E ? L / E : 0) + 1;
+        int lp = L + (L > E ? L / (E >= 16 ? 8 : E) : 0) + 1;  // E=16 plans may start with a radix-8 stage
         while (lp % G != want) ++lp;
         return lp;
     }
@@ -238,12 +238,16 @@ struct Xch {
 // MIRROR (real-to-complex transforms whose last stage has two radix-E/2 butterflies per thread):
 // the thread takes butterfly i and its mirror image S_last - i, so that after the last stage the
 // pairs (k, L-k) the Hermitian post-pass combines are both in its own registers.
-template <typename T, typename C, int S, bool FIRST, bool MIRROR = false>
+// MIRROR_IN (complex-to-real transforms, same lengths): the radix-8 stage comes FIRST and the thread
+// again owns butterfly i and its mirror, so the Hermitian pre-pass pairs X[k], X[L-k] come straight
+// from the thread's own global loads.
+template <typename T, typename C, int S, bool FIRST, bool MIRROR = false, bool MIRROR_IN = false>
 __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__ sm,
                                            const Cx<T>* __restrict__ tw, int tw_, int iw, int tr,
                                            int ir) {
     constexpr int L = C::L, E = C::E, TPL = C::TPL;
-    constexpr int R = (L / S >= E) ? E : (L / S);
+    constexpr int REM = 1 << (ilog2(L) % ilog2(E));  // the one radix smaller than E (1 = none)
+    constexpr int R = MIRROR_IN ? ((S == 1 && REM > 1) ? REM : E) : ((L / S >= E) ? E : (L / S));
     constexpr bool LAST = (S * R == L);
     constexpr int NB = E / R;  // butterflies per thread in this stage
     if constexpr (!LAST && !FIRST) __syncthreads();  // previous readers done before we overwrite
@@ -257,7 +261,10 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
 #pragma unroll
             for (int k = 0; k < R; ++k) a[b + k * NB] = v[k];
         } else {
-            const int ib = iw + b * TPL;
+            int ib = iw + b * TPL;
+            if constexpr (MIRROR_IN && S == 1 && NB == 2) {
+                if (b == 1) ib = iw == 0 ? (L / R) / 2 : (L / R) - iw;  // the mirror butterfly
+            }
             apply_twiddle_powers<R, T>(v, tw[ib & ~(S - 1)]);
             Cx<T>* dst = sm + tw_ * C::LP + Xch<C, R, S>::write_base(ib);
 #pragma unroll
@@ -268,7 +275,7 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
         __syncthreads();
         const Cx<T>* src = sm + tr * C::LP + Xch<C, R, S>::read_base(ir);
         constexpr int SN = S * R;                                  // stride of the next stage
-        constexpr int RN = (L / SN >= E) ? E : (L / SN);           // its radix
+        constexpr int RN = MIRROR_IN ? E : ((L / SN >= E) ? E : (L / SN));  // its radix
         if constexpr (MIRROR && SN * RN == L && E / RN == 2) {
             // butterfly 0 = ir (elements ir + r*SN), butterfly 1 = its mirror (SN - ir, or SN/2 for ir = 0)
             const Cx<T>* lane = sm + tr * C::LP;
@@ -283,7 +290,7 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
 #pragma unroll
             for (int m = 0; m < E; ++m) a[m] = src[Xch<C, R, S>::read_off(m)];
         }
-        run_stages<T, C, S * R, false, MIRROR>(a, sm, tw, tr, ir, tr, ir);
+        run_stages<T, C, S * R, false, MIRROR, MIRROR_IN>(a, sm, tw, tr, ir, tr, ir);
     }
 }
 
@@ -387,7 +394,45 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         const int64_t off = (int64_t)batch * p.in.batch_stride + (int64_t)lo * p.in.outer_stride +
                             (int64_t)li * p.in.inner_stride;
         const int64_t pos0 = (int64_t)lo * p.in.pos_ls;
-        if constexpr (MODE == TM_FAST_C2R) {
+        constexpr bool C2R_MIRROR = (MODE == TM_FAST_C2R) && E == 16 && L >= 128 && (ilog2(L) % 4 == 3);
+        if constexpr (C2R_MIRROR) {
+            // thread i loads butterfly i (X[i + r*SL]) and its mirror (X[SL - i + r*SL]) of the leading
+            // radix-8 stage: X[k] and X[L-k] are then both in its registers and the pre-twiddle
+            //   Z[k] = A + B,  Z[L-k] = conj(A - B),  A = X[k] + conj X[L-k],  B = i conj(W^k)(X[k] - conj X[L-k])
+            // needs neither staging nor a barrier.
+            constexpr int SL = L / 8;
+            const cx* __restrict__ src = reinterpret_cast<const cx*>(p.in.ptr) + off;
+            const int j2 = i0 == 0 ? SL / 2 : SL - i0;
+            cx u[8], v[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                u[r] = src[i0 + r * SL];
+                v[r] = src[j2 + r * SL];
+            }
+            auto pre = [&](cx xk, cx xp, cx w, cx& zk, cx& zp) {
+                const cx A = {xk.x + xp.x, xk.y - xp.y};
+                const cx D = {xk.x - xp.x, xk.y + xp.y};
+                const cx Bc = cmulc(D, w);            // conj(W) * D
+                zk = {A.x - Bc.y, A.y + Bc.x};        // A + i*Bc
+                zp = {A.x + Bc.y, -(A.y - Bc.x)};     // conj(A - i*Bc)
+            };
+            if (i0 != 0) {
+                const cx wi = reinterpret_cast<const cx*>(p.rtw)[i0];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    pre(u[r], v[7 - r], cmul(wi, w32<T>(2 * r)), a[2 * r], a[2 * (7 - r) + 1]);
+            } else {
+                cx x0 = u[0], xl = src[L], dummy;
+                x0.y = 0;  // imag of DC / Nyquist never reaches the real output
+                xl.y = 0;
+                pre(x0, xl, w32<T>(0), a[0], dummy);
+#pragma unroll
+                for (int r = 1; r < 4; ++r) pre(u[r], u[8 - r], w32<T>(2 * r), a[2 * r], a[2 * (8 - r)]);
+                pre(u[4], u[4], w32<T>(8), a[8], dummy);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) pre(v[r], v[7 - r], w32<T>(2 * r + 1), a[2 * r + 1], a[2 * (7 - r) + 1]);
+            }
+        } else if constexpr (MODE == TM_FAST_C2R) {
             // stage the L+1 Hermitian inputs of each lane (unit stride), then pre-twiddle.
             // (Measured alternative: every thread loading X[k] and its mirror X[L-k] straight from
             // global memory, no staging — 71 % -> 67 % of HBM peak, so staging stays.)
@@ -497,6 +542,8 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         (MODE == TM_FAST_R2C) && E == 16 && L >= 128 && (ilog2(L) % 4 == 3) && sizeof(T) == 8;  // f32: measured slower
     if constexpr (R2C_MIRROR) {
         run_stages<T, C, 1, true, true>(a, sm, tw, t0, i0, t1, i1);
+    } else if constexpr ((MODE == TM_FAST_C2R) && E == 16 && L >= 128 && (ilog2(L) % 4 == 3)) {
+        run_stages<T, C, 1, true, false, true>(a, sm, tw, t0, i0, t1, i1);
     } else if constexpr (MODE == TM_FAST_C2R) {
         run_stages<T, C, 1, false>(a, sm, tw, t0, i0, t1, i1);
     } else if constexpr (FAST) {
