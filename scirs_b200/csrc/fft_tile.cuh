@@ -185,16 +185,21 @@ __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x
 
 // ---- tile configuration ------------------------------------------------------
 
-template <typename T, int L_, int TL_, int EMAX_ = 16>
+// GROUPS > 1 splits the CTA into independent thread groups, each owning TL/GROUPS lanes and its own
+// named barrier: the groups drift apart like separate CTAs (load of one overlaps compute of the
+// other) while the tile keeps TL adjacent lanes, i.e. full 128 B rows, in one CTA at one time.
+template <typename T, int L_, int TL_, int EMAX_ = 16, int GROUPS_ = 1>
 struct TileCfg {
     static constexpr int L = L_;
     static constexpr int TL = TL_;
+    static constexpr int GROUPS = GROUPS_;
+    static constexpr int TLG = TL_ / GROUPS_;                 // lanes per group
     static constexpr int E = L < EMAX_ ? L : EMAX_;    // points per thread (= largest radix)
     static constexpr int TPL = L / E;                  // threads per lane
     static constexpr int NT = TPL * TL;                // threads per CTA
     static constexpr int G = 128 / (int)sizeof(Cx<T>);  // threads per smem wavefront
     static __host__ __device__ constexpr int lane_pitch() {
-        int want = (TL < G) ? (G / TL) % G : 1;
+        int want = (TLG < G) ? (G / TLG) % G : 1;
         // padded exchange layout (one pad slot per E elements) and >= L+1 because the
         // real-transform paths stage L+1 points per lane
         int lp = L + (L > E ? L / (E >= 16 ? 8 : E) : 0) + 1;  // E=16 plans may start with a radix-8 stage
@@ -204,6 +209,14 @@ struct TileCfg {
     static constexpr int LP = lane_pitch();
     static constexpr size_t SMEM = (size_t)TL * LP * sizeof(Cx<T>);
     // resident CTAs per SM the register allocator must leave room for
+    static constexpr int NTG = NT / GROUPS;                   // threads per group
+    static __device__ __forceinline__ void sync(int group) {
+        if constexpr (GROUPS == 1) {
+            __syncthreads();
+        } else {
+            asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(NTG) : "memory");
+        }
+    }
     static constexpr int MINB =
         (E <= 8) ? (NT <= 512 ? (sizeof(T) == 8 ? 2 : 3) : 1) : ((NT <= 256 && sizeof(T) == 8) ? 2 : (NT <= 256 ? 3 : 1));
 };
@@ -244,13 +257,13 @@ struct Xch {
 template <typename T, typename C, int S, bool FIRST, bool MIRROR = false, bool MIRROR_IN = false>
 __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__ sm,
                                            const Cx<T>* __restrict__ tw, int tw_, int iw, int tr,
-                                           int ir) {
+                                           int ir, int grp = 0) {
     constexpr int L = C::L, E = C::E, TPL = C::TPL;
     constexpr int REM = 1 << (ilog2(L) % ilog2(E));  // the one radix smaller than E (1 = none)
     constexpr int R = MIRROR_IN ? ((S == 1 && REM > 1) ? REM : E) : ((L / S >= E) ? E : (L / S));
     constexpr bool LAST = (S * R == L);
     constexpr int NB = E / R;  // butterflies per thread in this stage
-    if constexpr (!LAST && !FIRST) __syncthreads();  // previous readers done before we overwrite
+    if constexpr (!LAST && !FIRST) C::sync(grp);  // previous readers done before we overwrite
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         Cx<T> v[R];
@@ -272,7 +285,7 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
         }
     }
     if constexpr (!LAST) {
-        __syncthreads();
+        C::sync(grp);
         const Cx<T>* src = sm + tr * C::LP + Xch<C, R, S>::read_base(ir);
         constexpr int SN = S * R;                                  // stride of the next stage
         constexpr int RN = MIRROR_IN ? E : ((L / SN >= E) ? E : (L / SN));  // its radix
@@ -290,7 +303,7 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
 #pragma unroll
             for (int m = 0; m < E; ++m) a[m] = src[Xch<C, R, S>::read_off(m)];
         }
-        run_stages<T, C, S * R, false, MIRROR, MIRROR_IN>(a, sm, tw, tr, ir, tr, ir);
+        run_stages<T, C, S * R, false, MIRROR, MIRROR_IN>(a, sm, tw, tr, ir, tr, ir, grp);
     }
 }
 
@@ -364,10 +377,10 @@ __device__ __forceinline__ void c2r_pretwiddle(Cx<T> (&a)[C::E], const Cx<T>* ro
     }
 }
 
-template <typename T, int L, int TL, bool DOUBLE, int EMAX = 16, int MODE = TM_GENERIC>
-__global__ void __launch_bounds__(TileCfg<T, L, TL, EMAX>::NT, TileCfg<T, L, TL, EMAX>::MINB)
+template <typename T, int L, int TL, bool DOUBLE, int EMAX = 16, int MODE = TM_GENERIC, int GROUPS = 1>
+__global__ void __launch_bounds__(TileCfg<T, L, TL, EMAX, GROUPS>::NT, TileCfg<T, L, TL, EMAX, GROUPS>::MINB)
 tile_fft_kernel(const __grid_constant__ PassParams p) {
-    using C = TileCfg<T, L, TL, EMAX>;
+    using C = TileCfg<T, L, TL, EMAX, GROUPS>;
     using cx = Cx<T>;
     constexpr int E = C::E, TPL = C::TPL, LP = C::LP;
     constexpr bool FAST = MODE != TM_GENERIC;
@@ -379,8 +392,14 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
     const uint32_t batch = blockIdx.x / p.tiles_per_batch;
 
     int t0, i0, t1, i1;
-    map_thread<TL, TPL>(p.map_in, tid, t0, i0);
-    map_thread<TL, TPL>(p.map_out, tid, t1, i1);
+    const int grp = GROUPS == 1 ? 0 : tid / C::NTG;  // warp-uniform
+    {
+        const int tg = GROUPS == 1 ? tid : tid % C::NTG;
+        map_thread<C::TLG, TPL>(p.map_in, tg, t0, i0);
+        map_thread<C::TLG, TPL>(p.map_out, tg, t1, i1);
+        t0 += grp * C::TLG;
+        t1 += grp * C::TLG;
+    }
 
     cx a[E];
     bool staged = false;
@@ -441,7 +460,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
 #pragma unroll
             for (int m = 0; m < E; ++m) row[i0 + m * TPL] = src[m * TPL];
             if (i0 == 0) row[L] = src[L];
-            __syncthreads();
+            C::sync(grp);
             c2r_pretwiddle<T, C>(a, row, reinterpret_cast<const cx*>(p.rtw), i0);
             staged = true;
         } else if constexpr (FAST) {
@@ -488,7 +507,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
                 if (valid && (int64_t)L < p.in.len) v = src[(int64_t)L * p.in.elem_stride];
                 row[L] = v;
             }
-            __syncthreads();
+            C::sync(grp);
             c2r_pretwiddle<T, C>(a, row, reinterpret_cast<const cx*>(p.rtw), i0);
             staged = true;
         } else {
@@ -541,28 +560,28 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
     constexpr bool R2C_MIRROR =
         (MODE == TM_FAST_R2C) && E == 16 && L >= 128 && (ilog2(L) % 4 == 3) && sizeof(T) == 8;  // f32: measured slower
     if constexpr (R2C_MIRROR) {
-        run_stages<T, C, 1, true, true>(a, sm, tw, t0, i0, t1, i1);
+        run_stages<T, C, 1, true, true>(a, sm, tw, t0, i0, t1, i1, grp);
     } else if constexpr ((MODE == TM_FAST_C2R) && E == 16 && L >= 128 && (ilog2(L) % 4 == 3)) {
-        run_stages<T, C, 1, true, false, true>(a, sm, tw, t0, i0, t1, i1);
+        run_stages<T, C, 1, true, false, true>(a, sm, tw, t0, i0, t1, i1, grp);
     } else if constexpr (MODE == TM_FAST_C2R) {
-        run_stages<T, C, 1, false>(a, sm, tw, t0, i0, t1, i1);
+        run_stages<T, C, 1, false>(a, sm, tw, t0, i0, t1, i1, grp);
     } else if constexpr (FAST) {
-        run_stages<T, C, 1, true>(a, sm, tw, t0, i0, t1, i1);
+        run_stages<T, C, 1, true>(a, sm, tw, t0, i0, t1, i1, grp);
     } else {
         if (staged)
-            run_stages<T, C, 1, false>(a, sm, tw, t0, i0, t1, i1);
+            run_stages<T, C, 1, false>(a, sm, tw, t0, i0, t1, i1, grp);
         else
-            run_stages<T, C, 1, true>(a, sm, tw, t0, i0, t1, i1);
+            run_stages<T, C, 1, true>(a, sm, tw, t0, i0, t1, i1, grp);
     }
 
     if constexpr (C::E == C::L) {
         // single-stage tiles never touch shared memory: remap explicitly if the
         // store wants the other thread->lane mapping
         if (p.map_in != p.map_out) {
-            __syncthreads();
+            C::sync(grp);
 #pragma unroll
             for (int m = 0; m < E; ++m) sm[t0 * LP + m] = a[m];
-            __syncthreads();
+            C::sync(grp);
 #pragma unroll
             for (int m = 0; m < E; ++m) a[m] = sm[t1 * LP + m];
         }
@@ -583,7 +602,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
             cx w = mid[(int64_t)e * p.mid_es + mid0];
             a[m] = cconjf(cmul(a[m], w));
         }
-        run_stages<T, C, 1, false>(a, sm, tw, t1, i1, t1, i1);
+        run_stages<T, C, 1, false>(a, sm, tw, t1, i1, t1, i1, grp);
 #pragma unroll
         for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
     }
@@ -632,10 +651,10 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         if constexpr (E >= 8 && E != L && (MODE == TM_FAST_R2C || MODE == TM_GENERIC)) {
             // a[m] = Z[i1 + m*TPL] of the packed half-length transform
             cx* row = sm + t1 * LP;
-            __syncthreads();
+            C::sync(grp);
 #pragma unroll
             for (int m = 0; m < E; ++m) row[i1 + m * TPL] = a[m];
-            __syncthreads();
+            C::sync(grp);
             cx* __restrict__ dst = reinterpret_cast<cx*>(p.out.ptr) + off;
             const cx wi = reinterpret_cast<const cx*>(p.rtw)[i1];
             const T h = (T)0.5 * scale;

@@ -5,21 +5,21 @@
 
 namespace sfc {
 
-template <typename T, int L, int TL, bool DBL, int EMAX = 16, int MODE = 0>
+template <typename T, int L, int TL, bool DBL, int EMAX = 16, int MODE = 0, int GROUPS = 1>
 struct KernelInst {
-    using C = TileCfg<T, L, TL, EMAX>;
+    using C = TileCfg<T, L, TL, EMAX, GROUPS>;
     static cudaError_t launch(const PassParams& p, unsigned grid, cudaStream_t s) {
         static bool configured[64] = {};
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
         if (dev < 64 && !configured[dev]) {
-            e = cudaFuncSetAttribute(tile_fft_kernel<T, L, TL, DBL, EMAX, MODE>,
+            e = cudaFuncSetAttribute(tile_fft_kernel<T, L, TL, DBL, EMAX, MODE, GROUPS>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
             if (e != cudaSuccess) return e;
             configured[dev] = true;
         }
-        tile_fft_kernel<T, L, TL, DBL, EMAX, MODE><<<grid, C::NT, C::SMEM, s>>>(p);
+        tile_fft_kernel<T, L, TL, DBL, EMAX, MODE, GROUPS><<<grid, C::NT, C::SMEM, s>>>(p);
         return cudaGetLastError();
     }
     static KernelEntry entry() {
@@ -30,9 +30,10 @@ struct KernelInst {
         k.E = C::E;
         k.dbl = DBL ? 1 : 0;
         k.mode = MODE;
+        k.groups = GROUPS;
         k.threads = C::NT;
         k.smem = C::SMEM;
-        k.func = (const void*)tile_fft_kernel<T, L, TL, DBL, EMAX, MODE>;
+        k.func = (const void*)tile_fft_kernel<T, L, TL, DBL, EMAX, MODE, GROUPS>;
         k.launch = &launch;
         return k;
     }
@@ -48,4 +49,8 @@ struct KernelInst {
 #define SFC_ADD_REAL(T, L, TL)                                \
     add(::sfc::KernelInst<T, L, TL, false, 16, 2>::entry()); \
     add(::sfc::KernelInst<T, L, TL, false, 16, 3>::entry());
+// two independent thread groups per CTA (wide column tiles)
+#define SFC_ADD_G2(T, L, TL)                                      \
+    add(::sfc::KernelInst<T, L, TL, false, 16, 0, 2>::entry()); \
+    add(::sfc::KernelInst<T, L, TL, false, 16, 1, 2>::entry());
 #define SFC_ADD_E(T, L, TL, DBL, E) add(::sfc::KernelInst<T, L, TL, DBL, E>::entry());

@@ -15,6 +15,7 @@ struct KernelEntry {
     int E;          // points per thread (largest radix)
     int dbl;        // 1 = forward * table * inverse fused
     int mode;       // TileMode (0 generic, 1 fast c2c, 2 fast r2c, 3 fast c2r)
+    int groups;     // independent thread groups per CTA (1 or 2)
     int threads;    // CTA size
     size_t smem;    // dynamic shared memory bytes
     const void* func;

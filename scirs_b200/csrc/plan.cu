@@ -45,7 +45,8 @@ const KernelEntry* find_kernel(int prec, int L, int TL, int dbl, int mode) {
     int n = 0;
     const KernelEntry* t = kernel_table(&n);
     for (int i = 0; i < n; ++i)
-        if (t[i].prec == prec && t[i].L == L && t[i].TL == TL && t[i].dbl == dbl && t[i].mode == mode) return &t[i];
+        if (t[i].prec == prec && t[i].L == L && t[i].TL == TL && t[i].dbl == dbl && t[i].mode == mode && t[i].groups == 1)
+            return &t[i];
     return nullptr;
 }
 
@@ -55,7 +56,7 @@ static const KernelEntry* flavour_of(const KernelEntry* k, int mode) {
     const KernelEntry* t = kernel_table(&n);
     for (int i = 0; i < n; ++i)
         if (t[i].prec == k->prec && t[i].L == k->L && t[i].TL == k->TL && t[i].dbl == k->dbl && t[i].E == k->E &&
-            t[i].mode == mode)
+            t[i].groups == k->groups && t[i].mode == mode)
             return &t[i];
     return nullptr;
 }
@@ -70,6 +71,14 @@ static bool fast_enabled() {
 
 // ROW tiles want few lanes per CTA (small tiles, more CTAs per SM); COL tiles want
 // many adjacent lanes (>= 128 B contiguous per element row).
+static int groups_mode() {
+    static int v = [] {
+        const char* e = getenv("SFC_GROUPS");
+        return e ? atoi(e) : 0;  // measured on B200: two named-barrier groups per CTA are slower (1024^3: 69% -> 61%)
+    }();
+    return v;
+}
+
 static int col_tl_cap() {
     static int v = [] {
         const char* e = getenv("SFC_COL_TL");
@@ -98,13 +107,20 @@ static const KernelEntry* pick_kernel(int prec, int L, bool want_wide, int dbl) 
     const int cap = (want_wide && col_tl_cap() > 0) ? col_tl_cap() : (1 << 30);
     const KernelEntry* smallest = nullptr;
     for (int i = 0; i < n; ++i) {
-        if (t[i].mode != 0 || t[i].prec != prec || t[i].L != L || t[i].dbl != dbl) continue;
+        if (t[i].mode != 0 || t[i].groups != 1 || t[i].prec != prec || t[i].L != L || t[i].dbl != dbl) continue;
         if (have_e ? t[i].E != std::min(want_e, L) : t[i].E != std::min(16, L)) continue;
         if (!smallest || t[i].TL < smallest->TL) smallest = &t[i];
         if (t[i].TL > cap) continue;
         if (!best || (want_wide ? t[i].TL > best->TL : t[i].TL < best->TL)) best = &t[i];
     }
     if (!best) best = smallest;
+    if (best && want_wide && groups_mode() >= 1) {
+        // same tile, two independent thread groups (overlaps one group's loads with the other's math)
+        for (int i = 0; i < n; ++i)
+            if (t[i].mode == 0 && t[i].groups == 2 && t[i].prec == prec && t[i].L == L && t[i].TL == best->TL &&
+                t[i].dbl == dbl && t[i].E == best->E)
+                return &t[i];
+    }
     return best;
 }
 
@@ -115,10 +131,17 @@ static const KernelEntry* pick_kernel_two_per_sm(int prec, int L, int dbl) {
     const KernelEntry* t = kernel_table(&n);
     const KernelEntry *best = nullptr, *smallest = nullptr;
     for (int i = 0; i < n; ++i) {
-        if (t[i].mode != 0 || t[i].prec != prec || t[i].L != L || t[i].dbl != dbl || t[i].E != std::min(16, L)) continue;
+        if (t[i].mode != 0 || t[i].groups != 1 || t[i].prec != prec || t[i].L != L || t[i].dbl != dbl ||
+            t[i].E != std::min(16, L))
+            continue;
         if (!smallest || t[i].TL < smallest->TL) smallest = &t[i];
         if (t[i].smem > (size_t)100 * 1024) continue;
         if (!best || t[i].TL > best->TL) best = &t[i];
+    }
+    if (groups_mode() >= 2) {
+        // grouped wide tile instead of the narrow two-per-SM tile
+        for (int i = 0; i < n; ++i)
+            if (t[i].mode == 0 && t[i].groups == 2 && t[i].prec == prec && t[i].L == L && t[i].dbl == dbl) return &t[i];
     }
     return best ? best : smallest;
 }
@@ -422,7 +445,8 @@ struct PlanBuilder {
         char buf[256];
         snprintf(buf, sizeof buf, "%s: tile L=%d TL=%d%s%s threads=%d smem=%zu lanes=%lld batches=%lld map=%s->%s", what,
                  s.k->L, s.k->TL, s.k->dbl ? " fwd*tab*inv" : "",
-                 s.k->mode == 0 ? " generic" : (s.k->mode == 1 ? " fast" : (s.k->mode == 2 ? " fast-r2c" : " fast-c2r")), s.k->threads, s.k->smem, (long long)nlanes,
+                 s.k->groups > 1 ? (s.k->mode ? " fast 2-groups" : " generic 2-groups")
+                                  : (s.k->mode == 0 ? " generic" : (s.k->mode == 1 ? " fast" : (s.k->mode == 2 ? " fast-r2c" : " fast-c2r"))), s.k->threads, s.k->smem, (long long)nlanes,
                  (long long)nbatch, s.p.map_in == MAP_ROW ? "row" : "col", s.p.map_out == MAP_ROW ? "row" : "col");
         s.desc = buf;
         pl.steps_.push_back(s);
