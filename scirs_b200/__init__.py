@@ -14,5 +14,9 @@ from .fft import (fft, ifft, rfft, irfft, fft2, ifft2, fft2_parallel, ifft2_para
 from .plan import FftPlan, FftPlanExecutor
 from .plan_cache import PlanCache, CacheStats, get_global_cache
 from .backend import FftBackend, CudaFftBackend, BackendManager, BackendContext, get_backend_manager
+from .context import (WorkerConfig, WorkerPool, WorkerPoolInfo, get_global_pool, set_workers, get_workers, FftContext,
+                      FftContextBuilder, fft_context, with_fft_settings, with_backend, with_workers, without_cache)
+from .planning import (PlannerBackend, PlanningStrategy, AdvancedFftPlanner, PlanBuilder, ParallelExecutor,
+                       ParallelPlanner, get_global_planner, plan_ahead_of_time)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -113,3 +113,35 @@ def test_argument_validation_precedes_device_use(lib):
     assert str(e.value) == "Input and output sizes must match the specified size"
     with pytest.raises(sb.NotImplementedError_):
         sb.ifft2_simd(np.ones((2, 2)))  # simd_fft.rs:99-111
+
+
+def test_context_and_worker_pool_mirrors(lib, monkeypatch):
+    """worker_pool.rs:229-300, context.rs:216-276 (configuration holders; no device needed)"""
+    import scirs_b200 as sb
+    from scirs_b200 import context
+
+    monkeypatch.setenv("SCIRS2_FFT_WORKERS", "3")
+    assert context.WorkerConfig().num_workers == 3  # worker_pool.rs:32-35
+    pool = sb.WorkerPool()
+    pool.set_workers(5)
+    assert pool.get_workers() == 5 and pool.is_enabled()
+    assert pool.execute(lambda: 42) == 42 and pool.execute_with_workers(2, lambda: 7) == 7
+    assert pool.get_info().thread_name_prefix == "scirs2-fft-worker"
+    c = sb.get_global_cache()
+    assert c.is_enabled()
+    assert sb.without_cache(lambda: c.is_enabled()) is False and c.is_enabled()
+    assert sb.with_workers(4, lambda: 11) == 11
+    if lib.sfc_is_available():
+        assert sb.with_backend("cuda_fft", lambda: sb.get_backend_manager().get_backend_name()) == "cuda_fft"
+    else:
+        with pytest.raises(sb.ValueError_) as e:  # backend.rs:214-219: registered but unavailable
+            sb.with_backend("cuda_fft", lambda: 0)
+        assert "not available" in str(e.value)
+    with pytest.raises(sb.ValueError_):
+        sb.with_backend("nope", lambda: 0)
+    with sb.fft_context().workers(2).cache_enabled(False).build():
+        assert not c.is_enabled()
+    assert c.is_enabled()
+    with pytest.raises(sb.ValueError_):
+        sb.PlanBuilder().build()
+    assert sb.PlannerBackend.CUDA.value == "cuda"

@@ -420,3 +420,28 @@ def test_full_size_fft_2pow20(sb, orc):
     y = sb.fft(x)
     assert orc.rel_l2(y, orc.fft(x)) < TOL64
     assert orc.rel_l2(y[[0, 1, 12345]], orc.dft_longdouble(x, bins=[0, 1, 12345])) < TOL64
+
+
+def test_planner_and_parallel_executor_mirrors(sb, orc):
+    """planning.rs:701-823, planning_parallel.rs:408-477"""
+    rng = np.random.default_rng(31)
+    ex = sb.ParallelExecutor([256], True)
+    ins = [cplx(rng, 256) for _ in range(5)]
+    outs = [np.empty(256, dtype=np.complex128) for _ in range(5)]
+    times = ex.execute_batch(ins, outs)
+    assert len(times) == 5
+    for a, b in zip(ins, outs):
+        assert orc.rel_l2(b, orc.backend_fft(a)) < TOL64
+    with pytest.raises(sb.ValueError_) as e:
+        ex.execute_batch(ins, outs[:4])
+    assert str(e.value) == "Input and output counts must match"
+    with pytest.raises(sb.ValueError_) as e:
+        ex.execute_batch([np.zeros(8, dtype=np.complex128)], [np.zeros(256, dtype=np.complex128)])
+    assert str(e.value) == "Input 0 has wrong size: expected 256, got 8"
+    plan = sb.PlanBuilder().shape([8]).forward(True).backend(sb.PlannerBackend.CUDA).build()
+    out = np.empty(8, dtype=np.complex128)
+    plan.execute(G["kat_impulse_in"], out)  # planning.rs:733-754
+    assert np.max(np.abs(np.abs(out) - 1.0)) < 1e-10
+    sb.plan_ahead_of_time([64, 128])
+    assert sb.with_backend("cuda_fft", lambda: sb.get_backend_manager().get_backend().name()) == "cuda_fft"
+    assert orc.rel_l2(sb.without_cache(lambda: sb.fft(ins[0])), orc.fft(ins[0])) < TOL64
