@@ -388,8 +388,10 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
     cx* sm = reinterpret_cast<cx*>(smem_raw);
 
     const int tid = threadIdx.x;
-    const uint32_t tile = blockIdx.x % p.tiles_per_batch;
-    const uint32_t batch = blockIdx.x / p.tiles_per_batch;
+    // tile-major order (batch index fastest) lets consecutive CTAs reuse the same rows of the
+    // per-plan tables (Bluestein chirp / kernel spectrum) out of L2
+    const uint32_t tile = p.nbatch_fast ? blockIdx.x / p.nbatch_fast : blockIdx.x % p.tiles_per_batch;
+    const uint32_t batch = p.nbatch_fast ? blockIdx.x % p.nbatch_fast : blockIdx.x / p.tiles_per_batch;
 
     int t0, i0, t1, i1;
     const int grp = GROUPS == 1 ? 0 : tid / C::NTG;  // warp-uniform

@@ -59,6 +59,7 @@ struct PassParams {
     uint32_t nlanes;           // lanes per batch
     uint32_t inner_count;      // lanes per outer index (shared by in/out)
     uint32_t tiles_per_batch;  // ceil(nlanes / TL)
+    uint32_t nbatch_fast;      // != 0: blockIdx = tile * nbatch_fast + batch (set per launch), else batch * tiles + tile
     int32_t map_in, map_out;
     int32_t ld_op, st_op;
     uint32_t flags;

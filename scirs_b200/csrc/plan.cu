@@ -521,7 +521,12 @@ struct PlanBuilder {
         const int col_single_max = col_single_limit(prec);
         if (is_pow2(n) && n <= lmax && !(col && n > col_single_max)) {
             Step s;
-            s.k = pick_kernel(prec, (int)n, col, 0);
+            // measured (1024^3 f64): with element rows <= 16 KiB apart the 64 KiB two-per-SM tile wins
+            // (74 % vs 61 %); with multi-MiB strides (TLB-bound) the wide 128-byte-row tile wins (59 % vs 44 %)
+            if (col && (int64_t)I * (int64_t)cs <= (256 << 10))
+                s.k = pick_kernel_two_per_sm(prec, (int)n, 0);
+            else
+                s.k = pick_kernel(prec, (int)n, col, 0);
             s.src = src.role;
             s.dst = dst.role;
             s.src_esize = src_es;
@@ -658,6 +663,7 @@ struct PlanBuilder {
             a.p.map_in = a.p.map_out = MAP_COL;
             a.p.ld_op = src.real ? LD_R_MUL : LD_C_MUL;
             a.p.aux_in = chirp;
+            a.batch_fastest = true;
             a.p.st_op = ST_TW;
             a.p.tw_lo = lo;
             a.p.tw_hi = hi;
@@ -687,6 +693,7 @@ struct PlanBuilder {
             b.p.tw_shift = sh;
             b.p.flags = F_TW_CONJ;
             b.p.scale = 1.0;
+            b.batch_fastest = true;
             if (!finish_tile(b, L1 * I, I, O, "Bluestein pass B (rows: FFT * B * IFFT * conj twiddle)")) return false;
         }
         {
@@ -703,6 +710,7 @@ struct PlanBuilder {
             c.p.ld_op = LD_C;
             c.p.st_op = ST_MUL;
             c.p.aux_out = chirp;
+            c.batch_fastest = true;
             c.p.flags = F_CONJ_LD_POST | F_CONJ_ST_PRE | fl_out;
             c.p.scale = scale;
             dev_bytes += O * I * (std::min(n, src.n) * (int64_t)src_es + 5 * M * (int64_t)cs +
@@ -1115,6 +1123,7 @@ int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& 
                 if (t.dst != R_MS) ob += (size_t)b0 * (size_t)p.out.batch_stride * t.dst_esize;
                 p.in.ptr = ib;
                 p.out.ptr = ob;
+                if (t.batch_fastest) p.nbatch_fast = (uint32_t)nb;
                 const uint64_t grid = (uint64_t)p.tiles_per_batch * (uint64_t)nb;
                 if (grid == 0 || grid > 0x7FFFFFFFULL) {
                     es = "grid too large";

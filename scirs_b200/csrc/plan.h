@@ -32,6 +32,7 @@ struct Step {
     int src = R_IN, dst = R_OUT;
     size_t src_esize = 16, dst_esize = 16;  // bytes per addressed element (for batch offsets)
     int group = -1;                          // steps sharing a group are chunk-looped together
+    bool batch_fastest = false;              // CTA order: batch index fastest (table reuse in L2)
     bool scatter = false;                    // store through the caller's per-block pointer table
     int64_t nbatch = 1;                      // batches (blockIdx-level outer index)
     std::string desc;
