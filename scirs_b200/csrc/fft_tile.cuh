@@ -53,6 +53,58 @@ __device__ __forceinline__ Cx<T> cconj(Cx<T> a) { return {a.x, -a.y}; }
 template <typename T>
 __device__ __forceinline__ Cx<T> mul_mi(Cx<T> a) { return {a.y, -a.x}; }  // a * (-i)
 
+// ---- f32: Blackwell packed f32x2 arithmetic -----------------------------------------------
+// sm_100 has FADD2 / FMUL2 / FFMA2 on 64-bit register pairs with free half-swap / broadcast operand
+// modifiers, so one complex f32 add is ONE instruction and the -i rotation folds into the consumer.
+// These overloads are picked for Cx<float>; the generic templates above stay for f64.
+typedef unsigned long long u64p;
+__device__ __forceinline__ u64p pk2(float lo, float hi) {
+    u64p r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ u64p pk2(Cx<float> a) { return pk2(a.x, a.y); }
+__device__ __forceinline__ Cx<float> upk2(u64p v) {
+    Cx<float> r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ u64p add2(u64p a, u64p b) {
+    u64p r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64p sub2(u64p a, u64p b) {
+    u64p r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64p mul2(u64p a, u64p b) {
+    u64p r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64p fma2(u64p a, u64p b, u64p c) {
+    u64p r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ Cx<float> cadd(Cx<float> a, Cx<float> b) { return upk2(add2(pk2(a), pk2(b))); }
+__device__ __forceinline__ Cx<float> csub(Cx<float> a, Cx<float> b) { return upk2(sub2(pk2(a), pk2(b))); }
+// The half-negated swaps below ((-t.y, t.x) and (u.y, -u.x)) are written so that they feed an ADD:
+// ptxas folds them into FADD2's operand modifier (R.F32x2.LO_HI.NP); FMUL2 / FFMA2 cannot take them.
+__device__ __forceinline__ Cx<float> cmul(Cx<float> a, Cx<float> b) {
+    // ax*b + i*(ay*b)
+    const Cx<float> t = upk2(mul2(pk2(a.y, a.y), pk2(b)));
+    return upk2(add2(mul2(pk2(a.x, a.x), pk2(b)), pk2(-t.y, t.x)));
+}
+__device__ __forceinline__ Cx<float> cmulc(Cx<float> a, Cx<float> b) {  // a * conj(b)
+    // bx*a - i*(by*a)
+    const Cx<float> u = upk2(mul2(pk2(b.y, b.y), pk2(a)));
+    return upk2(add2(mul2(pk2(b.x, b.x), pk2(a)), pk2(u.y, -u.x)));
+}
+__device__ __forceinline__ Cx<float> csqr(Cx<float> a) { return cmul(a, a); }
+
 // ---- radix butterflies (forward, in place, natural-order output) ------------
 
 template <typename T>
@@ -86,6 +138,24 @@ __device__ __forceinline__ Cx<T> mul_w16(Cx<T> a) {
     else if constexpr (J == 6) return {(a.y - a.x) * H, -((a.x + a.y) * H)};
     else if constexpr (J == 9) return {-fma(a.y, S1, a.x * C1), fma(a.x, S1, -(a.y * C1))};
     else { static_assert(J < 0, "unsupported W16 power"); return a; }
+}
+
+// a * W16^J for f32 with packed operations
+template <int J>
+__device__ __forceinline__ Cx<float> mul_w16(Cx<float> a) {
+    constexpr float H = 0.70710678118654752440f, C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f;
+    if constexpr (J == 0) return a;
+    else if constexpr (J == 4) return {a.y, -a.x};
+    else if constexpr (J == 2) return upk2(mul2(add2(pk2(a), pk2(a.y, -a.x)), pk2(H, H)));
+    else if constexpr (J == 6) return upk2(mul2(sub2(pk2(a.y, -a.x), pk2(a)), pk2(H, H)));
+    else {
+        // a * (c - i s) = c*a - i*(s*a)
+        constexpr float c = J == 1 ? C1 : (J == 3 ? S1 : -C1);
+        constexpr float sn = J == 1 ? S1 : (J == 3 ? C1 : -S1);
+        static_assert(J == 1 || J == 3 || J == 9, "unsupported W16 power");
+        const Cx<float> u = upk2(mul2(pk2(sn, sn), pk2(a)));
+        return upk2(add2(mul2(pk2(c, c), pk2(a)), pk2(u.y, -u.x)));
+    }
 }
 
 template <int R, typename T>
