@@ -535,6 +535,26 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
             C::sync(grp);
             c2r_pretwiddle<T, C>(a, row, reinterpret_cast<const cx*>(p.rtw), i0);
             staged = true;
+        } else if (FAST && p.ld_op == LD_SPLIT2) {
+            // One 2L-point row is shared by two lanes (usually two CTAs): a radix-2 decimation-in-
+            // frequency stage folded into the load.  Both lanes read the whole row (the second read
+            // comes from L2); lane parity 0 transforms x[j] + x[j+L] -> even bins, parity 1 transforms
+            // (x[j] - x[j+L]) W_2L^j -> odd bins.  Two 64 KiB tiles per SM instead of one 128 KiB tile.
+            if constexpr (E == 16) {
+                const cx* __restrict__ src = reinterpret_cast<const cx*>(p.in.ptr) + off + i0;
+                const T sgn = li ? (T)-1 : (T)1;
+                const T cj = (p.flags & F_CONJ_LD_PRE) ? (T)-1 : (T)1;
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const cx u = src[m * TPL], v = src[m * TPL + L];
+                    a[m] = {fma(sgn, v.x, u.x), cj * fma(sgn, v.y, u.y)};
+                }
+                if (li) {
+                    const cx wi = reinterpret_cast<const cx*>(p.rtw)[i0];
+#pragma unroll
+                    for (int m = 0; m < E; ++m) a[m] = cmul(a[m], cmul(wi, w32<T>(m)));
+                }
+            }
         } else if constexpr (FAST) {
             const cx* __restrict__ src =
                 reinterpret_cast<const cx*>(p.in.ptr) + off + (int64_t)i0 * p.in.elem_stride;

@@ -22,6 +22,7 @@ enum LoadOp : int32_t {
     LD_C_MUL = 2,   // complex element * aux_in[pos]     (Bluestein chirp pre-multiply)
     LD_R_MUL = 3,   // real element * aux_in[pos]
     LD_C2R = 4,     // Hermitian half-spectrum -> packed N/2 complex (irfft fast path, rfft.rs:92-178)
+    LD_SPLIT2 = 5,  // radix-2 DIF pre-stage: lane parity 0 gets x[j] + x[j+L], parity 1 gets (x[j] - x[j+L]) W_2L^j
 };
 
 enum StoreOp : int32_t {

@@ -352,6 +352,17 @@ static int col_single_limit(int prec) {
     return prec == PREC_F64 ? 2048 : 4096;
 }
 
+// row length that is transformed as two half-length lanes (0 = never); SFC_ROW_SPLIT overrides
+static int row_split_len(int prec) {
+    static int v = [] {
+        const char* e = getenv("SFC_ROW_SPLIT");
+        return e ? atoi(e) : -1;
+    }();
+    if (v >= 0) return v;
+    (void)prec;
+    return 0;  // measured on B200: 8192-point f64 rows 52.3 % split vs 52.8 % single tile (interleaved 16 B stores)
+}
+
 static int64_t scratch_budget_bytes() {
     static int64_t v = [] {
         const char* e = getenv("SFC_WORK_MB");
@@ -428,7 +439,8 @@ struct PlanBuilder {
                     if (s.p.in.elem_stride == 1 && s.p.in.len >= s.k->L + 1 && out_max < s.p.out.len &&
                         s.p.st_op == ST_C && !(s.p.flags & F_ST_REAL))
                         mode = 3;
-                } else if (!(s.p.flags & F_ST_REAL) && (s.p.ld_op == LD_C || s.p.ld_op == LD_C_MUL)) {
+                } else if (!(s.p.flags & F_ST_REAL) &&
+                           (s.p.ld_op == LD_C || s.p.ld_op == LD_C_MUL || s.p.ld_op == LD_SPLIT2)) {
                     // masks (zero padding on load, crop on store) are handled by a per-thread element
                     // limit in 32-bit arithmetic
                     const int64_t lim = (int64_t)1 << 31;
@@ -519,6 +531,34 @@ struct PlanBuilder {
         // whole-column tile no longer fits shared memory with that many lanes, so the axis is
         // split into two strided sub-passes (four-step) instead
         const int col_single_max = col_single_limit(prec);
+        // Contiguous rows whose single tile would be 128 KiB (one CTA per SM): split every row over two
+        // lanes of half the length with a radix-2 stage folded into the load (LD_SPLIT2)
+        if (!col && is_pow2(n) && n <= lmax && n == row_split_len(prec) && !src.real && !store_real && src.n == n &&
+            dst.n == n && O * 2 <= 0xFFFFFFFFLL) {
+            Step s;
+            const int L = (int)(n / 2);
+            s.k = pick_kernel(prec, L, false, 0);
+            if (s.k && (O * 2) % s.k->TL == 0) {
+                s.src = src.role;
+                s.dst = dst.role;
+                s.src_esize = cs;
+                s.dst_esize = cs;
+                // lane = 2*row + parity: both parities read the same row, parity picks the output interleave
+                set_io(s.p.in, 0, n, 0, 1, n, 1, 0);
+                set_io(s.p.out, 0, n, 1, 2, n, 2, 0);
+                s.p.map_in = s.p.map_out = MAP_ROW;
+                s.p.ld_op = LD_SPLIT2;
+                s.p.st_op = ST_C;
+                s.p.flags = fl_in | fl_out;
+                s.p.scale = scale;
+                s.p.rtw = table_rtw(prec, L, err);
+                if (!s.p.rtw) return false;
+                dev_bytes += O * n * 2 * (int64_t)cs;
+                if (!finish_tile(s, O * 2, 2, 1, "single-pass rows, each row split over two half-length lanes")) return false;
+                if (pl.steps_.back().k->mode == 1) return true;
+                pl.steps_.pop_back();  // no fast flavour: fall through to the plain single tile
+            }
+        }
         if (is_pow2(n) && n <= lmax && !(col && n > col_single_max)) {
             Step s;
             // measured (1024^3 f64): with element rows <= 16 KiB apart the 64 KiB two-per-SM tile wins
