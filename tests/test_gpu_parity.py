@@ -445,3 +445,48 @@ def test_planner_and_parallel_executor_mirrors(sb, orc):
     sb.plan_ahead_of_time([64, 128])
     assert sb.with_backend("cuda_fft", lambda: sb.get_backend_manager().get_backend().name()) == "cuda_fft"
     assert orc.rel_l2(sb.without_cache(lambda: sb.fft(ins[0])), orc.fft(ins[0])) < TOL64
+
+
+def test_full_size_bluestein_batch_256(sb, orc):
+    """config 4: 256 signals x N = 1,000,003 (prime) and x 3^13, device resident — round trip over the
+    whole batch, sampled extended-precision bins of two signals, linearity across the batch"""
+    torch = _torch()
+    s = torch.cuda.current_stream().cuda_stream
+    for n, seed in ((1000003, 4), (1594323, 5)):
+        b = 256
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        x = torch.view_as_complex(torch.randn(b, n, 2, dtype=torch.float64, device="cuda", generator=g))
+        y = torch.empty_like(x)
+        sb.FftPlan([b, n], [1], "c2c", "f64", True).execute_device(x, y, s)
+        torch.cuda.synchronize()
+        bins = [0, 1, n // 2, n - 1]
+        for row in (0, 255):
+            ref = orc.dft_longdouble(x[row].cpu().numpy(), bins=bins)
+            assert orc.rel_l2(y[row, bins].cpu().numpy(), ref) < TOL64
+        z = torch.empty_like(x)
+        sb.FftPlan([b, n], [1], "c2c", "f64", False, 1.0 / n).execute_device(y, z, s)
+        torch.cuda.synchronize()
+        assert float((z - x).norm() / x.norm()) < TOL64
+        del x, y, z
+        torch.cuda.empty_cache()
+
+
+def test_full_size_fftn_1024_roundtrip(sb, orc):
+    """config 5b on one GPU: 1024^3 c128 (17.2 GB) forward + inverse, DC bin = sum, one lane per axis"""
+    torch = _torch()
+    n = 1024
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.view_as_complex(torch.randn(n, n, n, 2, dtype=torch.float64, device="cuda", generator=g))
+    y = torch.empty_like(x)
+    sb.FftPlan([n, n, n], [0, 1, 2], "c2c", "f64").execute_device(x, y, s)
+    torch.cuda.synchronize()
+    tot = complex(x.sum())
+    assert abs(complex(y[0, 0, 0]) - tot) / abs(tot) < 1e-9
+    # bin (1, 0, 0): sum_i0 w^i0 * (sum over the other two axes)
+    plane = x.sum(dim=(1, 2)).cpu().numpy()
+    ref = orc.dft_longdouble(plane, bins=[1, 513])
+    assert orc.rel_l2(np.array([complex(y[1, 0, 0]), complex(y[513, 0, 0])]), ref) < 1e-10
+    sb.FftPlan([n, n, n], [0, 1, 2], "c2c", "f64", False, 1.0 / n ** 3).execute_device(y, y, s)  # in place
+    torch.cuda.synchronize()
+    assert float((y - x).norm() / x.norm()) < TOL64
