@@ -1,8 +1,9 @@
 # Build libscirs2_fft_cuda.so (sm_100a only) and the CPU oracle.
 NVCC      ?= nvcc
+EXTRA     ?=
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
-             --expt-relaxed-constexpr -Xptxas -v
+             --expt-relaxed-constexpr -Xptxas -v $(EXTRA)
 CSRC      := scirs_b200/csrc
 BUILD     := build
 LIBDIR    := scirs_b200/lib

@@ -136,12 +136,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("SFC_LIB_PATH", LIB_PATH)  # developer knob: try another build of the same library
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()); "
+            f"{path} is missing: build it with `make` (or __graft_entry__.build()); "
             "scirs_b200 has no CPU fallback"
         )
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
         fn.restype = res

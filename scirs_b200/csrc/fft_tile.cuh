@@ -53,6 +53,36 @@ __device__ __forceinline__ Cx<T> cconj(Cx<T> a) { return {a.x, -a.y}; }
 template <typename T>
 __device__ __forceinline__ Cx<T> mul_mi(Cx<T> a) { return {a.y, -a.x}; }  // a * (-i)
 
+// ---- global loads with a cache policy ------------------------------------------------------
+// Tile data is read exactly once; SFC_LDPOL_DATA / SFC_LDPOL_AUX pick the PTX cache operator
+// (0 default, 1 .cg = L2 only, 2 .cs = streaming, 3 L1::no_allocate, 4 .nc read-only path).
+#ifndef SFC_LDPOL_DATA
+#define SFC_LDPOL_DATA 0
+#endif
+#ifndef SFC_LDPOL_AUX
+#define SFC_LDPOL_AUX 0
+#endif
+template <int POL>
+__device__ __forceinline__ Cx<double> ld_pol(const Cx<double>* p) {
+    Cx<double> r;
+    if constexpr (POL == 1) asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    else if constexpr (POL == 2) asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    else if constexpr (POL == 3) asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    else if constexpr (POL == 4) asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    else r = *p;
+    return r;
+}
+template <int POL>
+__device__ __forceinline__ Cx<float> ld_pol(const Cx<float>* p) {
+    Cx<float> r;
+    if constexpr (POL == 1) asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    else if constexpr (POL == 2) asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    else if constexpr (POL == 3) asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    else if constexpr (POL == 4) asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    else r = *p;
+    return r;
+}
+
 // ---- f32: Blackwell packed f32x2 arithmetic -----------------------------------------------
 // sm_100 has FADD2 / FMUL2 / FFMA2 on 64-bit register pairs with free half-swap / broadcast operand
 // modifiers, so one complex f32 add is ONE instruction and the -i rotation folds into the consumer.
@@ -400,6 +430,47 @@ __device__ __forceinline__ Cx<T> w32(int m) {
     }
 }
 
+// Bluestein chirp values chirp[P + m*D], m < E, chirp[n] = exp(-i*pi*n^2/N), without a table of N
+// entries: the phase n^2 mod 2N is reduced exactly in integers and looked up in a two-level root
+// table (2 * ~sqrt(2N) entries, cache resident); consecutive positions follow the second-order
+// recurrence c[m+1] = c[m] * r[m], r[m+1] = r[m] * q with r[0] = R(2PD + D^2), q = R(2D^2).  Two
+// anchored half-chains keep the rounding error at the table's own level (~1e-16).
+template <int E>
+__device__ __forceinline__ void chirp_gen(Cx<double> (&c)[E], const PassParams& p, uint64_t P, uint64_t D,
+                                          Cx<double> q) {
+    const Cx<double>* __restrict__ lo = reinterpret_cast<const Cx<double>*>(p.chirp_lo);
+    const Cx<double>* __restrict__ hi = reinterpret_cast<const Cx<double>*>(p.chirp_hi);
+    const uint64_t m2 = p.chirp_mod, mask = ((uint64_t)1 << p.chirp_shift) - 1;
+    auto root = [&](uint64_t k) { return cmul(hi[k >> p.chirp_shift], lo[k & mask]); };
+    constexpr int H = E >= 8 ? E / 2 : E;
+    const uint64_t dd = D * D;
+    c[0] = root((P * P) % m2);
+    Cx<double> r = root((2 * P * D + dd) % m2);
+#pragma unroll
+    for (int m = 1; m < H; ++m) {
+        c[m] = cmul(c[m - 1], r);
+        r = cmul(r, q);
+    }
+    if constexpr (E >= 8) {
+        const uint64_t P2 = P + (uint64_t)H * D;
+        c[H] = root((P2 * P2) % m2);
+        r = root((2 * P2 * D + dd) % m2);
+#pragma unroll
+        for (int m = H + 1; m < E; ++m) {
+            c[m] = cmul(c[m - 1], r);
+            r = cmul(r, q);
+        }
+    }
+}
+
+template <typename T, int E>
+__device__ __forceinline__ void chirp_apply(Cx<T> (&a)[E], const PassParams& p, int64_t P, int64_t D, const double* q) {
+    Cx<double> c[E];
+    chirp_gen<E>(c, p, (uint64_t)P, (uint64_t)D, Cx<double>{q[0], q[1]});
+#pragma unroll
+    for (int m = 0; m < E; ++m) a[m] = cmul(a[m], Cx<T>{(T)c[m].x, (T)c[m].y});
+}
+
 template <int TL, int TPL>
 __device__ __forceinline__ void map_thread(int mode, int tid, int& t, int& i) {
     if (mode == MAP_COL) {
@@ -412,6 +483,29 @@ __device__ __forceinline__ void map_thread(int mode, int tid, int& t, int& i) {
 }
 
 // ---- the kernel ---------------------------------------------------------------
+
+#ifdef SFC_PHASE_TIMING
+// developer build: thread 0 of every CTA adds the clocks spent between phase marks to p.dbg[k]
+#define SFC_PHASE(k)                                                                  \
+    do {                                                                              \
+        if (p.dbg && threadIdx.x == 0) {                                              \
+            const long long now_ = clock64();                                         \
+            atomicAdd(p.dbg + (k), (unsigned long long)(now_ - phase_t_));            \
+            phase_t_ = now_;                                                          \
+        }                                                                             \
+    } while (0)
+#define SFC_PHASE_FORCE(arr)                                                          \
+    do {                                                                              \
+        if (p.dbg && threadIdx.x == 0) {                                              \
+            double s_ = 0;                                                            \
+            _Pragma("unroll") for (int m_ = 0; m_ < E; ++m_) s_ += (double)arr[m_].x; \
+            if (s_ == 1.2345e300) atomicAdd(p.dbg + 15, 1ull);                        \
+        }                                                                             \
+    } while (0)
+#else
+#define SFC_PHASE(k) do { } while (0)
+#define SFC_PHASE_FORCE(arr) do { } while (0)
+#endif
 
 // Kernel flavours.  The planner picks a FAST flavour whenever every lane of every tile is valid
 // and no bounds mask is needed (PlanBuilder::finish_tile); they carry no predicates, no zero
@@ -459,9 +553,18 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
 
     const int tid = threadIdx.x;
     // tile-major order (batch index fastest) lets consecutive CTAs reuse the same rows of the
-    // per-plan tables (Bluestein chirp / kernel spectrum) out of L2
-    const uint32_t tile = p.nbatch_fast ? blockIdx.x / p.nbatch_fast : blockIdx.x % p.tiles_per_batch;
-    const uint32_t batch = p.nbatch_fast ? blockIdx.x % p.nbatch_fast : blockIdx.x / p.tiles_per_batch;
+    // per-plan tables (Bluestein chirp / kernel spectrum) out of L2; groups of 2^shift adjacent
+    // tiles stay adjacent in time so that their 64..128 B row segments merge into whole DRAM bursts
+    uint32_t tile, batch;
+    if (p.nbatch_fast) {
+        const uint32_t per = p.nbatch_fast << p.tile_group_shift;
+        const uint32_t th = blockIdx.x / per, r = blockIdx.x - th * per;
+        batch = r >> p.tile_group_shift;
+        tile = (th << p.tile_group_shift) + (r & ((1u << p.tile_group_shift) - 1u));
+    } else {
+        tile = blockIdx.x % p.tiles_per_batch;
+        batch = blockIdx.x / p.tiles_per_batch;
+    }
 
     int t0, i0, t1, i1;
     const int grp = GROUPS == 1 ? 0 : tid / C::NTG;  // warp-uniform
@@ -475,6 +578,10 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
 
     cx a[E];
     bool staged = false;
+#ifdef SFC_PHASE_TIMING
+    long long phase_t_ = clock64();
+    if (p.dbg && threadIdx.x == 0) atomicAdd(p.dbg + 14, 1ull);
+#endif
 
     // ------------------------------ load ------------------------------------
     {
@@ -567,22 +674,29 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
 #pragma unroll
                 for (int m = 0; m < E; ++m) {
                     cx v = {(T)0, (T)0};
-                    if (i0 + m * TPL < elim) v = src[m * step];
+                    if (i0 + m * TPL < elim) v = ld_pol<SFC_LDPOL_DATA>(src + m * step);
                     a[m] = v;
                 }
             } else {
 #pragma unroll
-                for (int m = 0; m < E; ++m) a[m] = src[m * step];
+                for (int m = 0; m < E; ++m) a[m] = ld_pol<SFC_LDPOL_DATA>(src + m * step);
             }
+            SFC_PHASE(0);          // address set-up + load issue
+            SFC_PHASE_FORCE(a);
+            SFC_PHASE(1);          // waiting for the tile data
             if (p.flags & F_CONJ_LD_PRE) {
 #pragma unroll
                 for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
             }
-            if (p.ld_op == LD_C_MUL) {
+            if (p.ld_op == LD_C_MUL && (p.flags & F_CHIRP_GEN)) {
+                // zero-padded elements stay zero whatever they are multiplied by: no predicate
+                chirp_apply<T, E>(a, p, (int64_t)i0 * p.in.pos_es + pos0, (int64_t)TPL * p.in.pos_es, p.chirp_q_in);
+            } else if (p.ld_op == LD_C_MUL) {
                 const cx* __restrict__ aux = reinterpret_cast<const cx*>(p.aux_in);
 #pragma unroll
                 for (int m = 0; m < E; ++m)
-                    if (i0 + m * TPL < elim) a[m] = cmul(a[m], aux[(int64_t)(i0 + m * TPL) * p.in.pos_es + pos0]);
+                    if (i0 + m * TPL < elim)
+                        a[m] = cmul(a[m], ld_pol<SFC_LDPOL_AUX>(aux + ((int64_t)(i0 + m * TPL) * p.in.pos_es + pos0)));
             }
         } else if (p.ld_op == LD_C2R) {
             const cx* __restrict__ src = reinterpret_cast<const cx*>(p.in.ptr) + off;
@@ -630,7 +744,9 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
 #pragma unroll
                 for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
             }
-            if (has_mul) {
+            if (has_mul && (p.flags & F_CHIRP_GEN)) {
+                chirp_apply<T, E>(a, p, (int64_t)i0 * p.in.pos_es + pos0, (int64_t)TPL * p.in.pos_es, p.chirp_q_in);
+            } else if (has_mul) {
                 const cx* __restrict__ aux = reinterpret_cast<const cx*>(p.aux_in);
 #pragma unroll
                 for (int m = 0; m < E; ++m) {
@@ -646,6 +762,8 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         }
     }
 
+    SFC_PHASE_FORCE(a);
+    SFC_PHASE(2);  // load operators (chirp multiply, ...)
     // ---------------------------- transform ---------------------------------
     const cx* __restrict__ tw = reinterpret_cast<const cx*>(p.tw);
     // last radix 8 with 16 points per thread = two butterflies per thread in the last stage
@@ -679,6 +797,8 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         }
     }
 
+    SFC_PHASE_FORCE(a);
+    SFC_PHASE(3);  // first transform
     const uint32_t lane = tile * TL + (uint32_t)t1;
     const bool valid = FAST ? true : (lane < p.nlanes);
     const uint32_t lo = lane / p.inner_count;
@@ -699,6 +819,8 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
     }
 
+    SFC_PHASE_FORCE(a);
+    SFC_PHASE(4);  // pointwise table + second transform (double kernels)
     // ------------------------------ store -----------------------------------
     const int64_t off = (int64_t)batch * p.out.batch_stride + (int64_t)lo * p.out.outer_stride +
                         (int64_t)li * p.out.inner_stride;
@@ -815,6 +937,9 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
                 w = cmul(w, s1);
             }
         }
+    } else if (p.st_op == ST_MUL && (p.flags & F_CHIRP_GEN)) {
+        // cropped positions (>= len) are multiplied by some unit-modulus value and never stored
+        chirp_apply<T, E>(a, p, (int64_t)i1 * p.out.pos_es + pos0, (int64_t)TPL * p.out.pos_es, p.chirp_q_out);
     } else if (p.st_op == ST_MUL) {
         const cx* __restrict__ aux = reinterpret_cast<const cx*>(p.aux_out);
 #pragma unroll
@@ -831,6 +956,8 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
 #pragma unroll
         for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
     }
+    SFC_PHASE_FORCE(a);
+    SFC_PHASE(5);  // store operators (twiddle / chirp / scale)
     if constexpr (FAST) {
         if (p.peer_shift >= 0) {
             // fused transpose: each block of the transform axis is stored straight into its
@@ -859,6 +986,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
 #pragma unroll
             for (int m = 0; m < E; ++m) dst[m * step] = a[m];
         }
+        SFC_PHASE(6);  // store issue
     } else if (p.flags & F_ST_REAL) {
         T* __restrict__ dst = reinterpret_cast<T*>(p.out.ptr) + off;
 #pragma unroll

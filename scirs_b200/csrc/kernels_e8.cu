@@ -3,6 +3,8 @@
 namespace sfc {
 void register_kernels_e8(void (*add)(const KernelEntry&)) {
     SFC_ADD_E(double, 4096, 1, false, 8)
+    SFC_ADD_E(double, 1024, 4, false, 8)
+    add(::sfc::KernelInst<double, 1024, 4, false, 8, 1>::entry());
     SFC_ADD_E(double, 2048, 2, false, 8)
     SFC_ADD_E(double, 512, 8, false, 8)
     SFC_ADD_E(double, 8192, 1, false, 8)

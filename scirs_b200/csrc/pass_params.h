@@ -41,7 +41,8 @@ enum PassFlags : uint32_t {
     F_TW_CONJ = 1u << 4,       // ST_TW uses conj(W)
     F_ST_REAL = 1u << 5,
     F_IN_NOMASK = 1u << 6,     // every (lane, e) position is < in.len: loads need no bounds predicate
-    F_OUT_NOMASK = 1u << 7,    // likewise for stores       // store only the real part into a real array (irfftn, rfft.rs:722)
+    F_OUT_NOMASK = 1u << 7,
+    F_CHIRP_GEN = 1u << 8,     // LD_*_MUL / ST_MUL: generate the Bluestein chirp in registers instead of reading aux_*    // likewise for stores       // store only the real part into a real array (irfftn, rfft.rs:722)
 };
 
 struct IoDesc {
@@ -61,6 +62,7 @@ struct PassParams {
     uint32_t inner_count;      // lanes per outer index (shared by in/out)
     uint32_t tiles_per_batch;  // ceil(nlanes / TL)
     uint32_t nbatch_fast;      // != 0: blockIdx = tile * nbatch_fast + batch (set per launch), else batch * tiles + tile
+    uint32_t tile_group_shift; // with nbatch_fast: 2^shift adjacent tiles stay adjacent in CTA order (DRAM row locality)
     int32_t map_in, map_out;
     int32_t ld_op, st_op;
     uint32_t flags;
@@ -73,12 +75,22 @@ struct PassParams {
     const void* mid;           // double kernels: pointwise table between the two transforms
     int64_t mid_es, mid_ls;    // mid index = e*mid_es + lane_outer*mid_ls
     const void* rtw;           // R2C/C2R: W_{2L}^i, i < L/E
+    // F_CHIRP_GEN: chirp[n] = exp(-i*pi*n^2/N) = R(n^2 mod 2N), R(k) = chirp_hi[k >> shift] * chirp_lo[k & mask]
+    // (f64 tables whatever the transform precision); q_* = exp(-i*pi*2*D^2/N) for the thread's position step D
+    const void* chirp_lo;
+    const void* chirp_hi;
+    int32_t chirp_shift;
+    uint64_t chirp_mod;        // 2N
+    double chirp_q_in[2], chirp_q_out[2];
     double scale;
     // split-axis scatter (slab transpose fused into the store): output element e of the transform
     // axis goes to peer_out[e >> peer_shift] at element index (e & ((1 << peer_shift) - 1)).
     // peer_shift < 0 = off.  The pointers may be peer-GPU memory mapped over NVLink.
     int32_t peer_shift;
     void* peer_out[16];
+#ifdef SFC_PHASE_TIMING
+    unsigned long long* dbg;   // developer build only: per-launch phase clock sums (thread 0 of every CTA)
+#endif
 };
 
 }  // namespace sfc

@@ -132,7 +132,7 @@ static const KernelEntry* pick_kernel_two_per_sm(int prec, int L, int dbl) {
     const KernelEntry *best = nullptr, *smallest = nullptr;
     for (int i = 0; i < n; ++i) {
         if (t[i].mode != 0 || t[i].groups != 1 || t[i].prec != prec || t[i].L != L || t[i].dbl != dbl ||
-            t[i].E != std::min(16, L))
+            t[i].E != std::min(forced_e() ? forced_e() : 16, L))
             continue;
         if (!smallest || t[i].TL < smallest->TL) smallest = &t[i];
         if (t[i].smem > (size_t)100 * 1024) continue;
@@ -154,7 +154,7 @@ static std::map<TableKey, const void*>& tables() {
     static std::map<TableKey, const void*> m;
     return m;
 }
-enum TableKind { TK_STAGE = 1, TK_RTW, TK_FS_LO, TK_FS_HI, TK_CHIRP, TK_BLUE };
+enum TableKind { TK_STAGE = 1, TK_RTW, TK_FS_LO, TK_FS_HI, TK_CHIRP, TK_BLUE, TK_CR_LO, TK_CR_HI };
 
 static inline void unit_root(long double num, long double den, long double& c, long double& s) {
     // exp(-2*pi*i*num/den) in extended precision
@@ -238,6 +238,29 @@ bool table_fourstep(int prec, int64_t M, const void** lo, const void** hi, int* 
     if (!*hi) return false;
     *shift = sh;
     return true;
+}
+
+// two-level table of R(k) = exp(-i*pi*k/N), k < 2N (always f64): R(k) = hi[k >> shift] * lo[k & mask]
+bool table_chirp_roots(int64_t N, const void** lo, const void** hi, int* shift, PlanError& err) {
+    int lg = 0;
+    while (((int64_t)1 << lg) < 2 * N) ++lg;
+    const int sh = (lg + 1) / 2;
+    const int64_t nlo = (int64_t)1 << sh;
+    const int64_t nhi = (2 * N + nlo - 1) / nlo;
+    *lo = roots_table(TK_CR_LO, PREC_F64, nlo, (long double)(2 * N), 1.0L, N, err);
+    if (!*lo) return false;
+    *hi = roots_table(TK_CR_HI, PREC_F64, nhi, (long double)(2 * N), (long double)nlo, N, err);
+    if (!*hi) return false;
+    *shift = sh;
+    return true;
+}
+
+static bool chirp_gen_enabled() {
+    static int v = [] {
+        const char* e = getenv("SFC_CHIRP_GEN");
+        return e ? atoi(e) : 1;
+    }();
+    return v != 0;
 }
 
 const void* table_chirp(int prec, int64_t N, PlanError& err) {
@@ -363,6 +386,58 @@ static int row_split_len(int prec) {
     return 0;  // measured on B200: 8192-point f64 rows 52.3 % split vs 52.8 % single tile (interleaved 16 B stores)
 }
 
+// L2 blocking of multi-pass transforms (four-step, Bluestein): a round covers at most this many
+// bytes of work area so that pass k+1 reads what pass k wrote out of the 126 MB L2, and `ways`
+// rounds run concurrently on side streams to keep every SM busy.  0 = off.
+static int64_t l2_chunk_bytes() {
+    static int64_t v = [] {
+        const char* e = getenv("SFC_L2_CHUNK_MB");
+        // measured on B200 (2^20 x 64 four-step, Bluestein 1,000,003 x 32): no gain from L2-resident
+        // rounds (75.6 % either way / 56 % vs 61 %) — the 64 KiB-tile passes are SM-bound, not DRAM-bound
+        int64_t mb = e ? atoll(e) : 0;
+        return mb << 20;
+    }();
+    return v;
+}
+static int l2_ways() {
+    static int v = [] {
+        const char* e = getenv("SFC_L2_WAYS");
+        int w = e ? atoi(e) : 3;
+        return std::max(1, std::min(w, 16));
+    }();
+    return v;
+}
+static int64_t l2_max_batch_bytes() {
+    static int64_t v = [] {
+        const char* e = getenv("SFC_L2_MAXB_MB");
+        return e ? (atoll(e) << 20) : l2_chunk_bytes();
+    }();
+    return v;
+}
+static int64_t l2_total_bytes() {
+    static int64_t v = [] {
+        const char* e = getenv("SFC_L2_TOTAL_MB");
+        int64_t mb = e ? atoll(e) : 72;
+        return mb << 20;
+    }();
+    return v;
+}
+
+static int tile_group_log2() {
+    static int v = [] {
+        const char* e = getenv("SFC_TILE_GROUP_LOG2");
+        return e ? std::max(0, std::min(atoi(e), 10)) : 3;  // table-driven Bluestein 57 % -> 61 %; neutral with generated chirps
+    }();
+    return v;
+}
+static int blue_l1_cap() {
+    static int v = [] {
+        const char* e = getenv("SFC_BLUE_L1");
+        return e ? atoi(e) : 1024;
+    }();
+    return v;
+}
+
 static int64_t scratch_budget_bytes() {
     static int64_t v = [] {
         const char* e = getenv("SFC_WORK_MB");
@@ -454,6 +529,20 @@ struct PlanBuilder {
                 if (f) s.k = f;
             }
         }
+        if (s.p.flags & F_CHIRP_GEN) {
+            // q = exp(-i*pi*2*D^2/N) for the per-thread position step D = (L/E) * pos_es, phase reduced exactly
+            const int64_t tpl = s.k->L / s.k->E;
+            auto qfor = [&](int64_t pes, double* q) {
+                const unsigned __int128 D = (unsigned __int128)(tpl * pes);
+                const uint64_t r = (uint64_t)((2 * D * D) % (unsigned __int128)s.p.chirp_mod);
+                long double c, sn;
+                unit_root((long double)r, (long double)s.p.chirp_mod, c, sn);
+                q[0] = (double)c;
+                q[1] = (double)sn;
+            };
+            qfor(s.p.in.pos_es, s.p.chirp_q_in);
+            qfor(s.p.out.pos_es, s.p.chirp_q_out);
+        }
         char buf[256];
         snprintf(buf, sizeof buf, "%s: tile L=%d TL=%d%s%s threads=%d smem=%zu lanes=%lld batches=%lld map=%s->%s", what,
                  s.k->L, s.k->TL, s.k->dbl ? " fwd*tab*inv" : "",
@@ -470,9 +559,19 @@ struct PlanBuilder {
         g.nbatch = nbatch;
         g.chunk = std::max<int64_t>(1, scratch_budget_bytes() / std::max<int64_t>(bytes_per_batch, 1));
         g.chunk = std::min(g.chunk, nbatch);
-        // keep at least ~2 waves of tiles in flight is handled by the caller's tile sizes
+        g.slice_bytes = (size_t)g.chunk * (size_t)bytes_per_batch;
+        if (l2_chunk_bytes() > 0 && bytes_per_batch <= l2_max_batch_bytes() && nbatch > 1) {
+            const int64_t c = std::max<int64_t>(1, l2_chunk_bytes() / bytes_per_batch);
+            if (c < g.chunk) {
+                g.chunk = c;
+                g.slice_bytes = (size_t)c * (size_t)bytes_per_batch;
+                const int64_t rounds = (nbatch + c - 1) / c;
+                const int64_t fit = std::max<int64_t>(1, l2_total_bytes() / (int64_t)g.slice_bytes);
+                g.ways = (int)std::min<int64_t>(std::min<int64_t>(l2_ways(), fit), rounds);
+            }
+        }
         pl.groups_.push_back(g);
-        need_ms((size_t)g.chunk * (size_t)bytes_per_batch);
+        need_ms(g.slice_bytes * (size_t)g.ways);
         return (int)pl.groups_.size() - 1;
     }
 
@@ -648,8 +747,19 @@ struct PlanBuilder {
 
         // Bluestein chirp-z over a padded power-of-two convolution of length M >= 2n-1
         const int64_t M = next_pow2(2 * n - 1);
-        const void* chirp = table_chirp(prec, n, err);
-        if (!chirp) return false;
+        const bool gen = chirp_gen_enabled() && M > lmax && M < ((int64_t)1 << 31);
+        const void* chirp = gen ? nullptr : table_chirp(prec, n, err);
+        if (!gen && !chirp) return false;
+        const void *cr_lo = nullptr, *cr_hi = nullptr;
+        int cr_sh = 0;
+        if (gen && !table_chirp_roots(n, &cr_lo, &cr_hi, &cr_sh, err)) return false;
+        auto set_chirp_gen = [&](Step& st) {
+            st.p.flags |= F_CHIRP_GEN;
+            st.p.chirp_lo = cr_lo;
+            st.p.chirp_hi = cr_hi;
+            st.p.chirp_shift = cr_sh;
+            st.p.chirp_mod = (uint64_t)(2 * n);
+        };
         if (M <= lmax) {
             const void* bf = table_bluestein_b(prec, n, M, 0, 0, err);
             if (!bf) return false;
@@ -678,7 +788,7 @@ struct PlanBuilder {
         const int lg = ilog2_64(M);
         // column passes (A, C) like short lanes (two CTAs per SM with >= 64 B rows); the fused row
         // pass B takes whatever is left
-        int64_t L1 = std::min<int64_t>((int64_t)1 << (lg / 2), 1024);
+        int64_t L1 = std::min<int64_t>((int64_t)1 << (lg / 2), blue_l1_cap());
         int64_t L2 = M / L1;
         if (L2 > lmax) {
             L2 = lmax;
@@ -710,6 +820,7 @@ struct PlanBuilder {
             a.p.tw_shift = sh;
             a.p.flags = fl_in;
             a.p.scale = 1.0;
+            if (gen) set_chirp_gen(a);
             if (!finish_tile(a, L2 * I, I, O, "Bluestein pass A (chirp, pad, columns, twiddle)")) return false;
         }
         {
@@ -753,6 +864,7 @@ struct PlanBuilder {
             c.batch_fastest = true;
             c.p.flags = F_CONJ_LD_POST | F_CONJ_ST_PRE | fl_out;
             c.p.scale = scale;
+            if (gen) set_chirp_gen(c);
             dev_bytes += O * I * (std::min(n, src.n) * (int64_t)src_es + 5 * M * (int64_t)cs +
                                   std::min(n, dst.n) * (int64_t)dst_es);
             return finish_tile(c, L2 * I, I, O, "Bluestein pass C (inverse columns, chirp, crop)");
@@ -1068,6 +1180,29 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
 Plan::~Plan() {
     if (sa_) cudaFree(sa_);
     if (ms_) cudaFree(ms_);
+    for (cudaEvent_t e : side_done_) cudaEventDestroy(e);
+    for (cudaStream_t s : side_) cudaStreamDestroy(s);
+    if (fork_ev_) cudaEventDestroy(fork_ev_);
+}
+
+bool Plan::ensure_side_streams(int n, std::string& es) {
+    if (!fork_ev_ && cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming) != cudaSuccess) {
+        es = "cudaEventCreate failed";
+        return false;
+    }
+    while ((int)side_.size() < n) {
+        cudaStream_t s;
+        cudaEvent_t e;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+            es = "could not create the side streams of an L2-blocked plan";
+            cudaGetLastError();
+            return false;
+        }
+        side_.push_back(s);
+        side_done_.push_back(e);
+    }
+    return true;
 }
 
 std::string Plan::describe() const {
@@ -1083,8 +1218,8 @@ std::string Plan::describe() const {
         s += b;
         s += st.desc;
         if (st.group >= 0) {
-            snprintf(b, sizeof b, " [group %d: %lld batches, %lld per round]", st.group,
-                     (long long)groups_[st.group].nbatch, (long long)groups_[st.group].chunk);
+            snprintf(b, sizeof b, " [group %d: %lld batches, %lld per round, %d rounds in flight]", st.group,
+                     (long long)groups_[st.group].nbatch, (long long)groups_[st.group].chunk, groups_[st.group].ways);
             s += b;
         }
         s += "\n";
@@ -1093,6 +1228,38 @@ std::string Plan::describe() const {
 }
 
 // ------------------------------------------------------------------ Plan::exec
+
+#ifdef SFC_PHASE_TIMING
+static unsigned long long* g_dbg = nullptr;
+static int g_dbg_launch = 0;
+static std::vector<std::string> g_dbg_names;
+static unsigned long long* dbg_slot(const std::string& name) {
+    if (!g_dbg) {
+        cudaMalloc(&g_dbg, 256 * 16 * 8);
+        cudaMemset(g_dbg, 0, 256 * 16 * 8);
+    }
+    if (g_dbg_launch >= 256) return nullptr;
+    g_dbg_names.push_back(name);
+    return g_dbg + 16 * (g_dbg_launch++);
+}
+extern "C" __attribute__((visibility("default"))) void sfc_debug_phase_dump(void) {
+    cudaDeviceSynchronize();
+    std::vector<unsigned long long> h(256 * 16);
+    cudaMemcpy(h.data(), g_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+    for (int l = 0; l < g_dbg_launch; ++l) {
+        const unsigned long long* r = &h[16 * l];
+        const double n = (double)std::max<unsigned long long>(r[14], 1);
+        double tot = 0;
+        for (int k = 0; k < 7; ++k) tot += (double)r[k];
+        printf("launch %d ctas %llu cyc/cta %.0f :", l, r[14], tot / n);
+        for (int k = 0; k < 7; ++k) printf(" p%d %.0f", k, (double)r[k] / n);
+        printf("  | %s\n", g_dbg_names[l].substr(0, 60).c_str());
+    }
+    cudaMemset(g_dbg, 0, 256 * 16 * 8);
+    g_dbg_launch = 0;
+    g_dbg_names.clear();
+}
+#endif
 
 int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& es, void* const* scatter, int nscatter) {
     std::lock_guard<std::mutex> lk(mu_);
@@ -1143,6 +1310,9 @@ int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& 
                 es = "grid too large";
                 return SFC_ERR_VALUE;
             }
+#ifdef SFC_PHASE_TIMING
+            p.dbg = getenv("SFC_PHASE_DBG") ? dbg_slot(s.desc) : nullptr;
+#endif
             cudaError_t e = s.k->launch(p, (unsigned)grid, stream);
             if (e != cudaSuccess) return fail(e, s);
             ++i;
@@ -1152,25 +1322,50 @@ int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& 
         size_t j = i;
         while (j < steps_.size() && steps_[j].group == s.group) ++j;
         const Group& g = groups_[s.group];
-        for (int64_t b0 = 0; b0 < g.nbatch; b0 += g.chunk) {
+        const int ways = g.ways;
+        if (ways > 1) {
+            if (!ensure_side_streams(ways, es)) return SFC_ERR_BACKEND;
+            cudaEventRecord(fork_ev_, stream);
+            for (int w = 0; w < ways; ++w) cudaStreamWaitEvent(side_[w], fork_ev_, 0);
+        }
+        int64_t round = 0;
+        for (int64_t b0 = 0; b0 < g.nbatch; b0 += g.chunk, ++round) {
             const int64_t nb = std::min(g.chunk, g.nbatch - b0);
+            const int way = ways > 1 ? (int)(round % ways) : 0;
+            cudaStream_t st = ways > 1 ? side_[way] : stream;
             for (size_t k = i; k < j; ++k) {
                 Step& t = steps_[k];
                 PassParams p = t.p;
                 char* ib = base(t.src);
                 char* ob = base(t.dst);
+                if (t.src == R_MS) ib += (size_t)way * g.slice_bytes;
+                if (t.dst == R_MS) ob += (size_t)way * g.slice_bytes;
                 if (t.src != R_MS) ib += (size_t)b0 * (size_t)p.in.batch_stride * t.src_esize;
                 if (t.dst != R_MS) ob += (size_t)b0 * (size_t)p.out.batch_stride * t.dst_esize;
                 p.in.ptr = ib;
                 p.out.ptr = ob;
-                if (t.batch_fastest) p.nbatch_fast = (uint32_t)nb;
+                if (t.batch_fastest) {
+                    p.nbatch_fast = (uint32_t)nb;
+                    int sh = tile_group_log2();
+                    while (sh > 0 && (p.tiles_per_batch & ((1u << sh) - 1u))) --sh;
+                    p.tile_group_shift = (uint32_t)sh;
+                }
                 const uint64_t grid = (uint64_t)p.tiles_per_batch * (uint64_t)nb;
                 if (grid == 0 || grid > 0x7FFFFFFFULL) {
                     es = "grid too large";
                     return SFC_ERR_VALUE;
                 }
-                cudaError_t e = t.k->launch(p, (unsigned)grid, stream);
+#ifdef SFC_PHASE_TIMING
+                p.dbg = getenv("SFC_PHASE_DBG") ? dbg_slot(t.desc) : nullptr;
+#endif
+                cudaError_t e = t.k->launch(p, (unsigned)grid, st);
                 if (e != cudaSuccess) return fail(e, t);
+            }
+        }
+        if (ways > 1) {
+            for (int w = 0; w < ways; ++w) {
+                cudaEventRecord(side_done_[w], side_[w]);
+                cudaStreamWaitEvent(stream, side_done_[w], 0);
             }
         }
         i = j;

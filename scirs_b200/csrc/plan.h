@@ -41,6 +41,10 @@ struct Step {
 struct Group {
     int64_t nbatch = 1;
     int64_t chunk = 1;  // batches per launch round
+    // L2 blocking: `ways` rounds are in flight at once, each on its own side stream with its own
+    // slice of the work area, small enough that the passes of one round hand their data over in L2
+    int ways = 1;
+    size_t slice_bytes = 0;  // work-area bytes per round
 };
 
 struct PlanError {
@@ -74,6 +78,11 @@ class Plan {
     void* ms_ = nullptr;  // four-step / Bluestein work area
     size_t ms_bytes_ = 0;
     std::mutex mu_;
+    // side streams for L2-blocked rounds (created on first use, on the plan's device)
+    std::vector<cudaStream_t> side_;
+    std::vector<cudaEvent_t> side_done_;
+    cudaEvent_t fork_ev_ = nullptr;
+    bool ensure_side_streams(int n, std::string& es);
     friend struct PlanBuilder;
 };
 
@@ -84,6 +93,7 @@ inline int lmax_for(int prec) { return prec == PREC_F64 ? 8192 : 16384; }
 const void* table_stage_tw(int prec, int L, PlanError& err);                // W_L^j, j < L
 const void* table_rtw(int prec, int L, PlanError& err);                     // W_{2L}^i, i < max(L/16,1)
 bool table_fourstep(int prec, int64_t M, const void** lo, const void** hi, int* shift, PlanError& err);
+bool table_chirp_roots(int64_t N, const void** lo, const void** hi, int* shift, PlanError& err);  // R(k) = exp(-i*pi*k/N)
 const void* table_chirp(int prec, int64_t N, PlanError& err);               // exp(-i*pi*n^2/N), n < N
 // FFT_M(conj chirp, wrapped)/M ; layout: natural (L1 == 0) or [k1][k2] four-step order
 const void* table_bluestein_b(int prec, int64_t N, int64_t M, int64_t L1, int64_t L2, PlanError& err);
