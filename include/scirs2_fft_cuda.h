@@ -95,8 +95,22 @@ typedef struct sfc_desc {
      * the slab transpose of a distributed fftn fused into the FFT store (distributed.rs:232-268) */
     int32_t scatter_parts;
     int32_t reserved;
+    /* C2C over ONE axis, with SFC_DESC_AXIS_LEN: the input array holds axis_in_len elements along that
+     * axis (zero-padded / cropped to shape[axis] on load) and the output array axis_out_len (cropped on
+     * store); 0 = shape[axis].  What the reference does with `x.resize(n)` / `[..n]` slices around its
+     * transforms (dct.rs, hfft/*.rs, spectrogram.rs:287-300) without the extra copies. */
+    int64_t axis_in_len, axis_out_len;
+    /* with SFC_DESC_AUX_MUL: device tables (complex, plan precision) multiplied into the data on the way
+     * in (aux_in[j], j = input index along the axis, axis_in_len entries) and on the way out
+     * (aux_out[k], axis_out_len entries); either may be NULL.  Power-of-two lengths only. */
+    const void* aux_in;
+    const void* aux_out;
 } sfc_desc;
 #define SFC_DESC_CUSTOM_IN_SHAPE 1
+#define SFC_DESC_AXIS_LEN 4
+#define SFC_DESC_AUX_MUL 8
+/* C2C only: store the real part of the result into a real array */
+#define SFC_DESC_REAL_OUTPUT 16
 /* C2C only: the input array is real (imag = 0), as when the reference widens real input
  * to Complex64 before the transform (fft/algorithms.rs:71-102) */
 #define SFC_DESC_REAL_INPUT 2
@@ -218,6 +232,36 @@ int sfc_execute_batch(const double* inputs, double* outputs, int64_t count, int6
  * x: [batch][n] real -> out: [batch][n/2+1] complex (rfft) and back (irfft). */
 int sfc_rfft_batch(const void* x, int64_t batch, int64_t n, int prec, void* out);
 int sfc_irfft_batch(const void* x, int64_t batch, int64_t n, int prec, void* out);
+
+/* ------------------------------------------------- consumers of the hot path
+ * Each is an O(n) pre-pass, the FFT above and an O(n) post-pass in the reference; here the passes are
+ * device tables fused into the FFT kernels (power-of-two lengths) or element-wise kernels around them.
+ *
+ * sfc_dct / sfc_dst: dct, idct, dct2, idct2, dctn, idctn (dct.rs:56-420) and the dst family
+ * (dst.rs:48-405) in one entry point: C-order f64 array of `shape`, transform of `type` 1..4 applied
+ * along every listed axis in order (axes == NULL: all axes, dct.rs:317); `norm` "ortho" or anything
+ * else / NULL for the reference's un-normalised definitions (dct.rs:425-757, dst.rs:409-702). */
+int sfc_dct(const double* x, int32_t ndim, const int64_t* shape, const int32_t* axes, int32_t naxes,
+            int32_t type, int32_t inverse, const char* norm, double* out);
+int sfc_dst(const double* x, int32_t ndim, const int64_t* shape, const int32_t* axes, int32_t naxes,
+            int32_t type, int32_t inverse, const char* norm, double* out);
+/* hartley.rs:37-130, 202-209: H[k] = Re F[k] - Im F[k] with F = fft(x, None) (padded to the next power
+ * of two, first n bins kept — as the reference); idht = dht / n; dht2 (hartley.rs:133-200). */
+int sfc_dht(const double* x, int64_t n, double* out);
+int sfc_idht(const double* h, int64_t n, double* out);
+int sfc_dht2(const double* x, int64_t rows, int64_t cols, int32_t axis0, int32_t axis1, double* out);
+/* hfft/complex_to_real.rs:58-135 and hfft/real_to_complex.rs:49-149 */
+int sfc_hfft(const void* x, int64_t len, int dtype, int64_t n, double* out, int64_t out_cap, int64_t* out_len);
+int sfc_ihfft(const double* x, int64_t len, int64_t n, double* out, int64_t out_cap, int64_t* out_len);
+/* lib.rs:437-516: analytic signal, n complex values out */
+int sfc_hilbert(const double* x, int64_t n, double* out);
+/* spectrogram.rs:76-310 (stft) and :312-420 (spectrogram).  `window`: nperseg samples; noverlap / nfft < 0
+ * (or 0 for nfft) = the reference defaults nperseg/2 and nperseg; boundary 0 none, 1 "reflect", 2 "zeros",
+ * 3 "constant"; out_mode 0 complex [freq][frame], 1 |z|^2*scale ("psd"), 2 |z|*sqrt(scale) ("magnitude"),
+ * 3 phase in radians, 4 in degrees; out_cap_elems counts output elements. */
+int sfc_stft(const double* x, int64_t len, const double* window, int64_t nperseg, int64_t noverlap, int64_t nfft,
+             int32_t detrend, int32_t onesided, int32_t boundary, int32_t out_mode, double scale, void* out,
+             int64_t out_cap_elems, int64_t* freq_len, int64_t* frames);
 
 #ifdef __cplusplus
 }

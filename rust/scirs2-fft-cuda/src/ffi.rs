@@ -23,6 +23,10 @@ pub struct sfc_desc {
     pub in_shape: [i64; SFC_MAX_DIMS],
     pub scatter_parts: i32,
     pub reserved: i32,
+    pub axis_in_len: i64,
+    pub axis_out_len: i64,
+    pub aux_in: *const core::ffi::c_void,
+    pub aux_out: *const core::ffi::c_void,
 }
 
 #[repr(C)]

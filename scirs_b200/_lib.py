@@ -29,6 +29,9 @@ SFC_PREC_F32, SFC_PREC_F64 = 0, 1
 SFC_FORWARD, SFC_INVERSE = 0, 1
 SFC_DESC_CUSTOM_IN_SHAPE = 1
 SFC_DESC_REAL_INPUT = 2
+SFC_DESC_AXIS_LEN = 4
+SFC_DESC_AUX_MUL = 8
+SFC_DESC_REAL_OUTPUT = 16
 
 
 class sfc_desc(C.Structure):
@@ -45,6 +48,10 @@ class sfc_desc(C.Structure):
         ("in_shape", C.c_int64 * SFC_MAX_DIMS),
         ("scatter_parts", C.c_int32),
         ("reserved", C.c_int32),
+        ("axis_in_len", C.c_int64),
+        ("axis_out_len", C.c_int64),
+        ("aux_in", C.c_void_p),
+        ("aux_out", C.c_void_p),
     ]
 
 
@@ -126,6 +133,15 @@ SIGNATURES = {
     "sfc_execute_batch": (_int, [_vp, _vp, _i64, _i64, _int]),
     "sfc_rfft_batch": (_int, [_vp, _i64, _i64, _int, _vp]),
     "sfc_irfft_batch": (_int, [_vp, _i64, _i64, _int, _vp]),
+    "sfc_dct": (_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _str, _vp]),
+    "sfc_dst": (_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _str, _vp]),
+    "sfc_dht": (_int, [_vp, _i64, _vp]),
+    "sfc_idht": (_int, [_vp, _i64, _vp]),
+    "sfc_dht2": (_int, [_vp, _i64, _i64, _i32, _i32, _vp]),
+    "sfc_hfft": (_int, [_vp, _i64, _int, _i64, _vp, _i64, _vp]),
+    "sfc_ihfft": (_int, [_vp, _i64, _i64, _vp, _i64, _vp]),
+    "sfc_hilbert": (_int, [_vp, _i64, _vp]),
+    "sfc_stft": (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, C.c_double, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "api_internal.h"
 #include "plan.h"
 
 using namespace sfc;
@@ -26,16 +27,19 @@ void set_error(int code, const std::string& msg) {
 }
 }  // namespace sfc
 
-static int fail(int code, const std::string& msg) {
+namespace sfc_api {
+int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
 
-static int cuda_fail(cudaError_t e, const char* what) {
+int cuda_fail(cudaError_t e, const char* what) {
     cudaGetLastError();
     const int code = (e == cudaErrorMemoryAllocation) ? SFC_ERR_MEMORY : SFC_ERR_BACKEND;
     return fail(code, std::string(what) + ": " + cudaGetErrorString(e));
 }
+}  // namespace sfc_api
+using namespace sfc_api;
 
 // ------------------------------------------------------------- plan handle
 
@@ -101,6 +105,14 @@ CacheKey make_key(const sfc_desc& d) {
     k.flags = d.flags;
     k.scale = d.scale;
     k.scatter_parts = d.scatter_parts;
+    if (d.flags & SFC_DESC_AXIS_LEN) {
+        k.axis_in_len = d.axis_in_len;
+        k.axis_out_len = d.axis_out_len;
+    }
+    if (d.flags & SFC_DESC_AUX_MUL) {
+        k.aux_in = d.aux_in;
+        k.aux_out = d.aux_out;
+    }
     if (d.flags & SFC_DESC_CUSTOM_IN_SHAPE)
         for (int i = 0; i < d.ndim && i < SFC_MAX_DIMS; ++i) k.in_shape[i] = d.in_shape[i];
     int dev = 0;
@@ -165,6 +177,10 @@ std::shared_ptr<Plan> get_or_create_plan(const sfc_desc& d, PlanError& err) {
 }
 
 }  // namespace
+
+namespace sfc_api {
+std::shared_ptr<Plan> cached_plan(const sfc_desc& d, PlanError& err) { return get_or_create_plan(d, err); }
+}  // namespace sfc_api
 
 // ------------------------------------------------------------------ runtime
 
@@ -293,7 +309,7 @@ extern "C" __attribute__((visibility("default"))) int sfc_stream_synchronize(voi
     return SFC_OK;
 }
 
-static int ensure(void** p, size_t* cap, size_t bytes) {
+int sfc_api::ensure_buf(void** p, size_t* cap, size_t bytes) {
     if (*cap >= bytes && *p) return SFC_OK;
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -360,8 +376,8 @@ extern "C" __attribute__((visibility("default"))) int sfc_exec_host(sfc_plan* pl
     if (!plan || !h_in || !h_out) return fail(SFC_ERR_VALUE, "null argument");
     Plan& p = *plan->p;
     int rc;
-    if ((rc = ensure(&plan->d_in, &plan->in_cap, (size_t)p.info.in_bytes)) != SFC_OK) return rc;
-    if ((rc = ensure(&plan->d_out, &plan->out_cap, (size_t)p.info.out_bytes)) != SFC_OK) return rc;
+    if ((rc = ensure_buf(&plan->d_in, &plan->in_cap, (size_t)p.info.in_bytes)) != SFC_OK) return rc;
+    if ((rc = ensure_buf(&plan->d_out, &plan->out_cap, (size_t)p.info.out_bytes)) != SFC_OK) return rc;
     if (!plan->stream) {
         cudaError_t e = cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
@@ -441,80 +457,8 @@ extern "C" __attribute__((visibility("default"))) int sfc_cache_configure(uint64
 
 // ====================================================== drop-in free functions
 
-namespace {
+namespace sfc_api {
 
-inline bool dtype_is_complex(int dt) { return dt == SFC_C64 || dt == SFC_C128; }
-inline bool dtype_is_f64(int dt) { return dt == SFC_F64 || dt == SFC_C128; }
-inline size_t dtype_bytes(int dt) {
-    switch (dt) {
-        case SFC_F32: return 4;
-        case SFC_F64: return 8;
-        case SFC_C64: return 8;
-        default: return 16;
-    }
-}
-inline bool dtype_ok(int dt) { return dt >= SFC_F32 && dt <= SFC_C128; }
-
-inline int64_t next_pow2_i64(int64_t n) {
-    int64_t p = 1;
-    while (p < n) p <<= 1;
-    return p;
-}
-
-// NormMode / parse_norm_mode, fft/algorithms.rs:19-50
-enum NormMode { NM_NONE, NM_BACKWARD, NM_ORTHO, NM_FORWARD };
-NormMode parse_norm_mode(const char* norm, bool inverse) {
-    if (!norm) return inverse ? NM_BACKWARD : NM_NONE;
-    if (!strcmp(norm, "backward")) return NM_BACKWARD;
-    if (!strcmp(norm, "ortho")) return NM_ORTHO;
-    if (!strcmp(norm, "forward")) return NM_FORWARD;
-    return NM_NONE;
-}
-// forward transforms: algorithms.rs:385-395 / 693-703 ; inverse: :528-534 / :876-884
-double norm_scale(NormMode m, bool inverse, double total) {
-    switch (m) {
-        case NM_NONE: return 1.0;
-        case NM_BACKWARD: return 1.0 / total;
-        case NM_ORTHO: return 1.0 / std::sqrt(total);
-        case NM_FORWARD: return inverse ? 1.0 : 1.0 / total;
-    }
-    return 1.0;
-}
-
-// per-thread device workspace for the host-pointer entry points
-struct Workspace {
-    void* buf[3] = {nullptr, nullptr, nullptr};
-    size_t cap[3] = {0, 0, 0};
-    cudaStream_t stream = nullptr;
-    int device = -1;
-    ~Workspace() {
-        for (int i = 0; i < 3; ++i)
-            if (buf[i]) cudaFree(buf[i]);
-        if (stream) cudaStreamDestroy(stream);
-    }
-    int get(int slot, size_t bytes, void** out) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev != device) {
-            for (int i = 0; i < 3; ++i) {
-                if (buf[i]) cudaFree(buf[i]);
-                buf[i] = nullptr;
-                cap[i] = 0;
-            }
-            if (stream) cudaStreamDestroy(stream);
-            stream = nullptr;
-            device = dev;
-        }
-        if (!stream) {
-            cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
-        }
-        int rc = ensure(&buf[slot], &cap[slot], bytes);
-        if (rc != SFC_OK) return rc;
-        *out = buf[slot];
-        return SFC_OK;
-    }
-};
 thread_local Workspace g_ws;
 
 int require_device() {
@@ -582,7 +526,7 @@ int run_c2c_host(const void* x, const std::vector<int64_t>& in_shape, int dtype,
         src = d_work;
     }
     PlanError perr{0, ""};
-    std::shared_ptr<Plan> p = get_or_create_plan(d, perr);
+    std::shared_ptr<Plan> p = cached_plan(d, perr);
     if (!p) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
     std::string es;
     rc = p->exec(src, d_work, s, es);
@@ -599,6 +543,10 @@ int download(void* h, const void* d, size_t bytes) {
     if (e != cudaSuccess) return cuda_fail(e, "transform execution");
     return SFC_OK;
 }
+
+}  // namespace sfc_api
+
+namespace {
 
 int fft1d_common(const void* x, int64_t len, int dtype, int64_t n, bool inverse, double* out, int64_t out_cap,
                  int64_t* out_len) {
@@ -686,7 +634,7 @@ extern "C" __attribute__((visibility("default"))) int sfc_rfft(const void* x, in
     d.prec = SFC_PREC_F64;
     d.scale = 1.0;
     PlanError perr{0, ""};
-    std::shared_ptr<Plan> p = get_or_create_plan(d, perr);
+    std::shared_ptr<Plan> p = cached_plan(d, perr);
     if (!p) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
     std::string es;
     rc = p->exec(src, d_outb, s, es);
@@ -739,7 +687,7 @@ extern "C" __attribute__((visibility("default"))) int sfc_irfft(const void* x, i
         d.prec = SFC_PREC_F64;
         d.scale = 1.0 / (double)n_output;
         PlanError perr{0, ""};
-        std::shared_ptr<Plan> p = get_or_create_plan(d, perr);
+        std::shared_ptr<Plan> p = cached_plan(d, perr);
         if (!p) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
         std::string es;
         rc = p->exec(d_in, d_o, s, es);
@@ -1139,7 +1087,7 @@ extern "C" __attribute__((visibility("default"))) int sfc_irfftn(const void* x, 
     d.scale = scale;
     d.flags = SFC_DESC_CUSTOM_IN_SHAPE;
     PlanError perr{0, ""};
-    std::shared_ptr<Plan> p = get_or_create_plan(d, perr);
+    std::shared_ptr<Plan> p = cached_plan(d, perr);
     if (!p) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
     std::string es;
     rc = p->exec(src, d_o, s, es);

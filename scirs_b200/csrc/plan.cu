@@ -462,6 +462,10 @@ struct PlanBuilder {
     PlanError& err;
     int64_t dev_bytes = 0;
     int scatter_parts = 0;  // > 1: the next single-pass axis stores through the scatter table
+    // SFC_DESC_AUX_MUL: tables multiplied into the next axis on load (indexed by input position) and
+    // on store (indexed by output position); power-of-two lengths only
+    const void* aux_in = nullptr;
+    const void* aux_out = nullptr;
 
     bool fail(int code, const std::string& m) {
         err = {code, m};
@@ -618,6 +622,8 @@ struct PlanBuilder {
         const bool col = I > 1;
         if (O <= 0 || I <= 0 || n <= 0) return fail(SFC_ERR_VALUE, "empty transform axis");
 
+        if ((aux_in || aux_out) && (!is_pow2(n) || n == 1 || n > (int64_t)lmax * lmax))
+            return fail(SFC_ERR_NOT_IMPLEMENTED, "fused table multiplies need a power-of-two transform length");
         if (n == 1) {
             // length-1 DFT is the identity
             std::vector<int64_t> ss{O, src.n, I}, ds{O, dst.n, I};
@@ -675,6 +681,14 @@ struct PlanBuilder {
             s.p.map_in = s.p.map_out = col ? MAP_COL : MAP_ROW;
             s.p.ld_op = src.real ? LD_R : LD_C;
             s.p.st_op = ST_C;
+            if (aux_in) {
+                s.p.ld_op = src.real ? LD_R_MUL : LD_C_MUL;
+                s.p.aux_in = aux_in;
+            }
+            if (aux_out) {
+                s.p.st_op = ST_MUL;
+                s.p.aux_out = aux_out;
+            }
             s.p.flags = fl_in | fl_out;
             s.p.scale = scale;
             dev_bytes += O * I * (std::min(n, src.n) * (int64_t)src_es + std::min(n, dst.n) * (int64_t)dst_es);
@@ -718,6 +732,10 @@ struct PlanBuilder {
             set_io(a.p.out, n * I, I, 1, L2 * I, n, L2, 1);
             a.p.map_in = a.p.map_out = MAP_COL;
             a.p.ld_op = src.real ? LD_R : LD_C;
+            if (aux_in) {
+                a.p.ld_op = src.real ? LD_R_MUL : LD_C_MUL;
+                a.p.aux_in = aux_in;
+            }
             a.p.st_op = ST_TW;
             a.p.tw_lo = lo;
             a.p.tw_hi = hi;
@@ -738,6 +756,10 @@ struct PlanBuilder {
             b.p.map_out = MAP_COL;
             b.p.ld_op = LD_C;
             b.p.st_op = ST_C;
+            if (aux_out) {
+                b.p.st_op = ST_MUL;
+                b.p.aux_out = aux_out;
+            }
             b.p.flags = fl_out;
             b.p.scale = scale;
             dev_bytes += O * I * (std::min(n, src.n) * (int64_t)src_es + 2 * n * (int64_t)cs +
@@ -988,7 +1010,26 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
         pl.in_esize = pl.out_esize = cs;
         const bool inv = d.direction == SFC_INVERSE;
         const bool real_in = (d.flags & SFC_DESC_REAL_INPUT) != 0;
+        const bool real_out = (d.flags & SFC_DESC_REAL_OUTPUT) != 0;
         if (real_in) pl.in_esize = rs;
+        if (real_out) pl.out_esize = rs;
+        int64_t ax_in = 0, ax_out = 0;  // custom extents of the (single) transformed axis
+        if (d.flags & (SFC_DESC_AXIS_LEN | SFC_DESC_AUX_MUL | SFC_DESC_REAL_OUTPUT)) {
+            if (axes.size() != 1 || d.scatter_parts > 1) {
+                err = {SFC_ERR_VALUE, "axis_in_len / axis_out_len / aux tables / real output need exactly one axis"};
+                return nullptr;
+            }
+            if (d.flags & SFC_DESC_AXIS_LEN) {
+                ax_in = d.axis_in_len > 0 ? d.axis_in_len : shape[axes[0]];
+                ax_out = d.axis_out_len > 0 ? d.axis_out_len : shape[axes[0]];
+                pl.in_elems = total / shape[axes[0]] * ax_in;
+                pl.out_elems = total / shape[axes[0]] * ax_out;
+            }
+            if (d.flags & SFC_DESC_AUX_MUL) {
+                B.aux_in = d.aux_in;
+                B.aux_out = d.aux_out;
+            }
+        }
         if (axes.empty()) {
             ok = B.add_copy({R_IN, real_in, 1}, {R_OUT, false, 1}, shape, shape, d.scale);
         }
@@ -1008,8 +1049,10 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
             // with a scatter the intermediate passes must not touch the caller's outputs: use scratch
             const int mid_role = d.scatter_parts > 1 ? R_SA : R_OUT;
             if (d.scatter_parts > 1) B.need_sa((size_t)total * cs);
-            ok = B.add_axis(n, O, I, {i == 0 ? R_IN : mid_role, i == 0 && real_in, n}, {last ? R_OUT : mid_role, false, n},
-                            inv, last ? d.scale : 1.0, false);
+            ok = B.add_axis(n, O, I, {i == 0 ? R_IN : mid_role, i == 0 && real_in, ax_in ? ax_in : n},
+                            {last ? R_OUT : mid_role, false, ax_out ? ax_out : n}, inv, last ? d.scale : 1.0,
+                            last && real_out);
+            B.aux_in = B.aux_out = nullptr;
             B.scatter_parts = 0;
             const int ap = axis_passes(n);
             passes += ap;

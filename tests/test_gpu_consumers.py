@@ -1,0 +1,181 @@
+"""GPU: the consumers of the FFT hot path (DCT/DST, Hartley, hfft/ihfft, hilbert,
+stft/spectrogram) through the C ABI against oracle/consumers_oracle.py.  f64 bar: rel-L2 <= 1e-12."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def sb(build_artifacts):
+    import scirs_b200 as m
+    from scirs_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.sfc_device_count() >= 1, "GPU tests need a CUDA device"
+    m.error.check(lib.sfc_init(0))
+    return m
+
+
+@pytest.fixture(scope="module")
+def co():
+    from oracle import consumers_oracle as o
+
+    return o
+
+
+def rel(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    d = np.linalg.norm((a - b).ravel()); r = np.linalg.norm(b.ravel())
+    return d / r if r > 0 else d
+
+
+# lengths: powers of two (fused single-kernel path), P = 2n not a power of two (Bluestein + explicit passes),
+# n = 2^k +- 1 (types I: P = 2(n -+ 1) is a power of two), and one four-step size
+@pytest.mark.parametrize("kind", ["dct", "dst"])
+@pytest.mark.parametrize("t", [1, 2, 3, 4])
+@pytest.mark.parametrize("n", [2, 3, 4, 7, 8, 9, 16, 33, 100, 255, 256, 257, 1000, 4096])
+def test_dct_dst_all_types_norms_directions(sb, co, kind, t, n):
+    rng = np.random.default_rng(1000 * t + n)
+    x = rng.standard_normal(n)
+    for norm in (None, "ortho"):
+        for inv in (False, True):
+            name = ("i" if inv else "") + kind
+            got = getattr(sb, name)(x, t, norm)
+            ref = getattr(co, name)(x, t, norm)
+            assert rel(got, ref) <= TOL, (name, t, n, norm, rel(got, ref))
+
+
+def test_dct_large_four_step_and_bluestein(sb, co):
+    rng = np.random.default_rng(3)
+    import scipy.fft as sf
+    for n in (16384, 65536, 30000):  # P = 2n: 32768 / 131072 (four-step, fused) and 60000 (three-pass Bluestein)
+        x = rng.standard_normal(n)
+        assert rel(sb.dct(x, 2, None), sf.dct(x, 2) / 2) <= TOL      # same sums as the oracle (tests/test_consumers_oracle.py)
+        assert rel(sb.dct(x, 4, "ortho"), sf.dct(x, 4, norm="ortho")) <= TOL
+        assert rel(sb.dst(x, 2, None), sf.dst(x, 2) / 2) <= TOL
+        assert rel(sb.idct(sb.dct(x, 2, "ortho"), 2, "ortho"), x) <= TOL
+
+
+def test_dct_dst_nd(sb, co):
+    rng = np.random.default_rng(4)
+    a = rng.standard_normal((6, 16, 10))
+    for t in (1, 2, 3, 4):
+        assert rel(sb.dctn(a, t, "ortho"), co.dctn(a, t, "ortho")) <= TOL
+        assert rel(sb.idctn(a, t, None, [2, 0]), co.idctn(a, t, None, [2, 0])) <= TOL
+        assert rel(sb.dstn(a, t, None, [1]), co.dstn(a, t, None, [1])) <= TOL
+        assert rel(sb.idstn(a, t, "ortho"), co.idstn(a, t, "ortho")) <= TOL
+    m = rng.standard_normal((32, 48))
+    assert rel(sb.dct2(m, 2, "ortho"), co.dct2(m, 2, "ortho")) <= TOL
+    assert rel(sb.idct2(m, 2, "ortho"), co.idct2(m, 2, "ortho")) <= TOL
+    assert rel(sb.dst2(m, 3), co.dst2(m, 3)) <= TOL
+    assert rel(sb.idst2(m, 1, "ortho"), co.idst2(m, 1, "ortho")) <= TOL
+    # reference unit tests (dct.rs:757-768, 826-840, 843-862)
+    sig = np.array([1.0, 2.0, 3.0, 4.0])
+    assert np.allclose(sb.idct(sb.dct(sig, sb.DCTType.Type2, "ortho"), sb.DCTType.Type2, "ortho"), sig, atol=1e-10)
+    c = sb.dct(np.full(4, 3.0), sb.DCTType.Type2, None)
+    assert abs(c[0]) > 1e-10 and np.all(np.abs(c[1:]) < 1e-10)
+    arr = np.array([[1.0, 2.0], [3.0, 4.0]])
+    assert np.allclose(sb.idct2(sb.dct2(arr, None, "ortho"), None, "ortho"), arr, atol=1e-10)
+
+
+def test_dct_errors(sb):
+    with pytest.raises(sb.ValueError_) as e:
+        sb.dct([1.0], sb.DCTType.Type1)
+    assert "at least 2 elements for DCT-I" in str(e.value)
+    with pytest.raises(sb.ValueError_) as e:
+        sb.idst([1.0], sb.DSTType.Type1)
+    assert "at least 2 elements for IDST-I" in str(e.value)
+    with pytest.raises(sb.ValueError_):
+        sb.dct([], None)
+
+
+def test_fused_and_unfused_paths_agree(sb, co, monkeypatch):
+    # the explicit pre/post-pass path is what non-power-of-two lengths use; force it for a power of two too
+    import subprocess, sys
+    code = ("import numpy as np, scirs_b200 as sb; from oracle import consumers_oracle as co;"
+            "x=np.random.default_rng(1).standard_normal((3,64,5));"
+            "e=max(np.linalg.norm(sb.dctn(x,t,'ortho',[1])-co.dctn(x,t,'ortho',[1]))/np.linalg.norm(co.dctn(x,t,'ortho',[1])) for t in (1,2,3,4));"
+            "print(e); assert e<1e-12")
+    env = dict(os.environ, SFC_EXT_FUSE="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 5, 16, 100, 1024, 5000])
+def test_hartley(sb, co, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    assert rel(sb.dht(x), co.dht(x)) <= TOL
+    assert rel(sb.idht(x), co.idht(x)) <= TOL
+    assert rel(sb.fht(x), co.dht(x)) <= TOL
+
+
+def test_hartley_reference_tests_and_2d(sb, co):
+    x = np.array([1.0, 2.0, 3.0, 4.0])
+    assert np.allclose(sb.idht(sb.dht(x)), x, atol=1e-10)  # hartley.rs:216-231
+    a = np.random.default_rng(2).standard_normal((12, 20))
+    for axes in (None, (0, 1), (1, 0), (0, 0), (1, 1)):
+        assert rel(sb.dht2(a, axes), co.dht2(a, axes)) <= TOL
+    with pytest.raises(sb.ValueError_):
+        sb.dht2(a, (0, 2))
+    with pytest.raises(sb.ValueError_):
+        sb.dht(np.array([]))
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 64, 1000])
+def test_hfft_ihfft_hilbert(sb, co, n):
+    rng = np.random.default_rng(n + 7)
+    z = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    assert rel(sb.hfft(z), co.hfft(z)) <= TOL
+    assert rel(sb.hfft(z, n + 5), co.hfft(z, n + 5)) <= TOL
+    assert rel(sb.hfft(z.real), co.hfft(z.real)) <= TOL
+    x = rng.standard_normal(n)
+    assert rel(sb.ihfft(x), co.ihfft(x)) <= TOL
+    assert rel(sb.ihfft(x, n + 3), co.ihfft(x, n + 3)) <= TOL
+    if n > 2:
+        assert rel(sb.ihfft(x, n - 1), co.ihfft(x, n - 1)) <= TOL
+    assert rel(sb.hilbert(x), co.hilbert(x)) <= TOL
+    assert rel(sb.hilbert(z), co.hilbert(z)) <= TOL  # complex input: real part only (lib.rs:455-463)
+
+
+def test_stft_spectrogram(sb, co):
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(5000)
+    for args in (dict(window="hann", nperseg=256), dict(window="hamming", nperseg=100, noverlap=25, nfft=128),
+                 dict(window="blackman", nperseg=64, noverlap=0, detrend=False),
+                 dict(window="rectangular", nperseg=128, return_onesided=False),
+                 dict(window="hann", nperseg=200, nfft=256, boundary="reflect", fs=48000.0),
+                 dict(window="hann", nperseg=64, boundary="zeros"), dict(window="hann", nperseg=64, boundary="constant")):
+        f, t, z = sb.stft(x, **args)
+        fr, tr, zr = co.stft(x, **args)
+        assert np.allclose(f, fr) and np.allclose(t, tr)
+        assert rel(z, zr) <= TOL, (args, rel(z, zr))
+    for mode in ("psd", "magnitude"):
+        for scaling in ("density", "spectrum"):
+            f, t, p = sb.spectrogram(x, 100.0, "hann", 128, 64, None, True, scaling, mode)
+            fr, tr, pr = co.spectrogram(x, 100.0, "hann", 128, 64, None, True, scaling, mode)
+            assert rel(p, pr) <= TOL
+    # phases: compare as unit vectors (atan2 at +-pi)
+    f, t, p = sb.spectrogram(x, None, None, 128, None, None, None, None, "phase")
+    _, _, pr = co.spectrogram(x, None, None, 128, None, None, None, None, "phase")
+    assert np.max(np.abs(np.exp(1j * p) - np.exp(1j * pr))) < 1e-9
+    f, t, p = sb.spectrogram(x, None, None, 128, None, None, None, None, "angle")
+    assert np.max(np.abs(np.exp(1j * p * np.pi / 180) - np.exp(1j * pr))) < 1e-9
+    with pytest.raises(sb.ValueError_):
+        sb.stft(x, "hann", 128, 128)
+    with pytest.raises(sb.ValueError_):
+        sb.stft(x, "hann", 128, 64, 64)
+    with pytest.raises(sb.ValueError_):
+        sb.spectrogram(x, scaling="bogus")
+    with pytest.raises(sb.ValueError_):
+        sb.stft([], "hann", 16)
+    w = np.hanning(50)
+    _, _, z = sb.stft(x, w, 50, 10, 64)
+    _, _, zr = co.stft(x, w, 50, 10, 64)
+    assert rel(z, zr) <= TOL
