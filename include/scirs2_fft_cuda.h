@@ -263,6 +263,17 @@ int sfc_stft(const double* x, int64_t len, const double* window, int64_t nperseg
              int32_t detrend, int32_t onesided, int32_t boundary, int32_t out_mode, double scale, void* out,
              int64_t out_cap_elems, int64_t* freq_len, int64_t* frames);
 
+/* ------------------------------------------------- SURVEY 8f rank 2 (what benches/fft_benchmarks.rs times)
+ * memory_efficient.rs:89-190 (fft_inplace: result written to BOTH buffers; returns n), :243-397 (fft2_efficient,
+ * out_rows/out_cols < 0 = input shape), :401-580 (fft_streaming: chunk_size <= 0 = the reference default;
+ * chunked mode concatenates independent per-chunk transforms exactly as the reference does) and
+ * ndim_optimized.rs:17-58 (fftn_optimized on a real f64 array; axes == NULL: all). */
+int sfc_fft_inplace(double* input, int64_t n, double* output, int64_t out_len, int32_t inverse, int32_t normalize);
+int sfc_fft2_efficient(const void* x, int64_t rows, int64_t cols, int dtype, int64_t out_rows, int64_t out_cols,
+                       int32_t inverse, int32_t normalize, double* out);
+int sfc_fft_streaming(const void* x, int64_t len, int dtype, int64_t n, int32_t inverse, int64_t chunk_size, double* out);
+int sfc_fftn_optimized(const double* x, int32_t ndim, const int64_t* shape, const int32_t* axes, int32_t naxes, double* out);
+
 #ifdef __cplusplus
 }
 #endif

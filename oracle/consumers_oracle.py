@@ -461,3 +461,76 @@ def spectrogram(x, fs=None, window=None, nperseg=None, noverlap=None, nfft=None,
     else:
         raise OracleError("ValueError", f"Unknown mode: {mode}. Use 'psd', 'magnitude', 'angle', or 'phase'.")
     return freqs, times, r
+
+
+# ----------------------------------------------------------------------------- memory_efficient.rs / ndim_optimized.rs
+
+def fft_inplace(inp: np.ndarray, out: np.ndarray, inverse: bool = False, normalize: bool = False) -> int:
+    """memory_efficient.rs:89-190 with simd_support_available() == true (x86_64 / aarch64)."""
+    n = inp.size
+    if n == 0:
+        raise OracleError("ValueError", "Input array is empty")
+    if out.size < n:
+        raise OracleError("ValueError", f"Output buffer is too small: got {out.size}, need {n}")
+    if n >= 32:
+        # fft_adaptive / ifft_adaptive ignore the 1-D norm (simd_fft.rs:37-60): fft(x, None) / ifft(x, None)
+        r = base.ifft(inp, None) if inverse else base.fft(inp, None)
+        if r.size > n:
+            raise OracleError("ValueError", "index out of bounds in the reference")
+    else:
+        r = base._process(np.asarray(inp, dtype=np.complex128).copy(), inverse) * (1.0 / n if normalize else 1.0)
+    inp[:n] = r[:n]
+    out[:n] = r[:n]
+    return n
+
+
+def fft2_efficient(x, shape=None, inverse: bool = False, normalize: bool = False) -> np.ndarray:  # :243-397
+    a = np.asarray(x)
+    r, c = a.shape if shape is None else shape
+    if r == 0 or c == 0:
+        raise OracleError("ValueError", "Output dimensions must be positive")
+    buf = np.zeros((r, c), dtype=np.complex128)
+    buf[:min(r, a.shape[0]), :min(c, a.shape[1])] = a[:min(r, a.shape[0]), :min(c, a.shape[1])]
+    for i in range(r):
+        buf[i, :] = base._process(buf[i, :].copy(), inverse)
+    for j in range(c):
+        buf[:, j] = base._process(buf[:, j].copy(), inverse)
+    return buf * (1.0 / (r * c) if normalize else 1.0)
+
+
+def fft_streaming(x, n=None, inverse: bool = False, chunk_size=None) -> np.ndarray:  # :401-580
+    a = np.asarray(x).reshape(-1).astype(np.complex128)
+    L = a.size
+    n_val = L if n is None else n
+    chunk = chunk_size if chunk_size is not None else (1_048_576 if L > 1_000_000 else (65_536 if L > 100_000 else L))
+    if L <= chunk or n_val <= chunk:
+        c = np.zeros(n_val, dtype=np.complex128)
+        m = min(n_val, L)
+        c[:m] = a[:m]
+        return base._process(c, inverse) * (1.0 / n_val if inverse else 1.0)
+    chunk = max(chunk, 1)
+    res = []
+    for start in range(0, n_val, chunk):
+        end = min(start + chunk, n_val)
+        c = np.zeros(end - start, dtype=np.complex128)
+        if start < L:
+            e2 = min(end, L)
+            c[:e2 - start] = a[start:e2]
+        res.append(base._process(c, inverse) * (1.0 / (end - start) if inverse else 1.0))
+    r = np.concatenate(res)
+    if inverse:
+        r = r * ((1.0 / n_val) / (1.0 / chunk))
+    return r
+
+
+def fftn_optimized(x, shape=None, axes=None) -> np.ndarray:  # ndim_optimized.rs:17-58
+    r = np.asarray(x, dtype=np.float64).astype(np.complex128)
+    axes = list(range(r.ndim)) if axes is None else list(axes)
+    for ax in axes:
+        if ax >= r.ndim:
+            raise OracleError("ValueError", f"Axis {ax} is out of bounds for array with {r.ndim} dimensions")
+    order = sorted(axes, key=lambda ax: int(np.prod(r.shape[ax + 1:])))
+    for ax in order:
+        n = r.shape[ax]
+        r = np.apply_along_axis(lambda lane: base.fft(lane, None)[:n], ax, r)
+    return r

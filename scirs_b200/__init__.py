@@ -12,7 +12,8 @@ from .fft import (fft, ifft, rfft, irfft, fft2, ifft2, fft2_parallel, ifft2_para
                   ifft_adaptive, fft2_simd, fft2_adaptive, fftn_simd, fftn_adaptive, ifft2_simd, ifftn_simd,
                   rfft_simd, irfft_simd, rfft_adaptive, irfft_adaptive, rfft_batch, irfft_batch)
 from .consumers import (DCTType, DSTType, dct, idct, dct2, idct2, dctn, idctn, dst, idst, dst2, idst2, dstn, idstn,
-                        dht, idht, dht2, fht, hfft, ihfft, hilbert, get_window, stft, spectrogram)
+                        dht, idht, dht2, fht, hfft, ihfft, hilbert, get_window, stft, spectrogram, FftMode, fft_inplace,
+                        process_in_chunks, fft2_efficient, fft_streaming, fftn_optimized)
 from .plan import FftPlan, FftPlanExecutor
 from .plan_cache import PlanCache, CacheStats, get_global_cache
 from .backend import FftBackend, CudaFftBackend, BackendManager, BackendContext, get_backend_manager

@@ -141,6 +141,10 @@ SIGNATURES = {
     "sfc_hfft": (_int, [_vp, _i64, _int, _i64, _vp, _i64, _vp]),
     "sfc_ihfft": (_int, [_vp, _i64, _i64, _vp, _i64, _vp]),
     "sfc_hilbert": (_int, [_vp, _i64, _vp]),
+    "sfc_fft_inplace": (_int, [_vp, _i64, _vp, _i64, _i32, _i32]),
+    "sfc_fft2_efficient": (_int, [_vp, _i64, _i64, _int, _i64, _i64, _i32, _i32, _vp]),
+    "sfc_fft_streaming": (_int, [_vp, _i64, _int, _i64, _i32, _i64, _vp]),
+    "sfc_fftn_optimized": (_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
     "sfc_stft": (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, C.c_double, _vp, _i64, _vp, _vp]),
 }
 

@@ -289,3 +289,70 @@ def spectrogram(x, fs: Optional[float] = None, window=None, nperseg: Optional[in
     freqs = np.arange(r.shape[0]) * fs / nfft_v
     times = (np.arange(r.shape[1]) * step + nperseg // 2) / fs
     return freqs, times, r
+
+
+# ------------------------------------------------------------------ memory_efficient.rs / ndim_optimized.rs
+
+class FftMode(enum.IntEnum):
+    """memory_efficient.rs:41-46"""
+    Forward = 0
+    Inverse = 1
+
+
+def fft_inplace(input: np.ndarray, output: np.ndarray, mode: FftMode = FftMode.Forward, normalize: bool = False) -> int:
+    """memory_efficient.rs:89-190: transforms `input` (complex128, modified in place) and mirrors the result into
+    `output`; returns the number of elements."""
+    lib = _lib.load()
+    if not (isinstance(input, np.ndarray) and input.dtype == np.complex128 and input.flags.c_contiguous):
+        raise ValueError_("fft_inplace needs a contiguous complex128 input buffer")
+    if not (isinstance(output, np.ndarray) and output.dtype == np.complex128 and output.flags.c_contiguous):
+        raise ValueError_("fft_inplace needs a contiguous complex128 output buffer")
+    rc = lib.sfc_fft_inplace(_ptr(input), input.size, _ptr(output), output.size, int(mode), int(bool(normalize)))
+    check(rc)
+    return input.size
+
+
+def process_in_chunks(input, chunk_size: int, op):
+    """memory_efficient.rs:194-226: apply `op` to consecutive chunks and concatenate."""
+    a = np.asarray(input).reshape(-1)
+    if a.size <= chunk_size:
+        return op(a)
+    chunk_size = max(int(chunk_size), 1)
+    return np.concatenate([np.asarray(op(a[s:s + chunk_size])) for s in range(0, a.size, chunk_size)])
+
+
+def fft2_efficient(input, shape: Optional[Tuple[int, int]] = None, mode: FftMode = FftMode.Forward,
+                   normalize: bool = False) -> np.ndarray:
+    """memory_efficient.rs:243-397"""
+    lib = _lib.load()
+    a, dt = _prep(input)
+    if a.ndim != 2:
+        raise ValueError_("fft2_efficient needs a 2-D array")
+    r, c = (a.shape if shape is None else (int(shape[0]), int(shape[1])))
+    out = np.empty((max(r, 1), max(c, 1)), dtype=np.complex128)
+    check(lib.sfc_fft2_efficient(_ptr(a), a.shape[0], a.shape[1], dt, r, c, int(mode), int(bool(normalize)), _ptr(out)))
+    return out
+
+
+def fft_streaming(input, n: Optional[int] = None, mode: FftMode = FftMode.Forward,
+                  chunk_size: Optional[int] = None) -> np.ndarray:
+    """memory_efficient.rs:401-580"""
+    lib = _lib.load()
+    a, dt = _prep(input)
+    a = a.reshape(-1)
+    n_val = a.size if n is None else int(n)
+    out = np.empty(max(n_val, 1), dtype=np.complex128)
+    check(lib.sfc_fft_streaming(_ptr(a), a.size, dt, -1 if n is None else n_val, int(mode),
+                                -1 if chunk_size is None else int(chunk_size), _ptr(out)))
+    return out[:n_val]
+
+
+def fftn_optimized(x, shape=None, axes: Optional[Sequence[int]] = None) -> np.ndarray:
+    """ndim_optimized.rs:17-58 (`shape` is ignored there too)."""
+    lib = _lib.load()
+    a = _real(x)
+    sh = (C.c_int64 * max(a.ndim, 1))(*([int(s) for s in a.shape] or [0]))
+    ax = None if axes is None else (C.c_int32 * max(len(axes), 1))(*[int(v) for v in axes])
+    out = np.empty(a.shape, dtype=np.complex128)
+    check(lib.sfc_fftn_optimized(_ptr(a), a.ndim, sh, ax, 0 if axes is None else len(axes), _ptr(out)))
+    return out

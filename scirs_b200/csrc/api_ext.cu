@@ -639,3 +639,186 @@ SFC_EXPORT int sfc_stft(const double* x, int64_t len, const double* window, int6
     if (e != cudaSuccess) return cuda_fail(e, "stft output kernel");
     return download(out, d_o, (size_t)frames * freq_len * out_es);
 }
+
+// ------------------------------------------------------------------------------------------------
+// memory_efficient.rs / ndim_optimized.rs — what benches/fft_benchmarks.rs:126-189 times.
+
+// memory_efficient.rs:89-190.  n >= 32 takes the reference's "SIMD" branch (simd_support_available() is true on
+// x86_64 / aarch64): fft_adaptive / ifft_adaptive, whose 1-D `norm` argument is ignored (simd_fft.rs:37-60) —
+// forward is never scaled, inverse always by 1/n — and whose result has next_pow2(n) entries, so a non-power-of-two
+// n indexes out of bounds there (ValueError here).  n < 32: rustfft directly, scale 1/n iff `normalize`.
+SFC_EXPORT int sfc_fft_inplace(double* input, int64_t n, double* output, int64_t out_len, int32_t inverse, int32_t normalize) {
+    int rc;
+    if ((rc = require_device()) != SFC_OK) return rc;
+    if (n <= 0 || !input) return fail(SFC_ERR_VALUE, "Input array is empty");
+    if (!output || out_len < n) {
+        char b[128];
+        snprintf(b, sizeof b, "Output buffer is too small: got %lld, need %lld", (long long)out_len, (long long)n);
+        return fail(SFC_ERR_VALUE, b);
+    }
+    if (n >= 32) {
+        // fft(x, None) / ifft(x, None): padded to the next power of two; the forward result then has more than n
+        // entries (out of bounds in the reference), the inverse one is truncated back to n (algorithms.rs:258-260)
+        if (!inverse && !is_pow2_i64(n))
+            return fail(SFC_ERR_VALUE, "fft_inplace (forward, n >= 32) needs a power-of-two length: the reference indexes out of bounds otherwise");
+        int64_t got = 0;
+        rc = inverse ? sfc_ifft(input, n, SFC_C128, -1, output, out_len, &got) : sfc_fft(input, n, SFC_C128, -1, output, out_len, &got);
+        if (rc != SFC_OK) return rc;
+    } else {
+        const double scale = normalize ? 1.0 / (double)n : 1.0;
+        void* d_res = nullptr;
+        if ((rc = run_c2c_host(input, {n}, SFC_C128, {n}, {0}, inverse != 0, scale, &d_res)) != SFC_OK) return rc;
+        if ((rc = download(output, d_res, (size_t)n * 16)) != SFC_OK) return rc;
+    }
+    memcpy(input, output, (size_t)n * 16);  // "copy the results back to the input and output buffers" (:121-124)
+    return (int)std::min<int64_t>(n, 0x7fffffff);
+}
+
+// memory_efficient.rs:243-397: pad / crop to `shape`, rows then columns, 1/(rows*cols) iff normalize (either direction)
+SFC_EXPORT int sfc_fft2_efficient(const void* x, int64_t rows, int64_t cols, int dtype, int64_t out_rows, int64_t out_cols,
+                                  int32_t inverse, int32_t normalize, double* out) {
+    int rc;
+    if ((rc = require_device()) != SFC_OK) return rc;
+    if (!dtype_ok(dtype)) return fail(SFC_ERR_VALUE, "unknown dtype");
+    if (out_rows < 0) out_rows = rows;
+    if (out_cols < 0) out_cols = cols;
+    if (out_rows == 0 || out_cols == 0) return fail(SFC_ERR_VALUE, "Output dimensions must be positive");  // :256-260
+    if (!x || rows <= 0 || cols <= 0 || !out) return fail(SFC_ERR_VALUE, "Input cannot be empty");
+    const double scale = normalize ? 1.0 / ((double)out_rows * (double)out_cols) : 1.0;
+    void* d_res = nullptr;
+    if ((rc = run_c2c_host(x, {rows, cols}, dtype, {out_rows, out_cols}, {1, 0}, inverse != 0, scale, &d_res)) != SFC_OK) return rc;
+    return download(out, d_res, (size_t)(out_rows * out_cols) * 16);
+}
+
+// memory_efficient.rs:401-580.  One transform of length n when it fits a chunk; otherwise — as the reference does —
+// INDEPENDENT transforms of consecutive chunks (the last one shorter), concatenated; inverse chunks end up scaled by
+// (1/len_chunk) * (chunk/n) (:566-577).  The full chunks run as one batched plan.
+SFC_EXPORT int sfc_fft_streaming(const void* x, int64_t len, int dtype, int64_t n, int32_t inverse, int64_t chunk_size, double* out) {
+    int rc;
+    if ((rc = require_device()) != SFC_OK) return rc;
+    if (!dtype_ok(dtype)) return fail(SFC_ERR_VALUE, "unknown dtype");
+    if (!x || len <= 0 || !out) return fail(SFC_ERR_VALUE, "Input cannot be empty");
+    const int64_t n_val = n > 0 ? n : len;
+    int64_t chunk = chunk_size > 0 ? chunk_size : (len > 1000000 ? 1048576 : (len > 100000 ? 65536 : len));  // :412-424
+    if (len <= chunk || n_val <= chunk) {  // :427
+        void* d_res = nullptr;
+        if ((rc = run_c2c_host(x, {std::min(len, n_val)}, dtype, {n_val}, {0}, inverse != 0, inverse ? 1.0 / (double)n_val : 1.0,
+                               &d_res)) != SFC_OK)
+            return rc;
+        return download(out, d_res, (size_t)n_val * 16);
+    }
+    const int64_t full = n_val / chunk, rem = n_val - full * chunk;
+    // full chunks: rows of a [full][chunk] array (input rows beyond `len` are zero: pad through the 2-D convert pass)
+    const int64_t avail = std::min(len, n_val);
+    void* d_res = nullptr;
+    // upload what exists, widen to complex f64 [n_val] with zero fill (the 1-D convert / pad pass, no transform)
+    if ((rc = run_c2c_host(x, {avail}, dtype, {n_val}, {}, false, 1.0, &d_res)) != SFC_OK) return rc;
+    cudaStream_t st = g_ws.stream;
+    void* d_out = nullptr;
+    if ((rc = g_ws.get(2, (size_t)n_val * 16, &d_out)) != SFC_OK) return rc;
+    auto run_rows = [&](int64_t rows_n, int64_t width, int64_t off, double scale) -> int {
+        sfc_desc d;
+        memset(&d, 0, sizeof d);
+        d.ndim = 2;
+        d.shape[0] = rows_n;
+        d.shape[1] = width;
+        d.naxes = 1;
+        d.axes[0] = 1;
+        d.kind = SFC_C2C;
+        d.prec = SFC_PREC_F64;
+        d.direction = inverse ? SFC_INVERSE : SFC_FORWARD;
+        d.scale = scale;
+        PlanError perr{0, ""};
+        std::shared_ptr<Plan> p = cached_plan(d, perr);
+        if (!p) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
+        std::string es2;
+        const int r = p->exec((const char*)d_res + (size_t)off * 16, (char*)d_out + (size_t)off * 16, st, es2);
+        if (r != 0) return fail(r, es2);
+        return SFC_OK;
+    };
+    const double adj = (double)chunk / (double)n_val;  // full_scale / chunk_scale (:569-571)
+    if ((rc = run_rows(full, chunk, 0, inverse ? (1.0 / (double)chunk) * adj : 1.0)) != SFC_OK) return rc;
+    if (rem > 0 && (rc = run_rows(1, rem, full * chunk, inverse ? (1.0 / (double)rem) * adj : 1.0)) != SFC_OK) return rc;
+    return download(out, d_out, (size_t)n_val * 16);
+}
+
+// ndim_optimized.rs:17-58: real input widened to complex; along every listed axis (sorted by stride, which commutes)
+// `fft(&lane, None)` — padded to the next power of two — of which the first axis_len bins are written back (:73-82).
+SFC_EXPORT int sfc_fftn_optimized(const double* x, int32_t ndim, const int64_t* shape, const int32_t* axes, int32_t naxes, double* out) {
+    int rc;
+    if ((rc = require_device()) != SFC_OK) return rc;
+    if (!x || !out || !shape || ndim < 1 || ndim > SFC_MAX_DIMS) return fail(SFC_ERR_VALUE, "Input cannot be empty");
+    std::vector<int64_t> sh(shape, shape + ndim);
+    for (int64_t v : sh)
+        if (v <= 0) return fail(SFC_ERR_VALUE, "Input cannot be empty");
+    std::vector<int> ax;
+    if (axes)
+        ax.assign(axes, axes + naxes);
+    else
+        for (int i = 0; i < ndim; ++i) ax.push_back(i);
+    for (int a : ax)
+        if (a < 0 || a >= ndim) {
+            char b[128];
+            snprintf(b, sizeof b, "Axis %d is out of bounds for array with %d dimensions", a, ndim);
+            return fail(SFC_ERR_VALUE, b);  // :135-142
+        }
+    std::stable_sort(ax.begin(), ax.end(), [](int p, int q) { return p > q; });  // smallest stride (last axis) first (:118-132)
+    const int64_t total = vprod(sh);
+    void *d_r = nullptr, *d_a = nullptr, *d_b = nullptr;
+    if ((rc = g_ws.get(0, (size_t)total * 8, &d_r)) != SFC_OK) return rc;
+    if ((rc = g_ws.get(1, (size_t)total * 16, &d_a)) != SFC_OK) return rc;
+    if ((rc = g_ws.get(2, (size_t)total * 16, &d_b)) != SFC_OK) return rc;
+    cudaStream_t st = g_ws.stream;
+    cudaError_t e = cudaMemcpyAsync(d_r, x, (size_t)total * 8, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+    const void* cur = d_r;
+    bool cur_real = true;
+    void* bufs[2] = {d_a, d_b};
+    int which = 0;
+    if (ax.empty()) {
+        CopyParams c;
+        memset(&c, 0, sizeof c);
+        c.ndim = 1;
+        c.dst_shape[0] = c.src_shape[0] = total;
+        c.src_complex = 0;
+        c.dst_complex = 1;
+        c.src_f64 = c.dst_f64 = 1;
+        c.scale = 1.0;
+        c.total = total;
+        c.src = d_r;
+        c.dst = d_a;
+        e = launch_nd_copy(c, st);
+        if (e != cudaSuccess) return cuda_fail(e, "convert kernel");
+        return download(out, d_a, (size_t)total * 16);
+    }
+    for (int a : ax) {
+        int64_t O = 1, I = 1;
+        for (int i = 0; i < a; ++i) O *= sh[i];
+        for (int i = a + 1; i < ndim; ++i) I *= sh[i];
+        sfc_desc d;
+        memset(&d, 0, sizeof d);
+        d.ndim = 3;
+        d.shape[0] = O;
+        d.shape[1] = next_pow2_i64(sh[a]);
+        d.shape[2] = I;
+        d.naxes = 1;
+        d.axes[0] = 1;
+        d.kind = SFC_C2C;
+        d.prec = SFC_PREC_F64;
+        d.direction = SFC_FORWARD;
+        d.scale = 1.0;
+        d.flags = SFC_DESC_AXIS_LEN | (cur_real ? SFC_DESC_REAL_INPUT : 0);
+        d.axis_in_len = sh[a];
+        d.axis_out_len = sh[a];
+        PlanError perr{0, ""};
+        std::shared_ptr<Plan> p = cached_plan(d, perr);
+        if (!p) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
+        std::string es;
+        rc = p->exec(cur, bufs[which], st, es);
+        if (rc != 0) return fail(rc, es);
+        cur = bufs[which];
+        cur_real = false;
+        which ^= 1;
+    }
+    return download(out, cur, (size_t)total * 16);
+}

@@ -179,3 +179,40 @@ def test_stft_spectrogram(sb, co):
     _, _, z = sb.stft(x, w, 50, 10, 64)
     _, _, zr = co.stft(x, w, 50, 10, 64)
     assert rel(z, zr) <= TOL
+
+
+def test_memory_efficient_and_ndim_optimized(sb, co):
+    rng = np.random.default_rng(21)
+    for n, inv, norm in ((8, False, False), (8, False, True), (16, True, True), (31, True, False), (64, False, True),
+                         (1024, True, False), (100, True, True)):
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        a, b = x.copy(), np.zeros(n + 3, dtype=np.complex128)
+        ra, rb = x.copy(), np.zeros(n + 3, dtype=np.complex128)
+        assert sb.fft_inplace(a, b, sb.FftMode.Inverse if inv else sb.FftMode.Forward, norm) == n
+        co.fft_inplace(ra, rb, inv, norm)
+        assert rel(a, ra) <= TOL and rel(b[:n], rb[:n]) <= TOL, (n, inv, norm)
+    with pytest.raises(sb.ValueError_):
+        sb.fft_inplace(np.zeros(100, dtype=np.complex128), np.zeros(100, dtype=np.complex128))  # forward, not a power of two
+    with pytest.raises(sb.ValueError_) as e:
+        sb.fft_inplace(np.zeros(8, dtype=np.complex128), np.zeros(4, dtype=np.complex128))
+    assert "Output buffer is too small: got 4, need 8" in str(e.value)
+    m = rng.standard_normal((24, 40))
+    for shape, inv, norm in ((None, False, False), ((32, 32), False, True), ((16, 64), True, True), (None, True, False)):
+        got = sb.fft2_efficient(m, shape, sb.FftMode.Inverse if inv else sb.FftMode.Forward, norm)
+        assert rel(got, co.fft2_efficient(m, shape, inv, norm)) <= TOL
+    mc = m + 1j * rng.standard_normal(m.shape)
+    assert rel(sb.fft2_efficient(mc), co.fft2_efficient(mc)) <= TOL
+    x = rng.standard_normal(5000)
+    for n, inv, chunk in ((None, False, None), (4096, False, None), (6000, True, None), (None, False, 1024), (None, True, 1000),
+                          (7000, False, 2048), (4500, True, 2048)):
+        got = sb.fft_streaming(x, n, sb.FftMode.Inverse if inv else sb.FftMode.Forward, chunk)
+        assert rel(got, co.fft_streaming(x, n, inv, chunk)) <= TOL, (n, inv, chunk)
+    assert np.allclose(sb.process_in_chunks(x, 1024, lambda c: sb.fft(c, len(c))),
+                       np.concatenate([np.fft.fft(x[s:s + 1024]) for s in range(0, 5000, 1024)]), atol=1e-9)
+    a = rng.standard_normal((6, 16, 10))
+    assert rel(sb.fftn_optimized(a), co.fftn_optimized(a)) <= TOL
+    assert rel(sb.fftn_optimized(a, None, [2, 0]), co.fftn_optimized(a, None, [2, 0])) <= TOL
+    a = rng.standard_normal((8, 32))
+    assert rel(sb.fftn_optimized(a), np.fft.fftn(a)) <= TOL  # power-of-two extents: the plain N-D transform
+    with pytest.raises(sb.ValueError_):
+        sb.fftn_optimized(a, None, [2])
