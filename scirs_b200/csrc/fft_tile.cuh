@@ -288,16 +288,21 @@ __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x
 // GROUPS > 1 splits the CTA into independent thread groups, each owning TL/GROUPS lanes and its own
 // named barrier: the groups drift apart like separate CTAs (load of one overlaps compute of the
 // other) while the tile keeps TL adjacent lanes, i.e. full 128 B rows, in one CTA at one time.
-template <typename T, int L_, int TL_, int EMAX_ = 16, int GROUPS_ = 1>
+// SPLIT_ exchanges the real and the imaginary parts in two rounds through a buffer of HALF the size (elements
+// of sizeof(T) instead of sizeof(Cx<T>)): the room this frees holds the TMA landing buffer of the pipelined
+// flavour (TM_PIPE_C2C), which prefetches the next tile while this one is transformed.
+template <typename T, int L_, int TL_, int EMAX_ = 16, int GROUPS_ = 1, bool SPLIT_ = false>
 struct TileCfg {
     static constexpr int L = L_;
     static constexpr int TL = TL_;
     static constexpr int GROUPS = GROUPS_;
+    static constexpr bool SPLIT = SPLIT_;
+    static constexpr int XBYTES = SPLIT_ ? (int)sizeof(T) : (int)sizeof(Cx<T>);  // bytes per exchange slot
     static constexpr int TLG = TL_ / GROUPS_;                 // lanes per group
     static constexpr int E = L < EMAX_ ? L : EMAX_;    // points per thread (= largest radix)
     static constexpr int TPL = L / E;                  // threads per lane
     static constexpr int NT = TPL * TL;                // threads per CTA
-    static constexpr int G = 128 / (int)sizeof(Cx<T>);  // threads per smem wavefront
+    static constexpr int G = 128 / XBYTES;  // threads per smem wavefront
     static __host__ __device__ constexpr int lane_pitch() {
         int want = (TLG < G) ? (G / TLG) % G : 1;
         // padded exchange layout (one pad slot per E elements) and >= L+1 because the
@@ -307,7 +312,10 @@ struct TileCfg {
         return lp;
     }
     static constexpr int LP = lane_pitch();
-    static constexpr size_t SMEM = (size_t)TL * LP * sizeof(Cx<T>);
+    static constexpr size_t XCH_BYTES = (((size_t)TL * LP * XBYTES) + 127) / 128 * 128;
+    static constexpr size_t LAND_BYTES = (size_t)TL * L * sizeof(Cx<T>);  // dense tile, TMA destination
+    // pipelined flavour: exchange buffer | landing buffer | one mbarrier
+    static constexpr size_t SMEM = SPLIT_ ? XCH_BYTES + LAND_BYTES + 16 : (size_t)TL * LP * sizeof(Cx<T>);
     // resident CTAs per SM the register allocator must leave room for
     static constexpr int NTG = NT / GROUPS;                   // threads per group
     static __device__ __forceinline__ void sync(int group) {
@@ -364,6 +372,43 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
     constexpr bool LAST = (S * R == L);
     constexpr int NB = E / R;  // butterflies per thread in this stage
     if constexpr (!LAST && !FIRST) C::sync(grp);  // previous readers done before we overwrite
+    if constexpr (C::SPLIT && !LAST) {
+        // half-size exchange buffer: real parts first, imaginary parts second (outputs parked in a[] meanwhile)
+        static_assert(!MIRROR && !MIRROR_IN, "split exchange is for the plain complex flavours");
+        T* __restrict__ smt = reinterpret_cast<T*>(sm);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            Cx<T> v[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] = a[b + r * NB];
+            Dft<R, T>::run(v);
+            apply_twiddle_powers<R, T>(v, tw[(iw + b * TPL) & ~(S - 1)]);
+#pragma unroll
+            for (int k = 0; k < R; ++k) a[b + k * NB] = v[k];
+        }
+        const T* src = smt + tr * C::LP + Xch<C, R, S>::read_base(ir);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            T* dst = smt + tw_ * C::LP + Xch<C, R, S>::write_base(iw + b * TPL);
+#pragma unroll
+            for (int k = 0; k < R; ++k) dst[k * S] = a[b + k * NB].x;
+        }
+        C::sync(grp);
+#pragma unroll
+        for (int m = 0; m < E; ++m) a[m].x = src[Xch<C, R, S>::read_off(m)];
+        C::sync(grp);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            T* dst = smt + tw_ * C::LP + Xch<C, R, S>::write_base(iw + b * TPL);
+#pragma unroll
+            for (int k = 0; k < R; ++k) dst[k * S] = a[b + k * NB].y;
+        }
+        C::sync(grp);
+#pragma unroll
+        for (int m = 0; m < E; ++m) a[m].y = src[Xch<C, R, S>::read_off(m)];
+        run_stages<T, C, S * R, false, MIRROR, MIRROR_IN>(a, sm, tw, tr, ir, tr, ir, grp);
+        return;
+    }
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         Cx<T> v[R];
@@ -515,7 +560,79 @@ enum TileMode : int {
     TM_FAST_C2C = 1,  // complex in, complex out, optional table multiplies / twiddles / scale
     TM_FAST_R2C = 2,  // packed real rows in, N/2+1 Hermitian half out (fused post-twiddle)
     TM_FAST_C2R = 3,  // N/2+1 Hermitian half in (fused pre-twiddle), packed real rows out
+    // TM_FAST_C2C made persistent and software-pipelined: one CTA walks over tiles blockIdx.x, +gridDim.x, ...;
+    // while it transforms a tile the TMA unit (cp.async.bulk + mbarrier) lands the next one in shared memory,
+    // so the global-load latency no longer sits in front of every tile's arithmetic.  Needs unmasked complex
+    // loads of tiles whose lanes are contiguous in memory (the planner checks).
+    TM_PIPE_C2C = 4,
 };
+
+// ---- TMA / mbarrier primitives (PTX) -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// blockIdx-level index -> (tile, batch)
+__device__ __forceinline__ void decode_block(const PassParams& p, uint32_t blk, uint32_t& tile, uint32_t& batch) {
+    if (p.nbatch_fast) {
+        const uint32_t per = p.nbatch_fast << p.tile_group_shift;
+        const uint32_t th = blk / per, r = blk - th * per;
+        batch = r >> p.tile_group_shift;
+        tile = (th << p.tile_group_shift) + (r & ((1u << p.tile_group_shift) - 1u));
+    } else {
+        tile = blk % p.tiles_per_batch;
+        batch = blk / p.tiles_per_batch;
+    }
+}
+
+// warp 0 of a pipelined CTA: land tile `blk` (TL lanes x L complex, dense) in shared memory
+template <typename T, int L, int TL>
+__device__ __forceinline__ void pipe_issue(const PassParams& p, uint32_t blk, uint32_t land, uint32_t bar) {
+    const int lane_id = threadIdx.x & 31;
+    uint32_t tile, batch;
+    decode_block(p, blk, tile, batch);
+    if (lane_id == 0) mbar_expect_tx(bar, (uint32_t)(TL * L * sizeof(Cx<T>)));
+    __syncwarp();
+    const Cx<T>* base = reinterpret_cast<const Cx<T>*>(p.in.ptr) + (int64_t)batch * p.in.batch_stride;
+    if (p.map_in == MAP_COL) {
+        // element rows of TL adjacent lanes: L copies of TL * sizeof(cx) bytes
+        const uint32_t lane0 = tile * TL;
+        const uint32_t lo = lane0 / p.inner_count, li = lane0 - lo * p.inner_count;
+        const Cx<T>* src = base + (int64_t)lo * p.in.outer_stride + (int64_t)li * p.in.inner_stride;
+        for (int e = lane_id; e < L; e += 32)
+            bulk_g2s(land + (uint32_t)(e * TL * sizeof(Cx<T>)), src + (int64_t)e * p.in.elem_stride,
+                     (uint32_t)(TL * sizeof(Cx<T>)), bar);
+    } else {
+        // contiguous rows: one copy per lane
+        for (int t = lane_id; t < TL; t += 32) {
+            const uint32_t lane = tile * TL + (uint32_t)t;
+            const uint32_t lo = lane / p.inner_count, li = lane - lo * p.inner_count;
+            const Cx<T>* src = base + (int64_t)lo * p.in.outer_stride + (int64_t)li * p.in.inner_stride;
+            bulk_g2s(land + (uint32_t)(t * L * sizeof(Cx<T>)), src, (uint32_t)(L * sizeof(Cx<T>)), bar);
+        }
+    }
+}
 
 // Z[k] = (X[k] + conj X[L-k]) + i*conj(W_2L^k)*(X[k] - conj X[L-k]) from a staged row
 template <typename T, typename C>
@@ -541,30 +658,23 @@ __device__ __forceinline__ void c2r_pretwiddle(Cx<T> (&a)[C::E], const Cx<T>* ro
     }
 }
 
-template <typename T, int L, int TL, bool DOUBLE, int EMAX = 16, int MODE = TM_GENERIC, int GROUPS = 1>
-__global__ void __launch_bounds__(TileCfg<T, L, TL, EMAX, GROUPS>::NT, TileCfg<T, L, TL, EMAX, GROUPS>::MINB)
-tile_fft_kernel(const __grid_constant__ PassParams p) {
-    using C = TileCfg<T, L, TL, EMAX, GROUPS>;
+// one tile: load -> transform -> store.  Pipelined flavour: `land` / `bar` are the landing buffer and its
+// mbarrier, `parity` the phase to wait for, `next_blk` the tile to prefetch once this one is in registers.
+template <typename T, int L, int TL, bool DOUBLE, int EMAX, int MODE, int GROUPS>
+__device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t blk, Cx<T>* sm, const Cx<T>* land,
+                                          uint32_t bar, uint32_t parity, uint32_t next_blk) {
+    constexpr bool PIPE = MODE == TM_PIPE_C2C;
+    using C = TileCfg<T, L, TL, EMAX, GROUPS, PIPE>;
     using cx = Cx<T>;
     constexpr int E = C::E, TPL = C::TPL, LP = C::LP;
     constexpr bool FAST = MODE != TM_GENERIC;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx* sm = reinterpret_cast<cx*>(smem_raw);
 
     const int tid = threadIdx.x;
     // tile-major order (batch index fastest) lets consecutive CTAs reuse the same rows of the
     // per-plan tables (Bluestein chirp / kernel spectrum) out of L2; groups of 2^shift adjacent
     // tiles stay adjacent in time so that their 64..128 B row segments merge into whole DRAM bursts
     uint32_t tile, batch;
-    if (p.nbatch_fast) {
-        const uint32_t per = p.nbatch_fast << p.tile_group_shift;
-        const uint32_t th = blockIdx.x / per, r = blockIdx.x - th * per;
-        batch = r >> p.tile_group_shift;
-        tile = (th << p.tile_group_shift) + (r & ((1u << p.tile_group_shift) - 1u));
-    } else {
-        tile = blockIdx.x % p.tiles_per_batch;
-        batch = blockIdx.x / p.tiles_per_batch;
-    }
+    decode_block(p, blk, tile, batch);
 
     int t0, i0, t1, i1;
     const int grp = GROUPS == 1 ? 0 : tid / C::NTG;  // warp-uniform
@@ -642,7 +752,7 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
             C::sync(grp);
             c2r_pretwiddle<T, C>(a, row, reinterpret_cast<const cx*>(p.rtw), i0);
             staged = true;
-        } else if (FAST && p.ld_op == LD_SPLIT2) {
+        } else if (FAST && !PIPE && p.ld_op == LD_SPLIT2) {
             // One 2L-point row is shared by two lanes (usually two CTAs): a radix-2 decimation-in-
             // frequency stage folded into the load.  Both lanes read the whole row (the second read
             // comes from L2); lane parity 0 transforms x[j] + x[j+L] -> even bins, parity 1 transforms
@@ -661,6 +771,29 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
 #pragma unroll
                     for (int m = 0; m < E; ++m) a[m] = cmul(a[m], cmul(wi, w32<T>(m)));
                 }
+            }
+        } else if constexpr (PIPE) {
+            // the tile was landed in shared memory by the TMA unit while the previous one was transformed
+            mbar_wait(bar, parity);
+            const cx* src = (p.map_in == MAP_COL) ? land + (i0 * TL + t0) : land + (t0 * L + i0);
+            const int step = (p.map_in == MAP_COL) ? TPL * TL : TPL;
+#pragma unroll
+            for (int m = 0; m < E; ++m) a[m] = src[m * step];
+            __syncthreads();  // everybody holds its elements: the landing buffer is free again
+            if (tid < 32 && next_blk < p.total_tiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                pipe_issue<T, L, TL>(p, next_blk, smem_u32(land), bar);
+            }
+            if (p.flags & F_CONJ_LD_PRE) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
+            }
+            if (p.ld_op == LD_C_MUL && (p.flags & F_CHIRP_GEN)) {
+                chirp_apply<T, E>(a, p, (int64_t)i0 * p.in.pos_es + pos0, (int64_t)TPL * p.in.pos_es, p.chirp_q_in);
+            } else if (p.ld_op == LD_C_MUL) {
+                const cx* __restrict__ aux = reinterpret_cast<const cx*>(p.aux_in);
+#pragma unroll
+                for (int m = 0; m < E; ++m) a[m] = cmul(a[m], aux[(int64_t)(i0 + m * TPL) * p.in.pos_es + pos0]);
             }
         } else if constexpr (FAST) {
             const cx* __restrict__ src =
@@ -1003,6 +1136,26 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
             const int64_t pos = (int64_t)e * p.out.pos_es + pos0;
             if (valid && pos < p.out.len) dst[(int64_t)e * p.out.elem_stride] = a[m];
         }
+    }
+}
+
+template <typename T, int L, int TL, bool DOUBLE, int EMAX = 16, int MODE = TM_GENERIC, int GROUPS = 1>
+__global__ void __launch_bounds__(TileCfg<T, L, TL, EMAX, GROUPS>::NT, TileCfg<T, L, TL, EMAX, GROUPS>::MINB)
+tile_fft_kernel(const __grid_constant__ PassParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Cx<T>* sm = reinterpret_cast<Cx<T>*>(smem_raw);
+    if constexpr (MODE != TM_PIPE_C2C) {
+        tile_body<T, L, TL, DOUBLE, EMAX, MODE, GROUPS>(p, blockIdx.x, sm, nullptr, 0u, 0u, 0u);
+    } else {
+        using C = TileCfg<T, L, TL, EMAX, GROUPS, true>;
+        const Cx<T>* land = reinterpret_cast<const Cx<T>*>(smem_raw + C::XCH_BYTES);
+        const uint32_t bar = smem_u32(smem_raw + C::XCH_BYTES + C::LAND_BYTES);
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x < 32 && blockIdx.x < p.total_tiles) pipe_issue<T, L, TL>(p, blockIdx.x, smem_u32(land), bar);
+        uint32_t parity = 0;
+        for (uint32_t blk = blockIdx.x; blk < p.total_tiles; blk += gridDim.x, parity ^= 1u)
+            tile_body<T, L, TL, DOUBLE, EMAX, MODE, GROUPS>(p, blk, sm, land, bar, parity, blk + gridDim.x);
     }
 }
 

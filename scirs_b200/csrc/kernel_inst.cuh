@@ -7,8 +7,9 @@ namespace sfc {
 
 template <typename T, int L, int TL, bool DBL, int EMAX = 16, int MODE = 0, int GROUPS = 1>
 struct KernelInst {
-    using C = TileCfg<T, L, TL, EMAX, GROUPS>;
-    static cudaError_t launch(const PassParams& p, unsigned grid, cudaStream_t s) {
+    using C = TileCfg<T, L, TL, EMAX, GROUPS, MODE == TM_PIPE_C2C>;
+    static cudaError_t launch(const PassParams& p0, unsigned grid, cudaStream_t s) {
+        PassParams p = p0;
         static bool configured[64] = {};
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
@@ -18,6 +19,20 @@ struct KernelInst {
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
             if (e != cudaSuccess) return e;
             configured[dev] = true;
+        }
+        if (MODE == TM_PIPE_C2C) {
+            // persistent: as many CTAs as can be resident (2 per SM), each walking over its share of the tiles
+            static int resident[64] = {};
+            if (dev < 64 && !resident[dev]) {
+                int sms = 0, per_sm = 0;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_fft_kernel<T, L, TL, DBL, EMAX, MODE, GROUPS>,
+                                                              C::NT, C::SMEM);
+                resident[dev] = sms * (per_sm > 0 ? per_sm : 1);
+            }
+            p.total_tiles = grid;
+            const unsigned cap = (unsigned)(dev < 64 ? resident[dev] : 296);
+            if (grid > cap) grid = cap;
         }
         tile_fft_kernel<T, L, TL, DBL, EMAX, MODE, GROUPS><<<grid, C::NT, C::SMEM, s>>>(p);
         return cudaGetLastError();
@@ -53,4 +68,6 @@ struct KernelInst {
 #define SFC_ADD_G2(T, L, TL)                                      \
     add(::sfc::KernelInst<T, L, TL, false, 16, 0, 2>::entry()); \
     add(::sfc::KernelInst<T, L, TL, false, 16, 1, 2>::entry());
+// persistent, TMA-pipelined complex flavour (64 KiB tiles: half-size exchange buffer + landing buffer, 2 CTAs / SM)
+#define SFC_ADD_PIPE(T, L, TL, DBL) add(::sfc::KernelInst<T, L, TL, DBL, 16, 4>::entry());
 #define SFC_ADD_E(T, L, TL, DBL, E) add(::sfc::KernelInst<T, L, TL, DBL, E>::entry());

@@ -62,6 +62,7 @@ struct PassParams {
     uint32_t inner_count;      // lanes per outer index (shared by in/out)
     uint32_t tiles_per_batch;  // ceil(nlanes / TL)
     uint32_t nbatch_fast;      // != 0: blockIdx = tile * nbatch_fast + batch (set per launch), else batch * tiles + tile
+    uint32_t total_tiles;      // pipelined flavour: tiles of this launch (the grid is smaller and persistent)
     uint32_t tile_group_shift; // with nbatch_fast: 2^shift adjacent tiles stay adjacent in CTA order (DRAM row locality)
     int32_t map_in, map_out;
     int32_t ld_op, st_op;

@@ -36,6 +36,8 @@ const KernelEntry* kernel_table(int* count) {
         register_kernels_e8(add_entry);
         register_kernels_f64_real(add_entry);
         register_kernels_f32_real(add_entry);
+        register_kernels_pipe(add_entry);
+        register_kernels_pipe_dbl(add_entry);
     });
     if (count) *count = (int)ktable().size();
     return ktable().data();
@@ -423,6 +425,24 @@ static int64_t l2_total_bytes() {
     return v;
 }
 
+static int pipe_enabled() {  // 0 off, 1 row and column tiles, 2 row tiles only
+    static int v = [] {
+        // measured on B200 (profiles/README.md): the half-size split exchange that makes room for the landing
+        // buffer costs more (FFT phase 4.7k -> 6.6k cycles per 4096-point tile) than the hidden load latency
+        // gains (c2c 92 % -> 88 %, Bluestein 59 % -> 57 %); per-row bulk copies for column tiles are far too
+        // slow (60 cycles each).  Kept selectable for the next round's tensor-map variant.
+        const char* e = getenv("SFC_PIPE");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+static int64_t pipe_min_tiles() {
+    static int64_t v = [] {
+        const char* e = getenv("SFC_PIPE_MIN_TILES");
+        return e ? atoll(e) : 1184;  // 4 tiles for each of the 296 resident CTAs
+    }();
+    return v;
+}
 static int tile_group_log2() {
     static int v = [] {
         const char* e = getenv("SFC_TILE_GROUP_LOG2");
@@ -532,6 +552,20 @@ struct PlanBuilder {
                 const KernelEntry* f = flavour_of(s.k, mode);
                 if (f) s.k = f;
             }
+            // persistent TMA-pipelined flavour: unmasked complex loads of tiles whose TL lanes are adjacent in
+            // memory (16-byte aligned bulk copies), and enough tiles for every resident CTA to pipeline a few
+            if (mode == 1 && s.k->mode == 1 && pipe_enabled() && (s.p.flags & F_IN_NOMASK) &&
+                (s.p.ld_op == LD_C || s.p.ld_op == LD_C_MUL) && prec == PREC_F64) {
+                const bool rows_ok = s.p.map_in == MAP_ROW && s.p.in.elem_stride == 1;
+                const bool cols_ok = pipe_enabled() == 1 && s.p.map_in == MAP_COL &&
+                                     ((s.p.in.inner_stride == 1 && (int64_t)s.p.inner_count % s.k->TL == 0) ||
+                                      (s.p.inner_count == 1 && s.p.in.outer_stride == 1));
+                const int64_t total_tiles = tiles * nbatch;
+                if ((rows_ok || cols_ok) && total_tiles >= pipe_min_tiles()) {
+                    const KernelEntry* f = flavour_of(s.k, 4);
+                    if (f) s.k = f;
+                }
+            }
         }
         if (s.p.flags & F_CHIRP_GEN) {
             // q = exp(-i*pi*2*D^2/N) for the per-thread position step D = (L/E) * pos_es, phase reduced exactly
@@ -551,7 +585,7 @@ struct PlanBuilder {
         snprintf(buf, sizeof buf, "%s: tile L=%d TL=%d%s%s threads=%d smem=%zu lanes=%lld batches=%lld map=%s->%s", what,
                  s.k->L, s.k->TL, s.k->dbl ? " fwd*tab*inv" : "",
                  s.k->groups > 1 ? (s.k->mode ? " fast 2-groups" : " generic 2-groups")
-                                  : (s.k->mode == 0 ? " generic" : (s.k->mode == 1 ? " fast" : (s.k->mode == 2 ? " fast-r2c" : " fast-c2r"))), s.k->threads, s.k->smem, (long long)nlanes,
+                                  : (s.k->mode == 0 ? " generic" : (s.k->mode == 1 ? " fast" : (s.k->mode == 2 ? " fast-r2c" : (s.k->mode == 3 ? " fast-c2r" : " pipelined")))), s.k->threads, s.k->smem, (long long)nlanes,
                  (long long)nbatch, s.p.map_in == MAP_ROW ? "row" : "col", s.p.map_out == MAP_ROW ? "row" : "col");
         s.desc = buf;
         pl.steps_.push_back(s);
