@@ -15,6 +15,8 @@ from .consumers import (DCTType, DSTType, dct, idct, dct2, idct2, dctn, idctn, d
                         dht, idht, dht2, fht, hfft, ihfft, hilbert, get_window, stft, spectrogram, FftMode, fft_inplace,
                         process_in_chunks, fft2_efficient, fft_streaming, fftn_optimized)
 from .plan import FftPlan, FftPlanExecutor
+from .plan_serialization import (PlanInfo, PlanMetrics, PlanDatabaseStats, PlanSerializationManager,
+                                 create_and_time_plan)
 from .plan_cache import PlanCache, CacheStats, get_global_cache
 from .backend import FftBackend, CudaFftBackend, BackendManager, BackendContext, get_backend_manager
 from .context import (WorkerConfig, WorkerPool, WorkerPoolInfo, get_global_pool, set_workers, get_workers, FftContext,
