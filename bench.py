@@ -49,6 +49,8 @@ WORKLOADS = {
     "fft_2p20": ([64, 1 << 20], [1], "c2c", "f64", True, "fft c128 2^20, batch 64 (configs[0] steady state)"),
     "fftn_512": ([512, 512, 512], [0, 1, 2], "c2c", "f64", True, "fftn c128 512^3 on one GPU (configs[4])"),
     "bluestein_1000003": ([32, 1000003], [1], "c2c", "f64", True, "fft c128 N=1,000,003 (prime, Bluestein), batch 32 (configs[3])"),
+    "bluestein_1594323": ([32, 1594323], [1], "c2c", "f64", True, "fft c128 N=3^13 (Bluestein), batch 32 (configs[3])"),
+    "fftn_1024": ([1024, 1024, 1024], [0, 1, 2], "c2c", "f64", True, "fftn c128 1024^3 on one GPU (configs[4])"),
 }
 
 
@@ -363,6 +365,38 @@ def run_gpu(args):
                 torch.cuda.empty_cache()
             except Exception as ex:
                 others[name] = {"error": str(ex)[:160]}
+        if world == 1:
+            # batched DCT-II (dct.rs:523-559) as ONE fused kernel per row (real load * u, 2n-point
+            # FFT, * w, real-part store); algorithmic bytes = n reals in + n reals out per row
+            try:
+                import numpy as np
+
+                B, n = 65536, 4096
+                k = np.arange(n)
+                u = torch.from_numpy(np.ones(n, dtype=np.complex128)).to(dev)
+                w = torch.from_numpy(np.exp(-1j * np.pi * k / (2 * n))).to(dev)
+                plan = sb.FftPlan([B, 2 * n], [1], "c2c", "f64", True, 1.0, real_input=True, axis_in_len=n, axis_out_len=n,
+                                  aux_in=u, aux_out=w, real_output=True)
+                x = torch.randn(B * n, dtype=torch.float64, device=dev)
+                y = torch.empty_like(x)
+                st = torch.cuda.current_stream()
+                for _ in range(3):
+                    plan.execute_device(x, y, st.cuda_stream)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                for _ in range(5):
+                    plan.execute_device(x, y, st.cuda_stream)
+                e1.record(st)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                byt = 2 * 8 * B * n
+                others["dct2_f64"] = {"what": "batched DCT-II f64, 65,536 x 4096 (SURVEY 8f rank 1; fused 2n-point FFT)",
+                                      "ms_per_step": round(ms, 4), "hbm_gbs": round(byt / ms / 1e6, 1),
+                                      "frac_of_hbm": round(byt / ms / 1e6 / hbm, 4), "launches_per_step": 1, "dtype": "f64"}
+                del x, y, plan
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                others["dct2_f64"] = {"error": str(ex)[:160]}
         if world > 1:
             try:
                 from scirs_b200.distributed import bench_slab_fftn

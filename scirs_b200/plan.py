@@ -28,7 +28,8 @@ class FftPlan:
 
     def __init__(self, shape: Sequence[int], axes: Optional[Sequence[int]] = None, kind: str = "c2c",
                  prec: str = "f64", forward: bool = True, scale: float = 1.0,
-                 in_shape: Optional[Sequence[int]] = None, real_input: bool = False, scatter_parts: int = 0):
+                 in_shape: Optional[Sequence[int]] = None, real_input: bool = False, scatter_parts: int = 0,
+                 axis_in_len: int = 0, axis_out_len: int = 0, aux_in=None, aux_out=None, real_output: bool = False):
         lib = _lib.load()
         shape = [int(s) for s in shape]
         if not 1 <= len(shape) <= _lib.SFC_MAX_DIMS:
@@ -53,6 +54,16 @@ class FftPlan:
         if real_input:
             d.flags |= _lib.SFC_DESC_REAL_INPUT
         d.scatter_parts = int(scatter_parts)
+        if axis_in_len or axis_out_len:  # SFC_DESC_AXIS_LEN: extents of the in / out arrays along the one transformed axis
+            d.flags |= _lib.SFC_DESC_AXIS_LEN
+            d.axis_in_len, d.axis_out_len = int(axis_in_len), int(axis_out_len)
+        if aux_in is not None or aux_out is not None:  # SFC_DESC_AUX_MUL: device tables fused into the load / store
+            d.flags |= _lib.SFC_DESC_AUX_MUL
+            d.aux_in = None if aux_in is None else _dev_ptr(aux_in)
+            d.aux_out = None if aux_out is None else _dev_ptr(aux_out)
+            self._keep = (aux_in, aux_out)
+        if real_output:
+            d.flags |= _lib.SFC_DESC_REAL_OUTPUT
         self._h = C.c_void_p()
         check(lib.sfc_plan_create(C.byref(self._h), C.byref(d)))
         self._lib = lib
