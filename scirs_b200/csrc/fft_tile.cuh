@@ -480,29 +480,42 @@ __device__ __forceinline__ Cx<T> w32(int m) {
 // table (2 * ~sqrt(2N) entries, cache resident); consecutive positions follow the second-order
 // recurrence c[m+1] = c[m] * r[m], r[m+1] = r[m] * q with r[0] = R(2PD + D^2), q = R(2D^2).  Two
 // anchored half-chains keep the rounding error at the table's own level (~1e-16).
+// x mod m for 0 <= x < 2^52, m < 2^32, in double arithmetic (exact: one fused multiply-add and two fix-ups
+// replace the ~150-instruction 64-bit integer remainder)
+__device__ __forceinline__ uint32_t mod_small(uint64_t x, double m, double inv_m) {
+    const double xd = (double)x;
+    const double q = floor(xd * inv_m);
+    double r = fma(-q, m, xd);
+    if (r < 0.0) r += m;
+    if (r >= m) r -= m;
+    return (uint32_t)r;
+}
+
 template <int E>
 __device__ __forceinline__ void chirp_gen(Cx<double> (&c)[E], const PassParams& p, uint64_t P, uint64_t D,
                                           Cx<double> q) {
     const Cx<double>* __restrict__ lo = reinterpret_cast<const Cx<double>*>(p.chirp_lo);
     const Cx<double>* __restrict__ hi = reinterpret_cast<const Cx<double>*>(p.chirp_hi);
-    const uint64_t m2 = p.chirp_mod, mask = ((uint64_t)1 << p.chirp_shift) - 1;
-    auto root = [&](uint64_t k) { return cmul(hi[k >> p.chirp_shift], lo[k & mask]); };
+    const uint32_t mask = (1u << p.chirp_shift) - 1u;
+    auto root = [&](uint32_t k) { return cmul(hi[k >> p.chirp_shift], lo[k & mask]); };
+    const double m = (double)p.chirp_mod, inv_m = 1.0 / m;
     constexpr int H = E >= 8 ? E / 2 : E;
+    // all products below stay under 2^52 (positions < 2^26: the planner checks)
     const uint64_t dd = D * D;
-    c[0] = root((P * P) % m2);
-    Cx<double> r = root((2 * P * D + dd) % m2);
+    c[0] = root(mod_small(P * P, m, inv_m));
+    Cx<double> r = root(mod_small(2 * P * D + dd, m, inv_m));
 #pragma unroll
-    for (int m = 1; m < H; ++m) {
-        c[m] = cmul(c[m - 1], r);
+    for (int k = 1; k < H; ++k) {
+        c[k] = cmul(c[k - 1], r);
         r = cmul(r, q);
     }
     if constexpr (E >= 8) {
         const uint64_t P2 = P + (uint64_t)H * D;
-        c[H] = root((P2 * P2) % m2);
-        r = root((2 * P2 * D + dd) % m2);
+        c[H] = root(mod_small(P2 * P2, m, inv_m));
+        r = root(mod_small(2 * P2 * D + dd, m, inv_m));
 #pragma unroll
-        for (int m = H + 1; m < E; ++m) {
-            c[m] = cmul(c[m - 1], r);
+        for (int k = H + 1; k < E; ++k) {
+            c[k] = cmul(c[k - 1], r);
             r = cmul(r, q);
         }
     }
