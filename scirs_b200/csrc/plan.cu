@@ -458,6 +458,14 @@ static int blue_l1_cap() {
     return v;
 }
 
+static int row_fourstep_len() {
+    static int v = [] {
+        const char* e = getenv("SFC_ROW_FOURSTEP");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+
 static int64_t scratch_budget_bytes() {
     static int64_t v = [] {
         const char* e = getenv("SFC_WORK_MB");
@@ -698,7 +706,11 @@ struct PlanBuilder {
                 pl.steps_.pop_back();  // no fast flavour: fall through to the plain single tile
             }
         }
-        if (is_pow2(n) && n <= lmax && !(col && n > col_single_max)) {
+        // contiguous rows whose single tile would be 128 KiB (one CTA per SM, no overlap): optionally two small
+        // passes instead (four-step), L2-blocked so that the intermediate never leaves the cache (SFC_ROW_FOURSTEP)
+        const bool row_fs = !col && is_pow2(n) && row_fourstep_len() > 0 && n >= row_fourstep_len() && !src.real &&
+                            !store_real && !aux_in && !aux_out && scatter_parts <= 1;
+        if (is_pow2(n) && n <= lmax && !(col && n > col_single_max) && !row_fs) {
             Step s;
             // measured (1024^3 f64): with element rows <= 16 KiB apart the 64 KiB two-per-SM tile wins
             // (74 % vs 61 %); with multi-MiB strides (TLB-bound) the wide 128-byte-row tile wins (59 % vs 44 %)
