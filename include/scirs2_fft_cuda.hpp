@@ -136,6 +136,91 @@ ArrayD<Complex64> fft2(const ArrayD<T>& x, const std::optional<std::pair<size_t,
     return out;
 }
 
+// ---- consumers of the path: dct.rs, dst.rs, hartley.rs, hfft/*.rs, lib.rs::hilbert -----------------
+enum class DCTType : int { Type1 = 1, Type2 = 2, Type3 = 3, Type4 = 4 };  // dct.rs:13-23
+enum class DSTType : int { Type1 = 1, Type2 = 2, Type3 = 3, Type4 = 4 };  // dst.rs:13-22
+namespace detail {
+inline std::vector<double> trig1d(decltype(&sfc_dct) fn, const std::vector<double>& x, int type, bool inverse, const char* norm) {
+    std::vector<double> out(std::max<size_t>(x.size(), 1));
+    const int64_t shape[1] = {(int64_t)x.size()};
+    const int32_t axes[1] = {0};
+    check(fn(x.data(), 1, shape, axes, 1, type, inverse ? 1 : 0, norm, out.data()));
+    out.resize(x.size());
+    return out;
+}
+inline ArrayD<double> trignd(decltype(&sfc_dct) fn, const ArrayD<double>& x, int type, bool inverse, const char* norm,
+                             const std::optional<std::vector<int32_t>>& axes) {
+    ArrayD<double> out{x.shape, std::vector<double>(x.data.size())};
+    check(fn(x.data.data(), (int32_t)x.shape.size(), x.shape.data(), axes ? axes->data() : nullptr,
+             axes ? (int32_t)axes->size() : 0, type, inverse ? 1 : 0, norm, out.data.data()));
+    return out;
+}
+}  // namespace detail
+// dct / idct / dctn / idctn — dct.rs:56-420 (norm: "ortho" or nullptr)
+inline std::vector<double> dct(const std::vector<double>& x, std::optional<DCTType> t = std::nullopt, const char* norm = nullptr) {
+    return detail::trig1d(sfc_dct, x, (int)t.value_or(DCTType::Type2), false, norm);
+}
+inline std::vector<double> idct(const std::vector<double>& x, std::optional<DCTType> t = std::nullopt, const char* norm = nullptr) {
+    return detail::trig1d(sfc_dct, x, (int)t.value_or(DCTType::Type2), true, norm);
+}
+inline ArrayD<double> dctn(const ArrayD<double>& x, std::optional<DCTType> t = std::nullopt, const char* norm = nullptr,
+                           const std::optional<std::vector<int32_t>>& axes = std::nullopt) {
+    return detail::trignd(sfc_dct, x, (int)t.value_or(DCTType::Type2), false, norm, axes);
+}
+inline ArrayD<double> idctn(const ArrayD<double>& x, std::optional<DCTType> t = std::nullopt, const char* norm = nullptr,
+                            const std::optional<std::vector<int32_t>>& axes = std::nullopt) {
+    return detail::trignd(sfc_dct, x, (int)t.value_or(DCTType::Type2), true, norm, axes);
+}
+// dst / idst / dstn / idstn — dst.rs:48-405
+inline std::vector<double> dst(const std::vector<double>& x, std::optional<DSTType> t = std::nullopt, const char* norm = nullptr) {
+    return detail::trig1d(sfc_dst, x, (int)t.value_or(DSTType::Type2), false, norm);
+}
+inline std::vector<double> idst(const std::vector<double>& x, std::optional<DSTType> t = std::nullopt, const char* norm = nullptr) {
+    return detail::trig1d(sfc_dst, x, (int)t.value_or(DSTType::Type2), true, norm);
+}
+inline ArrayD<double> dstn(const ArrayD<double>& x, std::optional<DSTType> t = std::nullopt, const char* norm = nullptr,
+                           const std::optional<std::vector<int32_t>>& axes = std::nullopt) {
+    return detail::trignd(sfc_dst, x, (int)t.value_or(DSTType::Type2), false, norm, axes);
+}
+inline ArrayD<double> idstn(const ArrayD<double>& x, std::optional<DSTType> t = std::nullopt, const char* norm = nullptr,
+                            const std::optional<std::vector<int32_t>>& axes = std::nullopt) {
+    return detail::trignd(sfc_dst, x, (int)t.value_or(DSTType::Type2), true, norm, axes);
+}
+// dht / idht — hartley.rs:37-130;  hilbert — lib.rs:437-516;  hfft / ihfft — hfft/*.rs
+inline std::vector<double> dht(const std::vector<double>& x) {
+    std::vector<double> out(std::max<size_t>(x.size(), 1));
+    check(sfc_dht(x.data(), (int64_t)x.size(), out.data()));
+    out.resize(x.size());
+    return out;
+}
+inline std::vector<double> idht(const std::vector<double>& h) {
+    std::vector<double> out(std::max<size_t>(h.size(), 1));
+    check(sfc_idht(h.data(), (int64_t)h.size(), out.data()));
+    out.resize(h.size());
+    return out;
+}
+inline std::vector<Complex64> hilbert(const std::vector<double>& x) {
+    std::vector<Complex64> out(std::max<size_t>(x.size(), 1));
+    check(sfc_hilbert(x.data(), (int64_t)x.size(), reinterpret_cast<double*>(out.data())));
+    out.resize(x.size());
+    return out;
+}
+template <typename T>
+std::vector<double> hfft(const std::vector<T>& x, std::optional<size_t> n = std::nullopt) {
+    std::vector<double> out((size_t)std::max<int64_t>(n ? (int64_t)*n : (int64_t)x.size(), 1));
+    int64_t len = 0;
+    check(sfc_hfft(x.data(), (int64_t)x.size(), detail::dtype_of<T>::v, n ? (int64_t)*n : -1, out.data(), (int64_t)out.size(), &len));
+    out.resize((size_t)len);
+    return out;
+}
+inline std::vector<Complex64> ihfft(const std::vector<double>& x, std::optional<size_t> n = std::nullopt) {
+    std::vector<Complex64> out((size_t)std::max<int64_t>(n ? (int64_t)*n : (int64_t)x.size(), 1));
+    int64_t len = 0;
+    check(sfc_ihfft(x.data(), (int64_t)x.size(), n ? (int64_t)*n : -1, reinterpret_cast<double*>(out.data()), (int64_t)out.size(), &len));
+    out.resize((size_t)len);
+    return out;
+}
+
 // PlanCache — plan_cache.rs:28-235 (the cache itself lives in the library)
 struct CacheStats { uint64_t hit_count, miss_count; double hit_rate; uint64_t size, max_size; };
 class PlanCache {

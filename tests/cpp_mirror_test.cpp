@@ -36,6 +36,16 @@ int main() {
     b->fft(imp, out);
     for (auto& c : out) REQUIRE(std::abs(std::abs(c) - 1.0) < 1e-10);
     try { b->fft_sized(imp, out, 4); return 1; } catch (const FFTError& e) { REQUIRE(e.kind == FFTError::Value); }
+    // consumers (dct.rs:757-768, 843-862; hartley.rs:216-231)
+    auto c = dct(sig, DCTType::Type2, "ortho");
+    auto rc = idct(c, DCTType::Type2, "ortho");
+    for (int i = 0; i < 4; ++i) REQUIRE(std::abs(rc[i] - sig[i]) < 1e-10);
+    auto cc = dct(std::vector<double>(4, 3.0));
+    REQUIRE(std::abs(cc[0]) > 1e-10 && std::abs(cc[1]) < 1e-10 && std::abs(cc[3]) < 1e-10);
+    auto hh = idht(dht(sig));
+    for (int i = 0; i < 4; ++i) REQUIRE(std::abs(hh[i] - sig[i]) < 1e-10);
+    REQUIRE(hilbert(sig).size() == 4 && hfft(sig).size() == 4 && ihfft(sig).size() == 4 && dst(sig).size() == 4);
+    try { dct(std::vector<double>{1.0}, DCTType::Type1); return 1; } catch (const FFTError& e) { REQUIRE(e.kind == FFTError::Value); }
     std::puts("cpp mirror ok");
     return 0;
 }
