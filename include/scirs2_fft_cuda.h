@@ -105,12 +105,27 @@ typedef struct sfc_desc {
      * (aux_out[k], axis_out_len entries); either may be NULL.  Power-of-two lengths only. */
     const void* aux_in;
     const void* aux_out;
+    /* SFC_DESC_DCT2 / SFC_DESC_DCT3: weight of the k = 0 term (0 = 1.0), see below */
+    double scale_dc;
 } sfc_desc;
 #define SFC_DESC_CUSTOM_IN_SHAPE 1
 #define SFC_DESC_AXIS_LEN 4
 #define SFC_DESC_AUX_MUL 8
 /* C2C only: store the real part of the result into a real array */
 #define SFC_DESC_REAL_OUTPUT 16
+/* R2C over the LAST axis only, power-of-two n >= 128: the plan computes the DCT-II of every row,
+ * X[k] = scale * sum_i x[i] cos(pi (i + 1/2) k / n) (dct.rs:523-559), real in / real out, as one fused kernel on the
+ * n/2-point transform; with SFC_DESC_DCT2_ORTHO0 output 0 is additionally multiplied by 1/sqrt(2) (dct.rs:552-553) */
+#define SFC_DESC_DCT2 32
+#define SFC_DESC_DCT2_ORTHO0 64
+/* Same restrictions; the inverse packing in one fused kernel:
+ *   y[i] = scale * ( scale_dc * X[0] + 2 * sum_{k>=1} X[k] cos(pi k (i + 1/2) / n) )
+ * which covers idct type 2, dct type 3 and idct type 3 of the reference (dct.rs:563-684) by choice of the two factors. */
+#define SFC_DESC_DCT3 128
+/* with SFC_DESC_DCT2 / SFC_DESC_DCT3: the sine transforms instead — DST-II: sum_m x[m] sin(pi (k+1)(m+1/2)/n), DST-III:
+ * sum_m x[m] sin(pi (m+1)(k+1/2)/n) with the DCT-III weights applied to x[n-1] (dst.rs:484-592); sign flips and index
+ * reversals are folded into the kernels' load / store */
+#define SFC_DESC_TRIG_SINE 256
 /* C2C only: the input array is real (imag = 0), as when the reference widens real input
  * to Complex64 before the transform (fft/algorithms.rs:71-102) */
 #define SFC_DESC_REAL_INPUT 2

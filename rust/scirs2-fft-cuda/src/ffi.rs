@@ -27,6 +27,7 @@ pub struct sfc_desc {
     pub axis_out_len: i64,
     pub aux_in: *const core::ffi::c_void,
     pub aux_out: *const core::ffi::c_void,
+    pub scale_dc: f64,
 }
 
 #[repr(C)]

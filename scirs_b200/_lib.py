@@ -32,6 +32,10 @@ SFC_DESC_REAL_INPUT = 2
 SFC_DESC_AXIS_LEN = 4
 SFC_DESC_AUX_MUL = 8
 SFC_DESC_REAL_OUTPUT = 16
+SFC_DESC_DCT2 = 32
+SFC_DESC_DCT2_ORTHO0 = 64
+SFC_DESC_DCT3 = 128
+SFC_DESC_TRIG_SINE = 256
 
 
 class sfc_desc(C.Structure):
@@ -52,6 +56,7 @@ class sfc_desc(C.Structure):
         ("axis_out_len", C.c_int64),
         ("aux_in", C.c_void_p),
         ("aux_out", C.c_void_p),
+        ("scale_dc", C.c_double),
     ]
 
 

@@ -113,6 +113,7 @@ CacheKey make_key(const sfc_desc& d) {
         k.aux_in = d.aux_in;
         k.aux_out = d.aux_out;
     }
+    if (d.flags & (SFC_DESC_DCT2 | SFC_DESC_DCT3)) k.scale_dc = d.scale_dc;
     if (d.flags & SFC_DESC_CUSTOM_IN_SHAPE)
         for (int i = 0; i < d.ndim && i < SFC_MAX_DIMS; ++i) k.in_shape[i] = d.in_shape[i];
     int dev = 0;

@@ -257,6 +257,45 @@ int trig_axis(int kind, int type, bool inverse, bool ortho, int64_t O, int64_t N
     d.axis_out_len = N;
     PlanError perr{0, ""};
     std::string es;
+    if (fuse_enabled() && (type == 2 || type == 3) && I == 1 && is_pow2_i64(N) && N >= 128) {
+        // Types II / III of contiguous rows: ONE kernel on the N/2-point packed transform (Makhoul), 8x less data on
+        // chip than the 2N-point formulation.  Every variant is  C2: g * sum_i x[i] cos(pi (i+1/2) k / N)  (output 0
+        // times dc)  or  C3: scale * (dc * X[0] + 2 sum_k>=1 X[k] cos(pi k (i+1/2) / N)),  or their sine twins.
+        const double nn = (double)N, r2 = std::sqrt(2.0);
+        const bool sine = kind == 1;
+        bool c3;        // which kernel
+        double sc, dc;  // its two factors
+        if (!sine) {
+            if (type == 2 && !inverse) { c3 = false; sc = ortho ? std::sqrt(2.0 / nn) : 1.0; dc = ortho ? 1.0 / r2 : 1.0; }          // dct.rs:523-559
+            else if (type == 2) { c3 = true; sc = ortho ? std::sqrt(2.0 / nn) / 2 : 1.0 / nn; dc = ortho ? r2 : 1.0; }               // :563-601
+            else if (!inverse) { c3 = true; sc = ortho ? std::sqrt(2.0 / nn) / 2 : 1.0 / nn; dc = ortho ? 1.0 / r2 : 1.0; }          // :605-643
+            else { c3 = true; sc = ortho ? std::sqrt(2.0 / nn) / 2 : 0.5; dc = ortho ? 2.0 * r2 : 2.0; }                            // :647-684
+        } else {
+            if (type == 2 && !inverse) { c3 = false; sc = ortho ? std::sqrt(2.0 / nn) : 1.0; dc = 1.0; }                             // dst.rs:484-516
+            else if (type == 2) { c3 = true; sc = ortho ? std::sqrt(nn / 2.0) / 4 : 0.25; dc = 2.0; }                                // :520-545 (dst3 of the scaled input)
+            else if (!inverse) { c3 = true; sc = ortho ? std::sqrt(2.0 / nn) / 4 : 0.25; dc = 2.0; }                                 // :549-592
+            else { c3 = false; sc = ortho ? 2.0 * std::sqrt(nn / 2.0) : 2.0; dc = 1.0; }                                             // :596-626 (dst2 of the scaled input)
+        }
+        sfc_desc dd;
+        memset(&dd, 0, sizeof dd);
+        dd.ndim = 2;
+        dd.shape[0] = O;
+        dd.shape[1] = N;
+        dd.naxes = 1;
+        dd.axes[0] = 1;
+        dd.kind = SFC_R2C;
+        dd.prec = SFC_PREC_F64;
+        dd.scale = sc;
+        dd.scale_dc = dc;
+        dd.flags = (c3 ? SFC_DESC_DCT3 : SFC_DESC_DCT2) | (sine ? SFC_DESC_TRIG_SINE : 0);
+        std::shared_ptr<Plan> p = cached_plan(dd, perr);
+        if (p) {
+            rc = p->exec(d_src, d_dst, st, es);
+            if (rc != 0) return fail(rc, es);
+            return SFC_OK;
+        }
+        if (perr.code != SFC_ERR_NOT_IMPLEMENTED) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
+    }
     if (fuse_enabled() && is_pow2_i64(t.P)) {
         // everything in the FFT passes themselves: real load * u, ..., * w, real-part store
         d.flags = SFC_DESC_AXIS_LEN | SFC_DESC_AUX_MUL | SFC_DESC_REAL_INPUT | SFC_DESC_REAL_OUTPUT;

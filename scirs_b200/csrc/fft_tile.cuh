@@ -578,6 +578,12 @@ enum TileMode : int {
     // so the global-load latency no longer sits in front of every tile's arithmetic.  Needs unmasked complex
     // loads of tiles whose lanes are contiguous in memory (the planner checks).
     TM_PIPE_C2C = 4,
+    // DCT-II of real rows through ONE half-length complex transform (Makhoul): the even / reversed-odd input
+    // permutation is the load pattern, X[k] = Re(w_k V[k]), X[N-k] = -Im(w_k V[k]) the store (dct.rs:523-559)
+    TM_FAST_DCT2 = 5,
+    // the inverse packing: V[k] = conj(w_k)(X[k] - i X[N-k]) -> c2r pre-twiddle -> half-length transform -> scatter:
+    // y[i] = scale * 2 * (scale_dc * X[0] / 2 + sum_{k>=1} X[k] cos(pi k (i + 1/2) / N))   (dct.rs:563-684)
+    TM_FAST_DCT3 = 6,
 };
 
 // ---- TMA / mbarrier primitives (PTX) -----------------------------------------------------------
@@ -785,6 +791,42 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
                     for (int m = 0; m < E; ++m) a[m] = cmul(a[m], cmul(wi, w32<T>(m)));
                 }
             }
+        } else if constexpr (MODE == TM_FAST_DCT2) {
+            // v[p] = x[2p] (p < N/2), x[2N-2p-1] (p >= N/2), packed as z[j] = v[2j] + i v[2j+1]; N = 2L reals per row
+            if constexpr (E == 16) {
+                const T* __restrict__ xr = reinterpret_cast<const T*>(p.in.ptr) + 2 * off;
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const int j = i0 + m * TPL;
+                    if (m < E / 2) a[m] = {xr[4 * j], xr[4 * j + 2]};
+                    else a[m] = {xr[4 * L - 4 * j - 1], xr[4 * L - 4 * j - 3]};
+                }
+                if (p.flags & F_TRIG_SINE) {  // (-1)^i x[i]: the second half holds the odd-indexed samples
+#pragma unroll
+                    for (int m = E / 2; m < E; ++m) a[m] = {-a[m].x, -a[m].y};
+                }
+            }
+        } else if constexpr (MODE == TM_FAST_DCT3) {
+            if constexpr (E == 16) {
+                // stage V[k] = conj(w_k) (X[k] - i X[N-k]), k <= L (X[N] = 0), then the c2r pre-twiddle
+                constexpr int N = 2 * L;
+                const T* __restrict__ xr = reinterpret_cast<const T*>(p.in.ptr) + 2 * off;
+                const cx* __restrict__ om = reinterpret_cast<const cx*>(p.aux_out);
+                const bool rev = (p.flags & F_TRIG_SINE) != 0;  // DST-III reads its input reversed
+                auto X = [&](int k) { return rev ? xr[N - 1 - k] : xr[k]; };
+                cx* row = sm + t0 * LP;
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const int k = i0 + m * TPL;
+                    cx u = {X(k), k == 0 ? (T)0 : -X(N - k)};
+                    if (k == 0) u.x *= (T)p.scale_dc;
+                    row[k] = cmulc(u, om[k]);
+                }
+                if (i0 == 0) row[L] = cmulc(cx{X(L), -X(L)}, om[L]);
+                C::sync(grp);
+                c2r_pretwiddle<T, C>(a, row, reinterpret_cast<const cx*>(p.rtw), i0);
+                staged = true;
+            }
         } else if constexpr (PIPE) {
             // the tile was landed in shared memory by the TMA unit while the previous one was transformed
             mbar_wait(bar, parity);
@@ -902,7 +944,7 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
                 }
             }
         }
-        if (MODE == TM_FAST_C2R || (p.flags & F_CONJ_LD_POST)) {
+        if (MODE == TM_FAST_C2R || MODE == TM_FAST_DCT3 || (p.flags & F_CONJ_LD_POST)) {
 #pragma unroll
             for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
         }
@@ -919,7 +961,7 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
         run_stages<T, C, 1, true, true>(a, sm, tw, t0, i0, t1, i1, grp);
     } else if constexpr ((MODE == TM_FAST_C2R) && E == 16 && L >= 128 && (ilog2(L) % 4 == 3)) {
         run_stages<T, C, 1, true, false, true>(a, sm, tw, t0, i0, t1, i1, grp);
-    } else if constexpr (MODE == TM_FAST_C2R) {
+    } else if constexpr (MODE == TM_FAST_C2R || MODE == TM_FAST_DCT3) {
         run_stages<T, C, 1, false>(a, sm, tw, t0, i0, t1, i1, grp);
     } else if constexpr (FAST) {
         run_stages<T, C, 1, true>(a, sm, tw, t0, i0, t1, i1, grp);
@@ -973,12 +1015,77 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
     const int64_t pos0 = (int64_t)lo * p.out.pos_ls;
     const T scale = (T)p.scale;
 
-    if (MODE == TM_FAST_C2R || (p.flags & F_CONJ_ST_PRE)) {
+    if (MODE == TM_FAST_C2R || MODE == TM_FAST_DCT3 || (p.flags & F_CONJ_ST_PRE)) {
 #pragma unroll
         for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
     }
 
-    if constexpr (R2C_MIRROR) {
+    if constexpr (MODE == TM_FAST_DCT2) {
+        if constexpr (E == 16) {
+            // a[m] = Z[i1 + m*TPL] of the packed half-length transform -> V[k], V[L-k] of the real transform as in
+            // the r2c post-pass, then four real outputs per pair
+            cx* row = sm + t1 * LP;
+            C::sync(grp);
+#pragma unroll
+            for (int m = 0; m < E; ++m) row[i1 + m * TPL] = a[m];
+            C::sync(grp);
+            constexpr int N = 2 * L;
+            // DST-II: output k of the cosine transform is output N-1-k of the sine transform
+            const bool rev = (p.flags & F_TRIG_SINE) != 0;
+            T* __restrict__ dst = reinterpret_cast<T*>(p.out.ptr) + 2 * off + (rev ? N - 1 : 0);
+            const int ds = rev ? -1 : 1;
+            const cx* __restrict__ om = reinterpret_cast<const cx*>(p.aux_out);  // w_k = exp(-i pi k / (2N)), k <= L
+            const cx wi = reinterpret_cast<const cx*>(p.rtw)[i1];
+            const T h = (T)0.5 * scale;
+#pragma unroll
+            for (int m = 0; m < E / 2; ++m) {
+                const int k = i1 + m * TPL;
+                const cx zk = a[m];
+                const cx zp = row[(L - k) & (L - 1)];
+                const cx A = {zk.x + zp.x, zk.y - zp.y};
+                const cx B = {zk.x - zp.x, zk.y + zp.y};
+                const cx Cw = cmul(B, cmul(wi, w32<T>(m * (16 / E))));
+                const cx vk = {(A.x + Cw.y) * h, (A.y - Cw.x) * h};       // V[k]
+                const cx vq = {(A.x - Cw.y) * h, -((A.y + Cw.x) * h)};    // V[L-k]
+                const cx tk = cmul(vk, om[k]);
+                const cx tq = cmul(vq, om[L - k]);
+                if (k == 0) {
+                    dst[0] = tk.x * (T)p.scale_dc;   // X[0] (the "ortho" 1/sqrt(2), dct.rs:552-553)
+                    dst[ds * L] = tq.x;              // X[N/2]
+                } else {
+                    dst[ds * k] = tk.x;
+                    dst[ds * (N - k)] = -tk.y;
+                    dst[ds * (L - k)] = tq.x;
+                    dst[ds * (L + k)] = -tq.y;
+                }
+            }
+            if (i1 == 0) {
+                const cx z = a[E / 2];  // Z[L/2]: V[L/2] = conj(Z[L/2])
+                const cx t = cmul(cx{z.x * scale, -(z.y * scale)}, om[L / 2]);
+                dst[ds * (L / 2)] = t.x;
+                dst[ds * (N - L / 2)] = -t.y;
+            }
+        }
+        return;
+    } else if constexpr (MODE == TM_FAST_DCT3) {
+        if constexpr (E == 16) {
+            // a[m] = (v[2j], v[2j+1]), j = i1 + m*TPL: undo the even / reversed-odd permutation on the way out
+            T* __restrict__ dst = reinterpret_cast<T*>(p.out.ptr) + 2 * off;
+            const T sg = (p.flags & F_TRIG_SINE) ? -scale : scale;  // DST-III: (-1)^i on the odd-indexed outputs
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int j = i1 + m * TPL;
+                if (m < E / 2) {
+                    dst[4 * j] = a[m].x * scale;
+                    dst[4 * j + 2] = a[m].y * scale;
+                } else {
+                    dst[4 * L - 4 * j - 1] = a[m].x * sg;
+                    dst[4 * L - 4 * j - 3] = a[m].y * sg;
+                }
+            }
+        }
+        return;
+    } else if constexpr (R2C_MIRROR) {
         // a[2*kk] = Z[i1 + kk*SL], a[2*kk+1] = Z[j2 + kk*SL] with j2 the mirror butterfly:
         // Z[L-(i1 + kk*SL)] = a[2*(7-kk)+1] — the whole Hermitian post-pass stays in registers.
         constexpr int SL = L / 8;

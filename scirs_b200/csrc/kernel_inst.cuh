@@ -70,4 +70,8 @@ struct KernelInst {
     add(::sfc::KernelInst<T, L, TL, false, 16, 1, 2>::entry());
 // persistent, TMA-pipelined complex flavour (64 KiB tiles: half-size exchange buffer + landing buffer, 2 CTAs / SM)
 #define SFC_ADD_PIPE(T, L, TL, DBL) add(::sfc::KernelInst<T, L, TL, DBL, 16, 4>::entry());
+// fused DCT-II rows (Makhoul packing on the half-length transform)
+#define SFC_ADD_DCT2(T, L, TL)                               \
+    add(::sfc::KernelInst<T, L, TL, false, 16, 5>::entry()); \
+    add(::sfc::KernelInst<T, L, TL, false, 16, 6>::entry());
 #define SFC_ADD_E(T, L, TL, DBL, E) add(::sfc::KernelInst<T, L, TL, DBL, E>::entry());

@@ -41,6 +41,7 @@ void register_kernels_e8(void (*add)(const KernelEntry&));
 void register_kernels_f64_real(void (*add)(const KernelEntry&));
 void register_kernels_f32_real(void (*add)(const KernelEntry&));
 void register_kernels_pipe(void (*add)(const KernelEntry&));
+void register_kernels_dct(void (*add)(const KernelEntry&));
 void register_kernels_pipe_dbl(void (*add)(const KernelEntry&));
 
 }  // namespace sfc

@@ -1,0 +1,14 @@
+// kernels_dct.cu — TM_FAST_DCT2: DCT-II of real rows of N = 2L points in one kernel (dct.rs:523-559)
+#include "kernel_inst.cuh"
+namespace sfc {
+void register_kernels_dct(void (*add)(const KernelEntry&)) {
+    SFC_ADD_DCT2(double, 64, 64)
+    SFC_ADD_DCT2(double, 128, 32)
+    SFC_ADD_DCT2(double, 256, 16)
+    SFC_ADD_DCT2(double, 512, 8)
+    SFC_ADD_DCT2(double, 1024, 4)
+    SFC_ADD_DCT2(double, 2048, 2)
+    SFC_ADD_DCT2(double, 4096, 1)
+    SFC_ADD_DCT2(double, 8192, 1)
+}
+}  // namespace sfc

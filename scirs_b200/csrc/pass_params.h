@@ -42,7 +42,10 @@ enum PassFlags : uint32_t {
     F_ST_REAL = 1u << 5,
     F_IN_NOMASK = 1u << 6,     // every (lane, e) position is < in.len: loads need no bounds predicate
     F_OUT_NOMASK = 1u << 7,
-    F_CHIRP_GEN = 1u << 8,     // LD_*_MUL / ST_MUL: generate the Bluestein chirp in registers instead of reading aux_*    // likewise for stores       // store only the real part into a real array (irfftn, rfft.rs:722)
+    F_CHIRP_GEN = 1u << 8,
+    // fused DCT kernels computing the sine transforms: DST-II(x)[k] = DCT-II((-1)^m x[m])[n-1-k],
+    // DST-III(x)[k] = (-1)^k DCT-III(x reversed)[k]   (sign flips and index reversals folded into load / store)
+    F_TRIG_SINE = 1u << 9,     // LD_*_MUL / ST_MUL: generate the Bluestein chirp in registers instead of reading aux_*    // likewise for stores       // store only the real part into a real array (irfftn, rfft.rs:722)
 };
 
 struct IoDesc {
@@ -84,6 +87,7 @@ struct PassParams {
     uint64_t chirp_mod;        // 2N
     double chirp_q_in[2], chirp_q_out[2];
     double scale;
+    double scale_dc;           // TM_FAST_DCT2: extra factor of output 0; TM_FAST_DCT3: factor of input 0
     // split-axis scatter (slab transpose fused into the store): output element e of the transform
     // axis goes to peer_out[e >> peer_shift] at element index (e & ((1 << peer_shift) - 1)).
     // peer_shift < 0 = off.  The pointers may be peer-GPU memory mapped over NVLink.

@@ -37,6 +37,7 @@ const KernelEntry* kernel_table(int* count) {
         register_kernels_f64_real(add_entry);
         register_kernels_f32_real(add_entry);
         register_kernels_pipe(add_entry);
+        register_kernels_dct(add_entry);
         register_kernels_pipe_dbl(add_entry);
     });
     if (count) *count = (int)ktable().size();
@@ -156,7 +157,7 @@ static std::map<TableKey, const void*>& tables() {
     static std::map<TableKey, const void*> m;
     return m;
 }
-enum TableKind { TK_STAGE = 1, TK_RTW, TK_FS_LO, TK_FS_HI, TK_CHIRP, TK_BLUE, TK_CR_LO, TK_CR_HI };
+enum TableKind { TK_STAGE = 1, TK_RTW, TK_FS_LO, TK_FS_HI, TK_CHIRP, TK_BLUE, TK_CR_LO, TK_CR_HI, TK_DCT2 };
 
 static inline void unit_root(long double num, long double den, long double& c, long double& s) {
     // exp(-2*pi*i*num/den) in extended precision
@@ -968,6 +969,46 @@ struct PlanBuilder {
         return finish_tile(s, O, 1, 1, "real->complex fused pack + post-twiddle");
     }
 
+    // rows of n reals -> rows of n reals, DCT-II (dct.rs:523-559) on the packed n/2-point transform
+    bool add_dct2(int64_t n, int64_t O, ArrayRef src, ArrayRef dst, double scale, double scale_dc, bool type3, bool sine) {
+        Step s;
+        const int L = (int)(n / 2);
+        const KernelEntry* base = pick_kernel(prec, L, false, 0);
+        s.k = base ? flavour_of(base, type3 ? 6 : 5) : nullptr;
+        if (!s.k || O % s.k->TL != 0) return fail(SFC_ERR_NOT_IMPLEMENTED, "no fused DCT-II kernel for this length / batch");
+        s.src = src.role;
+        s.dst = dst.role;
+        s.src_esize = cs;  // both arrays addressed as packed complex rows of n/2
+        s.dst_esize = cs;
+        set_io(s.p.in, 0, L, 1, 1, L, 1, 0);
+        set_io(s.p.out, 0, L, 1, 1, L, 1, 0);
+        s.p.map_in = s.p.map_out = MAP_ROW;
+        s.p.ld_op = LD_C;
+        s.p.st_op = ST_C;
+        s.p.flags = F_IN_NOMASK | F_OUT_NOMASK | (sine ? F_TRIG_SINE : 0);
+        // type 3: the kernel evaluates scale' * 2 * (dc' X0 / 2 + sum_k>=1 ...): scale' = scale, dc' = scale_dc
+        s.p.scale = scale;
+        s.p.scale_dc = scale_dc;
+        s.p.rtw = table_rtw(prec, L, err);
+        if (!s.p.rtw) return false;
+        s.p.aux_out = roots_table(TK_DCT2, prec, L + 1, 4.0L * (long double)n, 1.0L, n, err);  // exp(-i pi k / (2n)), k <= n/2
+        if (!s.p.aux_out) return false;
+        s.p.peer_shift = -1;
+        s.p.tw = table_stage_tw(prec, L, err);
+        if (!s.p.tw) return false;
+        s.p.nlanes = (uint32_t)O;
+        s.p.inner_count = 1;
+        s.p.tiles_per_batch = (uint32_t)(O / s.k->TL);
+        s.nbatch = 1;
+        dev_bytes += O * n * 2 * (int64_t)rs;
+        char buf[200];
+        snprintf(buf, sizeof buf, "fused %s-%s rows (Makhoul packing): tile L=%d TL=%d threads=%d smem=%zu lanes=%lld",
+                 sine ? "DST" : "DCT", type3 ? "III" : "II", s.k->L, s.k->TL, s.k->threads, s.k->smem, (long long)O);
+        s.desc = buf;
+        pl.steps_.push_back(s);
+        return true;
+    }
+
     // rows of src.n (<= n/2+1 used) complex -> rows of n reals (rfft.rs:92-178)
     bool add_c2r(int64_t n, int64_t O, ArrayRef src, ArrayRef dst, double scale) {
         Step s;
@@ -1117,6 +1158,27 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
             return nullptr;
         }
         const int la = axes.back();
+        if (d.flags & (SFC_DESC_DCT2 | SFC_DESC_DCT3)) {
+            const int64_t n = shape[la];
+            if (axes.size() != 1 || la != d.ndim - 1 || !is_pow2(n) || n < 128 || n / 2 > lmax_for(prec) || prec != PREC_F64) {
+                err = {SFC_ERR_NOT_IMPLEMENTED, "fused DCT-II needs f64 rows (last axis) of a power-of-two length in 128..16384"};
+                return nullptr;
+            }
+            pl.in_elems = pl.out_elems = total;
+            pl.in_esize = pl.out_esize = rs;
+            double dc = d.scale_dc != 0.0 ? d.scale_dc : 1.0;
+            if (d.flags & SFC_DESC_DCT2_ORTHO0) dc *= 0.70710678118654752440;
+            if (!B.add_dct2(n, total / n, {R_IN, true, n}, {R_OUT, true, n}, d.scale, dc, (d.flags & SFC_DESC_DCT3) != 0,
+                            (d.flags & SFC_DESC_TRIG_SINE) != 0))
+                return nullptr;
+            pl.info.in_bytes = pl.info.out_bytes = total * (int64_t)rs;
+            pl.info.algorithmic_bytes = 2 * total * (int64_t)rs;
+            pl.info.device_bytes = B.dev_bytes;
+            pl.info.num_passes = 1;
+            pl.info.num_launches = 1;
+            pl.info.nominal_flops = 2.5 * (double)total * std::log2((double)n);
+            return sp;
+        }
         std::vector<int64_t> hshape = shape;
         hshape[la] = shape[la] / 2 + 1;
         pl.in_elems = total;

@@ -29,7 +29,8 @@ class FftPlan:
     def __init__(self, shape: Sequence[int], axes: Optional[Sequence[int]] = None, kind: str = "c2c",
                  prec: str = "f64", forward: bool = True, scale: float = 1.0,
                  in_shape: Optional[Sequence[int]] = None, real_input: bool = False, scatter_parts: int = 0,
-                 axis_in_len: int = 0, axis_out_len: int = 0, aux_in=None, aux_out=None, real_output: bool = False):
+                 axis_in_len: int = 0, axis_out_len: int = 0, aux_in=None, aux_out=None, real_output: bool = False,
+                 dct2: bool = False, dct2_ortho: bool = False):
         lib = _lib.load()
         shape = [int(s) for s in shape]
         if not 1 <= len(shape) <= _lib.SFC_MAX_DIMS:
@@ -64,6 +65,8 @@ class FftPlan:
             self._keep = (aux_in, aux_out)
         if real_output:
             d.flags |= _lib.SFC_DESC_REAL_OUTPUT
+        if dct2:  # kind "r2c" over the last axis: fused DCT-II rows, real in / real out (dct.rs:523-559)
+            d.flags |= _lib.SFC_DESC_DCT2 | (_lib.SFC_DESC_DCT2_ORTHO0 if dct2_ortho else 0)
         self._h = C.c_void_p()
         check(lib.sfc_plan_create(C.byref(self._h), C.byref(d)))
         self._lib = lib

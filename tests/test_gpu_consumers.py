@@ -216,3 +216,39 @@ def test_memory_efficient_and_ndim_optimized(sb, co):
     assert rel(sb.fftn_optimized(a), np.fft.fftn(a)) <= TOL  # power-of-two extents: the plain N-D transform
     with pytest.raises(sb.ValueError_):
         sb.fftn_optimized(a, None, [2])
+
+
+@pytest.mark.parametrize("n", [128, 256, 512, 1024, 2048, 4096])
+def test_fused_dct_dst_types_2_3_rows(sb, co, n):
+    """Types II / III on contiguous power-of-two rows take the one-kernel Makhoul path (api_ext.cu); batches that do not
+    fill a tile fall back to the 2n-point path: both against the literal O(n^2) sums."""
+    rng = np.random.default_rng(n)
+    for rows in (64, 3):
+        a = rng.standard_normal((rows, n))
+        for t in (2, 3):
+            for norm in (None, "ortho"):
+                assert rel(sb.dctn(a, t, norm, [1]), co.dctn(a[:3], t, norm, [1]) if rows == 3 else
+                           np.vstack([co.dctn(a[:2], t, norm, [1]), sb.dctn(a, t, norm, [1])[2:]])) <= TOL
+                assert rel(sb.idctn(a, t, norm, [1])[:2], co.idctn(a[:2], t, norm, [1])) <= TOL, ("idct", t, norm, n, rows)
+                assert rel(sb.dstn(a, t, norm, [1])[:2], co.dstn(a[:2], t, norm, [1])) <= TOL, ("dst", t, norm, n, rows)
+                assert rel(sb.idstn(a, t, norm, [1])[:2], co.idstn(a[:2], t, norm, [1])) <= TOL, ("idst", t, norm, n, rows)
+    # last row of a full batch too (tile boundaries)
+    a = rng.standard_normal((64, n))
+    assert rel(sb.dctn(a, 2, "ortho", [1])[-1], co.dct(a[-1], 2, "ortho")) <= TOL
+    assert rel(sb.idstn(a, 3, None, [1])[-1], co.idst(a[-1], 3, None)) <= TOL
+
+
+@pytest.mark.parametrize("n", [8192, 16384])
+def test_fused_dct_dst_largest_rows_against_scipy(sb, n):
+    """At these lengths the literal O(n^2) sums of the reference (angles up to pi*n evaluated in f64) are themselves only
+    good to ~1e-12, so the fused kernels are checked against scipy's transforms through the identities pinned in
+    tests/test_consumers_oracle.py."""
+    import scipy.fft as sf
+    a = np.random.default_rng(n).standard_normal((16, n))
+    assert rel(sb.dctn(a, 2, None, [1]), sf.dct(a, 2, axis=1) / 2) <= TOL
+    assert rel(sb.dctn(a, 2, "ortho", [1]), sf.dct(a, 2, axis=1, norm="ortho")) <= TOL
+    assert rel(sb.idctn(a, 2, None, [1]), 2 * sf.idct(a, 2, axis=1)) <= TOL
+    assert rel(sb.dctn(a, 3, None, [1]), 2 * sf.idct(a, 2, axis=1)) <= TOL
+    assert rel(sb.idctn(a, 3, None, [1]), (sf.dct(a, 3, axis=1) + a[:, :1]) / 2) <= TOL
+    assert rel(sb.dstn(a, 2, None, [1]), sf.dst(a, 2, axis=1) / 2) <= TOL
+    assert rel(sb.idctn(sb.dctn(a, 2, "ortho", [1]), 2, "ortho", [1]), a) <= TOL
