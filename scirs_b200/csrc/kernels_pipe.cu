@@ -7,5 +7,6 @@ void register_kernels_pipe(void (*add)(const KernelEntry&)) {
     SFC_ADD_PIPE(double, 1024, 4, false)
     SFC_ADD_PIPE(double, 512, 8, false)
     SFC_ADD_PIPE(double, 256, 16, false)
+    SFC_ADD_PIPE(double, 8192, 1, false)
 }
 }  // namespace sfc

@@ -437,6 +437,13 @@ static int pipe_enabled() {  // 0 off, 1 row and column tiles, 2 row tiles only
     }();
     return v;
 }
+static bool pipe_big_enabled() {
+    static int v = [] {
+        const char* e = getenv("SFC_PIPE_BIG");
+        return e ? atoi(e) : 1;
+    }();
+    return v != 0;
+}
 static int64_t pipe_min_tiles() {
     static int64_t v = [] {
         const char* e = getenv("SFC_PIPE_MIN_TILES");
@@ -563,14 +570,16 @@ struct PlanBuilder {
             }
             // persistent TMA-pipelined flavour: unmasked complex loads of tiles whose TL lanes are adjacent in
             // memory (16-byte aligned bulk copies), and enough tiles for every resident CTA to pipeline a few
-            if (mode == 1 && s.k->mode == 1 && pipe_enabled() && (s.p.flags & F_IN_NOMASK) &&
+            // 128 KiB row tiles (one CTA per SM: nothing else overlaps its loads) always take it when they can
+            const bool big_row = s.k->L * s.k->TL * (int)cs > 65536 && s.p.map_in == MAP_ROW && pipe_big_enabled();
+            if (mode == 1 && s.k->mode == 1 && (pipe_enabled() || big_row) && (s.p.flags & F_IN_NOMASK) &&
                 (s.p.ld_op == LD_C || s.p.ld_op == LD_C_MUL) && prec == PREC_F64) {
                 const bool rows_ok = s.p.map_in == MAP_ROW && s.p.in.elem_stride == 1;
                 const bool cols_ok = pipe_enabled() == 1 && s.p.map_in == MAP_COL &&
                                      ((s.p.in.inner_stride == 1 && (int64_t)s.p.inner_count % s.k->TL == 0) ||
                                       (s.p.inner_count == 1 && s.p.in.outer_stride == 1));
                 const int64_t total_tiles = tiles * nbatch;
-                if ((rows_ok || cols_ok) && total_tiles >= pipe_min_tiles()) {
+                if ((rows_ok || cols_ok) && total_tiles >= (big_row ? 2 * 148 : pipe_min_tiles())) {
                     const KernelEntry* f = flavour_of(s.k, 4);
                     if (f) s.k = f;
                 }
