@@ -390,7 +390,7 @@ extern "C" __attribute__((visibility("default"))) int sfc_exec_host(sfc_plan* pl
         const int64_t bytes = p.info.in_bytes + p.info.out_bytes;
         static const int want = [] {
             const char* e = getenv("SFC_HOST_CHUNKS");
-            return e ? atoi(e) : 8;
+            return e ? atoi(e) : 16;  // fill + drain cost 1/chunks of a one-way transfer
         }();
         if (batch0 && want > 1 && bytes >= ((int64_t)64 << 20)) {
             const int nchunks = (int)std::min<int64_t>(want, p.desc.shape[0]);

@@ -18,9 +18,10 @@ cases = {
     "fftn1024": ([1024, 1024, 1024], [0, 1, 2], "c2c", "f64", 1024 ** 3 * 2, 1024 ** 3 * 2),
     "fft1m64": ([64, 1 << 20], [1], "c2c", "f64", (64 << 20) * 2, (64 << 20) * 2),
 }
+cases["dct2"] = ([65536, 4096], [1], "r2c", "f64", 65536 * 4096, 65536 * 4096)
 shape, axes, kind, prec, ni, no = cases[case]
 dt = torch.float64 if prec == "f64" else torch.float32
-p = FftPlan(shape, axes, kind, prec, True)
+p = FftPlan(shape, axes, kind, prec, True, dct2=(case == "dct2"))
 din = torch.randn(ni, device=dev, dtype=dt)
 dout = torch.empty(no, device=dev, dtype=dt)
 for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 3):
