@@ -132,10 +132,16 @@ static const KernelEntry* pick_kernel(int prec, int L, bool want_wide, int dbl) 
 static const KernelEntry* pick_kernel_two_per_sm(int prec, int L, int dbl) {
     int n = 0;
     const KernelEntry* t = kernel_table(&n);
+    // the forced points-per-thread variant only where it is compiled, else the default (16)
+    int want_e = std::min(16, L);
+    if (forced_e())
+        for (int i = 0; i < n; ++i)
+            if (t[i].mode == 0 && t[i].groups == 1 && t[i].prec == prec && t[i].L == L && t[i].dbl == dbl &&
+                t[i].E == std::min(forced_e(), L))
+                want_e = t[i].E;
     const KernelEntry *best = nullptr, *smallest = nullptr;
     for (int i = 0; i < n; ++i) {
-        if (t[i].mode != 0 || t[i].groups != 1 || t[i].prec != prec || t[i].L != L || t[i].dbl != dbl ||
-            t[i].E != std::min(forced_e() ? forced_e() : 16, L))
+        if (t[i].mode != 0 || t[i].groups != 1 || t[i].prec != prec || t[i].L != L || t[i].dbl != dbl || t[i].E != want_e)
             continue;
         if (!smallest || t[i].TL < smallest->TL) smallest = &t[i];
         if (t[i].smem > (size_t)100 * 1024) continue;
