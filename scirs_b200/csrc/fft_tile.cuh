@@ -859,7 +859,26 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
             const int64_t step = (int64_t)TPL * p.in.elem_stride;
             // optional zero padding: element e is real data iff e*pos_es + pos0 < len, i.e. e < elim
             int elim = L;
-            if (!(p.flags & F_IN_NOMASK)) {
+            bool staged_in = false;
+            if constexpr (L <= 64 && MODE == TM_FAST_C2C) staged_in = (p.flags & F_STAGE_IN) != 0;
+            if (staged_in) {
+                if constexpr (L <= 64 && MODE == TM_FAST_C2C) {
+                    // staging pitch: a quarter warp (8 threads x 16 B) reads TPL adjacent elements of 8/TPL rows
+                    constexpr int SP = L + (TPL < 8 ? TPL : 8);
+                    static_assert((size_t)TL * SP <= (size_t)TL * LP, "staging rows must fit the exchange buffer");
+                    const cx* __restrict__ tb = reinterpret_cast<const cx*>(p.in.ptr) + (int64_t)batch * p.in.batch_stride +
+                                                (int64_t)tile * (TL * L);
+#pragma unroll
+                    for (int k = 0; k < E; ++k) {
+                        const int f = tid + k * C::NT;
+                        sm[(f / L) * SP + (f % L)] = tb[f];
+                    }
+                    C::sync(grp);
+#pragma unroll
+                    for (int m = 0; m < E; ++m) a[m] = sm[t0 * SP + i0 + m * TPL];
+                    C::sync(grp);  // the exchange (or the staged store) reuses the buffer
+                }
+            } else if (!(p.flags & F_IN_NOMASK)) {
                 const int64_t rem = p.in.len - pos0;
                 elim = rem <= 0 ? 0 : (int)min((uint32_t)L, ((uint32_t)rem + (uint32_t)p.in.pos_es - 1u) / (uint32_t)p.in.pos_es);
 #pragma unroll
@@ -1227,6 +1246,22 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
                 *dst = a[m];
             }
             return;
+        }
+        if constexpr (L <= 64 && MODE == TM_FAST_C2C) {
+            if (p.flags & F_STAGE_OUT) {
+                constexpr int SP = L + (TPL < 8 ? TPL : 8);
+                C::sync(grp);  // the last exchange has been read by everybody
+#pragma unroll
+                for (int m = 0; m < E; ++m) sm[t1 * SP + i1 + m * TPL] = a[m];
+                C::sync(grp);
+                cx* __restrict__ tb = reinterpret_cast<cx*>(p.out.ptr) + (int64_t)batch * p.out.batch_stride + (int64_t)tile * (TL * L);
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    const int f = tid + k * C::NT;
+                    tb[f] = sm[(f / L) * SP + (f % L)];
+                }
+                return;
+            }
         }
         cx* __restrict__ dst = reinterpret_cast<cx*>(p.out.ptr) + off + (int64_t)i1 * p.out.elem_stride;
         const int64_t step = (int64_t)TPL * p.out.elem_stride;

@@ -45,7 +45,12 @@ enum PassFlags : uint32_t {
     F_CHIRP_GEN = 1u << 8,
     // fused DCT kernels computing the sine transforms: DST-II(x)[k] = DCT-II((-1)^m x[m])[n-1-k],
     // DST-III(x)[k] = (-1)^k DCT-III(x reversed)[k]   (sign flips and index reversals folded into load / store)
-    F_TRIG_SINE = 1u << 9,     // LD_*_MUL / ST_MUL: generate the Bluestein chirp in registers instead of reading aux_*    // likewise for stores       // store only the real part into a real array (irfftn, rfft.rs:722)
+    F_TRIG_SINE = 1u << 9,
+    // short contiguous rows (L <= 64): the tile is moved between global and shared memory with fully coalesced
+    // 128-bit accesses (thread t takes flat element t, t + NT, ...) and the per-thread rows are read from there;
+    // without it thread t walks its own 16..64-element row and every warp request touches 32 cache lines
+    F_STAGE_IN = 1u << 10,
+    F_STAGE_OUT = 1u << 11,     // LD_*_MUL / ST_MUL: generate the Bluestein chirp in registers instead of reading aux_*    // likewise for stores       // store only the real part into a real array (irfftn, rfft.rs:722)
 };
 
 struct IoDesc {

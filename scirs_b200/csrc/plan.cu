@@ -432,6 +432,16 @@ static int64_t l2_total_bytes() {
     return v;
 }
 
+// measured (rows, 4 GiB, f64 / f32): L = 16: 61 -> 103 % / 30 -> 96 % of the measured HBM peak, L = 8: 58 -> 80 % /
+// 53 -> 73 %; L = 2, 4 (32..64 B rows, already coalesced) lose 3-14 points; L = 32 / 64 (which also exchange through
+// the buffer) 69 -> 69 % / 89 -> 73 %: staged for 8 <= L <= 16 only
+static int stage_io_max_len() {
+    static int v = [] {
+        const char* e = getenv("SFC_STAGE_IO");
+        return e ? atoi(e) : 16;
+    }();
+    return v;
+}
 static int pipe_enabled() {  // 0 off, 1 row and column tiles, 2 row tiles only
     static int v = [] {
         // measured on B200 (profiles/README.md): the half-size split exchange that makes room for the landing
@@ -573,6 +583,15 @@ struct PlanBuilder {
             if (mode) {
                 const KernelEntry* f = flavour_of(s.k, mode);
                 if (f) s.k = f;
+            }
+            // short contiguous rows: coalesced staging of the whole tile through shared memory (F_STAGE_*)
+            if (mode == 1 && s.k->mode == 1 && s.k->L >= 8 && s.k->L <= stage_io_max_len() && s.p.inner_count == 1) {
+                if (s.p.map_in == MAP_ROW && s.p.ld_op == LD_C && (s.p.flags & F_IN_NOMASK) && s.p.in.elem_stride == 1 &&
+                    s.p.in.outer_stride == s.k->L)
+                    s.p.flags |= F_STAGE_IN;
+                if (s.p.map_out == MAP_ROW && (s.p.flags & F_OUT_NOMASK) && s.p.out.elem_stride == 1 &&
+                    s.p.out.outer_stride == s.k->L && !s.scatter)
+                    s.p.flags |= F_STAGE_OUT;
             }
             // persistent TMA-pipelined flavour: unmasked complex loads of tiles whose TL lanes are adjacent in
             // memory (16-byte aligned bulk copies), and enough tiles for every resident CTA to pipeline a few
