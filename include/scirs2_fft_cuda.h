@@ -113,7 +113,7 @@ typedef struct sfc_desc {
 #define SFC_DESC_AUX_MUL 8
 /* C2C only: store the real part of the result into a real array */
 #define SFC_DESC_REAL_OUTPUT 16
-/* R2C over the LAST axis only, power-of-two n >= 128: the plan computes the DCT-II of every row,
+/* R2C over ONE axis (any position), power-of-two n >= 128: the plan computes the DCT-II of every lane along it,
  * X[k] = scale * sum_i x[i] cos(pi (i + 1/2) k / n) (dct.rs:523-559), real in / real out, as one fused kernel on the
  * n/2-point transform; with SFC_DESC_DCT2_ORTHO0 output 0 is additionally multiplied by 1/sqrt(2) (dct.rs:552-553) */
 #define SFC_DESC_DCT2 32

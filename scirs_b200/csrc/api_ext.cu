@@ -257,7 +257,7 @@ int trig_axis(int kind, int type, bool inverse, bool ortho, int64_t O, int64_t N
     d.axis_out_len = N;
     PlanError perr{0, ""};
     std::string es;
-    if (fuse_enabled() && (type == 2 || type == 3) && I == 1 && is_pow2_i64(N) && N >= 128) {
+    if (fuse_enabled() && (type == 2 || type == 3) && is_pow2_i64(N) && N >= 128) {
         // Types II / III of contiguous rows: ONE kernel on the N/2-point packed transform (Makhoul), 8x less data on
         // chip than the 2N-point formulation.  Every variant is  C2: g * sum_i x[i] cos(pi (i+1/2) k / N)  (output 0
         // times dc)  or  C3: scale * (dc * X[0] + 2 sum_k>=1 X[k] cos(pi k (i+1/2) / N)),  or their sine twins.
@@ -278,9 +278,10 @@ int trig_axis(int kind, int type, bool inverse, bool ortho, int64_t O, int64_t N
         }
         sfc_desc dd;
         memset(&dd, 0, sizeof dd);
-        dd.ndim = 2;
+        dd.ndim = 3;
         dd.shape[0] = O;
         dd.shape[1] = N;
+        dd.shape[2] = I;
         dd.naxes = 1;
         dd.axes[0] = 1;
         dd.kind = SFC_R2C;

@@ -795,14 +795,17 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
                 }
             }
         } else if constexpr (MODE == TM_FAST_DCT2) {
-            // v[p] = x[2p] (p < N/2), x[2N-2p-1] (p >= N/2), packed as z[j] = v[2j] + i v[2j+1]; N = 2L reals per row
+            // v[p] = x[2p] (p < N/2), x[2N-2p-1] (p >= N/2), packed as z[j] = v[2j] + i v[2j+1]; N = 2L reals per lane.
+            // The I/O descriptors of the DCT flavours count REAL elements (rows: elem_stride 1; column tiles: the
+            // stride of the transformed axis, adjacent lanes adjacent in memory).
             if constexpr (E == 16) {
-                const T* __restrict__ xr = reinterpret_cast<const T*>(p.in.ptr) + 2 * off;
+                const T* __restrict__ xr = reinterpret_cast<const T*>(p.in.ptr) + off;
+                const int64_t es = p.in.elem_stride;
 #pragma unroll
                 for (int m = 0; m < E; ++m) {
                     const int j = i0 + m * TPL;
-                    if (m < E / 2) a[m] = {xr[4 * j], xr[4 * j + 2]};
-                    else a[m] = {xr[4 * L - 4 * j - 1], xr[4 * L - 4 * j - 3]};
+                    if (m < E / 2) a[m] = {xr[(4 * j) * es], xr[(4 * j + 2) * es]};
+                    else a[m] = {xr[(4 * L - 4 * j - 1) * es], xr[(4 * L - 4 * j - 3) * es]};
                 }
                 if (p.flags & F_TRIG_SINE) {  // (-1)^i x[i]: the second half holds the odd-indexed samples
 #pragma unroll
@@ -813,10 +816,11 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
             if constexpr (E == 16) {
                 // stage V[k] = conj(w_k) (X[k] - i X[N-k]), k <= L (X[N] = 0), then the c2r pre-twiddle
                 constexpr int N = 2 * L;
-                const T* __restrict__ xr = reinterpret_cast<const T*>(p.in.ptr) + 2 * off;
+                const T* __restrict__ xr = reinterpret_cast<const T*>(p.in.ptr) + off;
+                const int64_t es = p.in.elem_stride;
                 const cx* __restrict__ om = reinterpret_cast<const cx*>(p.aux_out);
                 const bool rev = (p.flags & F_TRIG_SINE) != 0;  // DST-III reads its input reversed
-                auto X = [&](int k) { return rev ? xr[N - 1 - k] : xr[k]; };
+                auto X = [&](int k) { return rev ? xr[(N - 1 - k) * es] : xr[k * es]; };
                 cx* row = sm + t0 * LP;
 #pragma unroll
                 for (int m = 0; m < E; ++m) {
@@ -1054,8 +1058,9 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
             constexpr int N = 2 * L;
             // DST-II: output k of the cosine transform is output N-1-k of the sine transform
             const bool rev = (p.flags & F_TRIG_SINE) != 0;
-            T* __restrict__ dst = reinterpret_cast<T*>(p.out.ptr) + 2 * off + (rev ? N - 1 : 0);
-            const int ds = rev ? -1 : 1;
+            const int64_t oes = p.out.elem_stride;
+            T* __restrict__ dst = reinterpret_cast<T*>(p.out.ptr) + off + (rev ? (N - 1) * oes : 0);
+            const int64_t ds = rev ? -oes : oes;
             const cx* __restrict__ om = reinterpret_cast<const cx*>(p.aux_out);  // w_k = exp(-i pi k / (2N)), k <= L
             const cx wi = reinterpret_cast<const cx*>(p.rtw)[i1];
             const T h = (T)0.5 * scale;
@@ -1092,17 +1097,18 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
     } else if constexpr (MODE == TM_FAST_DCT3) {
         if constexpr (E == 16) {
             // a[m] = (v[2j], v[2j+1]), j = i1 + m*TPL: undo the even / reversed-odd permutation on the way out
-            T* __restrict__ dst = reinterpret_cast<T*>(p.out.ptr) + 2 * off;
+            T* __restrict__ dst = reinterpret_cast<T*>(p.out.ptr) + off;
+            const int64_t oes = p.out.elem_stride;
             const T sg = (p.flags & F_TRIG_SINE) ? -scale : scale;  // DST-III: (-1)^i on the odd-indexed outputs
 #pragma unroll
             for (int m = 0; m < E; ++m) {
                 const int j = i1 + m * TPL;
                 if (m < E / 2) {
-                    dst[4 * j] = a[m].x * scale;
-                    dst[4 * j + 2] = a[m].y * scale;
+                    dst[(4 * j) * oes] = a[m].x * scale;
+                    dst[(4 * j + 2) * oes] = a[m].y * scale;
                 } else {
-                    dst[4 * L - 4 * j - 1] = a[m].x * sg;
-                    dst[4 * L - 4 * j - 3] = a[m].y * sg;
+                    dst[(4 * L - 4 * j - 1) * oes] = a[m].x * sg;
+                    dst[(4 * L - 4 * j - 3) * oes] = a[m].y * sg;
                 }
             }
         }

@@ -1003,24 +1003,33 @@ struct PlanBuilder {
         return finish_tile(s, O, 1, 1, "real->complex fused pack + post-twiddle");
     }
 
-    // rows of n reals -> rows of n reals, DCT-II (dct.rs:523-559) on the packed n/2-point transform
-    bool add_dct2(int64_t n, int64_t O, ArrayRef src, ArrayRef dst, double scale, double scale_dc, bool type3, bool sine) {
+    // lanes of n reals -> lanes of n reals along the middle axis of [O][n][I]: DCT/DST II or III (dct.rs:523-684,
+    // dst.rs:484-592) on the packed n/2-point transform.  The I/O descriptors count REAL elements.
+    bool add_dct2(int64_t n, int64_t O, int64_t I, ArrayRef src, ArrayRef dst, double scale, double scale_dc, bool type3,
+                  bool sine) {
         Step s;
         const int L = (int)(n / 2);
-        const KernelEntry* base = pick_kernel(prec, L, false, 0);
-        s.k = base ? flavour_of(base, type3 ? 6 : 5) : nullptr;
-        if (!s.k || O % s.k->TL != 0) return fail(SFC_ERR_NOT_IMPLEMENTED, "no fused DCT-II kernel for this length / batch");
+        const bool col = I > 1;
+        int cnt = 0;
+        const KernelEntry* t = kernel_table(&cnt);
+        s.k = nullptr;
+        for (int i = 0; i < cnt; ++i)
+            if (t[i].prec == prec && t[i].L == L && t[i].mode == (type3 ? 6 : 5)) s.k = &t[i];
+        const int64_t lanes = O * I;
+        if (!s.k || lanes % s.k->TL != 0 || (col && I % s.k->TL != 0) || lanes > 0xFFFFFFFFLL)
+            return fail(SFC_ERR_NOT_IMPLEMENTED, "no fused DCT kernel for this length / batch");
+        if (col && (int64_t)s.k->TL * (int64_t)rs < 32)
+            return fail(SFC_ERR_NOT_IMPLEMENTED, "column tiles of the fused DCT kernel would be narrower than a sector");
         s.src = src.role;
         s.dst = dst.role;
-        s.src_esize = cs;  // both arrays addressed as packed complex rows of n/2
-        s.dst_esize = cs;
-        set_io(s.p.in, 0, L, 1, 1, L, 1, 0);
-        set_io(s.p.out, 0, L, 1, 1, L, 1, 0);
-        s.p.map_in = s.p.map_out = MAP_ROW;
+        s.src_esize = rs;
+        s.dst_esize = rs;
+        set_io(s.p.in, 0, n * I, 1, I, n, 1, 0);
+        set_io(s.p.out, 0, n * I, 1, I, n, 1, 0);
+        s.p.map_in = s.p.map_out = col ? MAP_COL : MAP_ROW;
         s.p.ld_op = LD_C;
         s.p.st_op = ST_C;
         s.p.flags = F_IN_NOMASK | F_OUT_NOMASK | (sine ? F_TRIG_SINE : 0);
-        // type 3: the kernel evaluates scale' * 2 * (dc' X0 / 2 + sum_k>=1 ...): scale' = scale, dc' = scale_dc
         s.p.scale = scale;
         s.p.scale_dc = scale_dc;
         s.p.rtw = table_rtw(prec, L, err);
@@ -1030,14 +1039,15 @@ struct PlanBuilder {
         s.p.peer_shift = -1;
         s.p.tw = table_stage_tw(prec, L, err);
         if (!s.p.tw) return false;
-        s.p.nlanes = (uint32_t)O;
-        s.p.inner_count = 1;
-        s.p.tiles_per_batch = (uint32_t)(O / s.k->TL);
+        s.p.nlanes = (uint32_t)lanes;
+        s.p.inner_count = (uint32_t)I;
+        s.p.tiles_per_batch = (uint32_t)(lanes / s.k->TL);
         s.nbatch = 1;
-        dev_bytes += O * n * 2 * (int64_t)rs;
+        dev_bytes += lanes * n * 2 * (int64_t)rs;
         char buf[200];
-        snprintf(buf, sizeof buf, "fused %s-%s rows (Makhoul packing): tile L=%d TL=%d threads=%d smem=%zu lanes=%lld",
-                 sine ? "DST" : "DCT", type3 ? "III" : "II", s.k->L, s.k->TL, s.k->threads, s.k->smem, (long long)O);
+        snprintf(buf, sizeof buf, "fused %s-%s %s (Makhoul packing): tile L=%d TL=%d threads=%d smem=%zu lanes=%lld",
+                 sine ? "DST" : "DCT", type3 ? "III" : "II", col ? "columns" : "rows", s.k->L, s.k->TL, s.k->threads, s.k->smem,
+                 (long long)lanes);
         s.desc = buf;
         pl.steps_.push_back(s);
         return true;
@@ -1194,16 +1204,16 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
         const int la = axes.back();
         if (d.flags & (SFC_DESC_DCT2 | SFC_DESC_DCT3)) {
             const int64_t n = shape[la];
-            if (axes.size() != 1 || la != d.ndim - 1 || !is_pow2(n) || n < 128 || n / 2 > lmax_for(prec) || prec != PREC_F64) {
-                err = {SFC_ERR_NOT_IMPLEMENTED, "fused DCT-II needs f64 rows (last axis) of a power-of-two length in 128..16384"};
+            if (axes.size() != 1 || !is_pow2(n) || n < 128 || n / 2 > lmax_for(prec) || prec != PREC_F64) {
+                err = {SFC_ERR_NOT_IMPLEMENTED, "fused DCT needs ONE f64 axis of a power-of-two length in 128..16384"};
                 return nullptr;
             }
             pl.in_elems = pl.out_elems = total;
             pl.in_esize = pl.out_esize = rs;
             double dc = d.scale_dc != 0.0 ? d.scale_dc : 1.0;
             if (d.flags & SFC_DESC_DCT2_ORTHO0) dc *= 0.70710678118654752440;
-            if (!B.add_dct2(n, total / n, {R_IN, true, n}, {R_OUT, true, n}, d.scale, dc, (d.flags & SFC_DESC_DCT3) != 0,
-                            (d.flags & SFC_DESC_TRIG_SINE) != 0))
+            if (!B.add_dct2(n, prod(shape, 0, la), prod(shape, la + 1, shape.size()), {R_IN, true, n}, {R_OUT, true, n}, d.scale, dc,
+                            (d.flags & SFC_DESC_DCT3) != 0, (d.flags & SFC_DESC_TRIG_SINE) != 0))
                 return nullptr;
             pl.info.in_bytes = pl.info.out_bytes = total * (int64_t)rs;
             pl.info.algorithmic_bytes = 2 * total * (int64_t)rs;

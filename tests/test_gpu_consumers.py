@@ -252,3 +252,19 @@ def test_fused_dct_dst_largest_rows_against_scipy(sb, n):
     assert rel(sb.idctn(a, 3, None, [1]), (sf.dct(a, 3, axis=1) + a[:, :1]) / 2) <= TOL
     assert rel(sb.dstn(a, 2, None, [1]), sf.dst(a, 2, axis=1) / 2) <= TOL
     assert rel(sb.idctn(sb.dctn(a, 2, "ortho", [1]), 2, "ortho", [1]), a) <= TOL
+
+
+@pytest.mark.parametrize("shape,axis", [((256, 64), 0), ((1024, 32), 0), ((4, 128, 64), 1), ((2, 512, 16), 1), ((2048, 8), 0),
+                                        ((128, 64, 2), 0)])
+def test_fused_dct_dst_types_2_3_strided_axes(sb, co, shape, axis):
+    """Types II / III along a strided axis use the same fused kernels with column tiles (adjacent lanes adjacent in memory)."""
+    a = np.random.default_rng(sum(shape)).standard_normal(shape)
+    for t in (2, 3):
+        for norm in (None, "ortho"):
+            assert rel(sb.dctn(a, t, norm, [axis]), co.dctn(a, t, norm, [axis])) <= TOL, ("dct", t, norm)
+            assert rel(sb.idctn(a, t, norm, [axis]), co.idctn(a, t, norm, [axis])) <= TOL, ("idct", t, norm)
+            assert rel(sb.dstn(a, t, norm, [axis]), co.dstn(a, t, norm, [axis])) <= TOL, ("dst", t, norm)
+            assert rel(sb.idstn(a, t, norm, [axis]), co.idstn(a, t, norm, [axis])) <= TOL, ("idst", t, norm)
+    if len(shape) == 2:
+        assert rel(sb.dct2(a, 2, "ortho"), co.dct2(a, 2, "ortho")) <= TOL
+        assert rel(sb.idct2(a, 2, "ortho"), co.idct2(a, 2, "ortho")) <= TOL
