@@ -212,8 +212,6 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     sb.error.check(lib.sfc_init(local))
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     hbm, hbm_src = peaks()
@@ -471,4 +469,10 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner, ...) are sent to
+    # stderr for the whole run and the real stdout is only used by print() below
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     main()
