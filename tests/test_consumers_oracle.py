@@ -116,3 +116,34 @@ def test_stft_and_spectrogram_shapes_and_values():
         co.stft(x, "hann", 128, 128)
     with pytest.raises(co.OracleError):
         co.stft(x, "hann", 128, 64, 64)
+
+
+# ------------------------------------------------------------------ committed extended-precision vectors
+import os
+
+GC = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_consumers_v1.npz"))
+
+
+def _rel(a, b):
+    d = np.linalg.norm(np.asarray(a) - np.asarray(b)); r = np.linalg.norm(np.asarray(b))
+    return d / r if r > 0 else d
+
+
+def test_oracle_against_extended_precision_golden_vectors():
+    """tests/golden/make_golden_consumers.py evaluates the reference's formulas in long double; the f64 restatement
+    must agree to ~1e-13 (its own rounding), for every type / direction / norm and the Hartley / hfft / hilbert family."""
+    for n in (2, 5, 8, 16, 33, 128, 257):
+        x = GC[f"trig_x_{n}"]
+        for kind in ("dct", "dst"):
+            for t in (1, 2, 3, 4):
+                for inv in (0, 1):
+                    for ortho in (0, 1):
+                        fn = getattr(co, ("i" if inv else "") + kind)
+                        got = fn(x, t, "ortho" if ortho else None)
+                        assert _rel(got, GC[f"{kind}_{n}_t{t}_i{inv}_o{ortho}"]) < 2e-13, (kind, n, t, inv, ortho)
+    for n in (1, 4, 5, 12, 64, 100):
+        x, z, m = GC[f"real_{n}"], GC[f"cplx_{n}"], n + 3
+        assert _rel(co.dht(x), GC[f"dht_{n}"]) < 1e-13
+        assert _rel(co.hfft(z, m), GC[f"hfft_{n}_n{m}"]) < 1e-13
+        assert _rel(co.ihfft(x, m), GC[f"ihfft_{n}_n{m}"]) < 1e-13
+        assert _rel(co.hilbert(x), GC[f"hilbert_{n}"]) < 1e-13

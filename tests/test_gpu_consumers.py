@@ -268,3 +268,22 @@ def test_fused_dct_dst_types_2_3_strided_axes(sb, co, shape, axis):
     if len(shape) == 2:
         assert rel(sb.dct2(a, 2, "ortho"), co.dct2(a, 2, "ortho")) <= TOL
         assert rel(sb.idct2(a, 2, "ortho"), co.idct2(a, 2, "ortho")) <= TOL
+
+
+def test_against_committed_extended_precision_golden_vectors(sb):
+    """The product against tests/golden/golden_consumers_v1.npz (long-double evaluation of the reference's formulas)."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_consumers_v1.npz"))
+    for n in (2, 5, 8, 16, 33, 128, 257):
+        x = G[f"trig_x_{n}"]
+        for kind in ("dct", "dst"):
+            for t in (1, 2, 3, 4):
+                for inv in (0, 1):
+                    for ortho in (0, 1):
+                        got = getattr(sb, ("i" if inv else "") + kind)(x, t, "ortho" if ortho else None)
+                        assert rel(got, G[f"{kind}_{n}_t{t}_i{inv}_o{ortho}"]) <= TOL, (kind, n, t, inv, ortho)
+    for n in (1, 4, 5, 12, 64, 100):
+        x, z, m = G[f"real_{n}"], G[f"cplx_{n}"], n + 3
+        assert rel(sb.dht(x), G[f"dht_{n}"]) <= TOL
+        assert rel(sb.hfft(z, m), G[f"hfft_{n}_n{m}"]) <= TOL
+        assert rel(sb.ihfft(x, m), G[f"ihfft_{n}_n{m}"]) <= TOL
+        assert rel(sb.hilbert(x), G[f"hilbert_{n}"]) <= TOL
