@@ -482,6 +482,13 @@ static int blue_l1_cap() {
     return v;
 }
 
+static int64_t three_level_min() {  // test knob: exercise the three-level decomposition at small lengths
+    static int64_t v = [] {
+        const char* e = getenv("SFC_THREE_LEVEL_MIN");
+        return e ? atoll(e) : 0;
+    }();
+    return v;
+}
 static int row_fourstep_len() {
     static int v = [] {
         const char* e = getenv("SFC_ROW_FOURSTEP");
@@ -791,7 +798,12 @@ struct PlanBuilder {
         if (is_pow2(n)) {
             // four-step (Bailey): n = L1*L2, columns then rows, through the work area [O][n][I]
             const int lg = ilog2_64(n);
-            if (n > (int64_t)lmax * lmax) return fail(SFC_ERR_NOT_IMPLEMENTED, "transform length above lmax^2");
+            if (n > (int64_t)lmax * lmax || (three_level_min() > 0 && n >= three_level_min() && !col)) {
+                if (col || src.real || store_real || src.n != n || dst.n != n || aux_in || aux_out || scatter_parts > 1 ||
+                    lg > 3 * ilog2_64(lmax) || O > 0x7FFFFFFF / 8192)
+                    return fail(SFC_ERR_NOT_IMPLEMENTED, "transform length above lmax^2 (only contiguous complex rows go three levels deep)");
+                return add_three_level(n, O, src, dst, fl_in, fl_out, scale);
+            }
             int64_t L1 = (int64_t)1 << (lg / 2);
             int64_t L2 = n / L1;
             if (L2 > lmax) {
@@ -977,6 +989,82 @@ struct PlanBuilder {
         }
     }
 
+    // n = L1*L2*L3 > lmax^2, contiguous rows (I == 1): three passes through the work area [O][n]
+    //   A : L1-point columns at stride L2*L3, twiddle W_n^(k1*m)                     (m = n2*L3 + n3)
+    //   B1: inside every row k1 of L2*L3 points, L2-point columns at stride L3, twiddle W_(L2*L3)^(k2*n3)
+    //   B2: L3-point rows, stored transposed: X[k1 + L1*(k2 + L2*k3)]
+    bool add_three_level(int64_t n, int64_t O, ArrayRef src, ArrayRef dst, uint32_t fl_in, uint32_t fl_out, double scale) {
+        const int lg = ilog2_64(n);
+        const int l1 = lg / 3, l2 = (lg - l1) / 2, l3 = lg - l1 - l2;
+        const int64_t L1 = (int64_t)1 << l1, L2 = (int64_t)1 << l2, L3 = (int64_t)1 << l3, MM = L2 * L3;
+        const void *lo_n, *hi_n, *lo_m, *hi_m;
+        int sh_n, sh_m;
+        if (!table_fourstep(prec, n, &lo_n, &hi_n, &sh_n, err)) return false;
+        if (!table_fourstep(prec, MM, &lo_m, &hi_m, &sh_m, err)) return false;
+        const int g = new_group(O, n * (int64_t)cs);
+        {
+            Step a;
+            a.k = pick_kernel_two_per_sm(prec, (int)L1, 0);
+            a.src = src.role;
+            a.dst = R_MS;
+            a.src_esize = cs;
+            a.dst_esize = cs;
+            a.group = g;
+            set_io(a.p.in, n, 1, 1, MM, n, MM, 1);
+            set_io(a.p.out, n, 1, 1, MM, n, MM, 1);
+            a.p.map_in = a.p.map_out = MAP_COL;
+            a.p.ld_op = LD_C;
+            a.p.st_op = ST_TW;
+            a.p.tw_lo = lo_n;
+            a.p.tw_hi = hi_n;
+            a.p.tw_shift = sh_n;
+            a.p.flags = fl_in;
+            a.p.scale = 1.0;
+            if (!finish_tile(a, MM, 1, O, "three-level pass A (outer columns + twiddle)")) return false;
+        }
+        {
+            Step b;
+            b.k = pick_kernel_two_per_sm(prec, (int)L2, 0);
+            b.src = R_MS;
+            b.dst = R_MS;
+            b.src_esize = cs;
+            b.dst_esize = cs;
+            b.group = g;
+            b.batch_mult = L1;
+            set_io(b.p.in, MM, 1, 1, L3, MM, L3, 1);
+            set_io(b.p.out, MM, 1, 1, L3, MM, L3, 1);
+            b.p.map_in = b.p.map_out = MAP_COL;
+            b.p.ld_op = LD_C;
+            b.p.st_op = ST_TW;
+            b.p.tw_lo = lo_m;
+            b.p.tw_hi = hi_m;
+            b.p.tw_shift = sh_m;
+            b.p.flags = 0;
+            b.p.scale = 1.0;
+            if (!finish_tile(b, L3, 1, O, "three-level pass B1 (inner columns + twiddle)")) return false;
+        }
+        {
+            Step c;
+            c.k = pick_kernel_two_per_sm(prec, (int)L3, 0);
+            c.src = R_MS;
+            c.dst = dst.role;
+            c.src_esize = cs;
+            c.dst_esize = cs;
+            c.group = g;
+            // lane = k2*L1 + k1 (k1 fastest: adjacent lanes are adjacent outputs)
+            set_io(c.p.in, n, L3, MM, 1, n, 1, 0);
+            set_io(c.p.out, n, L1, 1, L1 * L2, n, 1, 0);
+            c.p.map_in = MAP_ROW;
+            c.p.map_out = MAP_COL;
+            c.p.ld_op = LD_C;
+            c.p.st_op = ST_C;
+            c.p.flags = fl_out;
+            c.p.scale = scale;
+            dev_bytes += O * 6 * n * (int64_t)cs;
+            return finish_tile(c, L1 * L2, L1, O, "three-level pass B2 (rows, transposed store)");
+        }
+    }
+
     bool r2c_fast_ok(int64_t n, int64_t I) const {
         return I == 1 && is_pow2(n) && n >= 64 && n / 2 <= lmax_for(prec);
     }
@@ -1134,7 +1222,7 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
     auto axis_passes = [&](int64_t n) {
         if (n == 1) return 0;
         const int lmax = lmax_for(prec);
-        if (is_pow2(n)) return n <= lmax ? 1 : 2;
+        if (is_pow2(n)) return n <= lmax ? 1 : (n <= (int64_t)lmax * lmax ? 2 : 3);
         return next_pow2(2 * n - 1) <= lmax ? 1 : 4;
     };
 
@@ -1548,7 +1636,7 @@ int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& 
                     while (sh > 0 && (p.tiles_per_batch & ((1u << sh) - 1u))) --sh;
                     p.tile_group_shift = (uint32_t)sh;
                 }
-                const uint64_t grid = (uint64_t)p.tiles_per_batch * (uint64_t)nb;
+                const uint64_t grid = (uint64_t)p.tiles_per_batch * (uint64_t)nb * (uint64_t)t.batch_mult;
                 if (grid == 0 || grid > 0x7FFFFFFFULL) {
                     es = "grid too large";
                     return SFC_ERR_VALUE;

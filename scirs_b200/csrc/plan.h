@@ -35,6 +35,7 @@ struct Step {
     bool batch_fastest = false;              // CTA order: batch index fastest (table reuse in L2)
     bool scatter = false;                    // store through the caller's per-block pointer table
     int64_t nbatch = 1;                      // batches (blockIdx-level outer index)
+    int64_t batch_mult = 1;                  // grouped steps: blockIdx-level batches per group batch (three-level inner passes)
     std::string desc;
 };
 

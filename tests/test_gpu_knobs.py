@@ -45,3 +45,54 @@ KNOBS = [
 def test_knob_combinations_keep_parity(env, build_artifacts):
     r = subprocess.run([sys.executable, "-c", CODE], env=dict(os.environ, **env), capture_output=True, text=True, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_three_level_decomposition_small_and_full_size(build_artifacts):
+    """n > lmax^2 = 2^26 goes three levels deep (plan.cu add_three_level).  Forced at small lengths against numpy, then
+    one real 2^27-point transform checked by a round trip (1e-12) and on sampled bins against direct sums."""
+    code = r'''
+import numpy as np
+from scirs_b200 import FftPlan
+rng = np.random.default_rng(3)
+for lg, b in ((15, 3), (17, 2), (20, 2), (22, 1)):
+    n = 1 << lg
+    a = rng.standard_normal((b, n)) + 1j * rng.standard_normal((b, n))
+    p = FftPlan([b, n], [1])
+    assert "three-level" in p.describe(), p.describe()
+    got = p.execute(a).reshape(b, n)
+    ref = np.fft.fft(a, axis=1)
+    e = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    inv = FftPlan([b, n], [1], "c2c", "f64", False, 1.0 / n).execute(got).reshape(b, n)
+    e2 = np.linalg.norm(inv - a) / np.linalg.norm(a)
+    print(lg, e, e2)
+    assert e < 1e-12 and e2 < 1e-12
+'''
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SFC_THREE_LEVEL_MIN="32768"), capture_output=True,
+                       text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    code2 = r'''
+import numpy as np, torch
+from scirs_b200 import FftPlan
+from oracle import scirs2_fft_oracle as orc
+n = 1 << 27
+g = torch.Generator(device="cuda").manual_seed(5)
+x = torch.randn(2 * n, dtype=torch.float64, device="cuda", generator=g)
+y = torch.empty_like(x); z = torch.empty_like(x)
+p = FftPlan([n], [0])
+assert "three-level" in p.describe(), p.describe()
+s = torch.cuda.current_stream().cuda_stream
+p.execute_device(x, y, s)
+FftPlan([n], [0], "c2c", "f64", False, 1.0 / n).execute_device(y, z, s)
+torch.cuda.synchronize()
+rt = float(torch.linalg.vector_norm(z - x) / torch.linalg.vector_norm(x))
+xc = torch.view_as_complex(x.view(n, 2)).cpu().numpy()
+bins = [1, 12345, n // 2 + 7, n - 1]
+j = np.arange(n, dtype=np.int64)
+ref = np.array([np.dot(xc, np.exp(-2j * np.pi * ((j * k) % n) / n)) for k in bins])   # exact integer phase reduction, f64 sum
+got = torch.view_as_complex(y.view(n, 2))[bins].cpu().numpy()
+e = np.abs(got - ref).max() / np.abs(ref).max()
+print("round trip", rt, "sampled bins", e)
+assert rt < 1e-12 and e < 1e-9
+'''
+    r = subprocess.run([sys.executable, "-c", code2], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
