@@ -482,10 +482,14 @@ static int blue_l1_cap() {
     return v;
 }
 
-static int64_t three_level_min() {  // test knob: exercise the three-level decomposition at small lengths
+// Contiguous rows of at least this many points take three passes of small tiles instead of two passes of 64..128 KiB
+// tiles.  Measured on B200 (f64, 2 GiB of rows): 2^22: 6.9 -> 7.4 TFLOP/s, 2^24: 3.6 -> 8.0, 2^26: 2.2 -> 8.1 (the
+// 2048..8192-point column tiles of the two-pass form have 16..32 B rows and one CTA per SM); 2^20 / 2^21 are faster
+// in two passes (7.7 / 7.5 vs 6.9 / 7.2).
+static int64_t three_level_min() {
     static int64_t v = [] {
         const char* e = getenv("SFC_THREE_LEVEL_MIN");
-        return e ? atoll(e) : 0;
+        return e ? atoll(e) : (int64_t)1 << 22;
     }();
     return v;
 }
@@ -798,12 +802,12 @@ struct PlanBuilder {
         if (is_pow2(n)) {
             // four-step (Bailey): n = L1*L2, columns then rows, through the work area [O][n][I]
             const int lg = ilog2_64(n);
-            if (n > (int64_t)lmax * lmax || (three_level_min() > 0 && n >= three_level_min() && !col)) {
-                if (col || src.real || store_real || src.n != n || dst.n != n || aux_in || aux_out || scatter_parts > 1 ||
-                    lg > 3 * ilog2_64(lmax) || O > 0x7FFFFFFF / 8192)
-                    return fail(SFC_ERR_NOT_IMPLEMENTED, "transform length above lmax^2 (only contiguous complex rows go three levels deep)");
+            const bool can3 = !(col || src.real || store_real || src.n != n || dst.n != n || aux_in || aux_out || scatter_parts > 1 ||
+                                lg > 3 * ilog2_64(lmax) || O > 0x7FFFFFFF / 8192);
+            if (n > (int64_t)lmax * lmax && !can3)
+                return fail(SFC_ERR_NOT_IMPLEMENTED, "transform length above lmax^2 (only contiguous complex rows go three levels deep)");
+            if (can3 && (n > (int64_t)lmax * lmax || (prec == PREC_F64 && three_level_min() > 0 && n >= three_level_min())))
                 return add_three_level(n, O, src, dst, fl_in, fl_out, scale);
-            }
             int64_t L1 = (int64_t)1 << (lg / 2);
             int64_t L2 = n / L1;
             if (L2 > lmax) {
@@ -1222,7 +1226,7 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
     auto axis_passes = [&](int64_t n) {
         if (n == 1) return 0;
         const int lmax = lmax_for(prec);
-        if (is_pow2(n)) return n <= lmax ? 1 : (n <= (int64_t)lmax * lmax ? 2 : 3);
+        if (is_pow2(n)) return n <= lmax ? 1 : 2;  // algorithmic passes; long rows may physically take three
         return next_pow2(2 * n - 1) <= lmax ? 1 : 4;
     };
 
