@@ -532,6 +532,45 @@ __device__ __forceinline__ void chirp_apply(Cx<T> (&a)[E], const PassParams& p, 
     for (int m = 0; m < E; ++m) a[m] = cmul(a[m], Cx<T>{(T)c[m].x, (T)c[m].y});
 }
 
+// four-step twiddle W_M^(e*lo), e = i + m*TPL:  w_m = W^(i*lo) * (W^(TPL*lo))^m.  Two two-level table lookups per
+// thread, then a depth-4 product tree (no per-element loads).
+template <typename T, int E, int TPL>
+__device__ __forceinline__ void fourstep_twiddle(Cx<T> (&a)[E], const void* lo_tab, const void* hi_tab, int shift,
+                                                 bool conj, int i, uint32_t lo) {
+    using cx = Cx<T>;
+    const cx* __restrict__ tlo = reinterpret_cast<const cx*>(lo_tab);
+    const cx* __restrict__ thi = reinterpret_cast<const cx*>(hi_tab);
+    const uint64_t lmask = ((uint64_t)1 << shift) - 1;
+    const T sgn = conj ? (T)-1 : (T)1;
+    const uint64_t e0 = (uint64_t)i * (uint64_t)lo, e1 = (uint64_t)TPL * (uint64_t)lo;
+    cx b = cmul(thi[e0 >> shift], tlo[e0 & lmask]);
+    cx s1 = cmul(thi[e1 >> shift], tlo[e1 & lmask]);
+    b.y *= sgn;
+    s1.y *= sgn;
+    if constexpr (E == 16) {
+        const cx s2 = csqr(s1), s4 = csqr(s2), s8 = csqr(s4);
+        cx w[8];
+        w[0] = b;
+        w[1] = cmul(b, s1);
+        w[2] = cmul(b, s2);
+        w[3] = cmul(w[1], s2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[4 + j] = cmul(w[j], s4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] = cmul(a[j], w[j]);
+            a[8 + j] = cmul(a[8 + j], cmul(w[j], s8));
+        }
+    } else {
+        cx w = b;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            a[m] = cmul(a[m], w);
+            w = cmul(w, s1);
+        }
+    }
+}
+
 template <int TL, int TPL>
 __device__ __forceinline__ void map_thread(int mode, int tid, int& t, int& i) {
     if (mode == MAP_COL) {
@@ -970,6 +1009,8 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
                 }
             }
         }
+        if (p.flags & F_LD_TW)
+            fourstep_twiddle<T, E, TPL>(a, p.ld_tw_lo, p.ld_tw_hi, p.ld_tw_shift, (p.flags & F_LD_TW_CONJ) != 0, i0, lo);
         if (MODE == TM_FAST_C2R || MODE == TM_FAST_DCT3 || (p.flags & F_CONJ_LD_POST)) {
 #pragma unroll
             for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
@@ -1021,7 +1062,7 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
     if constexpr (DOUBLE) {
         // forward transform -> pointwise table -> inverse transform, all on chip
         const cx* __restrict__ mid = reinterpret_cast<const cx*>(p.mid);
-        const int64_t mid0 = (int64_t)lo * p.mid_ls;
+        const int64_t mid0 = (int64_t)lo * p.mid_ls + (int64_t)li * p.mid_is;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int e = i1 + m * TPL;
@@ -1185,39 +1226,7 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
     }
 
     if (p.st_op == ST_TW) {
-        // four-step twiddle W_M^(e*lo), e = i1 + m*TPL:  w_m = W^(i1*lo) * (W^(TPL*lo))^m.  Two
-        // two-level table lookups per thread, then a depth-4 product tree (no per-element loads).
-        const cx* __restrict__ tlo = reinterpret_cast<const cx*>(p.tw_lo);
-        const cx* __restrict__ thi = reinterpret_cast<const cx*>(p.tw_hi);
-        const uint64_t lmask = ((uint64_t)1 << p.tw_shift) - 1;
-        const T sgn = (p.flags & F_TW_CONJ) ? (T)-1 : (T)1;
-        const uint64_t e0 = (uint64_t)i1 * (uint64_t)lo, e1 = (uint64_t)TPL * (uint64_t)lo;
-        cx b = cmul(thi[e0 >> p.tw_shift], tlo[e0 & lmask]);
-        cx s1 = cmul(thi[e1 >> p.tw_shift], tlo[e1 & lmask]);
-        b.y *= sgn;
-        s1.y *= sgn;
-        if constexpr (E == 16) {
-            const cx s2 = csqr(s1), s4 = csqr(s2), s8 = csqr(s4);
-            cx w[8];
-            w[0] = b;
-            w[1] = cmul(b, s1);
-            w[2] = cmul(b, s2);
-            w[3] = cmul(w[1], s2);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) w[4 + j] = cmul(w[j], s4);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                a[j] = cmul(a[j], w[j]);
-                a[8 + j] = cmul(a[8 + j], cmul(w[j], s8));
-            }
-        } else {
-            cx w = b;
-#pragma unroll
-            for (int m = 0; m < E; ++m) {
-                a[m] = cmul(a[m], w);
-                w = cmul(w, s1);
-            }
-        }
+        fourstep_twiddle<T, E, TPL>(a, p.tw_lo, p.tw_hi, p.tw_shift, (p.flags & F_TW_CONJ) != 0, i1, lo);
     } else if (p.st_op == ST_MUL && (p.flags & F_CHIRP_GEN)) {
         // cropped positions (>= len) are multiplied by some unit-modulus value and never stored
         chirp_apply<T, E>(a, p, (int64_t)i1 * p.out.pos_es + pos0, (int64_t)TPL * p.out.pos_es, p.chirp_q_out);

@@ -50,7 +50,11 @@ enum PassFlags : uint32_t {
     // 128-bit accesses (thread t takes flat element t, t + NT, ...) and the per-thread rows are read from there;
     // without it thread t walks its own 16..64-element row and every warp request touches 32 cache lines
     F_STAGE_IN = 1u << 10,
-    F_STAGE_OUT = 1u << 11,     // LD_*_MUL / ST_MUL: generate the Bluestein chirp in registers instead of reading aux_*    // likewise for stores       // store only the real part into a real array (irfftn, rfft.rs:722)
+    F_STAGE_OUT = 1u << 11,
+    // inter-pass twiddle applied on the way IN (W^(e * lane_outer) from ld_tw_*; conjugated with F_LD_TW_CONJ):
+    // the inverse half of the three-level Bluestein, whose twiddle index is (element, lane) of the NEXT pass
+    F_LD_TW = 1u << 12,
+    F_LD_TW_CONJ = 1u << 13,     // LD_*_MUL / ST_MUL: generate the Bluestein chirp in registers instead of reading aux_*    // likewise for stores       // store only the real part into a real array (irfftn, rfft.rs:722)
 };
 
 struct IoDesc {
@@ -82,7 +86,11 @@ struct PassParams {
     const void* tw_hi;         // ST_TW: W_M^(j << tw_shift)
     int32_t tw_shift;
     const void* mid;           // double kernels: pointwise table between the two transforms
-    int64_t mid_es, mid_ls;    // mid index = e*mid_es + lane_outer*mid_ls
+    int64_t mid_es, mid_ls;    // mid index = e*mid_es + lane_outer*mid_ls + lane_inner*mid_is
+    int64_t mid_is;
+    const void* ld_tw_lo;      // F_LD_TW tables (same two-level layout as tw_lo / tw_hi)
+    const void* ld_tw_hi;
+    int32_t ld_tw_shift;
     const void* rtw;           // R2C/C2R: W_{2L}^i, i < L/E
     // F_CHIRP_GEN: chirp[n] = exp(-i*pi*n^2/N) = R(n^2 mod 2N), R(k) = chirp_hi[k >> shift] * chirp_lo[k & mask]
     // (f64 tables whatever the transform precision); q_* = exp(-i*pi*2*D^2/N) for the thread's position step D

@@ -289,9 +289,9 @@ const void* table_chirp(int prec, int64_t N, PlanError& err) {
     return d;
 }
 
-const void* table_bluestein_b(int prec, int64_t N, int64_t M, int64_t L1, int64_t L2, PlanError& err) {
+const void* table_bluestein_b(int prec, int64_t N, int64_t M, int64_t L1, int64_t L2, PlanError& err, int64_t L3) {
     std::lock_guard<std::recursive_mutex> lk(g_table_mu);
-    TableKey key{cur_device(), TK_BLUE, prec, N, M, L1, L2};
+    TableKey key{cur_device(), TK_BLUE, prec, N, M, L1, L2 + (L3 << 32)};
     auto it = tables().find(key);
     if (it != tables().end()) return it->second;
 
@@ -343,7 +343,17 @@ const void* table_bluestein_b(int prec, int64_t N, int64_t M, int64_t L1, int64_
         return nullptr;
     }
     std::vector<long double> re(M), im(M);
-    if (L1 > 0) {
+    if (L3 > 0) {
+        // three-level work order: position k1*(L2*L3) + k2*L3 + k3 holds bin k = k1 + L1*(k2 + L2*k3)
+        for (int64_t k1 = 0; k1 < L1; ++k1)
+            for (int64_t k2 = 0; k2 < L2; ++k2)
+                for (int64_t k3 = 0; k3 < L3; ++k3) {
+                    const int64_t k = k1 + L1 * (k2 + L2 * k3);
+                    const int64_t pos = k1 * (L2 * L3) + k2 * L3 + k3;
+                    re[pos] = hb[2 * k];
+                    im[pos] = hb[2 * k + 1];
+                }
+    } else if (L1 > 0) {
         for (int64_t k1 = 0; k1 < L1; ++k1)
             for (int64_t k2 = 0; k2 < L2; ++k2) {
                 const int64_t k = k1 + L1 * k2;
@@ -490,6 +500,17 @@ static int64_t three_level_min() {
     static int64_t v = [] {
         const char* e = getenv("SFC_THREE_LEVEL_MIN");
         return e ? atoll(e) : (int64_t)1 << 22;
+    }();
+    return v;
+}
+// Bluestein with M >= this many points runs as five passes of small tiles (three-level M-point transforms) instead of
+// three passes of 64 KiB tiles; 0 = never.  Measured on B200: parity identical (2e-15), but 32 x 1,000,003: 1.70 -> 2.06 ms
+// and 32 x 3^13: 3.54 -> 4.00 ms — with chirp generation, twiddles and the fused transform pair the small-tile passes
+// are SM-bound too (4.7 TB/s average), so the two extra passes cost more than they save: off.
+static int64_t blue3_min() {
+    static int64_t v = [] {
+        const char* e = getenv("SFC_BLUE3_MIN");
+        return e ? atoll(e) : 0;
     }();
     return v;
 }
@@ -905,6 +926,130 @@ struct PlanBuilder {
         }
         if (M > (int64_t)lmax * lmax) return fail(SFC_ERR_NOT_IMPLEMENTED, "Bluestein length above lmax^2");
         const int lg = ilog2_64(M);
+        if (gen && !col && prec == PREC_F64 && blue3_min() > 0 && M >= blue3_min() && O <= 0x7FFFFFFF / 8192) {
+            // Five passes of small tiles (three-level M-point transforms, the innermost forward / inverse pair fused):
+            //   A (chirp, pad, outer columns, W_M) -> A2 (inner columns, W_MM) -> B (rows: FFT * B' * IFFT * conj W_MM)
+            //   -> C2 (inverse inner columns) -> C (conj W_M on load, inverse outer columns, chirp, crop)
+            const int l1 = lg / 3, l2 = (lg - l1) / 2, l3 = lg - l1 - l2;
+            const int64_t L1 = (int64_t)1 << l1, L2 = (int64_t)1 << l2, L3 = (int64_t)1 << l3, MM = L2 * L3;
+            const void* bf = table_bluestein_b(prec, n, M, L1, L2, err, L3);
+            if (!bf) return false;
+            const void *lo_n, *hi_n, *lo_m, *hi_m;
+            int sh_n, sh_m;
+            if (!table_fourstep(prec, M, &lo_n, &hi_n, &sh_n, err)) return false;
+            if (!table_fourstep(prec, MM, &lo_m, &hi_m, &sh_m, err)) return false;
+            const int g = new_group(O, M * (int64_t)cs);
+            {
+                Step a;
+                a.k = pick_kernel_two_per_sm(prec, (int)L1, 0);
+                a.src = src.role;
+                a.dst = R_MS;
+                a.src_esize = src_es;
+                a.dst_esize = cs;
+                a.group = g;
+                set_io(a.p.in, src.n, 1, 1, MM, std::min(n, src.n), MM, 1);
+                set_io(a.p.out, M, 1, 1, MM, M, MM, 1);
+                a.p.map_in = a.p.map_out = MAP_COL;
+                a.p.ld_op = src.real ? LD_R_MUL : LD_C_MUL;
+                a.batch_fastest = true;
+                a.p.st_op = ST_TW;
+                a.p.tw_lo = lo_n;
+                a.p.tw_hi = hi_n;
+                a.p.tw_shift = sh_n;
+                a.p.flags = fl_in;
+                a.p.scale = 1.0;
+                set_chirp_gen(a);
+                if (!finish_tile(a, MM, 1, O, "Bluestein-3 pass A (chirp, pad, outer columns, twiddle)")) return false;
+            }
+            {
+                Step a2;
+                a2.k = pick_kernel_two_per_sm(prec, (int)L2, 0);
+                a2.src = R_MS;
+                a2.dst = R_MS;
+                a2.src_esize = cs;
+                a2.dst_esize = cs;
+                a2.group = g;
+                a2.batch_mult = L1;
+                set_io(a2.p.in, MM, 1, 1, L3, MM, L3, 1);
+                set_io(a2.p.out, MM, 1, 1, L3, MM, L3, 1);
+                a2.p.map_in = a2.p.map_out = MAP_COL;
+                a2.p.ld_op = LD_C;
+                a2.p.st_op = ST_TW;
+                a2.p.tw_lo = lo_m;
+                a2.p.tw_hi = hi_m;
+                a2.p.tw_shift = sh_m;
+                a2.p.flags = 0;
+                a2.p.scale = 1.0;
+                if (!finish_tile(a2, L3, 1, O, "Bluestein-3 pass A2 (inner columns, twiddle)")) return false;
+            }
+            {
+                Step b;
+                b.k = pick_kernel(prec, (int)L3, false, 1);
+                b.src = R_MS;
+                b.dst = R_MS;
+                b.src_esize = cs;
+                b.dst_esize = cs;
+                b.group = g;
+                // lane = k2*L1 + k1: lane_outer = k2 (the twiddle index), lane_inner = k1
+                set_io(b.p.in, M, L3, MM, 1, L3, 1, 0);
+                set_io(b.p.out, M, L3, MM, 1, L3, 1, 0);
+                b.p.map_in = b.p.map_out = MAP_ROW;
+                b.p.ld_op = LD_C;
+                b.p.mid = bf;
+                b.p.mid_es = 1;
+                b.p.mid_ls = L3;
+                b.p.mid_is = MM;
+                b.p.st_op = ST_TW;
+                b.p.tw_lo = lo_m;
+                b.p.tw_hi = hi_m;
+                b.p.tw_shift = sh_m;
+                b.p.flags = F_TW_CONJ;
+                b.p.scale = 1.0;
+                b.batch_fastest = true;
+                if (!finish_tile(b, L1 * L2, L1, O, "Bluestein-3 pass B (rows: FFT * B * IFFT * conj twiddle)")) return false;
+            }
+            {
+                Step c2;
+                c2.k = pick_kernel_two_per_sm(prec, (int)L2, 0);
+                c2.src = R_MS;
+                c2.dst = R_MS;
+                c2.src_esize = cs;
+                c2.dst_esize = cs;
+                c2.group = g;
+                c2.batch_mult = L1;
+                set_io(c2.p.in, MM, 1, 1, L3, MM, L3, 1);
+                set_io(c2.p.out, MM, 1, 1, L3, MM, L3, 1);
+                c2.p.map_in = c2.p.map_out = MAP_COL;
+                c2.p.ld_op = LD_C;
+                c2.p.st_op = ST_C;
+                c2.p.flags = F_CONJ_LD_POST | F_CONJ_ST_PRE;
+                c2.p.scale = 1.0;
+                if (!finish_tile(c2, L3, 1, O, "Bluestein-3 pass C2 (inverse inner columns)")) return false;
+            }
+            {
+                Step c;
+                c.k = pick_kernel_two_per_sm(prec, (int)L1, 0);
+                c.src = R_MS;
+                c.dst = dst.role;
+                c.src_esize = cs;
+                c.dst_esize = dst_es;
+                c.group = g;
+                set_io(c.p.in, M, 1, 1, MM, M, MM, 1);
+                set_io(c.p.out, dst.n, 1, 1, MM, std::min(n, dst.n), MM, 1);
+                c.p.map_in = c.p.map_out = MAP_COL;
+                c.p.ld_op = LD_C;
+                c.p.ld_tw_lo = lo_n;
+                c.p.ld_tw_hi = hi_n;
+                c.p.ld_tw_shift = sh_n;
+                c.p.st_op = ST_MUL;
+                c.batch_fastest = true;
+                c.p.flags = F_LD_TW | F_LD_TW_CONJ | F_CONJ_LD_POST | F_CONJ_ST_PRE | fl_out;
+                c.p.scale = scale;
+                set_chirp_gen(c);
+                dev_bytes += O * (std::min(n, src.n) * (int64_t)src_es + 9 * M * (int64_t)cs + std::min(n, dst.n) * (int64_t)dst_es);
+                return finish_tile(c, MM, 1, O, "Bluestein-3 pass C (conj twiddle, inverse outer columns, chirp, crop)");
+            }
+        }
         // column passes (A, C) like short lanes (two CTAs per SM with >= 64 B rows); the fused row
         // pass B takes whatever is left
         // the fused row pass B is fastest on 4096-point rows (one 64 KiB tile, no spills): L2 = 4096 whenever that

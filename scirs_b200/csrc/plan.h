@@ -96,8 +96,8 @@ const void* table_rtw(int prec, int L, PlanError& err);                     // W
 bool table_fourstep(int prec, int64_t M, const void** lo, const void** hi, int* shift, PlanError& err);
 bool table_chirp_roots(int64_t N, const void** lo, const void** hi, int* shift, PlanError& err);  // R(k) = exp(-i*pi*k/N)
 const void* table_chirp(int prec, int64_t N, PlanError& err);               // exp(-i*pi*n^2/N), n < N
-// FFT_M(conj chirp, wrapped)/M ; layout: natural (L1 == 0) or [k1][k2] four-step order
-const void* table_bluestein_b(int prec, int64_t N, int64_t M, int64_t L1, int64_t L2, PlanError& err);
+// FFT_M(conj chirp, wrapped)/M ; layout: natural (L1 == 0), [k1][k2] four-step order, or [k1][k2][k3] (L3 > 0) three-level order
+const void* table_bluestein_b(int prec, int64_t N, int64_t M, int64_t L1, int64_t L2, PlanError& err, int64_t L3 = 0);
 
 void set_error(int code, const std::string& msg);
 

@@ -38,6 +38,7 @@ KNOBS = [
     {"SFC_FAST": "0"},                                                   # generic flavour everywhere
     {"SFC_FORCE_E": "8"},
     {"SFC_WORK_MB": "1"},                                                # many rounds through a tiny work area
+    {"SFC_BLUE3_MIN": "32768", "SFC_THREE_LEVEL_MIN": "32768"},          # five-pass Bluestein, three-level rows
 ]
 
 
