@@ -159,7 +159,7 @@ def test_pow2_lengths_batched(sb, orc, lg):
     assert orc.rel_l2(sb.FftPlan([2, n, inner], [1], "c2c", "f64").execute(xc), sf.fft(xc, axis=1).ravel()) < TOL64
 
 
-@pytest.mark.parametrize("n", [1 << 14, 1 << 16, 1 << 20])
+@pytest.mark.parametrize("n", [1 << 14, 1 << 16, 1 << 20, 1 << 22, 1 << 24])  # 2^22 and up: three-level form
 def test_four_step(sb, orc, n):
     import scipy.fft as sf
 
