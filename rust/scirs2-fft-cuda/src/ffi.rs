@@ -87,4 +87,24 @@ extern "C" {
     pub fn sfc_backend_ifft_sized(input: *const f64, in_len: i64, output: *mut f64, out_len: i64, size: i64) -> c_int;
     pub fn sfc_backend_supports_feature(feature: *const c_char) -> c_int;
     pub fn sfc_execute_batch(inputs: *const f64, outputs: *mut f64, count: i64, size: i64, inverse: c_int) -> c_int;
+
+    // consumers of the hot path (dct.rs, dst.rs, hartley.rs, hfft/*.rs, lib.rs::hilbert, spectrogram.rs, memory_efficient.rs)
+    pub fn sfc_dct(x: *const f64, ndim: i32, shape: *const i64, axes: *const i32, naxes: i32, ttype: i32, inverse: i32,
+                   norm: *const c_char, out: *mut f64) -> c_int;
+    pub fn sfc_dst(x: *const f64, ndim: i32, shape: *const i64, axes: *const i32, naxes: i32, ttype: i32, inverse: i32,
+                   norm: *const c_char, out: *mut f64) -> c_int;
+    pub fn sfc_dht(x: *const f64, n: i64, out: *mut f64) -> c_int;
+    pub fn sfc_idht(h: *const f64, n: i64, out: *mut f64) -> c_int;
+    pub fn sfc_dht2(x: *const f64, rows: i64, cols: i64, axis0: i32, axis1: i32, out: *mut f64) -> c_int;
+    pub fn sfc_hfft(x: *const c_void, len: i64, dtype: c_int, n: i64, out: *mut f64, cap: i64, out_len: *mut i64) -> c_int;
+    pub fn sfc_ihfft(x: *const f64, len: i64, n: i64, out: *mut f64, cap: i64, out_len: *mut i64) -> c_int;
+    pub fn sfc_hilbert(x: *const f64, n: i64, out: *mut f64) -> c_int;
+    pub fn sfc_stft(x: *const f64, len: i64, window: *const f64, nperseg: i64, noverlap: i64, nfft: i64, detrend: i32,
+                    onesided: i32, boundary: i32, out_mode: i32, scale: f64, out: *mut c_void, cap: i64,
+                    freq_len: *mut i64, frames: *mut i64) -> c_int;
+    pub fn sfc_fft_inplace(input: *mut f64, n: i64, output: *mut f64, out_len: i64, inverse: i32, normalize: i32) -> c_int;
+    pub fn sfc_fft2_efficient(x: *const c_void, rows: i64, cols: i64, dtype: c_int, out_rows: i64, out_cols: i64,
+                              inverse: i32, normalize: i32, out: *mut f64) -> c_int;
+    pub fn sfc_fft_streaming(x: *const c_void, len: i64, dtype: c_int, n: i64, inverse: i32, chunk: i64, out: *mut f64) -> c_int;
+    pub fn sfc_fftn_optimized(x: *const f64, ndim: i32, shape: *const i64, axes: *const i32, naxes: i32, out: *mut f64) -> c_int;
 }
