@@ -47,6 +47,7 @@ WORKLOADS = {
     "irfft_f32": ([65536, 4096], [1], "c2r", "f32", False, "batched irfft f32, 65,536 x 4096 (configs[1])"),
     "fft2_8192": ([8192, 8192], [1, 0], "c2c", "f64", True, "fft2 c128 8192 x 8192 (configs[2])"),
     "fft_2p20": ([64, 1 << 20], [1], "c2c", "f64", True, "fft c128 2^20, batch 64 (configs[0] steady state)"),
+    "fft_2p24": ([8, 1 << 24], [1], "c2c", "f64", True, "fft c128 2^24, batch 8 (large-N path: three passes of small tiles)"),
     "fftn_512": ([512, 512, 512], [0, 1, 2], "c2c", "f64", True, "fftn c128 512^3 on one GPU (configs[4])"),
     "bluestein_1000003": ([32, 1000003], [1], "c2c", "f64", True, "fft c128 N=1,000,003 (prime, Bluestein), batch 32 (configs[3])"),
     "bluestein_1594323": ([32, 1594323], [1], "c2c", "f64", True, "fft c128 N=3^13 (Bluestein), batch 32 (configs[3])"),
