@@ -17,6 +17,8 @@ from .consumers import (DCTType, DSTType, dct, idct, dct2, idct2, dctn, idctn, d
 from .plan import FftPlan, FftPlanExecutor
 from .plan_serialization import (PlanInfo, PlanMetrics, PlanDatabaseStats, PlanSerializationManager,
                                  create_and_time_plan)
+from .auto_tuning import (AutoTuner, AutoTuneConfig, BenchmarkResult, FftVariant, SizeRange, SizeStep, SystemInfo,
+                          TuningDatabase)
 from .plan_cache import PlanCache, CacheStats, get_global_cache
 from .backend import FftBackend, CudaFftBackend, BackendManager, BackendContext, get_backend_manager
 from .context import (WorkerConfig, WorkerPool, WorkerPoolInfo, get_global_pool, set_workers, get_workers, FftContext,
