@@ -316,6 +316,10 @@ struct TileCfg {
     static constexpr size_t LAND_BYTES = (size_t)TL * L * sizeof(Cx<T>);  // dense tile, TMA destination
     // pipelined flavour: exchange buffer | landing buffer | one mbarrier
     static constexpr size_t SMEM = SPLIT_ ? XCH_BYTES + LAND_BYTES + 16 : (size_t)TL * LP * sizeof(Cx<T>);
+    // group-pipelined flavour (TM_PIPE_C2C with GROUPS == 2): full-size exchange buffers for both groups, ONE landing
+    // buffer of a group's tile (TLG lanes) that the groups consume alternately, two mbarriers
+    static constexpr size_t LAND_G_BYTES = (size_t)(TL_ / GROUPS_) * L * sizeof(Cx<T>);
+    static constexpr size_t SMEM_GP = XCH_BYTES + LAND_G_BYTES + 32;
     // resident CTAs per SM the register allocator must leave room for
     static constexpr int NTG = NT / GROUPS;                   // threads per group
     static __device__ __forceinline__ void sync(int group) {
@@ -720,12 +724,15 @@ __device__ __forceinline__ void c2r_pretwiddle(Cx<T> (&a)[C::E], const Cx<T>* ro
 }
 
 // one tile: load -> transform -> store.  Pipelined flavour: `land` / `bar` are the landing buffer and its
-// mbarrier, `parity` the phase to wait for, `next_blk` the tile to prefetch once this one is in registers.
+// mbarrier, `parity` the phase to wait for, `next_blk` the tile to prefetch once this one is in registers and
+// `bar_next` the barrier that prefetch completes on (the other thread group's in the group-pipelined flavour).
 template <typename T, int L, int TL, bool DOUBLE, int EMAX, int MODE, int GROUPS>
 __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t blk, Cx<T>* sm, const Cx<T>* land,
-                                          uint32_t bar, uint32_t parity, uint32_t next_blk) {
+                                          uint32_t bar, uint32_t parity, uint32_t next_blk, uint32_t bar_next) {
     constexpr bool PIPE = MODE == TM_PIPE_C2C;
-    using C = TileCfg<T, L, TL, EMAX, GROUPS, PIPE>;
+    constexpr bool GP = PIPE && GROUPS == 2;  // group-pipelined: each thread group walks over its own tiles of TLG lanes
+    using C = TileCfg<T, L, TL, EMAX, GROUPS, PIPE && GROUPS == 1>;
+    constexpr int LT = GP ? C::TLG : TL;      // lanes per scheduled tile
     using cx = Cx<T>;
     constexpr int E = C::E, TPL = C::TPL, LP = C::LP;
     constexpr bool FAST = MODE != TM_GENERIC;
@@ -756,7 +763,7 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
 
     // ------------------------------ load ------------------------------------
     {
-        const uint32_t lane = tile * TL + (uint32_t)t0;
+        const uint32_t lane = tile * LT + (uint32_t)(GP ? t0 - grp * C::TLG : t0);
         const bool valid = lane < p.nlanes;
         const uint32_t lo = lane / p.inner_count;
         const uint32_t li = lane - lo * p.inner_count;
@@ -876,14 +883,16 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
         } else if constexpr (PIPE) {
             // the tile was landed in shared memory by the TMA unit while the previous one was transformed
             mbar_wait(bar, parity);
-            const cx* src = (p.map_in == MAP_COL) ? land + (i0 * TL + t0) : land + (t0 * L + i0);
-            const int step = (p.map_in == MAP_COL) ? TPL * TL : TPL;
+            const int tl = GP ? t0 - grp * C::TLG : t0;  // lane inside the landed tile
+            const cx* src = (p.map_in == MAP_COL) ? land + (i0 * LT + tl) : land + (tl * L + i0);
+            const int step = (p.map_in == MAP_COL) ? TPL * LT : TPL;
 #pragma unroll
             for (int m = 0; m < E; ++m) a[m] = src[m * step];
-            __syncthreads();  // everybody holds its elements: the landing buffer is free again
-            if (tid < 32 && next_blk < p.total_tiles) {
+            C::sync(grp);  // everybody (of this group) holds its elements: the landing buffer is free again
+            if ((GP ? tid - grp * C::NTG : tid) < 32 && next_blk < p.total_tiles) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                pipe_issue<T, L, TL>(p, next_blk, smem_u32(land), bar);
+                // group-pipelined: the next tile belongs to the OTHER group and completes on its barrier
+                pipe_issue<T, L, LT>(p, next_blk, smem_u32(land), bar_next);
             }
             if (p.flags & F_CONJ_LD_PRE) {
 #pragma unroll
@@ -1054,7 +1063,7 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
 
     SFC_PHASE_FORCE(a);
     SFC_PHASE(3);  // first transform
-    const uint32_t lane = tile * TL + (uint32_t)t1;
+    const uint32_t lane = tile * LT + (uint32_t)(GP ? t1 - grp * C::TLG : t1);
     const bool valid = FAST ? true : (lane < p.nlanes);
     const uint32_t lo = lane / p.inner_count;
     const uint32_t li = lane - lo * p.inner_count;
@@ -1318,8 +1327,8 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Cx<T>* sm = reinterpret_cast<Cx<T>*>(smem_raw);
     if constexpr (MODE != TM_PIPE_C2C) {
-        tile_body<T, L, TL, DOUBLE, EMAX, MODE, GROUPS>(p, blockIdx.x, sm, nullptr, 0u, 0u, 0u);
-    } else {
+        tile_body<T, L, TL, DOUBLE, EMAX, MODE, GROUPS>(p, blockIdx.x, sm, nullptr, 0u, 0u, 0u, 0u);
+    } else if constexpr (GROUPS == 1) {
         using C = TileCfg<T, L, TL, EMAX, GROUPS, true>;
         const Cx<T>* land = reinterpret_cast<const Cx<T>*>(smem_raw + C::XCH_BYTES);
         const uint32_t bar = smem_u32(smem_raw + C::XCH_BYTES + C::LAND_BYTES);
@@ -1328,7 +1337,26 @@ tile_fft_kernel(const __grid_constant__ PassParams p) {
         if (threadIdx.x < 32 && blockIdx.x < p.total_tiles) pipe_issue<T, L, TL>(p, blockIdx.x, smem_u32(land), bar);
         uint32_t parity = 0;
         for (uint32_t blk = blockIdx.x; blk < p.total_tiles; blk += gridDim.x, parity ^= 1u)
-            tile_body<T, L, TL, DOUBLE, EMAX, MODE, GROUPS>(p, blk, sm, land, bar, parity, blk + gridDim.x);
+            tile_body<T, L, TL, DOUBLE, EMAX, MODE, GROUPS>(p, blk, sm, land, bar, parity, blk + gridDim.x, bar);
+    } else {
+        // Group-pipelined: two thread groups, each transforming its own tile (TLG lanes) out of its own exchange buffer;
+        // ONE landing buffer, filled by the TMA unit with the tiles blockIdx.x, +gridDim.x, ... in order.  Tile j is
+        // consumed by group j % 2, which then starts the copy of tile j + 1 for the other group: while both groups
+        // compute, the next tile is always in flight.
+        using C = TileCfg<T, L, TL, EMAX, GROUPS, false>;
+        const Cx<T>* land = reinterpret_cast<const Cx<T>*>(smem_raw + C::XCH_BYTES);
+        const uint32_t bar0 = smem_u32(smem_raw + C::XCH_BYTES + C::LAND_G_BYTES);
+        const int grp = threadIdx.x / C::NTG;
+        if (threadIdx.x == 0) {
+            mbar_init(bar0, 1);
+            mbar_init(bar0 + 8, 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32 && blockIdx.x < p.total_tiles) pipe_issue<T, L, C::TLG>(p, blockIdx.x, smem_u32(land), bar0);
+        const uint32_t mine = bar0 + 8u * (uint32_t)grp, other = bar0 + 8u * (uint32_t)(grp ^ 1);
+        uint32_t k = 0;
+        for (uint32_t blk = blockIdx.x + (uint32_t)grp * gridDim.x; blk < p.total_tiles; blk += 2 * gridDim.x, ++k)
+            tile_body<T, L, TL, DOUBLE, EMAX, MODE, GROUPS>(p, blk, sm, land, mine, k & 1u, blk + gridDim.x, other);
     }
 }
 

@@ -7,7 +7,9 @@ namespace sfc {
 
 template <typename T, int L, int TL, bool DBL, int EMAX = 16, int MODE = 0, int GROUPS = 1>
 struct KernelInst {
-    using C = TileCfg<T, L, TL, EMAX, GROUPS, MODE == TM_PIPE_C2C>;
+    using C = TileCfg<T, L, TL, EMAX, GROUPS, MODE == TM_PIPE_C2C && GROUPS == 1>;
+    static constexpr bool GP = MODE == TM_PIPE_C2C && GROUPS == 2;
+    static constexpr size_t SMEM_BYTES = GP ? C::SMEM_GP : C::SMEM;
     static cudaError_t launch(const PassParams& p0, unsigned grid, cudaStream_t s) {
         PassParams p = p0;
         static bool configured[64] = {};
@@ -16,7 +18,7 @@ struct KernelInst {
         if (e != cudaSuccess) return e;
         if (dev < 64 && !configured[dev]) {
             e = cudaFuncSetAttribute(tile_fft_kernel<T, L, TL, DBL, EMAX, MODE, GROUPS>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
             if (e != cudaSuccess) return e;
             configured[dev] = true;
         }
@@ -27,27 +29,27 @@ struct KernelInst {
                 int sms = 0, per_sm = 0;
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_fft_kernel<T, L, TL, DBL, EMAX, MODE, GROUPS>,
-                                                              C::NT, C::SMEM);
+                                                              C::NT, SMEM_BYTES);
                 resident[dev] = sms * (per_sm > 0 ? per_sm : 1);
             }
             p.total_tiles = grid;
             const unsigned cap = (unsigned)(dev < 64 ? resident[dev] : 296);
             if (grid > cap) grid = cap;
         }
-        tile_fft_kernel<T, L, TL, DBL, EMAX, MODE, GROUPS><<<grid, C::NT, C::SMEM, s>>>(p);
+        tile_fft_kernel<T, L, TL, DBL, EMAX, MODE, GROUPS><<<grid, C::NT, SMEM_BYTES, s>>>(p);
         return cudaGetLastError();
     }
     static KernelEntry entry() {
         KernelEntry k;
         k.prec = sizeof(T) == 8 ? PREC_F64 : PREC_F32;
         k.L = L;
-        k.TL = TL;
+        k.TL = GP ? C::TLG : TL;  // lanes per SCHEDULED tile: a group-pipelined CTA works on two of them at a time
         k.E = C::E;
         k.dbl = DBL ? 1 : 0;
         k.mode = MODE;
         k.groups = GROUPS;
         k.threads = C::NT;
-        k.smem = C::SMEM;
+        k.smem = SMEM_BYTES;
         k.func = (const void*)tile_fft_kernel<T, L, TL, DBL, EMAX, MODE, GROUPS>;
         k.launch = &launch;
         return k;
@@ -70,6 +72,8 @@ struct KernelInst {
     add(::sfc::KernelInst<T, L, TL, false, 16, 1, 2>::entry());
 // persistent, TMA-pipelined complex flavour (64 KiB tiles: half-size exchange buffer + landing buffer, 2 CTAs / SM)
 #define SFC_ADD_PIPE(T, L, TL, DBL) add(::sfc::KernelInst<T, L, TL, DBL, 16, 4>::entry());
+// group-pipelined: TL2 = lanes of the two groups together (each group owns TL2 / 2)
+#define SFC_ADD_GPIPE(T, L, TL2, DBL) add(::sfc::KernelInst<T, L, TL2, DBL, 16, 4, 2>::entry());
 // fused DCT-II rows (Makhoul packing on the half-length transform)
 #define SFC_ADD_DCT2(T, L, TL)                               \
     add(::sfc::KernelInst<T, L, TL, false, 16, 5>::entry()); \

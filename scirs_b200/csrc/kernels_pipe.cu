@@ -8,5 +8,8 @@ void register_kernels_pipe(void (*add)(const KernelEntry&)) {
     SFC_ADD_PIPE(double, 512, 8, false)
     SFC_ADD_PIPE(double, 256, 16, false)
     SFC_ADD_PIPE(double, 8192, 1, false)
+    SFC_ADD_GPIPE(double, 4096, 2, false)
+    SFC_ADD_GPIPE(double, 2048, 4, false)
+    SFC_ADD_GPIPE(double, 1024, 8, false)
 }
 }  // namespace sfc

@@ -463,6 +463,23 @@ static int pipe_enabled() {  // 0 off, 1 row and column tiles, 2 row tiles only
     }();
     return v;
 }
+// measured on B200: parity identical, c2c 65,536 x 4096 93 -> 89 %, 1024 / 2048-point rows 98 -> 88 % / 88 -> 82 %: with ONE
+// landing buffer per SM (shared memory has no room for two next to two full-size exchange buffers) only 64 KiB of loads are
+// in flight per SM, less than the two independent CTAs of the plain flavour keep in flight.  Off.
+static bool gpipe_enabled() {
+    static int v = [] {
+        const char* e = getenv("SFC_GPIPE");
+        return e ? atoi(e) : 0;
+    }();
+    return v != 0;
+}
+static int64_t gpipe_min_tiles() {
+    static int64_t v = [] {
+        const char* e = getenv("SFC_GPIPE_MIN_TILES");
+        return e ? atoll(e) : 8 * 148;  // four tiles for each group of each of the 148 persistent CTAs
+    }();
+    return v;
+}
 static bool pipe_big_enabled() {
     static int v = [] {
         const char* e = getenv("SFC_PIPE_BIG");
@@ -625,6 +642,19 @@ struct PlanBuilder {
                     s.p.out.outer_stride == s.k->L && !s.scatter)
                     s.p.flags |= F_STAGE_OUT;
             }
+            // group-pipelined flavour for contiguous rows (two thread groups per CTA, one TMA landing buffer between them)
+            if (mode == 1 && s.k->mode == 1 && gpipe_enabled() && (s.p.flags & F_IN_NOMASK) &&
+                (s.p.ld_op == LD_C || s.p.ld_op == LD_C_MUL) && prec == PREC_F64 && s.p.map_in == MAP_ROW &&
+                s.p.in.elem_stride == 1 && tiles * nbatch >= gpipe_min_tiles()) {
+                int cnt = 0;
+                const KernelEntry* t = kernel_table(&cnt);
+                for (int i = 0; i < cnt; ++i)
+                    if (t[i].mode == 4 && t[i].groups == 2 && t[i].prec == s.k->prec && t[i].L == s.k->L && t[i].TL == s.k->TL &&
+                        t[i].dbl == s.k->dbl) {
+                        s.k = &t[i];
+                        break;
+                    }
+            }
             // persistent TMA-pipelined flavour: unmasked complex loads of tiles whose TL lanes are adjacent in
             // memory (16-byte aligned bulk copies), and enough tiles for every resident CTA to pipeline a few
             // 128 KiB row tiles (one CTA per SM: nothing else overlaps its loads) always take it when they can
@@ -659,8 +689,8 @@ struct PlanBuilder {
         char buf[256];
         snprintf(buf, sizeof buf, "%s: tile L=%d TL=%d%s%s threads=%d smem=%zu lanes=%lld batches=%lld map=%s->%s", what,
                  s.k->L, s.k->TL, s.k->dbl ? " fwd*tab*inv" : "",
-                 s.k->groups > 1 ? (s.k->mode ? " fast 2-groups" : " generic 2-groups")
-                                  : (s.k->mode == 0 ? " generic" : (s.k->mode == 1 ? " fast" : (s.k->mode == 2 ? " fast-r2c" : (s.k->mode == 3 ? " fast-c2r" : " pipelined")))), s.k->threads, s.k->smem, (long long)nlanes,
+                 s.k->groups > 1 ? (s.k->mode == 4 ? " group-pipelined" : (s.k->mode ? " fast 2-groups" : " generic 2-groups"))
+                                  : (s.k->mode == 0 ? " generic" : (s.k->mode == 1 ? " fast" : (s.k->mode == 2 ? " fast-r2c" : (s.k->mode == 3 ? " fast-c2r" : (s.k->groups == 2 ? " group-pipelined" : " pipelined"))))), s.k->threads, s.k->smem, (long long)nlanes,
                  (long long)nbatch, s.p.map_in == MAP_ROW ? "row" : "col", s.p.map_out == MAP_ROW ? "row" : "col");
         s.desc = buf;
         pl.steps_.push_back(s);

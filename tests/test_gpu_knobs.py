@@ -39,6 +39,7 @@ KNOBS = [
     {"SFC_FORCE_E": "8"},
     {"SFC_WORK_MB": "1"},                                                # many rounds through a tiny work area
     {"SFC_BLUE3_MIN": "32768", "SFC_THREE_LEVEL_MIN": "32768"},          # five-pass Bluestein, three-level rows
+    {"SFC_GPIPE": "1", "SFC_GPIPE_MIN_TILES": "1"},                      # group-pipelined flavour on every eligible row pass
 ]
 
 
