@@ -8,6 +8,8 @@ void register_kernels_dct(void (*add)(const KernelEntry&)) {
     SFC_ADD_DCT2(double, 512, 8)
     SFC_ADD_DCT2(double, 1024, 4)
     SFC_ADD_DCT2(double, 2048, 2)
+    SFC_ADD_DCT2(double, 2048, 1)
+    SFC_ADD_DCT2(double, 1024, 2)
     SFC_ADD_DCT2(double, 4096, 1)
     SFC_ADD_DCT2(double, 8192, 1)
 }

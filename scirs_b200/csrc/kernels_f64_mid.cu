@@ -4,8 +4,11 @@ namespace sfc {
 void register_kernels_f64_mid(void (*add)(const KernelEntry&)) {
     SFC_ADD(double, 256, 16, false)
     SFC_ADD(double, 512, 8, false)
+    SFC_ADD(double, 512, 4, false)
     SFC_ADD(double, 1024, 4, false)
     SFC_ADD(double, 1024, 8, false)
     SFC_ADD(double, 2048, 2, false)
+    SFC_ADD(double, 2048, 1, false)
+    SFC_ADD(double, 1024, 2, false)
 }
 }  // namespace sfc

@@ -9,6 +9,8 @@ void register_kernels_f64_real(void (*add)(const KernelEntry&)) {
     SFC_ADD_REAL(double, 512, 8)
     SFC_ADD_REAL(double, 1024, 4)
     SFC_ADD_REAL(double, 2048, 2)
+    SFC_ADD_REAL(double, 2048, 1)
+    SFC_ADD_REAL(double, 1024, 2)
     SFC_ADD_REAL(double, 4096, 1)
     SFC_ADD_REAL(double, 8192, 1)
 }

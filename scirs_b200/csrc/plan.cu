@@ -1280,8 +1280,10 @@ struct PlanBuilder {
         int cnt = 0;
         const KernelEntry* t = kernel_table(&cnt);
         s.k = nullptr;
-        for (int i = 0; i < cnt; ++i)
-            if (t[i].prec == prec && t[i].L == L && t[i].mode == (type3 ? 6 : 5)) s.k = &t[i];
+        for (int i = 0; i < cnt; ++i)  // rows: the narrowest tile (more CTAs per SM); strided lanes: the widest
+            if (t[i].prec == prec && t[i].L == L && t[i].mode == (type3 ? 6 : 5) &&
+                (!s.k || (col ? t[i].TL > s.k->TL : t[i].TL < s.k->TL)))
+                s.k = &t[i];
         const int64_t lanes = O * I;
         if (!s.k || lanes % s.k->TL != 0 || (col && I % s.k->TL != 0) || lanes > 0xFFFFFFFFLL)
             return fail(SFC_ERR_NOT_IMPLEMENTED, "no fused DCT kernel for this length / batch");
