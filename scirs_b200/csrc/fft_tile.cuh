@@ -334,7 +334,8 @@ struct TileCfg {
 #endif
     static constexpr int MINB =
         (E <= 8) ? (NT <= 512 ? (sizeof(T) == 8 ? 2 : 3) : 1)
-                 : ((NT <= 128 && sizeof(T) == 8) ? 2 * SFC_MINB_F64 : ((NT <= 256 && sizeof(T) == 8) ? SFC_MINB_F64 : (NT <= 256 ? 3 : 1)));
+                 : ((NT <= 128 && sizeof(T) == 8) ? 2 * SFC_MINB_F64
+                                                  : ((NT <= 256 && sizeof(T) == 8) ? SFC_MINB_F64 : (NT <= 128 ? 6 : (NT <= 256 ? 3 : 1))));
 };
 
 // Padded exchange layout: logical element e of a lane lives at slot e + (e >> log2(R*S)) * PADW,

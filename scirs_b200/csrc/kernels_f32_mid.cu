@@ -8,6 +8,8 @@ void register_kernels_f32_mid(void (*add)(const KernelEntry&)) {
     SFC_ADD(float, 1024, 4, false)
     SFC_ADD(float, 1024, 16, false)
     SFC_ADD(float, 2048, 2, false)
+    SFC_ADD(float, 2048, 1, false)
+    SFC_ADD(float, 1024, 2, false)
     SFC_ADD(float, 2048, 8, false)
 }
 }  // namespace sfc

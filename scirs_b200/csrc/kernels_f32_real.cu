@@ -9,6 +9,8 @@ void register_kernels_f32_real(void (*add)(const KernelEntry&)) {
     SFC_ADD_REAL(float, 512, 8)
     SFC_ADD_REAL(float, 1024, 4)
     SFC_ADD_REAL(float, 2048, 2)
+    SFC_ADD_REAL(float, 2048, 1)
+    SFC_ADD_REAL(float, 1024, 2)
     SFC_ADD_REAL(float, 4096, 1)
     SFC_ADD_REAL(float, 8192, 1)
     SFC_ADD_REAL(float, 16384, 1)
