@@ -3,6 +3,7 @@
 namespace sfc {
 void register_kernels_f64_mid(void (*add)(const KernelEntry&)) {
     SFC_ADD(double, 256, 16, false)
+    SFC_ADD(double, 256, 8, false)
     SFC_ADD(double, 512, 8, false)
     SFC_ADD(double, 512, 4, false)
     SFC_ADD(double, 1024, 4, false)

@@ -9,5 +9,7 @@ void register_kernels_f64_small(void (*add)(const KernelEntry&)) {
     SFC_ADD(double, 32, 128, false)
     SFC_ADD(double, 64, 64, false)
     SFC_ADD(double, 128, 32, false)
+    SFC_ADD(double, 128, 16, false)
+    SFC_ADD(double, 64, 32, false)
 }
 }  // namespace sfc

@@ -90,6 +90,15 @@ static int col_tl_cap() {
     return v;
 }
 
+// column tiles of internal passes: widest tile whose exchange buffer stays under this many KiB (100 = two 64 KiB
+// tiles per SM, 40 = four 32 KiB tiles per SM)
+static int col_smem_cap_kb() {
+    static int v = [] {
+        const char* e = getenv("SFC_COL_SMEM_KB");
+        return e ? atoi(e) : 100;
+    }();
+    return v;
+}
 static int forced_e() {
     static int v = [] {
         const char* e = getenv("SFC_FORCE_E");
@@ -144,7 +153,7 @@ static const KernelEntry* pick_kernel_two_per_sm(int prec, int L, int dbl) {
         if (t[i].mode != 0 || t[i].groups != 1 || t[i].prec != prec || t[i].L != L || t[i].dbl != dbl || t[i].E != want_e)
             continue;
         if (!smallest || t[i].TL < smallest->TL) smallest = &t[i];
-        if (t[i].smem > (size_t)100 * 1024) continue;
+        if (t[i].smem > (size_t)col_smem_cap_kb() * 1024) continue;
         if (!best || t[i].TL > best->TL) best = &t[i];
     }
     if (groups_mode() >= 2) {
