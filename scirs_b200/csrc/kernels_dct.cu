@@ -6,6 +6,7 @@ void register_kernels_dct(void (*add)(const KernelEntry&)) {
     SFC_ADD_DCT2(double, 128, 32)
     SFC_ADD_DCT2(double, 256, 16)
     SFC_ADD_DCT2(double, 512, 8)
+    SFC_ADD_DCT2(double, 512, 4)
     SFC_ADD_DCT2(double, 1024, 4)
     SFC_ADD_DCT2(double, 2048, 2)
     SFC_ADD_DCT2(double, 2048, 1)

@@ -4,6 +4,7 @@ namespace sfc {
 void register_kernels_f32_mid(void (*add)(const KernelEntry&)) {
     SFC_ADD(float, 256, 16, false)
     SFC_ADD(float, 512, 8, false)
+    SFC_ADD(float, 512, 4, false)
     SFC_ADD(float, 512, 16, false)
     SFC_ADD(float, 1024, 4, false)
     SFC_ADD(float, 1024, 16, false)

@@ -7,6 +7,7 @@ void register_kernels_f32_real(void (*add)(const KernelEntry&)) {
     SFC_ADD_REAL(float, 128, 32)
     SFC_ADD_REAL(float, 256, 16)
     SFC_ADD_REAL(float, 512, 8)
+    SFC_ADD_REAL(float, 512, 4)
     SFC_ADD_REAL(float, 1024, 4)
     SFC_ADD_REAL(float, 2048, 2)
     SFC_ADD_REAL(float, 2048, 1)
