@@ -289,6 +289,11 @@ int sfc_fft2_efficient(const void* x, int64_t rows, int64_t cols, int dtype, int
 int sfc_fft_streaming(const void* x, int64_t len, int dtype, int64_t n, int32_t inverse, int64_t chunk_size, double* out);
 int sfc_fftn_optimized(const double* x, int32_t ndim, const int64_t* shape, const int32_t* axes, int32_t naxes, double* out);
 
+/* chirp z-transform as czt.rs:45-275 sets it up, with the FFT calls that file stubs out (:110-113,
+ * :239-252) in place.  x: [rows][n] complex f64, out: [rows][m]; has_w == 0 takes w = exp(-2 pi i / m) (czt.rs:87-96). */
+int sfc_czt(const double* x, int64_t rows, int64_t n, int64_t m, int32_t has_w, double w_re, double w_im, double a_re,
+            double a_im, double* out);
+
 #ifdef __cplusplus
 }
 #endif

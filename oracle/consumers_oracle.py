@@ -534,3 +534,20 @@ def fftn_optimized(x, shape=None, axes=None) -> np.ndarray:  # ndim_optimized.rs
         n = r.shape[ax]
         r = np.apply_along_axis(lambda lane: base.fft(lane, None)[:n], ax, r)
     return r
+
+
+# ----------------------------------------------------------------------------- czt.rs (what the file sets up; its FFTs are stubs)
+
+def czt(x, m=None, w=None, a=None) -> np.ndarray:
+    """Direct evaluation X[k] = sum_j x[j] a^-j w^(jk) along the last axis (czt.rs:45-275 describes the fast form of this sum)."""
+    arr = np.asarray(x, dtype=np.complex128)
+    n = arr.shape[-1]
+    m = n if m is None else m
+    a = 1.0 + 0j if a is None else complex(a)
+    j = np.arange(n)[:, None].astype(np.float64)
+    k = np.arange(m)[None, :].astype(np.float64)
+    if w is None:
+        kern = np.exp(-2j * np.pi * ((np.arange(n)[:, None] * np.arange(m)[None, :]) % m) / m)
+    else:
+        kern = np.power(complex(w), j * k)
+    return (arr * np.power(a, -np.arange(n, dtype=np.float64))) @ kern

@@ -14,6 +14,7 @@ from .fft import (fft, ifft, rfft, irfft, fft2, ifft2, fft2_parallel, ifft2_para
 from .consumers import (DCTType, DSTType, dct, idct, dct2, idct2, dctn, idctn, dst, idst, dst2, idst2, dstn, idstn,
                         dht, idht, dht2, fht, hfft, ihfft, hilbert, get_window, stft, spectrogram, FftMode, fft_inplace,
                         process_in_chunks, fft2_efficient, fft_streaming, fftn_optimized)
+from .czt import CZT, czt, czt_points, zoom_fft
 from .plan import FftPlan, FftPlanExecutor
 from .plan_serialization import (PlanInfo, PlanMetrics, PlanDatabaseStats, PlanSerializationManager,
                                  create_and_time_plan)

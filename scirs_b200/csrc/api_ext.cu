@@ -11,6 +11,7 @@
 // n == 4 && norm == "ortho" (dct.rs:483-485, dst.rs:459-461, 528-530, 604-606, 679-681).
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -861,4 +862,123 @@ SFC_EXPORT int sfc_fftn_optimized(const double* x, int32_t ndim, const int64_t* 
         which ^= 1;
     }
     return download(out, cur, (size_t)total * 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the chirp z-transform of czt.rs:45-275 with its FFT calls in place (the reference stubs them out with
+// zero vectors, czt.rs:110-113, 239-252, so its czt returns zeros; this is the algorithm that file sets up):
+//   X[k] = sum_j x[j] a^-j w^(jk) = wk2[k] * sum_j (x[j] a^-j wk2[j]) / wk2[k - j],   wk2[k] = w^(k^2/2)
+// as a circular convolution of length nfft >= n + m - 1.  Two plan executions per call, everything else is tables:
+// forward FFT with the input weights a^-j wk2[j] fused into the load and the chirp spectrum (pre-rotated so that the
+// wanted window starts at 0) fused into the store; inverse FFT cropped to m outputs with wk2 fused into the store.
+namespace {
+
+struct CztTables {
+    int64_t nfft = 0;
+    void *d_awk2 = nullptr, *d_fwk2 = nullptr, *d_wk2c = nullptr;
+};
+std::mutex g_czt_mu;
+std::map<std::tuple<int, int64_t, int64_t, int, double, double, double, double>, CztTables> g_czt;
+
+int get_czt_tables(int64_t n, int64_t m, bool has_w, std::complex<double> w, std::complex<double> a, CztTables& out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const auto key = std::make_tuple(dev, n, m, (int)has_w, w.real(), w.imag(), a.real(), a.imag());
+    std::lock_guard<std::mutex> lk(g_czt_mu);
+    auto it = g_czt.find(key);
+    if (it != g_czt.end()) {
+        out = it->second;
+        return SFC_OK;
+    }
+    const int64_t mx = std::max(n, m);
+    std::vector<std::complex<double>> wk2((size_t)mx);
+    const double pi = 3.14159265358979323846;
+    for (int64_t k = 0; k < mx; ++k) {
+        if (has_w) {
+            wk2[k] = std::pow(w, (double)k * (double)k / 2.0);  // czt.rs:85
+        } else {  // czt.rs:89-95: exp(-i pi (k^2 mod 2m) / m)
+            const double ph = -(pi * (double)((k * k) % (2 * m))) / (double)m;
+            wk2[k] = std::polar(1.0, ph);
+        }
+    }
+    CztTables t;
+    t.nfft = next_pow2_i64(n + m - 1);  // the reference takes next_fast_len(n + m - 1): any length >= n + m - 1 gives the same result
+    std::vector<std::complex<double>> awk2((size_t)n), chirp((size_t)t.nfft, 0.0), wk2c((size_t)m);
+    for (int64_t k = 0; k < n; ++k) awk2[k] = std::pow(a, -(double)k) * wk2[k];  // czt.rs:103
+    for (int64_t i = 1; i < n; ++i) chirp[n - 1 - i] = 1.0 / wk2[i];             // czt.rs:108-113
+    for (int64_t i = 0; i < m; ++i) chirp[n - 1 + i] = 1.0 / wk2[i];
+    for (int64_t k = 0; k < m; ++k) wk2c[k] = std::conj(wk2[k]);  // the inverse plan multiplies by conj(table) (conjugation trick)
+    // spectrum of the reciprocal chirp with our own transform
+    void* d_res = nullptr;
+    int rc = run_c2c_host(chirp.data(), {t.nfft}, SFC_C128, {t.nfft}, {0}, false, 1.0, &d_res);
+    if (rc != SFC_OK) return rc;
+    std::vector<std::complex<double>> F((size_t)t.nfft);
+    if ((rc = download(F.data(), d_res, (size_t)t.nfft * 16)) != SFC_OK) return rc;
+    // rotate so that y[n-1 .. n-1+m) of the convolution lands at [0, m): multiply bin k by exp(+2 pi i (n-1) k / nfft)
+    for (int64_t k = 0; k < t.nfft; ++k) {
+        const int64_t r = ((n - 1) * k) % t.nfft;
+        F[k] *= std::polar(1.0, 2.0 * pi * (double)r / (double)t.nfft);
+    }
+    cudaError_t e = cudaMalloc(&t.d_awk2, (size_t)n * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&t.d_fwk2, (size_t)t.nfft * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&t.d_wk2c, (size_t)m * 16);
+    if (e == cudaSuccess) e = cudaMemcpy(t.d_awk2, awk2.data(), (size_t)n * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(t.d_fwk2, F.data(), (size_t)t.nfft * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(t.d_wk2c, wk2c.data(), (size_t)m * 16, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "CZT tables");
+    g_czt[key] = t;
+    out = t;
+    return SFC_OK;
+}
+
+}  // namespace
+
+// x: [rows][n] complex f64 -> out: [rows][m] complex f64; has_w == 0: w = exp(-2 pi i / m) (czt.rs:87-96)
+SFC_EXPORT int sfc_czt(const double* x, int64_t rows, int64_t n, int64_t m, int32_t has_w, double w_re, double w_im, double a_re,
+                       double a_im, double* out) {
+    int rc;
+    if ((rc = require_device()) != SFC_OK) return rc;
+    if (n < 1) return fail(SFC_ERR_VALUE, "n must be positive");  // czt.rs:70-72
+    if (m < 1) return fail(SFC_ERR_VALUE, "m must be positive");  // czt.rs:75-77
+    if (!x || !out || rows < 1) return fail(SFC_ERR_VALUE, "Input cannot be empty");
+    CztTables t;
+    if ((rc = get_czt_tables(n, m, has_w != 0, {w_re, w_im}, {a_re, a_im}, t)) != SFC_OK) return rc;
+    void *d_x = nullptr, *d_s = nullptr, *d_o = nullptr;
+    if ((rc = g_ws.get(0, (size_t)rows * n * 16, &d_x)) != SFC_OK) return rc;
+    if ((rc = g_ws.get(1, (size_t)rows * t.nfft * 16, &d_s)) != SFC_OK) return rc;
+    if ((rc = g_ws.get(2, (size_t)rows * m * 16, &d_o)) != SFC_OK) return rc;
+    cudaStream_t st = g_ws.stream;
+    cudaError_t e = cudaMemcpyAsync(d_x, x, (size_t)rows * n * 16, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+    sfc_desc d;
+    memset(&d, 0, sizeof d);
+    d.ndim = 2;
+    d.shape[0] = rows;
+    d.shape[1] = t.nfft;
+    d.naxes = 1;
+    d.axes[0] = 1;
+    d.kind = SFC_C2C;
+    d.prec = SFC_PREC_F64;
+    d.direction = SFC_FORWARD;
+    d.scale = 1.0;
+    d.flags = SFC_DESC_AXIS_LEN | SFC_DESC_AUX_MUL;
+    d.axis_in_len = n;
+    d.axis_out_len = t.nfft;
+    d.aux_in = t.d_awk2;
+    d.aux_out = t.d_fwk2;
+    PlanError perr{0, ""};
+    std::shared_ptr<Plan> pf = cached_plan(d, perr);
+    if (!pf) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
+    d.direction = SFC_INVERSE;
+    d.scale = 1.0 / (double)t.nfft;
+    d.axis_in_len = t.nfft;
+    d.axis_out_len = m;
+    d.aux_in = nullptr;
+    d.aux_out = t.d_wk2c;
+    std::shared_ptr<Plan> pi = cached_plan(d, perr);
+    if (!pi) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
+    std::string es;
+    if ((rc = pf->exec(d_x, d_s, st, es)) != 0) return fail(rc, es);
+    if ((rc = pi->exec(d_s, d_o, st, es)) != 0) return fail(rc, es);
+    return download(out, d_o, (size_t)rows * m * 16);
 }

@@ -287,3 +287,42 @@ def test_against_committed_extended_precision_golden_vectors(sb):
         assert rel(sb.hfft(z, m), G[f"hfft_{n}_n{m}"]) <= TOL
         assert rel(sb.ihfft(x, m), G[f"ihfft_{n}_n{m}"]) <= TOL
         assert rel(sb.hilbert(x), G[f"hilbert_{n}"]) <= TOL
+
+
+def test_czt_and_zoom_fft(sb, co):
+    """czt.rs: the reference's own properties (test_czt_points :371-393, test_czt_as_fft :396-410) and the direct sum."""
+    import importlib
+
+    cz = importlib.import_module("scirs_b200.czt")
+
+    pts = cz.czt_points(4)
+    assert len(pts) == 4 and np.allclose(np.abs(pts), 1.0, atol=1e-10)
+    a, w = 0.8 + 0j, 0.95 * np.exp(0.1j)
+    pts = cz.czt_points(5, a, w)
+    assert len(pts) == 5 and abs(pts[0] - a) < 1e-10
+    x = np.linspace(0.0, 7.0, 8) + 0j
+    assert np.allclose(cz.czt(x), np.fft.fft(x), atol=1e-10)                     # czt with defaults == fft
+    rng = np.random.default_rng(8)
+    for n, m in ((8, 8), (100, 37), (37, 100), (1000, 1000), (5000, 3000), (4096, 8192)):
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        assert rel(cz.czt(x, m), co.czt(x, m)) <= 1e-11, (n, m)
+        # off-circle spirals are ill-conditioned in the fast form (|a|^-k |w|^(k^2/2) spans many decades): small sizes only
+        damp = (0.9999, 0.98) if max(n, m) <= 100 else (1.0, 1.0)
+        w = np.exp(-2j * np.pi * 0.37 / m) * damp[0]
+        a = damp[1] * np.exp(0.3j)
+        assert rel(cz.czt(x, m, w, a), co.czt(x, m, w, a)) <= 1e-9, (n, m, "spiral")
+    x2 = rng.standard_normal((6, 50)) + 1j * rng.standard_normal((6, 50))
+    assert rel(cz.czt(x2, 20), co.czt(x2, 20)) <= 1e-11
+    assert rel(cz.czt(x2, 9, axis=0), np.moveaxis(co.czt(np.moveaxis(x2, 0, -1), 9), -1, 0)) <= 1e-11
+    # zoom_fft: m points of the (oversampled) spectrum between f0 and f1
+    x = rng.standard_normal(256) + 0j
+    z = cz.zoom_fft(x, 64, 0.1, 0.3)
+    k0, k1 = 0.1 * 256 * 2, 0.3 * 256 * 2
+    f = (k0 + (k1 - k0) / 63 * np.arange(64)) / (256 * 2)
+    ref = np.array([np.sum(x * np.exp(-2j * np.pi * fk * np.arange(256))) for fk in f])
+    assert rel(z, ref) <= 1e-11
+    for bad in (lambda: cz.zoom_fft(x, 8, 0.5, 0.2), lambda: cz.zoom_fft(x, 8, -0.1, 0.2), lambda: cz.zoom_fft(x, 8, 0.1, 0.2, 0.5),
+                lambda: cz.CZT(0), lambda: cz.CZT(4, 0), lambda: cz.CZT(4).transform(np.zeros(5, dtype=complex)),
+                lambda: cz.CZT(4).transform(np.zeros((2, 2, 4), dtype=complex))):
+        with pytest.raises(sb.ValueError_):
+            bad()
