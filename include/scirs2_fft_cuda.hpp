@@ -221,6 +221,18 @@ inline std::vector<Complex64> ihfft(const std::vector<double>& x, std::optional<
     return out;
 }
 
+// czt — czt.rs:279-303 (1-D; w / a as in CZT::new, czt.rs:64-131)
+inline std::vector<Complex64> czt(const std::vector<Complex64>& x, std::optional<size_t> m = std::nullopt,
+                                  std::optional<Complex64> w = std::nullopt, std::optional<Complex64> a = std::nullopt) {
+    const int64_t mm = m ? (int64_t)*m : (int64_t)x.size();
+    std::vector<Complex64> out((size_t)std::max<int64_t>(mm, 1));
+    const Complex64 wv = w.value_or(Complex64(0.0, 0.0)), av = a.value_or(Complex64(1.0, 0.0));
+    check(sfc_czt(reinterpret_cast<const double*>(x.data()), 1, (int64_t)x.size(), mm, w ? 1 : 0, wv.real(), wv.imag(), av.real(),
+                  av.imag(), reinterpret_cast<double*>(out.data())));
+    out.resize((size_t)mm);
+    return out;
+}
+
 // PlanCache — plan_cache.rs:28-235 (the cache itself lives in the library)
 struct CacheStats { uint64_t hit_count, miss_count; double hit_rate; uint64_t size, max_size; };
 class PlanCache {

@@ -46,6 +46,13 @@ int main() {
     for (int i = 0; i < 4; ++i) REQUIRE(std::abs(hh[i] - sig[i]) < 1e-10);
     REQUIRE(hilbert(sig).size() == 4 && hfft(sig).size() == 4 && ihfft(sig).size() == 4 && dst(sig).size() == 4);
     try { dct(std::vector<double>{1.0}, DCTType::Type1); return 1; } catch (const FFTError& e) { REQUIRE(e.kind == FFTError::Value); }
+    {  // czt with default parameters equals fft (czt.rs:396-410)
+        std::vector<Complex64> xc(8);
+        for (int i = 0; i < 8; ++i) xc[i] = Complex64((double)i, 0.0);
+        auto zc = czt(xc);
+        auto fc = fft(xc, 8);
+        for (int i = 0; i < 8; ++i) REQUIRE(std::abs(zc[i] - fc[i]) < 1e-10);
+    }
     std::puts("cpp mirror ok");
     return 0;
 }
