@@ -239,9 +239,18 @@ int get_trig_tables(int kind, int type, bool inverse, bool ortho, int64_t n, Tri
 // one 1-D trig transform along axis `a` of a real [O][N][I] array: d_src (real) -> d_dst (real)
 int trig_axis(int kind, int type, bool inverse, bool ortho, int64_t O, int64_t N, int64_t I, const void* d_src,
               void* d_dst, cudaStream_t st) {
+    int rc;
+    {
+        // argument checks (and error texts) of the reference come from the table builder's specification
+        int64_t D = 0;
+        int a2 = 0, b2 = 0;
+        std::vector<long double> s, g;
+        if (N < 2) {
+            const std::string msg = trig_spec(kind, type, inverse, ortho, N, D, a2, b2, s, g);
+            if (!msg.empty()) return fail(SFC_ERR_VALUE, msg);
+        }
+    }
     TrigTables t;
-    int rc = get_trig_tables(kind, type, inverse, ortho, N, t);
-    if (rc != SFC_OK) return rc;
     sfc_desc d;
     memset(&d, 0, sizeof d);
     d.ndim = 3;
@@ -298,6 +307,8 @@ int trig_axis(int kind, int type, bool inverse, bool ortho, int64_t O, int64_t N
         }
         if (perr.code != SFC_ERR_NOT_IMPLEMENTED) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
     }
+    if ((rc = get_trig_tables(kind, type, inverse, ortho, N, t)) != SFC_OK) return rc;  // only the 2N-point formulations need them
+    d.shape[1] = t.P;
     if (fuse_enabled() && is_pow2_i64(t.P)) {
         // everything in the FFT passes themselves: real load * u, ..., * w, real-part store
         d.flags = SFC_DESC_AXIS_LEN | SFC_DESC_AUX_MUL | SFC_DESC_REAL_INPUT | SFC_DESC_REAL_OUTPUT;

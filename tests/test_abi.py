@@ -75,7 +75,15 @@ def test_no_cpu_fallback(lib):
     assert lib.sfc_init(0) == -6
     for call in (lambda: sb.fft(np.ones(8)), lambda: sb.rfft(np.ones(8)), lambda: sb.fft2(np.ones((4, 4))),
                  lambda: sb.fftn(np.ones((2, 2, 2))), lambda: sb.irfftn(np.ones((2, 2, 2)) + 0j),
-                 lambda: sb.FftPlan([8], [0]), lambda: sb.rfft_batch(np.ones((2, 64)))):
+                 lambda: sb.FftPlan([8], [0]), lambda: sb.rfft_batch(np.ones((2, 64))),
+                 # the consumers of the path have no CPU fallback either
+                 lambda: sb.dct(np.ones(8)), lambda: sb.idst(np.ones(8), sb.DSTType.Type3, "ortho"), lambda: sb.dctn(np.ones((4, 4))),
+                 lambda: sb.dht(np.ones(8)), lambda: sb.dht2(np.ones((4, 4))), lambda: sb.hfft(np.ones(8) + 0j),
+                 lambda: sb.ihfft(np.ones(8)), lambda: sb.hilbert(np.ones(8)), lambda: sb.stft(np.ones(64), "hann", 16),
+                 lambda: sb.spectrogram(np.ones(64), nperseg=16), lambda: sb.fft2_efficient(np.ones((4, 4))),
+                 lambda: sb.fft_streaming(np.ones(8)), lambda: sb.fftn_optimized(np.ones((4, 4))),
+                 lambda: sb.fft_inplace(np.ones(8, dtype=np.complex128), np.ones(8, dtype=np.complex128)),
+                 lambda: sb.czt(np.ones(8) + 0j)):
         with pytest.raises(sb.BackendError) as e:
             call()
         assert "no CPU fallback" in str(e.value)
