@@ -281,6 +281,20 @@ __device__ __forceinline__ void apply_twiddle_powers(Cx<T> (&v)[R], Cx<T> w1) {
     }
 }
 
+// v[k] *= W_L^(base*k) read straight from the stage table, for stages whose stride S is >= 16: all threads of a
+// half warp then share `base`, every load touches one or two addresses (L1 broadcast), and the 53-instruction FP64
+// product tree above is saved.  Measured (tools/exp31.sh, 65536 x 4096): 1.5% SLOWER for f64 c2c (91.5% against 93.0%
+// of the HBM peak) and 3% slower for f64 rfft -- the 15 extra L1 loads per butterfly cost more issue slots next to the
+// tile's own global loads than the FP64 tree does.  Off; -DSFC_TW_LOAD=1 builds it.
+#ifndef SFC_TW_LOAD
+#define SFC_TW_LOAD 0
+#endif
+template <int R, typename T>
+__device__ __forceinline__ void apply_twiddle_table(Cx<T> (&v)[R], const Cx<T>* __restrict__ tw, int base) {
+#pragma unroll
+    for (int k = 1; k < R; ++k) v[k] = cmul(v[k], tw[base * k]);
+}
+
 __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
 
 // ---- tile configuration ------------------------------------------------------
@@ -391,7 +405,8 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
 #pragma unroll
             for (int r = 0; r < R; ++r) v[r] = a[b + r * NB];
             Dft<R, T>::run(v);
-            apply_twiddle_powers<R, T>(v, tw[(iw + b * TPL) & ~(S - 1)]);
+            if constexpr (SFC_TW_LOAD && S >= 16) apply_twiddle_table<R, T>(v, tw, (iw + b * TPL) & ~(S - 1));
+            else apply_twiddle_powers<R, T>(v, tw[(iw + b * TPL) & ~(S - 1)]);
 #pragma unroll
             for (int k = 0; k < R; ++k) a[b + k * NB] = v[k];
         }
@@ -432,7 +447,8 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
             if constexpr (MIRROR_IN && S == 1 && NB == 2) {
                 if (b == 1) ib = iw == 0 ? (L / R) / 2 : (L / R) - iw;  // the mirror butterfly
             }
-            apply_twiddle_powers<R, T>(v, tw[ib & ~(S - 1)]);
+            if constexpr (SFC_TW_LOAD && S >= 16) apply_twiddle_table<R, T>(v, tw, ib & ~(S - 1));
+            else apply_twiddle_powers<R, T>(v, tw[ib & ~(S - 1)]);
             Cx<T>* dst = sm + tw_ * C::LP + Xch<C, R, S>::write_base(ib);
 #pragma unroll
             for (int k = 0; k < R; ++k) dst[k * S] = v[k];
