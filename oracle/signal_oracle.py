@@ -1,0 +1,436 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement of the scirs2-signal callers of the FFT hot path
+(SURVEY 8f rank 4).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this.
+
+Written the way the reference is: one segment at a time, each through the oracle's own `fft` / `ifft`
+(scirs2_fft_oracle.py, which restates fft/algorithms.rs including the next-power-of-two padding of
+`fft(x, None)`), plain Python loops for the bin-by-bin passes.  Cited file:line ranges:
+
+  get_window / apply_detrend / periodogram / welch / stft / spectrogram
+                             scirs2-signal/src/spectral.rs:29-66, 77-117, 130-244, 257-410, 413-447, 468-628, 644-735
+  estimate_noise_power / wiener_filter_freq / spectral_subtraction / smooth_psd / psd_wiener_filter
+                             scirs2-signal/src/wiener.rs:709-739, 137-196, 439-546, 775-794, 560-655
+  window (hann .. cosine)    scirs2-signal/src/window/mod.rs:38-107, 133-260, 580-590
+  StreamingStft              scirs2-signal/src/streaming_stft.rs:124-438
+  bispectrum (direct, Welch) scirs2-signal/src/higher_order.rs:250-332, 359-461
+
+Pinning: the reference's unit tests for these modules hold no golden vectors (they assert peak positions,
+shapes and value ranges: spectral.rs:743-935, streaming_stft.rs tests, wiener.rs tests); those assertions
+are restated in tests/test_signal_oracle.py and cross-checked against scipy.signal where the two agree by
+definition.  Beyond that: parity unpinned by the reference.
+"""
+from __future__ import annotations
+
+import cmath
+import math
+from collections import deque
+from typing import List, Optional
+
+import numpy as np
+
+from . import scirs2_fft_oracle as base
+
+OracleError = base.OracleError
+
+
+# ---- spectral.rs ---------------------------------------------------------------------------------
+
+def get_window(window_type: str, nperseg: int) -> List[float]:  # spectral.rs:29-66
+    w = window_type.lower()
+    if w == "hann":
+        return [0.5 * (1.0 - math.cos(2.0 * math.pi * i / (nperseg - 1))) for i in range(nperseg)]
+    if w == "hamming":
+        return [0.54 - 0.46 * math.cos(2.0 * math.pi * i / (nperseg - 1)) for i in range(nperseg)]
+    if w == "blackman":
+        return [0.42 - 0.5 * math.cos(2.0 * math.pi * i / (nperseg - 1))
+                + 0.08 * math.cos(4.0 * math.pi * i / (nperseg - 1)) for i in range(nperseg)]
+    if w in ("boxcar", "rectangular"):
+        return [1.0] * nperseg
+    raise OracleError(f"Unknown window type: {window_type}")
+
+
+def apply_detrend(x: List[float], detrend_type: str) -> List[float]:  # spectral.rs:77-117
+    if detrend_type == "constant":
+        mean = sum(x) / len(x)
+        return [v - mean for v in x]
+    if detrend_type == "linear":
+        n = len(x)
+        sum_x = float(sum(range(n)))
+        sum_y = sum(x)
+        sum_xx = float(sum(i * i for i in range(n)))
+        sum_xy = sum(i * y for i, y in enumerate(x))
+        slope = (n * sum_xy - sum_x * sum_y) / (n * sum_xx - sum_x * sum_x)
+        intercept = (sum_y - slope * sum_x) / n
+        return [y - (slope * i + intercept) for i, y in enumerate(x)]
+    if detrend_type == "none":
+        return list(x)
+    raise OracleError(f"Unknown detrend option: {detrend_type}")
+
+
+def _fftfreq(n: int, d: float) -> List[float]:  # scirs2-fft/src/helper.rs fftfreq: k / (n d), negative half wrapped
+    val = 1.0 / (n * d)
+    half = (n - 1) // 2 + 1
+    return [k * val for k in range(half)] + [-(n // 2 - k) * val for k in range(n // 2)]
+
+
+def _segment_fft(seg: List[float], win: List[float], detrend: str, nfft: int) -> np.ndarray:
+    d = apply_detrend(seg, detrend)
+    padded = [a * w for a, w in zip(d, win)]
+    if nfft > len(padded):
+        padded = padded + [0.0] * (nfft - len(padded))
+    return base.fft(np.array(padded, dtype=np.float64), None)
+
+
+def periodogram(x, fs=None, window=None, nfft=None, detrend=None, scaling=None):  # spectral.rs:130-244
+    x = [float(v) for v in x]
+    if not x:
+        raise OracleError("Input array is empty")
+    fs = 1.0 if fs is None else fs
+    nfft = len(x) if nfft is None else nfft
+    window = window or "boxcar"
+    detrend = detrend or "constant"
+    scaling = scaling or "density"
+    if fs <= 0.0:
+        raise OracleError("Sampling frequency must be positive")
+    if nfft < len(x):
+        raise OracleError("NFFT must be at least as large as signal length")
+    win = get_window(window, len(x))
+    scale = 1.0 / sum(w * w for w in win)
+    spectrum = _segment_fft(x, win, detrend, nfft)
+    pg = [(c.real * c.real + c.imag * c.imag) * scale / (fs * len(x)) for c in spectrum]
+    freqs = _fftfreq(nfft, 1.0 / fs)
+    n_half = nfft // 2 + nfft % 2
+    rf, rp = [], []
+    for i in range(n_half):
+        if i < len(freqs) and i < len(pg):
+            rf.append(freqs[i])
+            rp.append(pg[i] if scaling == "density" else pg[i] * fs)
+    return np.array(rf), np.array(rp)
+
+
+def welch(x, fs=None, window=None, nperseg=None, noverlap=None, nfft=None, detrend=None, scaling=None):
+    # spectral.rs:257-410
+    x = [float(v) for v in x]
+    if not x:
+        raise OracleError("Input array is empty")
+    fs = 1.0 if fs is None else fs
+    nperseg = min(256, len(x)) if nperseg is None else nperseg
+    noverlap = nperseg // 2 if noverlap is None else noverlap
+    nfft = nperseg if nfft is None else nfft
+    window = window or "hann"
+    detrend = detrend or "constant"
+    scaling = scaling or "density"
+    if fs <= 0.0 or nfft < nperseg or noverlap >= nperseg:
+        raise OracleError("bad parameters")
+    win = get_window(window, nperseg)
+    scale = 1.0 / sum(w * w for w in win)
+    step = nperseg - noverlap
+    num_segments = (len(x) - noverlap) // step if len(x) >= noverlap else 0
+    if num_segments < 1:
+        raise OracleError("Not enough data points for given nperseg and noverlap")
+    n_half = nfft // 2 + nfft % 2
+    freqs = _fftfreq(nfft, 1.0 / fs)[:n_half]
+    avg = [0.0] * n_half
+    for i in range(num_segments):
+        start, end = i * step, i * step + nperseg
+        if end > len(x):
+            break
+        spectrum = _segment_fft(x[start:end], win, detrend, nfft)
+        for j, c in enumerate(spectrum[:n_half]):
+            avg[j] += (c.real * c.real + c.imag * c.imag) * scale / (fs * nperseg)
+    avg = [p / num_segments for p in avg]
+    if scaling != "density":
+        avg = [p * fs for p in avg]
+    return np.array(freqs), np.array(avg)
+
+
+def apply_boundary(x: List[float], nperseg: int, boundary: str) -> List[float]:  # spectral.rs:413-447
+    pad = nperseg // 2
+    if boundary == "zeros":
+        return [0.0] * pad + list(x) + [0.0] * pad
+    if boundary == "extend":
+        return [x[0]] * pad + list(x) + [x[-1]] * pad
+    if boundary == "none":
+        return list(x)
+    raise OracleError(f"Unknown boundary option: {boundary}")
+
+
+def stft(x, fs=None, window=None, nperseg=None, noverlap=None, nfft=None, detrend=None, boundary=None, padded=None):
+    # spectral.rs:468-628; returns (freqs, times, Z[segment][bin])
+    x = [float(v) for v in x]
+    if not x:
+        raise OracleError("Input array is empty")
+    fs = 1.0 if fs is None else fs
+    nperseg = min(256, len(x)) if nperseg is None else nperseg
+    noverlap = nperseg // 2 if noverlap is None else noverlap
+    nfft = nperseg if nfft is None else nfft
+    window = window or "hann"
+    detrend = detrend or "constant"
+    boundary = boundary or "zeros"
+    padded = True if padded is None else padded
+    if fs <= 0.0 or nfft < nperseg or noverlap >= nperseg:
+        raise OracleError("bad parameters")
+    win = get_window(window, nperseg)
+    sig = apply_boundary(x, nperseg, boundary) if padded else x
+    step = nperseg - noverlap
+    num_segments = (len(sig) - noverlap) // step if len(sig) >= noverlap else 0
+    if num_segments < 1:
+        raise OracleError("Not enough data points for given nperseg and noverlap")
+    n_half = nfft // 2 + nfft % 2
+    freqs = _fftfreq(nfft, 1.0 / fs)[:n_half]
+    times = [(i * step + nperseg // 2) / fs for i in range(num_segments)]
+    out = [[0j] * num_segments for _ in range(n_half)]
+    for i in range(num_segments):
+        start, end = i * step, i * step + nperseg
+        if end > len(sig):
+            break
+        spectrum = _segment_fft(sig[start:end], win, detrend, nfft)
+        for j, v in enumerate(spectrum[:n_half]):
+            out[j][i] = complex(v)
+    Z = [[out[j][i] for j in range(n_half)] for i in range(num_segments)]
+    return np.array(freqs), np.array(times), np.array(Z, dtype=np.complex128).reshape(num_segments, n_half)
+
+
+def spectrogram(x, fs=None, window=None, nperseg=None, noverlap=None, nfft=None, detrend=None, scaling=None,
+                mode=None):  # spectral.rs:644-735
+    mode = mode or "psd"
+    scaling = scaling or "density"
+    freqs, times, Z = stft(x, fs, window, nperseg, noverlap, nfft, detrend, "zeros", True)
+    if mode == "psd":
+        fsv = 1.0 if fs is None else fs
+        npg = min(256, len(x)) if nperseg is None else nperseg
+        win = get_window(window or "hann", npg)
+        scale = 1.0 / sum(w * w for w in win)
+        S = np.array([[(c.real ** 2 + c.imag ** 2) * scale / (fsv * npg) * (1.0 if scaling == "density" else fsv)
+                       for c in col] for col in Z])
+    elif mode == "magnitude":
+        S = np.array([[abs(c) for c in col] for col in Z])
+    elif mode in ("angle", "phase"):
+        S = np.array([[cmath.phase(c) for c in col] for col in Z])
+    else:
+        raise OracleError(f"mode {mode}")
+    return freqs, times, S
+
+
+# ---- wiener.rs -----------------------------------------------------------------------------------
+
+def _median(v: List[float]) -> float:
+    n = len(v)
+    return (v[n // 2 - 1] + v[n // 2]) / 2.0 if n % 2 == 0 else v[n // 2]
+
+
+def estimate_noise_power(signal) -> float:  # wiener.rs:709-739
+    values = sorted(float(v) for v in signal)
+    median = _median(values)
+    dev = sorted(abs(v - median) for v in values)
+    return (1.4826 * _median(dev)) ** 2
+
+
+def wiener_filter_freq(signal, noise_power=None, prior_snr=None, regularization=1e-10) -> np.ndarray:
+    # wiener.rs:137-196
+    s = np.asarray(signal, dtype=np.float64)
+    n = s.size
+    noise = noise_power if noise_power is not None else estimate_noise_power(s)
+    spec = base.fft(s, None)
+    out = []
+    for c in spec:
+        power = c.real * c.real + c.imag * c.imag
+        snr = 1.0 if prior_snr is None else prior_snr
+        out.append(c * (power / (power + snr * noise + regularization)))
+    return np.array([c.real for c in base.ifft(np.array(out), None)[:n]])
+
+
+def spectral_subtraction(signal, noise_power=None, alpha=None, beta=None) -> np.ndarray:  # wiener.rs:439-546
+    s = np.asarray(signal, dtype=np.float64)
+    n = s.size
+    a = 1.0 if alpha is None else alpha
+    b = 0.01 if beta is None else beta
+    spec = [complex(c) for c in base.fft(s, None)]
+    if noise_power is not None:
+        noise = [float(v) for v in noise_power]
+    else:
+        ns = int(min(n * 0.05, 100.0))
+        if ns < 4:
+            raise OracleError("Signal too short to estimate noise spectrum")
+        nf = base.fft(s[:ns], n)
+        noise = [(c.real ** 2 + c.imag ** 2) / n for c in nf[: n // 2 + 1]]
+    for i in range(n // 2 + 1):
+        mag, phase = abs(spec[i]), cmath.phase(spec[i])
+        npw = noise[i] if i < len(noise) else noise[-1]
+        new_mag = math.sqrt(max(mag ** 2 - a * npw, b * mag ** 2))
+        spec[i] = cmath.rect(new_mag, phase)
+        if 0 < i < n // 2:
+            spec[n - i] = cmath.rect(new_mag, -phase)
+    return np.array([c.real for c in base.ifft(np.array(spec), None)[:n]])
+
+
+def smooth_psd(psd: List[float]) -> List[float]:  # wiener.rs:775-794
+    n = len(psd)
+    window_size = int(min(max(n * 0.02, 3.0), 15.0))
+    half = window_size // 2
+    out = []
+    for i in range(n):
+        st, en = max(i - half, 0), min(i + half + 1, n)
+        out.append(sum(psd[st:en]) / (en - st))
+    return out
+
+
+def psd_wiener_filter(signal, signal_psd=None, noise_psd=None) -> np.ndarray:  # wiener.rs:560-655
+    s = np.asarray(signal, dtype=np.float64)
+    n = s.size
+    spec = [complex(c) for c in base.fft(s, None)]
+    if signal_psd is not None:
+        s_psd = [float(v) for v in signal_psd]
+    else:
+        s_psd = smooth_psd([(spec[i].real ** 2 + spec[i].imag ** 2) / n for i in range(n // 2 + 1)])
+    n_psd = [float(v) for v in noise_psd] if noise_psd is not None else [estimate_noise_power(s)] * (n // 2 + 1)
+    for i in range(n // 2 + 1):
+        mag, phase = abs(spec[i]), cmath.phase(spec[i])
+        sp = s_psd[i] if i < len(s_psd) else 0.0
+        npw = n_psd[i] if i < len(n_psd) else 0.0
+        gain = sp / (sp + npw) if sp + npw > 1e-10 else 0.0
+        spec[i] = cmath.rect(mag * gain, phase)
+        if 0 < i < n // 2:
+            spec[n - i] = cmath.rect(mag * gain, -phase)
+    return np.array([c.real for c in base.ifft(np.array(spec), None)[:n]])
+
+
+# ---- window/mod.rs (subset) and streaming_stft.rs ------------------------------------------------
+
+def signal_window(window_type: str, length: int, periodic: bool) -> List[float]:  # window/mod.rs:38-107 ...
+    if length == 0:
+        raise OracleError("Window length must be positive")
+    if length <= 1:
+        return [1.0] * length
+    n = length if not periodic else length + 1  # _extend(m, sym = !periodic)
+    w = window_type.lower()
+    if w in ("hann", "hanning"):
+        v = [0.5 * (1.0 - math.cos(2.0 * math.pi * i / (n - 1))) for i in range(n)]
+    elif w == "hamming":
+        v = [0.54 - 0.46 * math.cos(2.0 * math.pi * i / (n - 1)) for i in range(n)]
+    elif w == "blackman":
+        v = [0.42 - 0.5 * math.cos(2.0 * math.pi * i / (n - 1)) + 0.08 * math.cos(4.0 * math.pi * i / (n - 1))
+             for i in range(n)]
+    elif w == "bartlett":
+        m2 = (n - 1) / 2.0
+        v = [1.0 - abs((i - m2) / m2) for i in range(n)]
+    elif w == "cosine":
+        v = [math.sin(math.pi * i / (n - 1)) for i in range(n)]
+    elif w in ("boxcar", "rectangular"):
+        v = [1.0] * n
+    else:
+        raise OracleError(f"Unknown window type: {window_type}")
+    return v[:length]  # _truncate
+
+
+class StreamingStft:  # streaming_stft.rs:124-438
+    def __init__(self, frame_length=512, hop_length=256, window="hann", center=True, magnitude_only=False,
+                 log_magnitude=False, power=1.0, log_epsilon=1e-10):
+        self.L, self.hop, self.center = frame_length, hop_length, center
+        self.magnitude_only, self.log_magnitude, self.power, self.eps = magnitude_only, log_magnitude, power, log_epsilon
+        self.window = signal_window(window, frame_length, True)
+        self.buf = deque([0.0] * (frame_length // 2) if center else [])
+        self.frames_generated = 0
+
+    def _fft(self, frame):
+        spec = base.fft(np.array(frame, dtype=np.float64), None)[: self.L // 2 + 1]
+        if not self.magnitude_only:
+            return np.array(spec)
+        if self.power == 1.0:
+            m = [abs(c) for c in spec]
+        elif self.power == 2.0:
+            m = [c.real ** 2 + c.imag ** 2 for c in spec]
+        else:
+            m = [abs(c) ** self.power for c in spec]
+        if self.log_magnitude:
+            m = [math.log(v + self.eps) for v in m]
+        return np.array(m, dtype=np.complex128)
+
+    def process_frame(self, samples):
+        self.buf.extend(float(v) for v in samples)
+        if len(self.buf) < self.L:
+            return None
+        frame = [self.buf[i] * self.window[i] for i in range(self.L)]
+        out = self._fft(frame)
+        for _ in range(self.hop):
+            if self.buf:
+                self.buf.popleft()
+        self.frames_generated += 1
+        return out
+
+    def process_batch(self, data, frame_size):
+        res, start = [], 0
+        while start + frame_size <= len(data):
+            r = self.process_frame(data[start:start + frame_size])
+            if r is not None:
+                res.append(r)
+            start += frame_size
+        if start < len(data):
+            r = self.process_frame(data[start:])
+            if r is not None:
+                res.append(r)
+        return res
+
+    def flush(self):
+        res = []
+        while len(self.buf) >= self.hop:
+            frame = [0.0] * self.L
+            for i in range(min(len(self.buf), self.L)):
+                frame[i] = self.buf[i]
+            res.append(self._fft([f * w for f, w in zip(frame, self.window)]))
+            for _ in range(self.hop):
+                if self.buf:
+                    self.buf.popleft()
+            self.frames_generated += 1
+        return res
+
+
+# ---- higher_order.rs -----------------------------------------------------------------------------
+
+def direct_bispectrum(signal, nfft: int, window: Optional[str]) -> np.ndarray:  # higher_order.rs:289-332
+    s = np.asarray(signal, dtype=np.float64)
+    if window is not None:
+        s = s * np.array(signal_window(window, s.size, True))
+    X = base.fft(s, nfft)
+    nb = nfft // 2 + 1
+    B = np.zeros((nb, nb), dtype=np.complex128)
+    for i in range(nb):
+        for j in range(i + 1):
+            v = X[i] * X[j] * np.conj(X[(i + j) % nfft])
+            B[i, j] = v
+            B[j, i] = v
+    return B
+
+
+def welch_bispectrum(signal, nfft: int, window: Optional[str], overlap: float = 0.5,
+                     n_segments: Optional[int] = None) -> np.ndarray:  # higher_order.rs:359-431
+    s = np.asarray(signal, dtype=np.float64)
+    n = s.size
+    size = min(nfft, n)
+    ov = int(round(size * overlap))  # f64::round is half away from zero; equal for the .5 cases used in tests
+    step = size - ov
+    if step == 0:
+        raise OracleError("Overlap too large")
+    nseg = n_segments if n_segments is not None else int(math.floor((n - ov) / step))
+    if nseg == 0:
+        raise OracleError("Signal too short")
+    nb = nfft // 2 + 1
+    acc = np.zeros((nb, nb), dtype=np.complex128)
+    for i in range(nseg):
+        st = i * step
+        en = min(st + size, n)
+        if en - st < 4:
+            continue
+        acc += direct_bispectrum(s[st:en], nfft, window)
+    return acc / nseg
+
+
+def power_spectrum(signal, nfft: int, window: Optional[str]) -> np.ndarray:  # higher_order.rs:464-508
+    s = np.asarray(signal, dtype=np.float64)
+    if window is not None:
+        s = s * np.array(signal_window(window, s.size, True))
+    X = base.fft(s, nfft)
+    nb = nfft // 2 + 1
+    p = np.array([(X[i].real ** 2 + X[i].imag ** 2) / nfft for i in range(nb)])
+    if nb > 2:
+        p[1:nb - 1] *= 2.0
+    return p

@@ -15,6 +15,7 @@ from .consumers import (DCTType, DSTType, dct, idct, dct2, idct2, dctn, idctn, d
                         dht, idht, dht2, fht, hfft, ihfft, hilbert, get_window, stft, spectrogram, FftMode, fft_inplace,
                         process_in_chunks, fft2_efficient, fft_streaming, fftn_optimized)
 from .czt import CZT, czt, czt_points, zoom_fft
+from . import signal  # the scirs2-signal callers keep their own namespace (their stft / spectrogram differ from scirs2-fft's)
 from .plan import FftPlan, FftPlanExecutor
 from .plan_serialization import (PlanInfo, PlanMetrics, PlanDatabaseStats, PlanSerializationManager,
                                  create_and_time_plan)

@@ -1,0 +1,708 @@
+"""Downstream callers of the FFT hot path in scirs2-signal, re-stated over this package.
+
+The reference functions are host code that loops over segments and calls ``scirs2_fft::fft`` once per
+segment.  Here the segment loop becomes ONE batched device transform (``rfft_batch`` / ``fftn`` over the
+frame matrix): framing, detrending and windowing are O(n) host passes, every FFT goes through the C ABI
+(there is no CPU transform in this file; without the CUDA library every function raises).
+
+Reference behaviour that is reproduced as written, because a drop-in must return the same numbers:
+
+* ``scirs2_fft::fft(x, None)`` pads to the next power of two (fft/algorithms.rs:131-176), so
+  ``periodogram`` / ``welch`` / ``stft`` of a non-power-of-two ``nfft`` return the first
+  ``nfft/2 + nfft%2`` bins of a LONGER transform while the frequency axis is built for ``nfft``
+  (spectral.rs:201-219, 376-380, 604-608).
+* ``spectral_subtraction`` / ``psd_wiener_filter`` mirror bins around ``n`` (the signal length), not
+  around the padded length (wiener.rs:497-529, 604-638).
+* the spectral-density results are NOT doubled for the one-sided half (spectral.rs:203-207).
+
+Covered: spectral.rs (periodogram, welch, stft, spectrogram), wiener.rs (the frequency-domain filters),
+streaming_stft.rs (StreamingStft), higher_order.rs (direct and Welch bispectrum, power spectrum).
+"""
+from __future__ import annotations
+
+from collections import deque
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .error import ValueError_
+from .fft import fft, fftn, ifft, rfft_batch
+
+
+# ------------------------------------------------------------------------------------------------
+# spectral.rs
+# ------------------------------------------------------------------------------------------------
+
+def spectral_window(window_type: str, nperseg: int) -> np.ndarray:
+    """The private ``get_window`` of spectral.rs:29-66 (symmetric hann / hamming / blackman / boxcar)."""
+    w = window_type.lower()
+    i = np.arange(nperseg, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if w == "hann":
+            return 0.5 * (1.0 - np.cos(2.0 * np.pi * i / (nperseg - 1)))
+        if w == "hamming":
+            return 0.54 - 0.46 * np.cos(2.0 * np.pi * i / (nperseg - 1))
+        if w == "blackman":
+            return (0.42 - 0.5 * np.cos(2.0 * np.pi * i / (nperseg - 1))
+                    + 0.08 * np.cos(4.0 * np.pi * i / (nperseg - 1)))
+    if w in ("boxcar", "rectangular"):
+        return np.ones(nperseg)
+    raise ValueError_(f"Unknown window type: {window_type}")
+
+
+def _detrend_rows(frames: np.ndarray, detrend_type: str) -> np.ndarray:
+    """``apply_detrend`` (spectral.rs:77-117) on every row of a [segments, n] matrix."""
+    if detrend_type == "none":
+        return frames
+    n = frames.shape[1]
+    if detrend_type == "constant":
+        return frames - (frames.sum(axis=1) / n)[:, None]
+    if detrend_type == "linear":
+        t = np.arange(n, dtype=np.float64)
+        sum_x, sum_xx = t.sum(), (t * t).sum()
+        sum_y, sum_xy = frames.sum(axis=1), frames @ t
+        with np.errstate(divide="ignore", invalid="ignore"):
+            slope = (n * sum_xy - sum_x * sum_y) / (n * sum_xx - sum_x * sum_x)
+        intercept = (sum_y - slope * sum_x) / n
+        return frames - (slope[:, None] * t[None, :] + intercept[:, None])
+    raise ValueError_(f"Unknown detrend option: {detrend_type}")
+
+
+def _fftfreq_head(nfft: int, fs: float, count: int) -> np.ndarray:
+    """First ``count`` entries of ``helper::fftfreq(nfft, 1/fs)`` (helper.rs; count <= ceil(nfft/2), all non-negative)."""
+    return np.arange(count, dtype=np.float64) / (nfft * (1.0 / fs))
+
+
+def _next_pow2(n: int) -> int:
+    p = 1
+    while p < n:
+        p <<= 1
+    return p
+
+
+def _check_common(fs: float, nfft: int, nperseg: int, noverlap: Optional[int]) -> None:
+    if fs <= 0.0:
+        raise ValueError_(f"Sampling frequency must be positive, got {fs}")
+    if nfft < nperseg:
+        raise ValueError_(f"nfft must be at least as large as nperseg, got {nfft} < {nperseg}")
+    if noverlap is not None and noverlap >= nperseg:
+        raise ValueError_(f"noverlap must be less than nperseg, got {noverlap} >= {nperseg}")
+
+
+def _segment_spectra(x: np.ndarray, nperseg: int, step: int, count: int, win: np.ndarray, detrend: str,
+                     nfft: int, n_half: int) -> np.ndarray:
+    """Rows ``x[i*step : i*step + nperseg]`` -> detrend -> window -> zero-pad to the next power of two of
+    ``nfft`` (what ``fft(&padded, None)`` does) -> ONE batched real-to-complex device transform -> the
+    first ``n_half`` bins.  The reference keeps bins of the full complex transform; for real input those
+    are the same numbers."""
+    idx = (np.arange(count) * step)[:, None] + np.arange(nperseg)[None, :]
+    frames = _detrend_rows(x[idx], detrend) * win[None, :]
+    P = _next_pow2(max(nfft, 1))
+    padded = np.zeros((count, P), dtype=np.float64)
+    padded[:, :nperseg] = frames
+    return rfft_batch(padded)[:, :n_half]
+
+
+def periodogram(x, fs: Optional[float] = None, window: Optional[str] = None, nfft: Optional[int] = None,
+                detrend: Optional[str] = None, scaling: Optional[str] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """spectral.rs:130-244."""
+    a = np.asarray(x, dtype=np.float64).reshape(-1)
+    if a.size == 0:
+        raise ValueError_("Input array is empty")
+    fs_val = 1.0 if fs is None else float(fs)
+    nfft_val = a.size if nfft is None else int(nfft)
+    window_val = "boxcar" if window is None else window
+    detrend_val = "constant" if detrend is None else detrend
+    scaling_val = "density" if scaling is None else scaling
+    if fs_val <= 0.0:
+        raise ValueError_(f"Sampling frequency must be positive, got {fs_val}")
+    if nfft_val < a.size:
+        raise ValueError_(f"NFFT must be at least as large as signal length, got {nfft_val} < {a.size}")
+    win = spectral_window(window_val, a.size)
+    scale = 1.0 / np.sum(win * win)
+    n_half = nfft_val // 2 + nfft_val % 2
+    spec = _segment_spectra(a, a.size, 1, 1, win, detrend_val, nfft_val, n_half)[0]
+    psd = (spec.real ** 2 + spec.imag ** 2) * scale / (fs_val * a.size)
+    if scaling_val != "density":
+        psd = psd * fs_val
+    return _fftfreq_head(nfft_val, fs_val, n_half), psd
+
+
+def welch(x, fs: Optional[float] = None, window: Optional[str] = None, nperseg: Optional[int] = None,
+          noverlap: Optional[int] = None, nfft: Optional[int] = None, detrend: Optional[str] = None,
+          scaling: Optional[str] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """spectral.rs:257-410: all segments in one batched transform, then the average of |X|^2."""
+    a = np.asarray(x, dtype=np.float64).reshape(-1)
+    if a.size == 0:
+        raise ValueError_("Input array is empty")
+    fs_val = 1.0 if fs is None else float(fs)
+    nperseg_val = min(256, a.size) if nperseg is None else int(nperseg)
+    noverlap_val = nperseg_val // 2 if noverlap is None else int(noverlap)
+    nfft_val = nperseg_val if nfft is None else int(nfft)
+    window_val = "hann" if window is None else window
+    detrend_val = "constant" if detrend is None else detrend
+    scaling_val = "density" if scaling is None else scaling
+    _check_common(fs_val, nfft_val, nperseg_val, noverlap_val)
+    win = spectral_window(window_val, nperseg_val)
+    scale = 1.0 / np.sum(win * win)
+    step = nperseg_val - noverlap_val
+    num_segments = (a.size - noverlap_val) // step if a.size >= noverlap_val else 0
+    if num_segments < 1:
+        raise ValueError_("Not enough data points for given nperseg and noverlap")
+    n_half = nfft_val // 2 + nfft_val % 2
+    # the reference divides by num_segments even when its loop breaks early on a short last segment
+    usable = min(num_segments, (a.size - nperseg_val) // step + 1 if a.size >= nperseg_val else 0)
+    psd = np.zeros(n_half)
+    if usable > 0:
+        spec = _segment_spectra(a, nperseg_val, step, usable, win, detrend_val, nfft_val, n_half)
+        psd = ((spec.real ** 2 + spec.imag ** 2) * (scale / (fs_val * nperseg_val))).sum(axis=0)
+    psd /= num_segments
+    if scaling_val != "density":
+        psd = psd * fs_val
+    return _fftfreq_head(nfft_val, fs_val, n_half), psd
+
+
+def _apply_boundary(x: np.ndarray, nperseg: int, boundary: str) -> np.ndarray:
+    """spectral.rs:413-447: nperseg/2 samples of zeros or of the edge value on both sides."""
+    pad = nperseg // 2
+    if boundary == "zeros":
+        return np.concatenate([np.zeros(pad), x, np.zeros(pad)])
+    if boundary == "extend":
+        return np.concatenate([np.full(pad, x[0]), x, np.full(pad, x[-1])])
+    if boundary == "none":
+        return x
+    raise ValueError_(f"Unknown boundary option: {boundary}")
+
+
+def stft(x, fs: Optional[float] = None, window: Optional[str] = None, nperseg: Optional[int] = None,
+         noverlap: Optional[int] = None, nfft: Optional[int] = None, detrend: Optional[str] = None,
+         boundary: Optional[str] = None, padded: Optional[bool] = None
+         ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """spectral.rs:468-628.  Returns (freqs, times, Z) with Z[segment][bin] (the reference's final
+    transposition leaves segments as the outer index)."""
+    a = np.asarray(x, dtype=np.float64).reshape(-1)
+    if a.size == 0:
+        raise ValueError_("Input array is empty")
+    fs_val = 1.0 if fs is None else float(fs)
+    nperseg_val = min(256, a.size) if nperseg is None else int(nperseg)
+    noverlap_val = nperseg_val // 2 if noverlap is None else int(noverlap)
+    nfft_val = nperseg_val if nfft is None else int(nfft)
+    window_val = "hann" if window is None else window
+    detrend_val = "constant" if detrend is None else detrend
+    boundary_val = "zeros" if boundary is None else boundary
+    padded_val = True if padded is None else bool(padded)
+    _check_common(fs_val, nfft_val, nperseg_val, noverlap_val)
+    win = spectral_window(window_val, nperseg_val)
+    sig = _apply_boundary(a, nperseg_val, boundary_val) if padded_val else a
+    step = nperseg_val - noverlap_val
+    num_segments = (sig.size - noverlap_val) // step if sig.size >= noverlap_val else 0
+    if num_segments < 1:
+        raise ValueError_("Not enough data points for given nperseg and noverlap")
+    n_half = nfft_val // 2 + nfft_val % 2
+    times = (np.arange(num_segments) * step + nperseg_val // 2) / fs_val
+    Z = np.zeros((num_segments, n_half), dtype=np.complex128)
+    usable = min(num_segments, (sig.size - nperseg_val) // step + 1 if sig.size >= nperseg_val else 0)
+    if usable > 0:
+        Z[:usable] = _segment_spectra(sig, nperseg_val, step, usable, win, detrend_val, nfft_val, n_half)
+    return _fftfreq_head(nfft_val, fs_val, n_half), times, Z
+
+
+def spectrogram(x, fs: Optional[float] = None, window: Optional[str] = None, nperseg: Optional[int] = None,
+                noverlap: Optional[int] = None, nfft: Optional[int] = None, detrend: Optional[str] = None,
+                scaling: Optional[str] = None, mode: Optional[str] = None
+                ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """spectral.rs:644-735 (modes psd / magnitude / angle / phase; "complex" is an error there too)."""
+    mode_val = "psd" if mode is None else mode
+    scaling_val = "density" if scaling is None else scaling
+    n_in = np.asarray(x).size
+    freqs, times, Z = stft(x, fs, window, nperseg, noverlap, nfft, detrend, "zeros", True)
+    if mode_val == "psd":
+        fs_val = 1.0 if fs is None else float(fs)
+        nperseg_val = min(256, n_in) if nperseg is None else int(nperseg)
+        win = spectral_window("hann" if window is None else window, nperseg_val)
+        scale = 1.0 / np.sum(win * win)
+        S = (Z.real ** 2 + Z.imag ** 2) * scale / (fs_val * nperseg_val)
+        if scaling_val != "density":
+            S = S * fs_val
+    elif mode_val == "magnitude":
+        S = np.abs(Z)
+    elif mode_val in ("angle", "phase"):
+        S = np.angle(Z)
+    elif mode_val == "complex":
+        raise ValueError_("Mode 'complex' returns complex values and is not supported for spectrogram")
+    else:
+        raise ValueError_(f"Unknown mode option: {mode_val}, expected 'psd', 'magnitude', 'angle', or 'phase'")
+    return freqs, times, S
+
+
+# ------------------------------------------------------------------------------------------------
+# wiener.rs (the frequency-domain filters)
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class WienerConfig:
+    """wiener.rs:50-84."""
+    window_size: int = 15
+    noise_power: Optional[float] = None
+    frequency_domain: bool = True
+    max_iterations: int = 1
+    prior_snr: Optional[float] = None
+    regularization: float = 1e-10
+    boundary: bool = True
+
+
+def _median_sorted(v: np.ndarray) -> float:
+    n = v.size
+    return float((v[n // 2 - 1] + v[n // 2]) / 2.0) if n % 2 == 0 else float(v[n // 2])
+
+
+def estimate_noise_power(signal: np.ndarray) -> float:
+    """wiener.rs:709-739: (1.4826 * median absolute deviation)^2."""
+    v = np.sort(np.asarray(signal, dtype=np.float64).reshape(-1))
+    med = _median_sorted(v)
+    mad = _median_sorted(np.sort(np.abs(v - med)))
+    return (1.4826 * mad) ** 2
+
+
+def estimate_signal_power(signal: np.ndarray) -> float:
+    """wiener.rs:742-750."""
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    return float(np.sum((s - s.mean()) ** 2) / s.size)
+
+
+def wiener_filter_freq(signal, config: Optional[WienerConfig] = None) -> np.ndarray:
+    """wiener.rs:137-196: gain = P / (P + snr * noise + reg) on every bin of the padded transform."""
+    cfg = config or WienerConfig()
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    n = s.size
+    noise_power = cfg.noise_power if cfg.noise_power is not None else estimate_noise_power(s)
+    spec = fft(s, None)
+    power = spec.real ** 2 + spec.imag ** 2
+    snr = 1.0 if cfg.prior_snr is None else cfg.prior_snr
+    gain = power / (power + snr * noise_power + cfg.regularization)
+    return ifft(spec * gain, None)[:n].real.copy()
+
+
+def wiener_filter(signal, noise_power: Optional[float] = None, window_size: Optional[int] = None) -> np.ndarray:
+    """wiener.rs:110-127."""
+    cfg = WienerConfig()
+    if noise_power is not None:
+        cfg.noise_power = noise_power
+    if window_size is not None:
+        cfg.window_size = window_size
+    return wiener_filter_freq(signal, cfg)
+
+
+def iterative_wiener_filter(signal, config: Optional[WienerConfig] = None) -> np.ndarray:
+    """wiener.rs:304-345 (frequency-domain branch only; the time-domain filter has no FFT in it)."""
+    cfg = config or WienerConfig()
+    if not cfg.frequency_domain:
+        raise ValueError_("only the frequency-domain Wiener filter is on the FFT path")
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    noise_power = cfg.noise_power if cfg.noise_power is not None else estimate_noise_power(s)
+    cur = s.copy()
+    for _ in range(cfg.max_iterations):
+        sp = estimate_signal_power(cur)
+        if sp < cfg.regularization:
+            break
+        it = WienerConfig(**{**cfg.__dict__, "prior_snr": sp / noise_power})
+        cur = wiener_filter_freq(cur, it)
+    return cur
+
+
+def _mirror_gain(spec: np.ndarray, n: int, new_mag: np.ndarray) -> np.ndarray:
+    """Bins 0..=n/2 get magnitude ``new_mag`` with their own phase; bin n-i gets the conjugate for
+    0 < i < n/2 (wiener.rs:497-529 / 604-638: ``n`` is the SIGNAL length, the array may be longer)."""
+    out = spec.copy()
+    half = n // 2
+    phase = np.angle(spec[: half + 1])
+    out[: half + 1] = new_mag * np.exp(1j * phase)
+    i = np.arange(1, half)
+    if i.size:
+        out[n - i] = new_mag[i] * np.exp(-1j * phase[i])
+    return out
+
+
+def spectral_subtraction(signal, noise_power: Optional[Sequence[float]] = None, alpha: Optional[float] = None,
+                         beta: Optional[float] = None) -> np.ndarray:
+    """wiener.rs:439-546."""
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    n = s.size
+    a = 1.0 if alpha is None else alpha
+    b = 0.01 if beta is None else beta
+    spec = fft(s, None)
+    if noise_power is not None:
+        noise = np.asarray(noise_power, dtype=np.float64).reshape(-1)
+    else:
+        ns = int(min(n * 0.05, 100.0))
+        if ns < 4:
+            raise ValueError_("Signal too short to estimate noise spectrum")
+        nf = fft(s[:ns], n)[: n // 2 + 1]
+        noise = (nf.real ** 2 + nf.imag ** 2) / n
+    half = n // 2
+    idx = np.minimum(np.arange(half + 1), noise.size - 1)
+    mag2 = np.abs(spec[: half + 1]) ** 2
+    new_mag = np.sqrt(np.maximum(mag2 - a * noise[idx], b * mag2))
+    return ifft(_mirror_gain(spec, n, new_mag), None)[:n].real.copy()
+
+
+def smooth_psd(psd: np.ndarray) -> np.ndarray:
+    """wiener.rs:775-794: moving average, window 2% of the length clamped to [3, 15]."""
+    n = psd.size
+    half = int(min(max(n * 0.02, 3.0), 15.0)) // 2
+    c = np.concatenate([[0.0], np.cumsum(psd)])
+    i = np.arange(n)
+    lo, hi = np.maximum(i - half, 0), np.minimum(i + half + 1, n)
+    return (c[hi] - c[lo]) / (hi - lo)
+
+
+def psd_wiener_filter(signal, signal_psd: Optional[Sequence[float]] = None,
+                      noise_psd: Optional[Sequence[float]] = None) -> np.ndarray:
+    """wiener.rs:560-655."""
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    n = s.size
+    spec = fft(s, None)
+    half = n // 2
+    if signal_psd is not None:
+        s_psd = np.asarray(signal_psd, dtype=np.float64).reshape(-1)
+    else:
+        head = spec[: half + 1]
+        s_psd = smooth_psd((head.real ** 2 + head.imag ** 2) / n)
+    if noise_psd is not None:
+        n_psd = np.asarray(noise_psd, dtype=np.float64).reshape(-1)
+    else:
+        n_psd = np.full(half + 1, estimate_noise_power(s))
+    i = np.arange(half + 1)
+    sp = np.where(i < s_psd.size, s_psd[np.minimum(i, s_psd.size - 1)], 0.0)
+    npw = np.where(i < n_psd.size, n_psd[np.minimum(i, n_psd.size - 1)], 0.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gain = np.where(sp + npw > 1e-10, sp / (sp + npw), 0.0)
+    return ifft(_mirror_gain(spec, n, np.abs(spec[: half + 1]) * gain), None)[:n].real.copy()
+
+
+# ------------------------------------------------------------------------------------------------
+# window/mod.rs (the subset the callers below use) and streaming_stft.rs
+# ------------------------------------------------------------------------------------------------
+
+def signal_window(window_type: str, length: int, periodic: bool) -> np.ndarray:
+    """window/mod.rs:38-83 for hann / hamming / blackman / bartlett / cosine / boxcar: periodic windows are the
+    (length+1)-point symmetric window without its last sample (``_extend`` / ``_truncate``)."""
+    if length == 0:
+        raise ValueError_("Window length must be positive")
+    if length <= 1:
+        return np.ones(length)
+    n = length + 1 if periodic else length
+    i = np.arange(n, dtype=np.float64)
+    w = window_type.lower()
+    if w in ("hann", "hanning"):
+        v = 0.5 * (1.0 - np.cos(2.0 * np.pi * i / (n - 1)))
+    elif w == "hamming":
+        v = 0.54 - 0.46 * np.cos(2.0 * np.pi * i / (n - 1))
+    elif w == "blackman":
+        v = 0.42 - 0.5 * np.cos(2.0 * np.pi * i / (n - 1)) + 0.08 * np.cos(4.0 * np.pi * i / (n - 1))
+    elif w == "bartlett":
+        m2 = (n - 1) / 2.0
+        v = 1.0 - np.abs((i - m2) / m2)
+    elif w == "cosine":
+        v = np.sin(np.pi * i / (n - 1))
+    elif w in ("boxcar", "rectangular"):
+        v = np.ones(n)
+    else:
+        raise ValueError_(f"Unknown window type: {window_type}")
+    return v[:length]
+
+
+@dataclass
+class StreamingStftConfig:
+    """streaming_stft.rs:58-94."""
+    frame_length: int = 512
+    hop_length: int = 256
+    window: str = "hann"
+    center: bool = True
+    pad_mode: str = "constant"
+    magnitude_only: bool = False
+    log_magnitude: bool = False
+    power: float = 1.0
+    log_epsilon: float = 1e-10
+
+
+@dataclass
+class StreamingStftStatistics:
+    samples_processed: int
+    frames_generated: int
+    buffer_size: int
+    latency_samples: int
+
+
+class StreamingStft:
+    """streaming_stft.rs:96-438.  ``process_batch`` gathers every frame the call completes and sends them to
+    the device as one batched transform; the buffer bookkeeping is the reference's."""
+
+    def __init__(self, config: Optional[StreamingStftConfig] = None):
+        cfg = config or StreamingStftConfig()
+        if cfg.frame_length == 0:
+            raise ValueError_("Frame length must be greater than 0")
+        if cfg.hop_length == 0:
+            raise ValueError_("Hop length must be greater than 0")
+        if cfg.hop_length > cfg.frame_length:
+            raise ValueError_("Hop length should not exceed frame length")
+        if cfg.power <= 0.0:
+            raise ValueError_("Power must be positive")
+        if cfg.center and cfg.pad_mode not in ("constant", "reflect", "symmetric"):
+            raise ValueError_(f"Unknown pad mode: {cfg.pad_mode}")
+        self.config = cfg
+        self.window = signal_window(cfg.window, cfg.frame_length, True)
+        self._buf: deque = deque()
+        self.samples_processed = 0
+        self.frames_generated = 0
+        self._prefill()
+
+    def _prefill(self) -> None:
+        if self.config.center:  # every pad mode pre-fills zeros (streaming_stft.rs:166-190)
+            self._buf.extend([0.0] * (self.config.frame_length // 2))
+
+    # -- frame bookkeeping: returns the windowed frame this push completes, or None
+    def _push(self, samples: np.ndarray) -> Optional[np.ndarray]:
+        self._buf.extend(float(v) for v in samples)
+        self.samples_processed += len(samples)
+        L = self.config.frame_length
+        if len(self._buf) < L:
+            return None
+        frame = np.fromiter((self._buf[i] for i in range(L)), dtype=np.float64, count=L) * self.window
+        for _ in range(min(self.config.hop_length, len(self._buf))):
+            self._buf.popleft()
+        self.frames_generated += 1
+        return frame
+
+    def _spectra(self, frames: List[np.ndarray]) -> List[np.ndarray]:
+        """``compute_fft`` + ``process_spectrum`` (streaming_stft.rs:399-438) for a list of frames at once."""
+        if not frames:
+            return []
+        L = self.config.frame_length
+        P = _next_pow2(L)
+        m = np.zeros((len(frames), P))
+        m[:, :L] = np.stack(frames)
+        spec = rfft_batch(m)[:, : L // 2 + 1]
+        cfg = self.config
+        if cfg.magnitude_only:
+            mag = np.abs(spec)
+            if cfg.power == 2.0:
+                mag = spec.real ** 2 + spec.imag ** 2
+            elif cfg.power != 1.0:
+                mag = mag ** cfg.power
+            if cfg.log_magnitude:
+                mag = np.log(mag + cfg.log_epsilon)
+            spec = mag.astype(np.complex128)
+        return [row.copy() for row in spec]
+
+    def process_frame(self, input_frame) -> Optional[np.ndarray]:
+        f = self._push(np.asarray(input_frame, dtype=np.float64).reshape(-1))
+        return None if f is None else self._spectra([f])[0]
+
+    def process_batch(self, input_data, frame_size: int) -> List[np.ndarray]:
+        d = np.asarray(input_data, dtype=np.float64).reshape(-1)
+        frames = []
+        start = 0
+        while start + frame_size <= d.size:
+            f = self._push(d[start:start + frame_size])
+            if f is not None:
+                frames.append(f)
+            start += frame_size
+        if start < d.size:
+            f = self._push(d[start:])
+            if f is not None:
+                frames.append(f)
+        return self._spectra(frames)
+
+    def process_magnitude_frame(self, input_frame) -> Optional[np.ndarray]:
+        s = self.process_frame(input_frame)
+        if s is None:
+            return None
+        cfg = self.config
+        mag = np.abs(s) if cfg.power == 1.0 else (s.real ** 2 + s.imag ** 2 if cfg.power == 2.0 else np.abs(s) ** cfg.power)
+        return np.log(mag + cfg.log_epsilon) if cfg.log_magnitude else mag
+
+    def get_latency_samples(self) -> int:
+        c = self.config
+        return c.frame_length // 2 + c.hop_length if c.center else c.frame_length
+
+    def get_latency_seconds(self, sample_rate: float) -> float:
+        return self.get_latency_samples() / sample_rate
+
+    def get_statistics(self) -> StreamingStftStatistics:
+        return StreamingStftStatistics(self.samples_processed, self.frames_generated, len(self._buf),
+                                       self.get_latency_samples())
+
+    def reset(self) -> None:
+        self._buf.clear()
+        self.samples_processed = 0
+        self.frames_generated = 0
+        self._prefill()
+
+    def flush(self) -> List[np.ndarray]:
+        L, hop = self.config.frame_length, self.config.hop_length
+        frames = []
+        while len(self._buf) >= hop:
+            frame = np.zeros(L)
+            avail = min(len(self._buf), L)
+            frame[:avail] = [self._buf[i] for i in range(avail)]
+            frames.append(frame * self.window)
+            for _ in range(min(hop, len(self._buf))):
+                self._buf.popleft()
+            self.frames_generated += 1
+        return self._spectra(frames)
+
+
+@dataclass
+class RealTimeStftStatistics:
+    base_statistics: StreamingStftStatistics
+    output_buffer_size: int
+    output_buffer_capacity: int
+    block_size: int
+
+
+class RealTimeStft:
+    """streaming_stft.rs:453-570: fixed-size input blocks, a bounded queue of finished spectra."""
+
+    def __init__(self, config: Optional[StreamingStftConfig], block_size: int, max_buffer_size: int):
+        self.streaming_stft = StreamingStft(config)
+        self.block_size = int(block_size)
+        self.max_output_buffer_size = int(max_buffer_size)
+        self._out: deque = deque()
+
+    def process_block(self, input_block) -> int:
+        b = np.asarray(input_block, dtype=np.float64).reshape(-1)
+        if b.size != self.block_size:
+            raise ValueError_(f"Input block size {b.size} does not match expected size {self.block_size}")
+        s = self.streaming_stft.process_frame(b)
+        if s is None:
+            return 0
+        self._out.append(s)
+        while len(self._out) > self.max_output_buffer_size:
+            self._out.popleft()
+        return 1
+
+    def get_spectrum(self) -> Optional[np.ndarray]:
+        return self._out.popleft() if self._out else None
+
+    def get_all_spectra(self) -> List[np.ndarray]:
+        r = list(self._out)
+        self._out.clear()
+        return r
+
+    def peek_latest_spectrum(self) -> Optional[np.ndarray]:
+        return self._out[-1] if self._out else None
+
+    def available_spectra_count(self) -> int:
+        return len(self._out)
+
+    def is_buffer_full(self) -> bool:
+        return len(self._out) >= self.max_output_buffer_size
+
+    def reset(self) -> None:
+        self.streaming_stft.reset()
+        self._out.clear()
+
+    def get_statistics(self) -> RealTimeStftStatistics:
+        return RealTimeStftStatistics(self.streaming_stft.get_statistics(), len(self._out),
+                                      self.max_output_buffer_size, self.block_size)
+
+
+# ------------------------------------------------------------------------------------------------
+# higher_order.rs (direct and Welch bispectrum, power spectrum)
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class HigherOrderConfig:
+    """higher_order.rs:71-110 (``estimator``: "direct" or "welch"; the indirect estimator goes through a
+    triple-correlation matrix and is not an FFT-path caller of note)."""
+    estimator: str = "welch"
+    fs: float = 1.0
+    window: Optional[str] = "hann"
+    n_segments: Optional[int] = None
+    overlap: float = 0.5
+    nfft: Optional[int] = None
+    detrend: bool = True
+    pad: bool = True
+    non_redundant: bool = True
+
+
+def _default_nfft(n: int) -> int:
+    return max(2 ** int(np.ceil(np.log2(n))), 256)
+
+
+def _direct_bispectra(spectra: np.ndarray, nfft: int) -> np.ndarray:
+    """B[s][i][j] = X_s[i] X_s[j] conj(X_s[(i+j) % nfft]) on the full square (higher_order.rs:313-329: the
+    triangle is mirrored, and the diagonal is written either way, so the square is symmetric and complete)."""
+    nb = nfft // 2 + 1
+    i = np.arange(nb)
+    k = (i[:, None] + i[None, :]) % nfft
+    head = spectra[:, :nb]
+    return head[:, :, None] * head[:, None, :] * np.conj(spectra[:, k])
+
+
+def _segment_rows(sig: np.ndarray, window: Optional[str], nfft: int, starts: Sequence[int], size: int) -> np.ndarray:
+    """Windowed segments (each with a window of ITS OWN length: the last may be short) cut or zero-padded to
+    ``nfft`` as ``fft(x, Some(nfft))`` does, transformed as one batch."""
+    rows = np.zeros((len(starts), nfft), dtype=np.complex128)
+    for r, st in enumerate(starts):
+        seg = sig[st:min(st + size, sig.size)]
+        if window is not None:
+            seg = seg * signal_window(window, seg.size, True)
+        m = min(seg.size, nfft)
+        rows[r, :m] = seg[:m]
+    return fftn(rows, None, [1]).reshape(len(starts), nfft)
+
+
+def compute_bispectrum(signal, config: Optional[HigherOrderConfig] = None
+                       ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """higher_order.rs:250-287 with the direct (:289-332) and Welch (:359-431) estimators."""
+    cfg = config or HigherOrderConfig()
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    n = s.size
+    if n < 4:
+        raise ValueError_("Signal must have at least 4 data points")
+    nfft = cfg.nfft if cfg.nfft is not None else _default_nfft(n)
+    axis = np.linspace(0.0, cfg.fs / 2.0, nfft // 2 + 1)
+    if cfg.estimator == "direct":
+        B = _direct_bispectra(_segment_rows(s, cfg.window, nfft, [0], n), nfft)[0]
+    elif cfg.estimator == "welch":
+        size = min(nfft, n)
+        ov = int(round(size * cfg.overlap))
+        step = size - ov
+        if step == 0:
+            raise ValueError_("Overlap too large, resulting in zero step size")
+        nseg = cfg.n_segments if cfg.n_segments is not None else int(np.floor((n - ov) / step))
+        if nseg == 0:
+            raise ValueError_("Signal too short for the specified segment size and overlap")
+        starts = [i * step for i in range(nseg) if min(i * step + size, n) - i * step >= 4]
+        nb = nfft // 2 + 1
+        B = np.zeros((nb, nb), dtype=np.complex128)
+        if starts:
+            B = _direct_bispectra(_segment_rows(s, cfg.window, nfft, starts, size), nfft).sum(axis=0)
+        B = B / nseg
+    else:
+        raise ValueError_(f"estimator {cfg.estimator!r} is not on the FFT path")
+    return B, axis, axis.copy()
+
+
+def bispectrum(signal, nfft: int, window: Optional[str] = None, n_segments: Optional[int] = None, fs: float = 1.0
+               ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """higher_order.rs:142-165: magnitude of the Welch bispectrum."""
+    B, f1, f2 = compute_bispectrum(signal, HigherOrderConfig(fs=fs, nfft=nfft, window=window, n_segments=n_segments))
+    return np.abs(B), f1, f2
+
+
+def compute_power_spectrum(signal, config: Optional[HigherOrderConfig] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """higher_order.rs:464-508: |X|^2 / nfft, doubled away from DC and Nyquist."""
+    cfg = config or HigherOrderConfig()
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    nfft = cfg.nfft if cfg.nfft is not None else _default_nfft(s.size)
+    nb = nfft // 2 + 1
+    w = s * signal_window(cfg.window, s.size, True) if cfg.window is not None else s
+    X = fft(w, nfft)[:nb]
+    p = (X.real ** 2 + X.imag ** 2) / nfft
+    if nb > 2:
+        p[1:nb - 1] *= 2.0
+    return p, np.linspace(0.0, cfg.fs / 2.0, nb)

@@ -1,0 +1,89 @@
+"""Shared case list for the scirs2-signal caller tests: each entry runs the same call on the product
+module (scirs_b200.signal) and on the oracle (oracle/signal_oracle.py) and returns both results."""
+import numpy as np
+
+
+def _sig(n, seed=0):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / 100.0
+    return np.sin(2 * np.pi * 10.0 * t) + 0.5 * np.sin(2 * np.pi * 23.0 * t + 0.3) + 0.1 * rng.standard_normal(n) + 0.2 * t
+
+
+def cases():
+    out = []
+
+    def add(name, fn):
+        out.append((name, fn))
+
+    for n, kw in ((1000, {}), (1024, dict(window="hann")), (777, dict(window="blackman", nfft=900, detrend="linear",
+                                                                       scaling="spectrum")),
+                  (64, dict(window="hamming", detrend="none", fs=8.0))):
+        x = _sig(n, n)
+        add(f"periodogram-{n}", lambda sg, so, x=x, kw=kw: (sg.periodogram(x, kw.get("fs", 100.0), kw.get("window"), kw.get("nfft"), kw.get("detrend"), kw.get("scaling")),
+                                                            so.periodogram(x, kw.get("fs", 100.0), kw.get("window"), kw.get("nfft"), kw.get("detrend"), kw.get("scaling"))))
+    for n, args in ((2000, (100.0, None, 256, 128, None, None, None)),
+                    (3001, (50.0, "hamming", 200, 37, 300, "linear", "spectrum")),
+                    (500, (1.0, "boxcar", None, None, None, "none", None)),
+                    (4096, (1.0, "blackman", 512, 448, 512, None, None))):
+        x = _sig(n, n + 1)
+        add(f"welch-{n}", lambda sg, so, x=x, a=args: (sg.welch(x, *a), so.welch(x, *a)))
+    for n, args in ((2000, (1000.0, None, 128, 64, None, None, None, None)),
+                    (1500, (10.0, "hamming", 100, 30, 160, "linear", "extend", True)),
+                    (900, (1.0, "blackman", 64, 63, None, "none", "none", False)),
+                    (700, (2.0, "boxcar", 50, 0, 64, "constant", "zeros", True))):
+        x = _sig(n, n + 2)
+        add(f"stft-{n}", lambda sg, so, x=x, a=args: (sg.stft(x, *a), so.stft(x, *a)))
+    x = _sig(1000, 5)
+    for mode in ("psd", "magnitude", "phase"):
+        add(f"spectrogram-{mode}", lambda sg, so, x=x, m=mode: (sg.spectrogram(x, 100.0, None, 128, None, None, None, "spectrum" if m == "psd" else None, m),
+                                                                so.spectrogram(x, 100.0, None, 128, None, None, None, "spectrum" if m == "psd" else None, m)))
+    for n in (1000, 1024, 333):
+        x = _sig(n, n + 3)
+        add(f"wiener-{n}", lambda sg, so, x=x: (sg.wiener_filter(x), so.wiener_filter_freq(x)))
+        add(f"wiener-snr-{n}", lambda sg, so, x=x: (sg.wiener_filter_freq(x, sg.WienerConfig(noise_power=0.02, prior_snr=3.0)),
+                                                    so.wiener_filter_freq(x, 0.02, 3.0)))
+        add(f"specsub-{n}", lambda sg, so, x=x: (sg.spectral_subtraction(x), so.spectral_subtraction(x)))
+        add(f"specsub-given-{n}", lambda sg, so, x=x: (sg.spectral_subtraction(x, np.full(10, 0.3), 2.0, 0.05),
+                                                       so.spectral_subtraction(x, np.full(10, 0.3), 2.0, 0.05)))
+        add(f"psdwiener-{n}", lambda sg, so, x=x: (sg.psd_wiener_filter(x), so.psd_wiener_filter(x)))
+        add(f"psdwiener-given-{n}", lambda sg, so, x=x: (sg.psd_wiener_filter(x, np.linspace(1, 2, 40), np.full(50, 0.5)),
+                                                         so.psd_wiener_filter(x, np.linspace(1, 2, 40), np.full(50, 0.5))))
+
+    def streaming(sg, so, L, hop, center, kw, n, block):
+        x = _sig(n, L)
+        a = sg.StreamingStft(sg.StreamingStftConfig(frame_length=L, hop_length=hop, center=center, **kw))
+        b = so.StreamingStft(L, hop, kw.get("window", "hann"), center, kw.get("magnitude_only", False),
+                             kw.get("log_magnitude", False), kw.get("power", 1.0))
+        ra = a.process_batch(x, block) + a.flush()
+        rb = b.process_batch(list(x), block) + b.flush()
+        assert a.frames_generated == b.frames_generated
+        return (np.array(ra),), (np.array(rb),)
+
+    for L, hop, center, kw, n, block in ((128, 64, False, {}, 512, 64), (256, 128, True, dict(window="hamming"), 2000, 100),
+                                         (100, 30, True, dict(magnitude_only=True, power=2.0, log_magnitude=True), 1000, 77),
+                                         (96, 96, False, dict(magnitude_only=True, power=1.5, window="bartlett"), 700, 200)):
+        add(f"streaming-{L}-{hop}", lambda sg, so, a=(L, hop, center, kw, n, block): streaming(sg, so, *a))
+
+    for n, nfft, win in ((256, 64, "hann"), (1000, 128, None), (300, 100, "hamming")):
+        x = _sig(n, n + 9) ** 2  # quadratic coupling, so the bispectrum is not numerically zero
+        add(f"bispec-direct-{n}", lambda sg, so, x=x, nfft=nfft, win=win: (
+            (sg.compute_bispectrum(x, sg.HigherOrderConfig(estimator="direct", nfft=nfft, window=win))[0],),
+            (so.direct_bispectrum(x, nfft, win),)))
+        add(f"bispec-welch-{n}", lambda sg, so, x=x, nfft=nfft, win=win: (
+            (sg.compute_bispectrum(x, sg.HigherOrderConfig(estimator="welch", nfft=nfft, window=win))[0],),
+            (so.welch_bispectrum(x, nfft, win),)))
+        add(f"powerspec-{n}", lambda sg, so, x=x, nfft=nfft, win=win: (
+            (sg.compute_power_spectrum(x, sg.HigherOrderConfig(nfft=nfft, window=win))[0],),
+            (so.power_spectrum(x, nfft, win),)))
+    return out
+
+
+def compare(got, ref, tol):
+    got = got if isinstance(got, tuple) else (got,)
+    ref = ref if isinstance(ref, tuple) else (ref,)
+    assert len(got) == len(ref)
+    for g, r in zip(got, ref):
+        g, r = np.asarray(g), np.asarray(r)
+        assert g.shape == r.shape, (g.shape, r.shape)
+        d, s = np.linalg.norm((g - r).ravel()), np.linalg.norm(r.ravel())
+        assert (d / s if s > 0 else d) <= tol, (d, s)

@@ -83,7 +83,13 @@ def test_no_cpu_fallback(lib):
                  lambda: sb.spectrogram(np.ones(64), nperseg=16), lambda: sb.fft2_efficient(np.ones((4, 4))),
                  lambda: sb.fft_streaming(np.ones(8)), lambda: sb.fftn_optimized(np.ones((4, 4))),
                  lambda: sb.fft_inplace(np.ones(8, dtype=np.complex128), np.ones(8, dtype=np.complex128)),
-                 lambda: sb.czt(np.ones(8) + 0j)):
+                 lambda: sb.czt(np.ones(8) + 0j),
+                 # ... nor do the scirs2-signal callers (8f rank 4)
+                 lambda: sb.signal.periodogram(np.arange(16.0)), lambda: sb.signal.welch(np.arange(64.0), nperseg=16),
+                 lambda: sb.signal.stft(np.arange(64.0), nperseg=16), lambda: sb.signal.wiener_filter(np.arange(32.0)),
+                 lambda: sb.signal.spectral_subtraction(np.arange(128.0)), lambda: sb.signal.psd_wiener_filter(np.arange(32.0)),
+                 lambda: sb.signal.StreamingStft(sb.signal.StreamingStftConfig(16, 8)).process_frame(np.ones(32)),
+                 lambda: sb.signal.bispectrum(np.arange(64.0), 16)):
         with pytest.raises(sb.BackendError) as e:
             call()
         assert "no CPU fallback" in str(e.value)

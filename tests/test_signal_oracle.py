@@ -1,0 +1,126 @@
+"""CPU tests for the scirs2-signal callers.
+
+1. oracle/signal_oracle.py against the reference's own unit-test assertions (spectral.rs:743-935,
+   streaming_stft.rs tests) and against scipy.signal where the two definitions agree up to the
+   reference's extra 1/nperseg (spectral.rs:203-207 divides by fs * len on top of 1 / sum(w^2)).
+2. the HOST logic of scirs_b200/signal.py (framing, detrending, bookkeeping, bin passes) with its four
+   device transforms replaced by the oracle's — tests only; the product itself has no CPU transform.
+"""
+import numpy as np
+import pytest
+import scipy.signal as ss
+
+from oracle import scirs2_fft_oracle as orc
+from oracle import signal_oracle as so
+
+import _signal_cases as sc
+
+
+def test_reference_spectral_unit_tests():
+    fs = 100.0
+    x = np.sin(2 * np.pi * 10.0 * np.arange(1000) / fs)
+    f, p = so.periodogram(x, fs)  # spectral.rs:744-770
+    assert abs(f[np.argmax(p)] - 10.0) <= 1.0 and 500 <= len(f) <= 502
+    xn = np.sin(2 * np.pi * 10.0 * np.arange(2000) / fs) + np.random.default_rng(0).uniform(-0.1, 0.1, 2000)
+    f, p = so.welch(xn, fs, None, 256, 128)  # spectral.rs:773-802
+    assert abs(f[np.argmax(p)] - 10.0) <= 1.0
+    t = np.arange(2000) / 1000.0
+    f, tt, Z = so.stft(np.sin(2 * np.pi * (10.0 + 50.0 * t) * t), 1000.0, None, 128, 64)  # spectral.rs:805-863
+    assert Z.shape == (len(tt), len(f))
+    assert f[np.argmax(np.abs(Z[-1]))] > f[np.argmax(np.abs(Z[0]))]
+    for mode in ("psd", "magnitude", "phase"):  # spectral.rs:866-935
+        _, _, S = so.spectrogram(x, fs, None, 128, None, None, None, None, mode)
+        assert S.size > 0
+        assert np.all(S >= 0.0) if mode != "phase" else np.all((S >= -np.pi) & (S <= np.pi))
+
+
+def test_oracle_against_scipy_for_power_of_two_lengths():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(1024)
+    f, p = so.periodogram(x, 4.0, "hann")
+    fr, pr = ss.periodogram(x, 4.0, window=np.array(so.get_window("hann", 1024)), detrend="constant",
+                            return_onesided=False, scaling="density")
+    assert np.allclose(f, fr[:512]) and np.allclose(p, pr[:512] / 1024, rtol=1e-10, atol=1e-18)
+    x = rng.standard_normal(4000)
+    f, p = so.welch(x, 2.0, "hamming", 256, 100)
+    fr, pr = ss.welch(x, 2.0, window=np.array(so.get_window("hamming", 256)), nperseg=256, noverlap=100,
+                      detrend="constant", return_onesided=False, scaling="density")
+    assert np.allclose(f, fr[:128]) and np.allclose(p, pr[:128] / 256, rtol=1e-10, atol=1e-18)
+    # linear detrend is scipy's
+    seg = rng.standard_normal(100) + 0.3 * np.arange(100)
+    assert np.allclose(so.apply_detrend(list(seg), "linear"), ss.detrend(seg, type="linear"), atol=1e-10)
+    # periodic windows = scipy's fftbins windows
+    for name in ("hann", "hamming", "blackman", "bartlett"):
+        assert np.allclose(so.signal_window(name, 37, True), ss.get_window(name, 37, fftbins=True), atol=1e-14)
+        assert np.allclose(so.signal_window(name, 38, False), ss.get_window(name, 38, fftbins=False), atol=1e-14)
+
+
+def test_reference_streaming_unit_tests():
+    s = so.StreamingStft(256, 128, center=False)  # streaming_stft.rs test_streaming_stft_processing
+    r = s.process_frame(np.sin(2 * np.pi * 100.0 * np.arange(256) / 1000.0))
+    assert r is not None and len(r) == 129
+    s = so.StreamingStft(128, 64, center=False, magnitude_only=True)  # test_streaming_stft_magnitude
+    assert len(s.process_frame([1.0] * 128)) == 65
+    s = so.StreamingStft(128, 64, center=False)  # test_streaming_stft_batch_processing / _flush
+    assert len(s.process_batch([1.0] * 512, 64)) > 0
+    s = so.StreamingStft(128, 64, center=False)
+    s.process_frame([1.0] * 100)
+    assert len(s.flush()) > 0 or len(s.buf) == 0
+
+
+@pytest.fixture()
+def host_signal(monkeypatch):
+    """scirs_b200.signal with its device transforms swapped for the oracle's (host-logic check only)."""
+    import scirs_b200.signal as sg
+
+    monkeypatch.setattr(sg, "fft", lambda x, n=None: orc.fft(np.asarray(x), n))
+    monkeypatch.setattr(sg, "ifft", lambda x, n=None: orc.ifft(np.asarray(x), n))
+    monkeypatch.setattr(sg, "rfft_batch", lambda m: np.fft.rfft(np.asarray(m, dtype=np.float64), axis=1))
+    monkeypatch.setattr(sg, "fftn", lambda x, shape=None, axes=None: np.fft.fft(np.asarray(x), axis=axes[0]))
+    return sg
+
+
+@pytest.mark.parametrize("name,fn", sc.cases(), ids=[c[0] for c in sc.cases()])
+def test_host_logic_matches_oracle(host_signal, name, fn):
+    got, ref = fn(host_signal, so)
+    sc.compare(got, ref, 1e-11)
+
+
+def test_host_errors_and_bookkeeping(host_signal):
+    sg = host_signal
+    from scirs_b200.error import ValueError_
+
+    with pytest.raises(ValueError_):
+        sg.periodogram([])
+    with pytest.raises(ValueError_):
+        sg.periodogram(np.ones(8), nfft=4)
+    with pytest.raises(ValueError_):
+        sg.welch(np.ones(64), nperseg=16, noverlap=16)
+    with pytest.raises(ValueError_):
+        sg.welch(np.ones(64), fs=-1.0)
+    with pytest.raises(ValueError_):
+        sg.stft(np.ones(64), nperseg=16, nfft=8)
+    with pytest.raises(ValueError_):
+        sg.stft(np.ones(64), window="nope")
+    with pytest.raises(ValueError_):
+        sg.spectrogram(np.ones(64), mode="complex")
+    with pytest.raises(ValueError_):
+        sg.spectral_subtraction(np.ones(20))
+    with pytest.raises(ValueError_):
+        sg.StreamingStft(sg.StreamingStftConfig(frame_length=8, hop_length=9))
+    with pytest.raises(ValueError_):
+        sg.compute_bispectrum(np.ones(3))
+    # streaming_stft.rs test_streaming_stft_latency / test_real_time_stft
+    st = sg.StreamingStft(sg.StreamingStftConfig(frame_length=512, hop_length=256, center=True))
+    assert st.get_latency_samples() == 512 and st.get_latency_seconds(1000.0) == 0.512
+    rt = sg.RealTimeStft(sg.StreamingStftConfig(frame_length=256, hop_length=128, center=False), 128, 2)
+    assert rt.process_block(np.full(128, 0.5)) == 0
+    for _ in range(4):
+        assert rt.process_block(np.full(128, 0.5)) == 1
+    assert rt.available_spectra_count() == 2 and rt.is_buffer_full()
+    assert rt.get_statistics().base_statistics.frames_generated == 4
+    with pytest.raises(ValueError_):
+        rt.process_block(np.ones(5))
+    assert len(rt.get_all_spectra()) == 2 and rt.get_spectrum() is None
+    rt.reset()
+    assert rt.get_statistics().base_statistics.samples_processed == 0
