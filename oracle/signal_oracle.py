@@ -434,3 +434,113 @@ def power_spectrum(signal, nfft: int, window: Optional[str]) -> np.ndarray:  # h
     if nb > 2:
         p[1:nb - 1] *= 2.0
     return p
+
+
+# ---- cqt.rs --------------------------------------------------------------------------------------
+
+def _odd_ceil(v: float) -> int:
+    k = int(math.ceil(v))
+    return k + 1 if k % 2 == 0 else k
+
+
+def _pow2(n: int) -> int:  # cqt.rs:496-502
+    p = 1
+    while p < n:
+        p *= 2
+    return p
+
+
+def cqt_kernel(f_min, f_max, bins_per_octave, q, fs, window_type="hann", window_scaling=None, use_sparse=True):
+    """cqt.rs:229-347 -> (list of (indices, values), frequencies, n_fft)."""
+    n_bins = int(math.ceil(math.log2(f_max / f_min) * bins_per_octave))
+    freqs = [f_min * 2.0 ** (k / bins_per_octave) for k in range(n_bins)]
+    ws = 1.0 if window_scaling is None else window_scaling
+    n_fft = _pow2(_odd_ceil(ws * q * fs / f_min))
+    kernels = []
+    for f in freqs:
+        klen = _odd_ceil(ws * q * fs / f)
+        if window_type.lower() not in ("hann", "hanning", "hamming", "blackman", "bartlett", "rectangular", "boxcar"):
+            raise OracleError(f"Unsupported window type: {window_type}")
+        win = signal_window(window_type, klen, False)
+        center = (klen - 1) / 2.0
+        vals = []
+        for n in range(klen):
+            ph = 2.0 * math.pi * f * ((n - center) / fs)
+            vals.append(complex(math.cos(ph), math.sin(ph)) * win[n])
+        norm = math.sqrt(sum(v.real ** 2 + v.imag ** 2 for v in vals))
+        padded = np.zeros(n_fft, dtype=np.complex128)
+        for n in range(klen):
+            padded[n] = vals[n] / norm
+        K = base.fft(padded, None)
+        if use_sparse:
+            idx = [i for i, v in enumerate(K) if abs(v) > 1e-6]
+        else:
+            idx = list(range(n_fft))
+        kernels.append((np.array(idx, dtype=np.int64), np.array([K[i] for i in idx], dtype=np.complex128)))
+    return kernels, np.array(freqs), n_fft
+
+
+def cqt_frame(signal, kernels, n_fft) -> np.ndarray:  # cqt.rs:351-428
+    s = np.asarray(signal, dtype=np.float64)
+    n_chunks = 1 if s.size < n_fft else int(math.ceil(s.size / n_fft))
+    acc = np.zeros(len(kernels), dtype=np.complex128)
+    for c in range(n_chunks):
+        padded = np.zeros(n_fft, dtype=np.complex128)
+        seg = s[c * n_fft: min((c + 1) * n_fft, s.size)]
+        padded[: seg.size] = seg
+        X = base.fft(padded, None)
+        for k, (idx, vals) in enumerate(kernels):
+            acc[k] += np.sum(X[idx] * np.conj(vals)) / 1.0
+    return acc / n_chunks
+
+
+def cqt_spectrogram(signal, kernels, n_fft, fs, hop):  # cqt.rs:430-478 -> (cqt[n_bins][n_frames], times)
+    s = np.asarray(signal, dtype=np.float64)
+    n_frames = int(math.ceil(s.size / hop))
+    out = np.zeros((len(kernels), n_frames), dtype=np.complex128)
+    times = np.zeros(n_frames)
+    for f in range(n_frames):
+        st = f * hop
+        en = min(st + n_fft, s.size)
+        times[f] = (st + (en - st) // 2) / fs
+        frame = np.zeros(n_fft)
+        frame[: en - st] = s[st:en]
+        out[:, f] = cqt_frame(frame, kernels, n_fft)
+    return out, times
+
+
+def icqt(cq, kernels, n_fft, fs, times=None, target_length=None) -> np.ndarray:  # cqt.rs:609-700
+    n_bins, n_frames = cq.shape
+    if n_frames > 1 and times is not None:
+        hop = int(math.floor((times[1] - times[0]) * fs + 0.5)) if len(times) > 1 else n_fft // 2
+    else:
+        hop = n_fft
+    out_len = target_length if target_length is not None else ((n_frames - 1) * hop + n_fft if n_frames > 1 else n_fft)
+    out = np.zeros(out_len)
+    for f in range(n_frames):
+        spec = np.zeros(n_fft, dtype=np.complex128)
+        for b in range(n_bins):
+            idx, vals = kernels[b]
+            spec[idx] += cq[b, f] * vals
+        sig = base.ifft(spec, None)
+        st = f * hop
+        for i in range(st, min(st + n_fft, out_len)):
+            out[i] += sig[i - st].real
+    peak = max((abs(v) for v in out), default=0.0)
+    return out / peak if peak > 0.0 else out
+
+
+def chromagram(cq, freqs, n_chroma=12, ref_note=0) -> np.ndarray:  # cqt.rs:713-760
+    ref = ref_note % n_chroma
+    chroma = np.zeros((n_chroma, cq.shape[1]))
+    for i, f in enumerate(freqs):
+        midi = int(69.0 + 12.0 * math.log2(f / 440.0))  # `as isize` truncates toward zero
+        r = int(math.fmod(midi, n_chroma))
+        b = int(math.fmod(r + n_chroma - ref, n_chroma))
+        if 0 <= b < n_chroma:
+            chroma[b] += np.abs(cq[i])
+    for j in range(cq.shape[1]):
+        t = chroma[:, j].sum()
+        if t > 0.0:
+            chroma[:, j] /= t
+    return chroma

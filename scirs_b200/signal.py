@@ -16,7 +16,8 @@ Reference behaviour that is reproduced as written, because a drop-in must return
 * the spectral-density results are NOT doubled for the one-sided half (spectral.rs:203-207).
 
 Covered: spectral.rs (periodogram, welch, stft, spectrogram), wiener.rs (the frequency-domain filters),
-streaming_stft.rs (StreamingStft), higher_order.rs (direct and Welch bispectrum, power spectrum).
+streaming_stft.rs (StreamingStft, RealTimeStft), higher_order.rs (direct and Welch bispectrum, power spectrum),
+cqt.rs (constant-Q kernel, frame, spectrogram, inverse, chromagram).
 """
 from __future__ import annotations
 
@@ -27,7 +28,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from .error import ValueError_
-from .fft import fft, fftn, ifft, rfft_batch
+from .fft import fft, fftn, ifft, ifftn, rfft_batch
 
 
 # ------------------------------------------------------------------------------------------------
@@ -706,3 +707,191 @@ def compute_power_spectrum(signal, config: Optional[HigherOrderConfig] = None) -
     if nb > 2:
         p[1:nb - 1] *= 2.0
     return p, np.linspace(0.0, cfg.fs / 2.0, nb)
+
+
+# ------------------------------------------------------------------------------------------------
+# cqt.rs
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class CqtConfig:
+    """cqt.rs:24-68."""
+    f_min: float = 32.7
+    f_max: float = 8000.0
+    bins_per_octave: int = 12
+    q_factor: Optional[float] = None
+    window_type: str = "hann"
+    fs: float = 44100.0
+    use_sparse: bool = True
+    window_scaling: Optional[float] = None
+    hop_size: Optional[int] = None
+
+
+@dataclass
+class SparseKernel:
+    indices: np.ndarray
+    values: np.ndarray
+    normalization: float = 1.0
+
+
+@dataclass
+class CqtKernel:
+    """cqt.rs:87-112.  ``spectra`` holds the kernel spectra as one [n_bins, n_fft] matrix with the entries
+    the reference's sparse form drops (|K| <= 1e-6, cqt.rs:310-327) set to zero, so that applying the kernels
+    is one matrix product; ``kernels`` gives the reference's per-bin sparse view of the same numbers."""
+    spectra: np.ndarray
+    mask: np.ndarray
+    frequencies: np.ndarray
+    n_fft: int
+    q: float
+    fs: float
+    f_min: float
+    f_max: float
+    bins_per_octave: int
+
+    @property
+    def kernels(self) -> List[SparseKernel]:
+        return [SparseKernel(np.nonzero(m)[0], row[m], 1.0) for row, m in zip(self.spectra, self.mask)]
+
+
+@dataclass
+class CqtResult:
+    cqt: np.ndarray
+    frequencies: np.ndarray
+    kernel: Optional[CqtKernel] = None
+    times: Optional[np.ndarray] = None
+
+
+def _cqt_window(window_type: str, length: int) -> np.ndarray:
+    """``create_window`` (cqt.rs:481-494): symmetric windows of window/mod.rs."""
+    w = window_type.lower()
+    if w not in ("hann", "hanning", "hamming", "blackman", "bartlett", "rectangular", "boxcar"):
+        raise ValueError_(f"Unsupported window type: {window_type}")
+    return signal_window(w, length, False)
+
+
+def _odd_ceil(v: float) -> int:
+    k = int(np.ceil(v))
+    return k + 1 if k % 2 == 0 else k
+
+
+def compute_cqt_kernel(f_min: float, f_max: float, bins_per_octave: int, q: float, fs: float, window_type: str,
+                       window_scaling: Optional[float], use_sparse: bool) -> CqtKernel:
+    """cqt.rs:229-347: windowed complex exponentials, unit energy, zero-padded to n_fft; all n_bins
+    transforms run as one batched device FFT."""
+    n_bins = int(np.ceil(np.log2(f_max / f_min) * bins_per_octave))
+    freqs = f_min * 2.0 ** (np.arange(n_bins) / bins_per_octave)
+    scale = 1.0 if window_scaling is None else window_scaling
+    n_fft = _next_pow2(_odd_ceil(scale * q * fs / f_min))
+    rows = np.zeros((n_bins, n_fft), dtype=np.complex128)
+    for k, f in enumerate(freqs):
+        klen = _odd_ceil(scale * q * fs / f)
+        t = (np.arange(klen) - (klen - 1) / 2.0) / fs
+        vals = np.exp(1j * (2.0 * np.pi * f * t)) * _cqt_window(window_type, klen)
+        rows[k, :klen] = vals / np.sqrt(np.sum(vals.real ** 2 + vals.imag ** 2))
+    spectra = fftn(rows, None, [1]).reshape(n_bins, n_fft) if n_bins else rows
+    mask = np.abs(spectra) > 1e-6 if use_sparse else np.ones(spectra.shape, dtype=bool)
+    return CqtKernel(np.where(mask, spectra, 0.0), mask, freqs, n_fft, q, fs, f_min, f_max, bins_per_octave)
+
+
+def _cqt_rows(rows: np.ndarray, kernel: CqtKernel) -> np.ndarray:
+    """[m, n_fft] real rows -> [m, n_bins]: sum over idx of FFT(row)[idx] * conj(K[bin][idx])."""
+    X = fftn(rows.astype(np.complex128), None, [1]).reshape(rows.shape)
+    return X @ np.conj(kernel.spectra).T
+
+
+def compute_cqt_frame(signal, kernel: CqtKernel) -> np.ndarray:
+    """cqt.rs:351-428: one padded transform, or the mean over consecutive n_fft chunks."""
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    n_fft = kernel.n_fft
+    n_chunks = 1 if s.size < n_fft else int(np.ceil(s.size / n_fft))
+    rows = np.zeros((n_chunks, n_fft))
+    rows.reshape(-1)[: s.size] = s
+    return _cqt_rows(rows, kernel).sum(axis=0) / n_chunks
+
+
+def compute_cqt_spectrogram(signal, kernel: CqtKernel, hop_size: int) -> CqtResult:
+    """cqt.rs:430-478: frame f = signal[f*hop : f*hop + n_fft], zero-padded; all frames in one batch."""
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    n_fft = kernel.n_fft
+    n_frames = int(np.ceil(s.size / hop_size))
+    start = np.arange(n_frames) * hop_size
+    end = np.minimum(start + n_fft, s.size)
+    times = (start + (end - start) // 2) / kernel.fs
+    idx = start[:, None] + np.arange(n_fft)[None, :]
+    rows = np.where(idx < s.size, s[np.minimum(idx, s.size - 1)], 0.0) if s.size else np.zeros((0, n_fft))
+    cq = _cqt_rows(rows, kernel).T.copy() if n_frames else np.zeros((len(kernel.frequencies), 0), dtype=np.complex128)
+    return CqtResult(cq, kernel.frequencies.copy(), kernel, times)
+
+
+def constant_q_transform(signal, config: Optional[CqtConfig] = None) -> CqtResult:
+    """cqt.rs:175-226."""
+    cfg = config or CqtConfig()
+    q = cfg.q_factor if cfg.q_factor is not None else 1.0 / (2.0 ** (1.0 / cfg.bins_per_octave) - 1.0)
+    kernel = compute_cqt_kernel(cfg.f_min, cfg.f_max, cfg.bins_per_octave, q, cfg.fs, cfg.window_type,
+                                cfg.window_scaling, cfg.use_sparse)
+    if cfg.hop_size is not None:
+        return compute_cqt_spectrogram(signal, kernel, cfg.hop_size)
+    return CqtResult(compute_cqt_frame(signal, kernel).reshape(-1, 1), kernel.frequencies.copy(), kernel, None)
+
+
+def cqt_magnitude(cqt: CqtResult, log_scale: bool = False, ref_value: Optional[float] = None) -> np.ndarray:
+    """cqt.rs:515-540."""
+    mag = np.abs(cqt.cqt)
+    if log_scale:
+        ref = ref_value if ref_value is not None else float(mag.max(initial=0.0))
+        with np.errstate(divide="ignore"):
+            mag = 20.0 * np.log10(mag / (ref + 1e-10))
+    return mag
+
+
+def cqt_phase(cqt: CqtResult) -> np.ndarray:
+    """cqt.rs:551-563."""
+    return np.angle(cqt.cqt)
+
+
+def inverse_constant_q_transform(cqt: CqtResult, target_length: Optional[int] = None) -> np.ndarray:
+    """cqt.rs:609-700: frame spectra = weighted sums of the kernel spectra, one batched inverse transform,
+    overlap-add, peak normalisation."""
+    kernel = cqt.kernel
+    if kernel is None:
+        raise ValueError_("CQT kernel not available for inverse transform")
+    n_frames = cqt.cqt.shape[1]
+    n_fft = kernel.n_fft
+    if n_frames > 1 and cqt.times is not None:
+        # f64::round: half away from zero (time differences are positive)
+        hop = int(np.floor((cqt.times[1] - cqt.times[0]) * kernel.fs + 0.5)) if len(cqt.times) > 1 else n_fft // 2
+    else:
+        hop = n_fft
+    out_len = target_length if target_length is not None else ((n_frames - 1) * hop + n_fft if n_frames > 1 else n_fft)
+    out = np.zeros(out_len)
+    if n_frames:
+        spectra = cqt.cqt.T @ kernel.spectra  # [frames, n_fft]
+        frames = ifftn(spectra, None, [1]).reshape(n_frames, n_fft).real
+        for f in range(n_frames):
+            st = f * hop
+            en = min(st + n_fft, out_len)
+            if en > st:
+                out[st:en] += frames[f, : en - st]
+    peak = float(np.max(np.abs(out), initial=0.0))
+    return out / peak if peak > 0.0 else out
+
+
+def _rem(a: int, b: int) -> int:
+    """Rust's ``%`` on isize: the remainder takes the sign of the dividend."""
+    return a - b * int(a / b)
+
+
+def chromagram(cqt: CqtResult, n_chroma: Optional[int] = None, ref_note: Optional[int] = None) -> np.ndarray:
+    """cqt.rs:713-760."""
+    nc = 12 if n_chroma is None else n_chroma
+    ref = (0 if ref_note is None else ref_note) % nc
+    midi = 69.0 + 12.0 * np.log2(cqt.frequencies / 440.0)
+    mag = np.abs(cqt.cqt)
+    chroma = np.zeros((nc, cqt.cqt.shape[1]))
+    for i, m in enumerate(midi):
+        b = _rem(_rem(int(m), nc) + nc - ref, nc)
+        if 0 <= b < nc:
+            chroma[b] += mag[i]
+    tot = chroma.sum(axis=0)
+    return np.where(tot > 0.0, chroma / np.where(tot > 0.0, tot, 1.0), chroma)

@@ -75,6 +75,39 @@ def cases():
         add(f"powerspec-{n}", lambda sg, so, x=x, nfft=nfft, win=win: (
             (sg.compute_power_spectrum(x, sg.HigherOrderConfig(nfft=nfft, window=win))[0],),
             (so.power_spectrum(x, nfft, win),)))
+
+    def cqt_case(sg, so, cfgkw, n, seed, inverse):
+        fs = cfgkw["fs"]
+        t = np.arange(n) / fs
+        x = np.sin(2 * np.pi * 440.0 * t) + 0.3 * np.sin(2 * np.pi * 700.0 * t) + 0.05 * np.random.default_rng(seed).standard_normal(n)
+        cfg = sg.CqtConfig(**cfgkw)
+        r = sg.constant_q_transform(x, cfg)
+        q = cfg.q_factor if cfg.q_factor is not None else 1.0 / (2.0 ** (1.0 / cfg.bins_per_octave) - 1.0)
+        kern, freqs, n_fft = so.cqt_kernel(cfg.f_min, cfg.f_max, cfg.bins_per_octave, q, fs, cfg.window_type,
+                                           cfg.window_scaling, cfg.use_sparse)
+        assert r.kernel.n_fft == n_fft and [len(k.indices) for k in r.kernel.kernels] == [len(i) for i, _ in kern]
+        if cfg.hop_size is None:
+            ref, times = so.cqt_frame(x, kern, n_fft).reshape(-1, 1), None
+            got = (r.cqt, r.frequencies)
+            exp = (ref, freqs)
+        else:
+            ref, times = so.cqt_spectrogram(x, kern, n_fft, fs, cfg.hop_size)
+            got = (r.cqt, r.frequencies, r.times)
+            exp = (ref, freqs, times)
+        got += (sg.chromagram(r), sg.cqt_magnitude(r, True), sg.cqt_phase(r))
+        exp += (so.chromagram(ref, freqs), 20.0 * np.log10(np.abs(ref) / (np.abs(ref).max() + 1e-10)), np.angle(ref))
+        if inverse:
+            got += (sg.inverse_constant_q_transform(r),)
+            exp += (so.icqt(ref, kern, n_fft, fs, times),)
+        return got, exp
+
+    for name, kw, n, inverse in (
+            ("frame-short", dict(f_min=220.0, f_max=880.0, bins_per_octave=12, fs=8000.0), 500, True),
+            ("frame-chunks", dict(f_min=220.0, f_max=1760.0, bins_per_octave=12, fs=8000.0, window_type="hamming"), 3000, False),
+            ("spec", dict(f_min=200.0, f_max=1600.0, bins_per_octave=6, fs=8000.0, hop_size=128, window_type="blackman"), 2000, True),
+            ("dense", dict(f_min=300.0, f_max=1200.0, bins_per_octave=4, fs=8000.0, hop_size=100, use_sparse=False, q_factor=5.0,
+                           window_scaling=1.5, window_type="bartlett"), 900, True)):
+        add(f"cqt-{name}", lambda sg, so, a=(kw, n, len(name), inverse): cqt_case(sg, so, *a))
     return out
 
 

@@ -68,6 +68,30 @@ def test_reference_streaming_unit_tests():
     assert len(s.flush()) > 0 or len(s.buf) == 0
 
 
+def test_reference_cqt_unit_tests():
+    q = 1.0 / (2.0 ** (1.0 / 12) - 1.0)
+    kern, freqs, n_fft = so.cqt_kernel(55.0, 440.0, 12, q, 22050.0)  # cqt.rs:800-818 test_cqt_kernel
+    assert len(kern) == int(np.ceil(np.log2(440.0 / 55.0) * 12)) and abs(freqs[0] - 55.0) < 0.1
+    assert freqs[-1] >= 440.0 * 0.9 and n_fft & (n_fft - 1) == 0
+    # cqt.rs test_create_window: symmetric hann, zero at both ends, ~1 in the middle
+    w = so.signal_window("hann", 128, False)
+    assert w[0] < 1e-10 and w[127] < 1e-10 and w[64] > 0.9
+    # cqt.rs test_constant_q_transform (smaller rate so the literal oracle stays fast): the strongest bin is
+    # within one bin of the tone
+    fs = 4000.0
+    x = np.sin(2 * np.pi * 440.0 * np.linspace(0.0, 0.5, 2000))
+    kern, freqs, n_fft = so.cqt_kernel(110.0, 1000.0, 12, q, fs)
+    c = so.cqt_frame(x, kern, n_fft)
+    assert abs(int(np.argmax(np.abs(c))) - int(np.argmin(np.abs(freqs - 440.0)))) <= 1
+    # cqt.rs test_cqt_spectrogram: shapes
+    S, times = so.cqt_spectrogram(x, kern, n_fft, fs, 512)
+    assert S.shape == (len(kern), int(np.ceil(2000 / 512.0))) and len(times) == S.shape[1]
+    # cqt.rs test_chromagram: A (index 9 from C) carries energy, frames sum to one
+    kern, freqs, n_fft = so.cqt_kernel(220.0, 880.0, 12, q, fs)
+    ch = so.chromagram(so.cqt_frame(x, kern, n_fft).reshape(-1, 1), freqs)
+    assert ch.shape == (12, 1) and ch[9, 0] > 0.1 and abs(ch[:, 0].sum() - 1.0) < 1e-6
+
+
 @pytest.fixture()
 def host_signal(monkeypatch):
     """scirs_b200.signal with its device transforms swapped for the oracle's (host-logic check only)."""
@@ -77,6 +101,7 @@ def host_signal(monkeypatch):
     monkeypatch.setattr(sg, "ifft", lambda x, n=None: orc.ifft(np.asarray(x), n))
     monkeypatch.setattr(sg, "rfft_batch", lambda m: np.fft.rfft(np.asarray(m, dtype=np.float64), axis=1))
     monkeypatch.setattr(sg, "fftn", lambda x, shape=None, axes=None: np.fft.fft(np.asarray(x), axis=axes[0]))
+    monkeypatch.setattr(sg, "ifftn", lambda x, shape=None, axes=None: np.fft.ifft(np.asarray(x), axis=axes[0]))
     return sg
 
 
