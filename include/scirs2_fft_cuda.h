@@ -278,6 +278,14 @@ int sfc_stft(const double* x, int64_t len, const double* window, int64_t nperseg
              int32_t detrend, int32_t onesided, int32_t boundary, int32_t out_mode, double scale, void* out,
              int64_t out_cap_elems, int64_t* freq_len, int64_t* frames);
 
+/* SURVEY 8f rank 4 — the per-segment `scirs2_fft::fft` loops of scirs2-signal/src/spectral.rs (periodogram :186-207,
+ * welch :346-395, stft :580-616) as ONE framed, batched transform: row f = window * detrend(x[f*step .. f*step+nperseg))
+ * zero-padded to P (the power of two `fft(&padded, None)` pads to; detrend 0 none, 1 "constant", 2 "linear",
+ * spectral.rs:77-117), real-to-complex, first `bins` bins kept.  reduce = 0: out = complex f64 [frames][bins];
+ * reduce = 1: out = f64 [bins] = scale * sum over frames of |X|^2 (welch's average with scale folded in). */
+int sfc_signal_spectra(const double* x, int64_t len, const double* window, int64_t nperseg, int64_t step, int64_t frames,
+                       int64_t P, int32_t detrend, int32_t reduce, int64_t bins, double scale, void* out);
+
 /* ------------------------------------------------- SURVEY 8f rank 2 (what benches/fft_benchmarks.rs times)
  * memory_efficient.rs:89-190 (fft_inplace: result written to BOTH buffers; returns n), :243-397 (fft2_efficient,
  * out_rows/out_cols < 0 = input shape), :401-580 (fft_streaming: chunk_size <= 0 = the reference default;

@@ -151,6 +151,7 @@ SIGNATURES = {
     "sfc_fft_streaming": (_int, [_vp, _i64, _int, _i64, _i32, _i64, _vp]),
     "sfc_fftn_optimized": (_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
     "sfc_czt": (_int, [_vp, _i64, _i64, _i64, _i32, C.c_double, C.c_double, C.c_double, C.c_double, _vp]),
+    "sfc_signal_spectra": (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i64, C.c_double, _vp]),
     "sfc_stft": (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, C.c_double, _vp, _i64, _vp, _vp]),
 }
 

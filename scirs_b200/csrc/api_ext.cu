@@ -693,6 +693,89 @@ SFC_EXPORT int sfc_stft(const double* x, int64_t len, const double* window, int6
 }
 
 // ------------------------------------------------------------------------------------------------
+// the segment loops of scirs2-signal (spectral.rs:346-395 welch, :580-616 stft, :186-207 periodogram).
+// Rows x[f*step .. f*step + nperseg) -> detrend (0 none, 1 constant, 2 linear: spectral.rs:77-117) -> window -> zero-pad to P
+// (the power of two `fft(&padded, None)` pads to) -> one batched real-to-complex plan -> the first `bins` bins.
+// reduce = 0: out = complex f64 [frames][bins];  reduce = 1: out = f64 [bins] = scale * sum over frames of |X|^2.
+SFC_EXPORT int sfc_signal_spectra(const double* x, int64_t len, const double* window, int64_t nperseg, int64_t step,
+                                  int64_t frames, int64_t P, int32_t detrend, int32_t reduce, int64_t bins, double scale,
+                                  void* out) {
+    int rc;
+    if ((rc = require_device()) != SFC_OK) return rc;
+    if (!x || len <= 0) return fail(SFC_ERR_VALUE, "Input array is empty");
+    if (nperseg <= 0 || !window || step <= 0 || frames <= 0) return fail(SFC_ERR_VALUE, "Segment length, step and count must be positive");
+    if ((frames - 1) * step + nperseg > len) return fail(SFC_ERR_VALUE, "Not enough data points for given nperseg and noverlap");
+    if (P < nperseg || !is_pow2_i64(P)) return fail(SFC_ERR_VALUE, "padded length must be a power of two >= nperseg");
+    if (bins <= 0 || bins > P / 2 + 1) return fail(SFC_ERR_VALUE, "bins must be in 1 ..= P/2 + 1");
+    if (detrend < 0 || detrend > 2 || reduce < 0 || reduce > 1 || !out) return fail(SFC_ERR_VALUE, "unknown detrend / reduce option");
+    const int64_t pitch = P / 2 + 1;
+    void *d_x = nullptr, *d_w = nullptr, *d_f = nullptr, *d_z = nullptr;
+    if ((rc = g_ws.get(0, (size_t)len * 8, &d_x)) != SFC_OK) return rc;
+    if ((rc = g_ws.get(4, (size_t)nperseg * 8, &d_w)) != SFC_OK) return rc;
+    if ((rc = g_ws.get(3, (size_t)frames * P * 8, &d_f)) != SFC_OK) return rc;
+    if ((rc = g_ws.get(1, (size_t)frames * pitch * 16, &d_z)) != SFC_OK) return rc;
+    cudaStream_t st = g_ws.stream;
+    cudaError_t e = cudaMemcpyAsync(d_x, x, (size_t)len * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_w, window, (size_t)nperseg * 8, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+    FrameParams fp{};
+    fp.x = (const double*)d_x;
+    fp.win = (const double*)d_w;
+    fp.dst = (double*)d_f;
+    fp.len = len;
+    fp.nperseg = nperseg;
+    fp.step = step;
+    fp.frames = frames;
+    fp.P = P;
+    fp.boundary = 0;
+    fp.detrend = detrend;
+    e = launch_frames(fp, st);
+    if (e != cudaSuccess) return cuda_fail(e, "framing kernel");
+    sfc_desc d;
+    memset(&d, 0, sizeof d);
+    d.ndim = 2;
+    d.shape[0] = frames;
+    d.shape[1] = P;
+    d.naxes = 1;
+    d.axes[0] = 1;
+    d.prec = SFC_PREC_F64;
+    d.scale = 1.0;
+    d.kind = SFC_R2C;
+    PlanError perr{0, ""};
+    std::shared_ptr<Plan> p = cached_plan(d, perr);
+    if (!p) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
+    std::string es;
+    rc = p->exec(d_f, d_z, st, es);
+    if (rc != 0) return fail(rc, es);
+    if (reduce) {
+        void *d_p = nullptr, *d_o = nullptr;
+        const int64_t want = (frames + 63) / 64;
+        const int32_t parts = (int32_t)(want < 1 ? 1 : (want > 1024 ? 1024 : want));
+        if ((rc = g_ws.get(2, (size_t)parts * bins * 8, &d_p)) != SFC_OK) return rc;
+        if ((rc = g_ws.get(5, (size_t)bins * 8, &d_o)) != SFC_OK) return rc;
+        PsdSumParams sp{};
+        sp.src = d_z;
+        sp.partial = (double*)d_p;
+        sp.dst = (double*)d_o;
+        sp.frames = frames;
+        sp.src_pitch = pitch;
+        sp.bins = bins;
+        sp.parts = parts;
+        sp.scale = scale;
+        e = launch_psd_sum(sp, st);
+        if (e != cudaSuccess) return cuda_fail(e, "psd reduction kernel");
+        return download(out, d_o, (size_t)bins * 8);
+    }
+    // rows of `pitch` complex entries on the device, rows of `bins` on the host
+    e = cudaMemcpy2DAsync(out, (size_t)bins * 16, d_z, (size_t)pitch * 16, (size_t)bins * 16, (size_t)frames,
+                          cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "D2H copy");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "transform execution");
+    return SFC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // memory_efficient.rs / ndim_optimized.rs — what benches/fft_benchmarks.rs:126-189 times.
 
 // memory_efficient.rs:89-190.  n >= 32 takes the reference's "SIMD" branch (simd_support_available() is true on

@@ -67,31 +67,74 @@ __device__ __forceinline__ double padded_sample(const FrameParams& p, int64_t t)
     return p.boundary == 2 ? 0.0 : p.x[p.len - 1];
 }
 
+// sum of `v` over the CTA (256 threads), returned to every thread
+__device__ __forceinline__ double block_sum(double v, double* red, double* bcast) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) *bcast = t;
+    }
+    __syncthreads();
+    const double r = *bcast;
+    __syncthreads();
+    return r;
+}
+
 __global__ void __launch_bounds__(256) frame_kernel(const FrameParams p) {
     __shared__ double red[32];
-    __shared__ double mean_s;
+    __shared__ double bc;
     for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
         const int64_t start = f * p.step;
-        double mean = 0.0;
+        double mean = 0.0, slope = 0.0;
         if (p.detrend) {
-            double s = 0.0;
-            for (int64_t j = threadIdx.x; j < p.nperseg; j += blockDim.x) s += padded_sample(p, start + j);
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (threadIdx.x == 0) mean_s = v / (double)p.nperseg;
+            double s = 0.0, sj = 0.0;
+            for (int64_t j = threadIdx.x; j < p.nperseg; j += blockDim.x) {
+                const double v = padded_sample(p, start + j);
+                s += v;
+                sj += (double)j * v;
             }
-            __syncthreads();
-            mean = mean_s;
+            const double sum_y = block_sum(s, red, &bc);
+            const double n = (double)p.nperseg;
+            mean = sum_y / n;
+            if (p.detrend == 2) {
+                // y - (slope * j + intercept), the regression sums of spectral.rs:88-100 in closed form
+                const double sum_xy = block_sum(sj, red, &bc);
+                const double sum_x = n * (n - 1.0) * 0.5, sum_xx = (n - 1.0) * n * (2.0 * n - 1.0) / 6.0;
+                slope = (n * sum_xy - sum_x * sum_y) / (n * sum_xx - sum_x * sum_x);
+                mean = (sum_y - slope * sum_x) / n;  // the intercept
+            }
         }
         double* row = p.dst + f * p.P;
         for (int64_t j = threadIdx.x; j < p.P; j += blockDim.x)
-            row[j] = j < p.nperseg ? (padded_sample(p, start + j) - mean) * p.win[j] : 0.0;
-        __syncthreads();
+            row[j] = j < p.nperseg ? (padded_sample(p, start + j) - (slope * (double)j + mean)) * p.win[j] : 0.0;
     }
+}
+
+// one thread per bin, consecutive threads on consecutive bins (coalesced 16-byte loads); blockIdx.y = frame range
+__global__ void __launch_bounds__(256) psd_partial_kernel(const PsdSumParams p) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p.bins) return;
+    const int64_t per = (p.frames + p.parts - 1) / p.parts;
+    const int64_t f0 = (int64_t)blockIdx.y * per;
+    const int64_t f1 = f0 + per < p.frames ? f0 + per : p.frames;
+    const double2* __restrict__ z = reinterpret_cast<const double2*>(p.src);
+    double acc = 0.0;
+    for (int64_t f = f0; f < f1; ++f) {
+        const double2 v = z[f * p.src_pitch + k];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    p.partial[(int64_t)blockIdx.y * p.bins + k] = acc;
+}
+
+__global__ void __launch_bounds__(256) psd_final_kernel(const PsdSumParams p) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p.bins) return;
+    double acc = 0.0;
+    for (int q = 0; q < p.parts; ++q) acc += p.partial[(int64_t)q * p.bins + k];
+    p.dst[k] = acc * p.scale;
 }
 
 // 32 x 32 tile transpose through shared memory: reads rows of frames, writes rows of frequencies
@@ -140,6 +183,14 @@ cudaError_t launch_map(const MapParams& p, cudaStream_t s) {
 cudaError_t launch_frames(const FrameParams& p, cudaStream_t s) {
     if (p.frames <= 0) return cudaSuccess;
     frame_kernel<<<grid_for(p.frames, 1), 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_psd_sum(const PsdSumParams& p, cudaStream_t s) {
+    if (p.bins <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((p.bins + 255) / 256), (unsigned)p.parts);
+    psd_partial_kernel<<<grid, 256, 0, s>>>(p);
+    psd_final_kernel<<<grid.x, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 

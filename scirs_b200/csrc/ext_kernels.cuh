@@ -35,7 +35,8 @@ struct FrameParams {
     double* dst;         // [frames][P]
     int64_t len, nperseg, step, frames, P;
     int32_t boundary;    // 0 none, 1 reflect, 2 zeros, 3 constant (spectrogram.rs:141-189), pad = nperseg each side
-    int32_t detrend;     // subtract the frame mean first (spectrogram.rs:253-257)
+    int32_t detrend;     // 1: subtract the frame mean first (spectrogram.rs:253-257); 2: subtract the least-squares line
+                         // (scirs2-signal spectral.rs:84-107)
 };
 cudaError_t launch_frames(const FrameParams& p, cudaStream_t s);
 
@@ -49,5 +50,17 @@ struct StftOutParams {
     double scale;  // psd: |z|^2 * scale, magnitude: |z| * sqrt(scale)
 };
 cudaError_t launch_stft_out(const StftOutParams& p, cudaStream_t s);
+
+// Welch reduction: out[k] = scale * sum over frames of |src[f][k]|^2, k < bins (src rows have src_pitch complex entries).
+// Two deterministic stages: `parts` partial sums over contiguous frame ranges, then their sum.
+struct PsdSumParams {
+    const void* src;
+    double* partial;  // [parts][bins]
+    double* dst;      // [bins]
+    int64_t frames, src_pitch, bins;
+    int32_t parts;
+    double scale;
+};
+cudaError_t launch_psd_sum(const PsdSumParams& p, cudaStream_t s);
 
 }  // namespace sfc

@@ -1,8 +1,9 @@
 """Downstream callers of the FFT hot path in scirs2-signal, re-stated over this package.
 
 The reference functions are host code that loops over segments and calls ``scirs2_fft::fft`` once per
-segment.  Here the segment loop becomes ONE batched device transform (``rfft_batch`` / ``fftn`` over the
-frame matrix): framing, detrending and windowing are O(n) host passes, every FFT goes through the C ABI
+segment.  Here the segment loop becomes ONE batched device transform: for spectral.rs the framing, detrending,
+windowing, transform and (welch) the |X|^2 average all run on the device (``sfc_signal_spectra``); the other
+callers build their frame matrix on the host and hand it to ``rfft_batch`` / ``fftn``.  Every FFT goes through the C ABI
 (there is no CPU transform in this file; without the CUDA library every function raises).
 
 Reference behaviour that is reproduced as written, because a drop-in must return the same numbers:
@@ -27,8 +28,9 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .error import ValueError_
-from .fft import fft, fftn, ifft, ifftn, rfft_batch
+from . import _lib
+from .error import ValueError_, check
+from .fft import _ptr, fft, fftn, ifft, ifftn, rfft_batch
 
 
 # ------------------------------------------------------------------------------------------------
@@ -52,24 +54,6 @@ def spectral_window(window_type: str, nperseg: int) -> np.ndarray:
     raise ValueError_(f"Unknown window type: {window_type}")
 
 
-def _detrend_rows(frames: np.ndarray, detrend_type: str) -> np.ndarray:
-    """``apply_detrend`` (spectral.rs:77-117) on every row of a [segments, n] matrix."""
-    if detrend_type == "none":
-        return frames
-    n = frames.shape[1]
-    if detrend_type == "constant":
-        return frames - (frames.sum(axis=1) / n)[:, None]
-    if detrend_type == "linear":
-        t = np.arange(n, dtype=np.float64)
-        sum_x, sum_xx = t.sum(), (t * t).sum()
-        sum_y, sum_xy = frames.sum(axis=1), frames @ t
-        with np.errstate(divide="ignore", invalid="ignore"):
-            slope = (n * sum_xy - sum_x * sum_y) / (n * sum_xx - sum_x * sum_x)
-        intercept = (sum_y - slope * sum_x) / n
-        return frames - (slope[:, None] * t[None, :] + intercept[:, None])
-    raise ValueError_(f"Unknown detrend option: {detrend_type}")
-
-
 def _fftfreq_head(nfft: int, fs: float, count: int) -> np.ndarray:
     """First ``count`` entries of ``helper::fftfreq(nfft, 1/fs)`` (helper.rs; count <= ceil(nfft/2), all non-negative)."""
     return np.arange(count, dtype=np.float64) / (nfft * (1.0 / fs))
@@ -91,18 +75,29 @@ def _check_common(fs: float, nfft: int, nperseg: int, noverlap: Optional[int]) -
         raise ValueError_(f"noverlap must be less than nperseg, got {noverlap} >= {nperseg}")
 
 
+_DETREND = {"none": 0, "constant": 1, "linear": 2}
+
+
 def _segment_spectra(x: np.ndarray, nperseg: int, step: int, count: int, win: np.ndarray, detrend: str,
-                     nfft: int, n_half: int) -> np.ndarray:
-    """Rows ``x[i*step : i*step + nperseg]`` -> detrend -> window -> zero-pad to the next power of two of
-    ``nfft`` (what ``fft(&padded, None)`` does) -> ONE batched real-to-complex device transform -> the
-    first ``n_half`` bins.  The reference keeps bins of the full complex transform; for real input those
-    are the same numbers."""
-    idx = (np.arange(count) * step)[:, None] + np.arange(nperseg)[None, :]
-    frames = _detrend_rows(x[idx], detrend) * win[None, :]
-    P = _next_pow2(max(nfft, 1))
-    padded = np.zeros((count, P), dtype=np.float64)
-    padded[:, :nperseg] = frames
-    return rfft_batch(padded)[:, :n_half]
+                     nfft: int, n_half: int, psd_scale: Optional[float] = None) -> np.ndarray:
+    """Rows ``x[i*step : i*step + nperseg]`` -> detrend (``apply_detrend``, spectral.rs:77-117) -> window -> zero-pad
+    to the next power of two of ``nfft`` (what ``fft(&padded, None)`` does) -> ONE batched real-to-complex
+    transform -> the first ``n_half`` bins, all on the device (``sfc_signal_spectra``: framing kernel, plan,
+    strided copy back).  With ``psd_scale`` the device also sums |X|^2 over the rows and only ``n_half`` reals
+    come back.  The reference keeps bins of the full complex transform; for real input those are the same numbers."""
+    if detrend not in _DETREND:
+        raise ValueError_(f"Unknown detrend option: {detrend}")
+    lib = _lib.load()
+    xs = np.ascontiguousarray(x, dtype=np.float64)
+    w = np.ascontiguousarray(win, dtype=np.float64)
+    if psd_scale is None:
+        out = np.empty((count, n_half), dtype=np.complex128)
+    else:
+        out = np.empty(n_half, dtype=np.float64)
+    check(lib.sfc_signal_spectra(_ptr(xs), xs.size, _ptr(w), nperseg, step, count, _next_pow2(max(nfft, 1)),
+                                 _DETREND[detrend], 0 if psd_scale is None else 1, n_half,
+                                 1.0 if psd_scale is None else float(psd_scale), _ptr(out)))
+    return out
 
 
 def periodogram(x, fs: Optional[float] = None, window: Optional[str] = None, nfft: Optional[int] = None,
@@ -156,8 +151,8 @@ def welch(x, fs: Optional[float] = None, window: Optional[str] = None, nperseg: 
     usable = min(num_segments, (a.size - nperseg_val) // step + 1 if a.size >= nperseg_val else 0)
     psd = np.zeros(n_half)
     if usable > 0:
-        spec = _segment_spectra(a, nperseg_val, step, usable, win, detrend_val, nfft_val, n_half)
-        psd = ((spec.real ** 2 + spec.imag ** 2) * (scale / (fs_val * nperseg_val))).sum(axis=0)
+        psd = _segment_spectra(a, nperseg_val, step, usable, win, detrend_val, nfft_val, n_half,
+                               psd_scale=scale / (fs_val * nperseg_val))
     psd /= num_segments
     if scaling_val != "density":
         psd = psd * fs_val

@@ -97,6 +97,18 @@ def host_signal(monkeypatch):
     """scirs_b200.signal with its device transforms swapped for the oracle's (host-logic check only)."""
     import scirs_b200.signal as sg
 
+    def spectra(x, nperseg, step, count, win, detrend, nfft, n_half, psd_scale=None):
+        # what sfc_signal_spectra does on the device, with the oracle's own detrend
+        P = 1
+        while P < nfft:
+            P *= 2
+        rows = np.zeros((count, P))
+        for i in range(count):
+            rows[i, :nperseg] = np.array(so.apply_detrend(list(x[i * step:i * step + nperseg]), detrend)) * win
+        Z = np.fft.rfft(rows, axis=1)[:, :n_half]
+        return Z if psd_scale is None else (np.abs(Z) ** 2).sum(axis=0) * psd_scale
+
+    monkeypatch.setattr(sg, "_segment_spectra", spectra)
     monkeypatch.setattr(sg, "fft", lambda x, n=None: orc.fft(np.asarray(x), n))
     monkeypatch.setattr(sg, "ifft", lambda x, n=None: orc.ifft(np.asarray(x), n))
     monkeypatch.setattr(sg, "rfft_batch", lambda m: np.fft.rfft(np.asarray(m, dtype=np.float64), axis=1))
