@@ -233,6 +233,30 @@ inline std::vector<Complex64> czt(const std::vector<Complex64>& x, std::optional
     return out;
 }
 
+// scirs2-signal spectral.rs:257-410 (welch) as one framed, batched device transform.  `window` holds the
+// nperseg samples the caller's get_window produced; detrend: "none" | "constant" | "linear".  Returns the averaged density
+// for the first nfft/2 + nfft%2 bins (multiply by fs for the "spectrum" scaling, spectral.rs:402-407).
+inline std::vector<double> welch_psd(const std::vector<double>& x, double fs, const std::vector<double>& window, size_t noverlap,
+                                     size_t nfft, const std::string& detrend = "constant") {
+    const size_t nperseg = window.size();
+    if (x.empty()) throw FFTError(FFTError::Value, "Input array is empty");
+    if (nperseg == 0 || nfft < nperseg || noverlap >= nperseg) throw FFTError(FFTError::Value, "bad nperseg / noverlap / nfft");
+    const int d = detrend == "none" ? 0 : detrend == "constant" ? 1 : detrend == "linear" ? 2 : -1;
+    if (d < 0) throw FFTError(FFTError::Value, "Unknown detrend option: " + detrend);
+    const size_t step = nperseg - noverlap;
+    const size_t segs = x.size() >= noverlap ? (x.size() - noverlap) / step : 0;
+    if (segs < 1) throw FFTError(FFTError::Value, "Not enough data points for given nperseg and noverlap");
+    size_t P = 1;
+    while (P < nfft) P <<= 1;
+    double w2 = 0.0;
+    for (double w : window) w2 += w * w;
+    std::vector<double> psd(nfft / 2 + nfft % 2);
+    check(sfc_signal_spectra(x.data(), (int64_t)x.size(), window.data(), (int64_t)nperseg, (int64_t)step, (int64_t)segs, (int64_t)P, d, 1,
+                             (int64_t)psd.size(), 1.0 / w2 / (fs * (double)nperseg), psd.data()));
+    for (double& v : psd) v /= (double)segs;
+    return psd;
+}
+
 // PlanCache — plan_cache.rs:28-235 (the cache itself lives in the library)
 struct CacheStats { uint64_t hit_count, miss_count; double hit_rate; uint64_t size, max_size; };
 class PlanCache {

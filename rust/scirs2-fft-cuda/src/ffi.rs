@@ -102,6 +102,8 @@ extern "C" {
     pub fn sfc_stft(x: *const f64, len: i64, window: *const f64, nperseg: i64, noverlap: i64, nfft: i64, detrend: i32,
                     onesided: i32, boundary: i32, out_mode: i32, scale: f64, out: *mut c_void, cap: i64,
                     freq_len: *mut i64, frames: *mut i64) -> c_int;
+    pub fn sfc_signal_spectra(x: *const f64, len: i64, window: *const f64, nperseg: i64, step: i64, frames: i64, p: i64,
+                              detrend: i32, reduce: i32, bins: i64, scale: f64, out: *mut c_void) -> c_int;
     pub fn sfc_fft_inplace(input: *mut f64, n: i64, output: *mut f64, out_len: i64, inverse: i32, normalize: i32) -> c_int;
     pub fn sfc_fft2_efficient(x: *const c_void, rows: i64, cols: i64, dtype: c_int, out_rows: i64, out_cols: i64,
                               inverse: i32, normalize: i32, out: *mut f64) -> c_int;

@@ -53,6 +53,15 @@ int main() {
         auto fc = fft(xc, 8);
         for (int i = 0; i < 8; ++i) REQUIRE(std::abs(zc[i] - fc[i]) < 1e-10);
     }
+    {  // welch (scirs2-signal spectral.rs:257-410): a tone on bin 4 of 64, boxcar, no detrend, no overlap:
+       // every segment has |X[4]|^2 = 32^2, so the density is 1024 / sum(w^2) / (fs * nperseg) = 0.25 there and 0 elsewhere
+        std::vector<double> tone(640), box(64, 1.0);
+        for (int i = 0; i < 640; ++i) tone[i] = std::cos(2.0 * 3.14159265358979323846 * 4.0 * i / 64.0);
+        auto psd = welch_psd(tone, 1.0, box, 0, 64, "none");
+        REQUIRE(psd.size() == 32);
+        for (int k = 0; k < 32; ++k) REQUIRE(std::abs(psd[k] - (k == 4 ? 0.25 : 0.0)) < 1e-12);
+        try { welch_psd(tone, 1.0, box, 0, 64, "bogus"); return 1; } catch (const FFTError& e) { REQUIRE(e.kind == FFTError::Value); }
+    }
     std::puts("cpp mirror ok");
     return 0;
 }
