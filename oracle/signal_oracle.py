@@ -544,3 +544,188 @@ def chromagram(cq, freqs, n_chroma=12, ref_note=0) -> np.ndarray:  # cqt.rs:713-
         if t > 0.0:
             chroma[:, j] /= t
     return chroma
+
+
+# ---- higher_order.rs, continued ------------------------------------------------------------------
+
+def triple_correlation(signal, size: int) -> np.ndarray:  # higher_order.rs:511-556
+    s = [float(v) for v in signal]
+    n = len(s)
+    mean = sum(s) / n
+    c = [v - mean for v in s]
+    max_lag = min(size, n // 3)
+    if max_lag < 2:
+        raise OracleError("Signal too short for triple correlation calculation")
+    out = np.zeros((2 * max_lag - 1, 2 * max_lag - 1))
+    for i in range(n):
+        for t1 in range(max_lag):
+            if i + t1 >= n:
+                continue
+            for t2 in range(max_lag):
+                if i + t2 >= n:
+                    continue
+                out[t1 + max_lag - 1, t2 + max_lag - 1] += c[i] * c[i + t1] * c[i + t2]
+    return out / n
+
+
+def fft_2d(matrix: np.ndarray, nfft: int) -> np.ndarray:  # higher_order.rs:559-635
+    rows, cols = matrix.shape
+    nb = nfft // 2 + 1
+    row_fft = []
+    for i in range(rows):
+        row = list(matrix[i].astype(np.complex128))
+        if len(row) < nfft:
+            row = row + [0j] * (nfft - len(row))
+        row_fft.append(base.fft(np.array(row), None))
+    res = np.zeros((nb, nb), dtype=np.complex128)
+    for j in range(nb):
+        col = [row_fft[i][j] for i in range(rows)]
+        if len(col) < nfft:
+            col = col + [0j] * (nfft - len(col))
+        f = base.fft(np.array(col), None)
+        for i in range(nb):
+            res[i, j] = f[i]
+    return res
+
+
+def indirect_bispectrum(signal, nfft: int, window: Optional[str]) -> np.ndarray:  # higher_order.rs:334-356
+    s = np.asarray(signal, dtype=np.float64)
+    if window is not None:
+        s = s * np.array(signal_window(window, s.size, True))
+    return fft_2d(triple_correlation(s, nfft // 2 + 1), nfft)
+
+
+def _round(v: float) -> int:  # f64::round, half away from zero
+    return int(math.floor(v + 0.5)) if v >= 0 else -int(math.floor(-v + 0.5))
+
+
+def bicoherence(signal, nfft: int, window: Optional[str] = None, n_segments=None, fs: float = 1.0) -> np.ndarray:
+    # higher_order.rs:192-247
+    B = welch_bispectrum(signal, nfft, window, 0.5, n_segments)
+    P = power_spectrum(signal, nfft, window)
+    nb = nfft // 2 + 1
+    axis = np.linspace(0.0, fs / 2.0, nb)
+    out = np.zeros((nb, nb))
+    for i in range(nb):
+        ii = _round(axis[i] * nfft / fs)
+        for j in range(nb):
+            jj = _round(axis[j] * nfft / fs)
+            ss = _round((axis[i] + axis[j]) * nfft / fs) % nfft
+            if ii < len(P) and jj < len(P) and ss < len(P):
+                nf = math.sqrt(P[ii] * P[jj] * P[ss])
+                if nf > 1e-10:
+                    out[i, j] = abs(B[i, j]) / nf
+    return out
+
+
+# ---- hilbert.rs ----------------------------------------------------------------------------------
+
+def hilbert(x) -> np.ndarray:  # scirs2-signal hilbert.rs:58-150
+    s = np.asarray(x, dtype=np.float64)
+    n = s.size
+    if n == 0:
+        raise OracleError("Input array is empty")
+    spectrum = base.fft(s, None)
+    h = [1 + 0j] * n
+    if n % 2 == 0:
+        h[0] = 1 + 0j
+        h[n // 2] = 1 + 0j
+        for i in range(1, n // 2):
+            h[i] = -2j
+        for i in range(n // 2 + 1, n):
+            h[i] = 0j
+    else:
+        h[0] = 1 + 0j
+        for i in range(1, (n + 1) // 2):
+            h[i] = -2j
+        for i in range((n + 1) // 2, n):
+            h[i] = 0j
+    filtered = np.array([sv * hv for sv, hv in zip(spectrum, h)])  # zip stops at n
+    buf = base._process(filtered.astype(np.complex128).copy(), True)  # rustfft inverse, unscaled
+    return buf * (1.0 / n)
+
+
+def unwrap_phase(phase) -> np.ndarray:  # hilbert.rs:258-279
+    out = [phase[0]]
+    prev = phase[0]
+    for p in phase[1:]:
+        d = p - prev
+        while d > math.pi:
+            d -= 2.0 * math.pi
+        while d < -math.pi:
+            d += 2.0 * math.pi
+        out.append(out[-1] + d)
+        prev = p
+    return np.array(out)
+
+
+def instantaneous_phase(x, unwrap=False) -> np.ndarray:  # hilbert.rs:322-366
+    a = hilbert(x)
+    ph = np.array([math.atan2(c.imag, c.real) for c in a])
+    return unwrap_phase(ph) if unwrap else ph
+
+
+def instantaneous_frequency(x, fs) -> np.ndarray:  # hilbert.rs:228-292
+    u = instantaneous_phase(x, True)
+    f = [fs * (u[1] - u[0]) / (2.0 * math.pi)]
+    for i in range(1, len(u) - 1):
+        f.append(fs * (u[i + 1] - u[i - 1]) / (4.0 * math.pi))
+    f.append(fs * (u[-1] - u[-2]) / (2.0 * math.pi))
+    return np.array(f)
+
+
+# ---- wvd.rs --------------------------------------------------------------------------------------
+
+def cross_wvd(s1, s2, zero_padding=True, time_window=None, freq_window=None) -> np.ndarray:  # wvd.rs:232-344
+    n = len(s1)
+    n_fft = 2 * n if zero_padding else n
+    out = np.zeros((n_fft // 2 + 1, n), dtype=np.complex128)
+    tw = None
+    if time_window is not None:
+        w = list(time_window)
+        if len(w) % 2 == 0:
+            half = len(w) // 2
+            tw = [0.0] * (len(w) + 1)
+            for i in range(len(w)):
+                tw[i + (1 if i >= half else 0)] = w[i]
+        else:
+            tw = w
+    fw = None
+    if freq_window is not None:
+        w = list(freq_window)
+        if len(w) < n_fft:
+            fw = [0.0] * n_fft
+            off = (n_fft - len(w)) // 2
+            for i in range(len(w)):
+                fw[i + off] = w[i]
+        elif len(w) > n_fft:
+            off = (len(w) - n_fft) // 2
+            fw = w[off:off + n_fft]
+        else:
+            fw = w
+    for t in range(n):
+        acorr = np.zeros(n_fft, dtype=np.complex128)
+        whl = len(tw) // 2 if tw is not None else n // 2
+        for tau in range(-min(t, whl), min(n - t, whl + 1)):
+            idx = tau + n_fft // 2
+            if tw is not None:
+                wi = tau + whl
+                wv = tw[wi] if wi < len(tw) else 0.0
+            else:
+                wv = 1.0
+            i1, i2 = t + tau, t - tau
+            if 0 <= i1 < n and 0 <= i2 < n:
+                acorr[idx] = s1[i1] * np.conj(s2[i2]) * wv
+        if fw is not None:
+            for i in range(n_fft):
+                acorr[i] *= fw[i]
+        spectrum = base.fft(acorr, None)
+        for k in range(n_fft // 2 + 1):
+            out[k, t] = spectrum[k]
+    return out
+
+
+def wigner_ville(signal, analytic=True, zero_padding=True, time_window=None, freq_window=None) -> np.ndarray:
+    # wvd.rs:79-90, 192-229
+    a = hilbert(signal) if analytic else np.asarray(signal, dtype=np.float64).astype(np.complex128)
+    return cross_wvd(a, a, zero_padding, time_window, freq_window).real

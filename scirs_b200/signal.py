@@ -18,7 +18,8 @@ Reference behaviour that is reproduced as written, because a drop-in must return
 
 Covered: spectral.rs (periodogram, welch, stft, spectrogram), wiener.rs (the frequency-domain filters),
 streaming_stft.rs (StreamingStft, RealTimeStft), higher_order.rs (direct and Welch bispectrum, power spectrum),
-cqt.rs (constant-Q kernel, frame, spectrogram, inverse, chromagram).
+cqt.rs (constant-Q kernel, frame, spectrogram, inverse, chromagram), hilbert.rs (analytic signal, envelope,
+instantaneous phase / frequency), wvd.rs (Wigner-Ville, cross and smoothed pseudo distributions).
 """
 from __future__ import annotations
 
@@ -611,8 +612,7 @@ class RealTimeStft:
 
 @dataclass
 class HigherOrderConfig:
-    """higher_order.rs:71-110 (``estimator``: "direct" or "welch"; the indirect estimator goes through a
-    triple-correlation matrix and is not an FFT-path caller of note)."""
+    """higher_order.rs:71-110 (``estimator``: "direct", "indirect" or "welch")."""
     estimator: str = "welch"
     fs: float = 1.0
     window: Optional[str] = "hann"
@@ -678,8 +678,10 @@ def compute_bispectrum(signal, config: Optional[HigherOrderConfig] = None
         if starts:
             B = _direct_bispectra(_segment_rows(s, cfg.window, nfft, starts, size), nfft).sum(axis=0)
         B = B / nseg
+    elif cfg.estimator == "indirect":
+        B = compute_indirect_bispectrum(s, nfft, cfg.window)
     else:
-        raise ValueError_(f"estimator {cfg.estimator!r} is not on the FFT path")
+        raise ValueError_(f"unknown bispectrum estimator {cfg.estimator!r}")
     return B, axis, axis.copy()
 
 
@@ -890,3 +892,233 @@ def chromagram(cqt: CqtResult, n_chroma: Optional[int] = None, ref_note: Optiona
             chroma[b] += mag[i]
     tot = chroma.sum(axis=0)
     return np.where(tot > 0.0, chroma / np.where(tot > 0.0, tot, 1.0), chroma)
+
+
+# ------------------------------------------------------------------------------------------------
+# higher_order.rs, continued: bicoherence and the indirect (triple-correlation) estimator
+# ------------------------------------------------------------------------------------------------
+
+def _round_half_away(v: np.ndarray) -> np.ndarray:
+    """f64::round for non-negative values."""
+    return np.floor(np.asarray(v, dtype=np.float64) + 0.5).astype(np.int64)
+
+
+def compute_triple_correlation(signal, size: int) -> np.ndarray:
+    """higher_order.rs:511-556: C(t1, t2) = sum_i c[i] c[i+t1] c[i+t2] / n for 0 <= t1, t2 < max_lag, stored in the
+    lower-right quadrant of a (2 max_lag - 1)^2 matrix (the other quadrants stay zero there too)."""
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    n = s.size
+    c = s - s.sum() / n
+    max_lag = min(size, n // 3)
+    if max_lag < 2:
+        raise ValueError_("Signal too short for triple correlation calculation")
+    # shifted[t][i] = c[i + t] (zero past the end): C = (c * shifted) @ shifted^T
+    shifted = np.zeros((max_lag, n))
+    for t in range(max_lag):
+        shifted[t, : n - t] = c[t:]
+    q = (shifted * c[None, :]) @ shifted.T / n
+    out = np.zeros((2 * max_lag - 1, 2 * max_lag - 1))
+    out[max_lag - 1:, max_lag - 1:] = q
+    return out
+
+
+def compute_2d_fft(matrix: np.ndarray, nfft: int) -> np.ndarray:
+    """higher_order.rs:559-635: rows padded to max(cols, nfft) then to the next power of two (``fft(row, None)``), the
+    first nfft/2+1 columns of that transformed the same way; two batched device passes."""
+    m = np.asarray(matrix, dtype=np.float64)
+    rows, cols = m.shape
+    nb = nfft // 2 + 1
+    p1 = _next_pow2(max(cols, nfft))
+    a = np.zeros((rows, p1), dtype=np.complex128)
+    a[:, :cols] = m
+    r = fftn(a, None, [1]).reshape(rows, p1)[:, :nb]
+    p2 = _next_pow2(max(rows, nfft))
+    b = np.zeros((nb, p2), dtype=np.complex128)
+    b[:, :rows] = r.T
+    c = fftn(b, None, [1]).reshape(nb, p2)[:, :nb]
+    return c.T.copy()
+
+
+def compute_indirect_bispectrum(signal, nfft: int, window: Optional[str] = "hann") -> np.ndarray:
+    """higher_order.rs:334-356."""
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    if window is not None:
+        s = s * signal_window(window, s.size, True)
+    return compute_2d_fft(compute_triple_correlation(s, nfft // 2 + 1), nfft)
+
+
+def bicoherence(signal, nfft: int, window: Optional[str] = None, n_segments: Optional[int] = None, fs: float = 1.0
+                ) -> Tuple[np.ndarray, Tuple[np.ndarray, np.ndarray]]:
+    """higher_order.rs:192-247: |B(f1, f2)| / sqrt(P(f1) P(f2) P(f1 + f2)) with the Welch bispectrum."""
+    cfg = HigherOrderConfig(fs=fs, nfft=nfft, window=window, n_segments=n_segments)
+    B, f1, f2 = compute_bispectrum(signal, cfg)
+    P, _ = compute_power_spectrum(signal, cfg)
+    i_idx = _round_half_away(f1 * nfft / fs)
+    j_idx = _round_half_away(f2 * nfft / fs)
+    s_idx = _round_half_away((f1[:, None] + f2[None, :]) * nfft / fs) % nfft
+    ok = (i_idx[:, None] < P.size) & (j_idx[None, :] < P.size) & (s_idx < P.size)
+    ii = np.minimum(i_idx, P.size - 1)[:, None]
+    jj = np.minimum(j_idx, P.size - 1)[None, :]
+    norm = np.sqrt(P[ii] * P[jj] * P[np.minimum(s_idx, P.size - 1)])
+    ok &= norm > 1e-10
+    out = np.zeros(B.shape)
+    out[ok] = np.abs(B)[ok] / norm[ok]
+    return out, (f1, f2)
+
+
+# ------------------------------------------------------------------------------------------------
+# hilbert.rs
+# ------------------------------------------------------------------------------------------------
+
+def hilbert(x) -> np.ndarray:
+    """scirs2-signal hilbert.rs:58-150, as written: the spectrum comes from ``fft(x, None)`` (next power of two), its
+    first n bins are multiplied by h (1 at DC and Nyquist, -2i on the positive half, 0 on the negative half) and an
+    n-point inverse transform with 1/n follows.  (Not scirs2-fft's own ``hilbert``, which `consumers.py` mirrors.)"""
+    s = np.asarray(x, dtype=np.float64).reshape(-1)
+    n = s.size
+    if n == 0:
+        raise ValueError_("Input array is empty")
+    spec = fft(s, None)[:n]
+    h = np.ones(n, dtype=np.complex128)
+    half = n // 2 if n % 2 == 0 else (n + 1) // 2
+    h[1:half] = -2.0j
+    h[half + 1 if n % 2 == 0 else half:] = 0.0
+    return ifft(spec * h, n)
+
+
+def envelope(x) -> np.ndarray:
+    """hilbert.rs:180-196."""
+    return np.abs(hilbert(x))
+
+
+def _unwrap(phase: np.ndarray) -> np.ndarray:
+    """hilbert.rs:258-279: differences folded into [-pi, pi] by repeated +-2 pi, then re-accumulated."""
+    d = np.diff(phase)
+    d = np.where(d > np.pi, d - 2.0 * np.pi * np.ceil((d - np.pi) / (2.0 * np.pi)), d)    # while d > pi: d -= 2 pi
+    d = np.where(d < -np.pi, d + 2.0 * np.pi * np.ceil((-np.pi - d) / (2.0 * np.pi)), d)  # while d < -pi: d += 2 pi
+    return np.concatenate([[phase[0]], phase[0] + np.cumsum(d)])
+
+
+def instantaneous_phase(x, unwrap: bool = False) -> np.ndarray:
+    """hilbert.rs:322-366."""
+    a = hilbert(x)
+    ph = np.arctan2(a.imag, a.real)
+    return _unwrap(ph) if unwrap else ph
+
+
+def instantaneous_frequency(x, fs: float) -> np.ndarray:
+    """hilbert.rs:228-292: central differences of the unwrapped phase (one-sided at both ends)."""
+    if np.asarray(x).size == 0:
+        raise ValueError_("Input array is empty")
+    if fs <= 0.0:
+        raise ValueError_("Sampling frequency must be positive")
+    u = instantaneous_phase(x, True)
+    f = np.empty(u.size)
+    f[0] = fs * (u[1] - u[0]) / (2.0 * np.pi)
+    f[1:-1] = fs * (u[2:] - u[:-2]) / (4.0 * np.pi)
+    f[-1] = fs * (u[-1] - u[-2]) / (2.0 * np.pi)
+    return f
+
+
+# ------------------------------------------------------------------------------------------------
+# wvd.rs
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class WvdConfig:
+    """wvd.rs:18-44."""
+    analytic: bool = True
+    time_window: Optional[np.ndarray] = None
+    freq_window: Optional[np.ndarray] = None
+    zero_padding: bool = True
+    fs: float = 1.0
+
+
+def _wvd_signal(signal, analytic: bool) -> np.ndarray:
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    return hilbert(s) if analytic else s.astype(np.complex128)
+
+
+def compute_cross_wvd(s1: np.ndarray, s2: np.ndarray, config: WvdConfig) -> np.ndarray:
+    """wvd.rs:232-344: for every time t the lag product s1[t+tau] conj(s2[t-tau]) (windowed) is laid out around
+    n_fft/2 and transformed; all n transforms run as one batched device FFT.  Returns [n_fft/2+1, n]."""
+    n = s1.size
+    n_fft = 2 * n if config.zero_padding else n
+    tw = None
+    if config.time_window is not None:
+        w = np.asarray(config.time_window, dtype=np.float64).reshape(-1)
+        if w.size % 2 == 0:  # even length: a zero is inserted in the middle (wvd.rs:249-256)
+            half = w.size // 2
+            tw = np.zeros(w.size + 1)
+            tw[:half] = w[:half]
+            tw[half + 1:] = w[half:]
+        else:
+            tw = w.copy()
+    fw = None
+    if config.freq_window is not None:
+        w = np.asarray(config.freq_window, dtype=np.float64).reshape(-1)
+        if w.size < n_fft:
+            fw = np.zeros(n_fft)
+            off = (n_fft - w.size) // 2
+            fw[off:off + w.size] = w
+        elif w.size > n_fft:
+            off = (w.size - n_fft) // 2
+            fw = w[off:off + n_fft].copy()
+        else:
+            fw = w.copy()
+    whl = tw.size // 2 if tw is not None else n // 2
+    t = np.arange(n)[:, None]
+    tau = np.arange(-whl, whl + 1)[None, :]
+    valid = (tau >= -np.minimum(t, whl)) & (tau < np.minimum(n - t, whl + 1))
+    i1, i2 = t + tau, t - tau
+    valid &= (i1 >= 0) & (i1 < n) & (i2 >= 0) & (i2 < n)
+    idx = tau + n_fft // 2
+    valid &= (idx >= 0) & (idx < n_fft)
+    vals = s1[np.clip(i1, 0, n - 1)] * np.conj(s2[np.clip(i2, 0, n - 1)])
+    if tw is not None:
+        wi = tau + whl
+        vals = vals * np.where(wi < tw.size, tw[np.minimum(wi, tw.size - 1)], 0.0)
+    P = _next_pow2(max(n_fft, 1))
+    acorr = np.zeros((n, P), dtype=np.complex128)
+    rows = np.broadcast_to(t, valid.shape)[valid]
+    acorr[rows, np.broadcast_to(idx, valid.shape)[valid]] = vals[valid]
+    if fw is not None:
+        acorr[:, :n_fft] *= fw[None, :]
+    spec = fftn(acorr, None, [1]).reshape(n, P)
+    return spec[:, : n_fft // 2 + 1].T.copy()
+
+
+def wigner_ville(signal, config: Optional[WvdConfig] = None) -> np.ndarray:
+    """wvd.rs:79-90."""
+    cfg = config or WvdConfig()
+    a = _wvd_signal(signal, cfg.analytic)
+    return compute_cross_wvd(a, a, cfg).real.copy()
+
+
+def cross_wigner_ville(signal1, signal2, config: Optional[WvdConfig] = None) -> np.ndarray:
+    """wvd.rs:124-154."""
+    from .error import DimensionError
+
+    cfg = config or WvdConfig()
+    if np.asarray(signal1).size != np.asarray(signal2).size:
+        raise DimensionError("Signals must have the same length for cross-WVD")
+    return compute_cross_wvd(_wvd_signal(signal1, cfg.analytic), _wvd_signal(signal2, cfg.analytic), cfg)
+
+
+def smoothed_pseudo_wigner_ville(signal, time_window, freq_window, config: Optional[WvdConfig] = None) -> np.ndarray:
+    """wvd.rs:192-213."""
+    base = config or WvdConfig()
+    cfg = WvdConfig(base.analytic, np.asarray(time_window, dtype=np.float64), np.asarray(freq_window, dtype=np.float64),
+                    base.zero_padding, base.fs)
+    a = _wvd_signal(signal, cfg.analytic)
+    return compute_cross_wvd(a, a, cfg).real.copy()
+
+
+def frequency_axis(n_freqs: int, fs: float) -> np.ndarray:
+    """wvd.rs:353-355."""
+    return np.linspace(0.0, fs / 2.0, n_freqs)
+
+
+def time_axis(n_times: int, fs: float) -> np.ndarray:
+    """wvd.rs:367-370."""
+    return np.linspace(0.0, (n_times - 1.0) / fs, n_times)

@@ -108,6 +108,37 @@ def cases():
             ("dense", dict(f_min=300.0, f_max=1200.0, bins_per_octave=4, fs=8000.0, hop_size=100, use_sparse=False, q_factor=5.0,
                            window_scaling=1.5, window_type="bartlett"), 900, True)):
         add(f"cqt-{name}", lambda sg, so, a=(kw, n, len(name), inverse): cqt_case(sg, so, *a))
+
+    for n in (1000, 1024, 255, 2, 1):
+        x = _sig(max(n, 4), n + 20)[:n]
+        add(f"hilbert-{n}", lambda sg, so, x=x: ((sg.hilbert(x), sg.envelope(x)), (so.hilbert(x), np.abs(so.hilbert(x)))))
+    for n in (1000, 512):
+        x = _sig(n, n + 21)
+        add(f"instphase-{n}", lambda sg, so, x=x: ((sg.instantaneous_phase(x), sg.instantaneous_phase(x, True), sg.instantaneous_frequency(x, 100.0)),
+                                                   (so.instantaneous_phase(x), so.instantaneous_phase(x, True), so.instantaneous_frequency(x, 100.0))))
+    hann = lambda m: 0.5 * (1.0 - np.cos(2.0 * np.pi * np.arange(m) / (m - 1)))
+    for name, n, kw in (("plain", 64, dict()), ("nopad-raw", 50, dict(analytic=False, zero_padding=False)),
+                        ("sp-odd", 48, dict(zero_padding=False, time_window=hann(11), freq_window=hann(31))),
+                        ("sp-even", 40, dict(time_window=hann(12), freq_window=hann(100))),
+                        ("long-window", 33, dict(time_window=hann(81), freq_window=hann(200), zero_padding=False))):
+        x = _sig(n, n + 22)
+        add(f"wvd-{name}", lambda sg, so, x=x, kw=kw: (
+            (sg.wigner_ville(x, sg.WvdConfig(**kw)),),
+            (so.wigner_ville(x, kw.get("analytic", True), kw.get("zero_padding", True), kw.get("time_window"), kw.get("freq_window")),)))
+    x, y = _sig(40, 1), _sig(40, 2)
+    add("wvd-cross", lambda sg, so, x=x, y=y: ((sg.cross_wigner_ville(x, y, sg.WvdConfig(zero_padding=False)),),
+                                     (so.cross_wvd(so.hilbert(x), so.hilbert(y), False),)))
+    add("wvd-spwv", lambda sg, so, x=x: ((sg.smoothed_pseudo_wigner_ville(x, hann(9), hann(21), sg.WvdConfig(zero_padding=False)),),
+                                    (so.wigner_ville(x, True, False, hann(9), hann(21)),)))
+    for n, nfft, win in ((90, 32, "hann"), (200, 64, None), (61, 100, "hamming")):
+        x = _sig(n, n + 23) ** 2
+        add(f"bispec-indirect-{n}", lambda sg, so, x=x, nfft=nfft, win=win: (
+            (sg.compute_bispectrum(x, sg.HigherOrderConfig(estimator="indirect", nfft=nfft, window=win))[0],
+             sg.compute_triple_correlation(x, 9)),
+            (so.indirect_bispectrum(x, nfft, win), so.triple_correlation(x, 9))))
+    for n, nfft, win, fs in ((300, 64, None, 1.0), (500, 50, "hann", 8.0), (256, 33, "hamming", 2.0)):
+        x = _sig(n, n + 24) ** 2
+        add(f"bicoherence-{n}", lambda sg, so, x=x, a=(nfft, win, None, fs): ((sg.bicoherence(x, *a)[0],), (so.bicoherence(x, *a),)))
     return out
 
 

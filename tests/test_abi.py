@@ -89,7 +89,9 @@ def test_no_cpu_fallback(lib):
                  lambda: sb.signal.stft(np.arange(64.0), nperseg=16), lambda: sb.signal.wiener_filter(np.arange(32.0)),
                  lambda: sb.signal.spectral_subtraction(np.arange(128.0)), lambda: sb.signal.psd_wiener_filter(np.arange(32.0)),
                  lambda: sb.signal.StreamingStft(sb.signal.StreamingStftConfig(16, 8)).process_frame(np.ones(32)),
-                 lambda: sb.signal.bispectrum(np.arange(64.0), 16)):
+                 lambda: sb.signal.bispectrum(np.arange(64.0), 16), lambda: sb.signal.hilbert(np.arange(16.0)),
+                 lambda: sb.signal.wigner_ville(np.arange(16.0)), lambda: sb.signal.constant_q_transform(np.arange(64.0), sb.signal.CqtConfig(f_min=200.0, f_max=400.0, fs=2000.0)),
+                 lambda: sb.signal.bicoherence(np.arange(64.0), 16)):
         with pytest.raises(sb.BackendError) as e:
             call()
         assert "no CPU fallback" in str(e.value)

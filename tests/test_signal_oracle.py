@@ -92,6 +92,25 @@ def test_reference_cqt_unit_tests():
     assert ch.shape == (12, 1) and ch[9, 0] > 0.1 and abs(ch[:, 0].sum() - 1.0) < 1e-6
 
 
+def test_reference_hilbert_and_wvd_unit_tests():
+    # hilbert.rs test_hilbert_transform: |analytic| of a 5 Hz cosine (n = 1000, fs = 100) is 1 within 0.1 in the middle half
+    x = np.cos(2 * np.pi * 5.0 * np.arange(1000) / 100.0)
+    a = so.hilbert(x)
+    assert np.all(np.abs(np.abs(a[250:750]) - 1.0) < 0.1)
+    # power-of-two length: the quirks vanish and the result is -i times (scipy's analytic signal minus DC / Nyquist terms);
+    # checked through the magnitude of a bin-centred tone
+    y = np.cos(2 * np.pi * 8 * np.arange(256) / 256.0)
+    assert np.allclose(np.abs(so.hilbert(y)), 1.0, atol=1e-12)
+    # wvd.rs test_wigner_ville_chirp / test_cross_wigner_ville: shapes, finite values, positive energy
+    n = 64
+    t = np.arange(n) / 64.0
+    chirp = np.sin(2 * np.pi * (5.0 + 10.0 * t) * t)
+    w = so.wigner_ville(chirp)
+    assert w.shape == (n + 1, n) and np.all(np.isfinite(w))
+    xw = so.cross_wvd(so.hilbert(chirp), so.hilbert(chirp[::-1].copy()), False)
+    assert xw.shape == (n // 2 + 1, n) and np.all(np.isfinite(xw)) and np.sum(np.abs(xw)) > 0.0
+
+
 @pytest.fixture()
 def host_signal(monkeypatch):
     """scirs_b200.signal with its device transforms swapped for the oracle's (host-logic check only)."""
