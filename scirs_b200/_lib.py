@@ -36,6 +36,7 @@ SFC_DESC_DCT2 = 32
 SFC_DESC_DCT2_ORTHO0 = 64
 SFC_DESC_DCT3 = 128
 SFC_DESC_TRIG_SINE = 256
+SFC_DESC_DCT4 = 512
 
 
 class sfc_desc(C.Structure):

@@ -648,6 +648,12 @@ enum TileMode : int {
     // the inverse packing: V[k] = conj(w_k)(X[k] - i X[N-k]) -> c2r pre-twiddle -> half-length transform -> scatter:
     // y[i] = scale * 2 * (scale_dc * X[0] / 2 + sum_{k>=1} X[k] cos(pi k (i + 1/2) / N))   (dct.rs:563-684)
     TM_FAST_DCT3 = 6,
+    // DCT-IV / DST-IV of N = 2L reals through ONE L-point complex transform (dct.rs:688-720, dst.rs:630-667):
+    //   z[j] = (x[2j] + i x[N-1-2j]) exp(-i pi (4j+1) / (4N)),  Z = FFT_L(z),  y[k] = Z[k] exp(-i pi k / N),
+    //   X[2k] = Re y[k],  X[N-1-2k] = -Im y[k];  the sine transform is the cosine transform of the reversed input with
+    //   (-1)^k on the output.  NOT YET RUN ON A GPU (written after the round's GPU budget was spent): the planner only
+    //   takes it with SFC_DCT4_FUSED=1, and tests/test_gpu_experimental.py is the parity check to run first.
+    TM_FAST_DCT4 = 7,
 };
 
 // ---- TMA / mbarrier primitives (PTX) -----------------------------------------------------------
@@ -898,6 +904,20 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
                 c2r_pretwiddle<T, C>(a, row, reinterpret_cast<const cx*>(p.rtw), i0);
                 staged = true;
             }
+        } else if constexpr (MODE == TM_FAST_DCT4) {
+            if constexpr (E == 16) {
+                constexpr int N = 2 * L;
+                const T* __restrict__ xr = reinterpret_cast<const T*>(p.in.ptr) + off;
+                const int64_t es = p.in.elem_stride;
+                const cx* __restrict__ pre = reinterpret_cast<const cx*>(p.aux_in);  // exp(-i pi (4j+1) / (4N)), j < L
+                const bool sine = (p.flags & F_TRIG_SINE) != 0;
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const int j = i0 + m * TPL;
+                    const T ev = xr[(2 * j) * es], od = xr[(N - 1 - 2 * j) * es];
+                    a[m] = cmul(sine ? cx{od, ev} : cx{ev, od}, pre[j]);
+                }
+            }
         } else if constexpr (PIPE) {
             // the tile was landed in shared memory by the TMA unit while the previous one was transformed
             mbar_wait(bar, parity);
@@ -1114,7 +1134,23 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
         for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
     }
 
-    if constexpr (MODE == TM_FAST_DCT2) {
+    if constexpr (MODE == TM_FAST_DCT4) {
+        if constexpr (E == 16) {
+            constexpr int N = 2 * L;
+            T* __restrict__ dst = reinterpret_cast<T*>(p.out.ptr) + off;
+            const int64_t oes = p.out.elem_stride;
+            const cx* __restrict__ post = reinterpret_cast<const cx*>(p.aux_out);  // exp(-i pi k / N), k < L
+            const T so = (p.flags & F_TRIG_SINE) ? scale : -scale;  // odd outputs: -Im y (cosine), +Im y (sine: (-1)^(N-1-2k) = -1)
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int k = i1 + m * TPL;
+                const cx y = cmul(a[m], post[k]);
+                dst[(2 * k) * oes] = y.x * scale;
+                dst[(N - 1 - 2 * k) * oes] = y.y * so;
+            }
+        }
+        return;
+    } else if constexpr (MODE == TM_FAST_DCT2) {
         if constexpr (E == 16) {
             // a[m] = Z[i1 + m*TPL] of the packed half-length transform -> V[k], V[L-k] of the real transform as in
             // the r2c post-pass, then four real outputs per pair

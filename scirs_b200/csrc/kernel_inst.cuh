@@ -78,4 +78,6 @@ struct KernelInst {
 #define SFC_ADD_DCT2(T, L, TL)                               \
     add(::sfc::KernelInst<T, L, TL, false, 16, 5>::entry()); \
     add(::sfc::KernelInst<T, L, TL, false, 16, 6>::entry());
+// fused DCT-IV / DST-IV rows (one half-length complex transform, twiddles on load and store)
+#define SFC_ADD_DCT4(T, L, TL) add(::sfc::KernelInst<T, L, TL, false, 16, 7>::entry());
 #define SFC_ADD_E(T, L, TL, DBL, E) add(::sfc::KernelInst<T, L, TL, DBL, E>::entry());

@@ -13,5 +13,14 @@ void register_kernels_dct(void (*add)(const KernelEntry&)) {
     SFC_ADD_DCT2(double, 1024, 2)
     SFC_ADD_DCT2(double, 4096, 1)
     SFC_ADD_DCT2(double, 8192, 1)
+    // TM_FAST_DCT4 (experimental, SFC_DCT4_FUSED=1): rows only, 32 KiB tiles where they exist
+    SFC_ADD_DCT4(double, 64, 32)
+    SFC_ADD_DCT4(double, 128, 16)
+    SFC_ADD_DCT4(double, 256, 8)
+    SFC_ADD_DCT4(double, 512, 4)
+    SFC_ADD_DCT4(double, 1024, 2)
+    SFC_ADD_DCT4(double, 2048, 1)
+    SFC_ADD_DCT4(double, 4096, 1)
+    SFC_ADD_DCT4(double, 8192, 1)
 }
 }  // namespace sfc

@@ -172,7 +172,7 @@ static std::map<TableKey, const void*>& tables() {
     static std::map<TableKey, const void*> m;
     return m;
 }
-enum TableKind { TK_STAGE = 1, TK_RTW, TK_FS_LO, TK_FS_HI, TK_CHIRP, TK_BLUE, TK_CR_LO, TK_CR_HI, TK_DCT2 };
+enum TableKind { TK_STAGE = 1, TK_RTW, TK_FS_LO, TK_FS_HI, TK_CHIRP, TK_BLUE, TK_CR_LO, TK_CR_HI, TK_DCT2, TK_DCT4_PRE, TK_DCT4_POST };
 
 static inline void unit_root(long double num, long double den, long double& c, long double& s) {
     // exp(-2*pi*i*num/den) in extended precision
@@ -230,6 +230,19 @@ static const void* roots_table(int kind, int prec, int64_t count, long double de
     if (it != tables().end()) return it->second;
     std::vector<long double> re(count), im(count);
     for (int64_t j = 0; j < count; ++j) unit_root((long double)j * mult, den, re[j], im[j]);
+    const void* d = upload_table(re, im, prec, err);
+    if (d) tables()[key] = d;
+    return d;
+}
+
+// DCT-IV load twiddles exp(-i pi (4j+1) / (4N)), j < N/2
+static const void* table_dct4_pre(int prec, int64_t N, PlanError& err) {
+    std::lock_guard<std::recursive_mutex> lk(g_table_mu);
+    TableKey key{cur_device(), TK_DCT4_PRE, prec, N, N / 2, 0, 0};
+    auto it = tables().find(key);
+    if (it != tables().end()) return it->second;
+    std::vector<long double> re(N / 2), im(N / 2);
+    for (int64_t j = 0; j < N / 2; ++j) unit_root((long double)(4 * j + 1), 8.0L * (long double)N, re[j], im[j]);
     const void* d = upload_table(re, im, prec, err);
     if (d) tables()[key] = d;
     return d;
@@ -1331,6 +1344,48 @@ struct PlanBuilder {
         return true;
     }
 
+    // DCT-IV / DST-IV of contiguous rows of n reals in one kernel (TM_FAST_DCT4); experimental, see fft_tile.cuh
+    bool add_dct4(int64_t n, int64_t O, ArrayRef src, ArrayRef dst, double scale, bool sine) {
+        Step s;
+        const int L = (int)(n / 2);
+        int cnt = 0;
+        const KernelEntry* t = kernel_table(&cnt);
+        s.k = nullptr;
+        for (int i = 0; i < cnt; ++i)
+            if (t[i].prec == prec && t[i].L == L && t[i].mode == 7 && (!s.k || t[i].TL < s.k->TL)) s.k = &t[i];
+        if (!s.k || O % s.k->TL != 0 || O > 0xFFFFFFFFLL)
+            return fail(SFC_ERR_NOT_IMPLEMENTED, "no fused DCT-IV kernel for this length / batch");
+        s.src = src.role;
+        s.dst = dst.role;
+        s.src_esize = rs;
+        s.dst_esize = rs;
+        set_io(s.p.in, 0, n, 1, 1, n, 1, 0);
+        set_io(s.p.out, 0, n, 1, 1, n, 1, 0);
+        s.p.map_in = s.p.map_out = MAP_ROW;
+        s.p.ld_op = LD_C;
+        s.p.st_op = ST_C;
+        s.p.flags = F_IN_NOMASK | F_OUT_NOMASK | (sine ? F_TRIG_SINE : 0);
+        s.p.scale = scale;
+        s.p.aux_in = table_dct4_pre(prec, n, err);
+        if (!s.p.aux_in) return false;
+        s.p.aux_out = roots_table(TK_DCT4_POST, prec, L, 2.0L * (long double)n, 1.0L, n, err);  // exp(-i pi k / n), k < n/2
+        if (!s.p.aux_out) return false;
+        s.p.peer_shift = -1;
+        s.p.tw = table_stage_tw(prec, L, err);
+        if (!s.p.tw) return false;
+        s.p.nlanes = (uint32_t)O;
+        s.p.inner_count = 1;
+        s.p.tiles_per_batch = (uint32_t)(O / s.k->TL);
+        s.nbatch = 1;
+        dev_bytes += O * n * 2 * (int64_t)rs;
+        char buf[200];
+        snprintf(buf, sizeof buf, "fused %s-IV rows (half-length complex transform): tile L=%d TL=%d threads=%d smem=%zu lanes=%lld",
+                 sine ? "DST" : "DCT", s.k->L, s.k->TL, s.k->threads, s.k->smem, (long long)O);
+        s.desc = buf;
+        pl.steps_.push_back(s);
+        return true;
+    }
+
     // rows of src.n (<= n/2+1 used) complex -> rows of n reals (rfft.rs:92-178)
     bool add_c2r(int64_t n, int64_t O, ArrayRef src, ArrayRef dst, double scale) {
         Step s;
@@ -1480,6 +1535,24 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
             return nullptr;
         }
         const int la = axes.back();
+        if (d.flags & SFC_DESC_DCT4) {
+            const int64_t n = shape[la];
+            if (axes.size() != 1 || la != (int)shape.size() - 1 || !is_pow2(n) || n < 128 || n / 2 > lmax_for(prec) || prec != PREC_F64) {
+                err = {SFC_ERR_NOT_IMPLEMENTED, "fused DCT-IV needs the last axis, f64, a power-of-two length in 128..16384"};
+                return nullptr;
+            }
+            pl.in_elems = pl.out_elems = total;
+            pl.in_esize = pl.out_esize = rs;
+            if (!B.add_dct4(n, prod(shape, 0, la), {R_IN, true, n}, {R_OUT, true, n}, d.scale, (d.flags & SFC_DESC_TRIG_SINE) != 0))
+                return nullptr;
+            pl.info.in_bytes = pl.info.out_bytes = total * (int64_t)rs;
+            pl.info.algorithmic_bytes = 2 * total * (int64_t)rs;
+            pl.info.device_bytes = B.dev_bytes;
+            pl.info.num_passes = 1;
+            pl.info.num_launches = 1;
+            pl.info.nominal_flops = 2.5 * (double)total * std::log2((double)n);
+            return sp;
+        }
         if (d.flags & (SFC_DESC_DCT2 | SFC_DESC_DCT3)) {
             const int64_t n = shape[la];
             if (axes.size() != 1 || !is_pow2(n) || n < 128 || n / 2 > lmax_for(prec) || prec != PREC_F64) {

@@ -147,3 +147,38 @@ def test_oracle_against_extended_precision_golden_vectors():
         assert _rel(co.hfft(z, m), GC[f"hfft_{n}_n{m}"]) < 1e-13
         assert _rel(co.ihfft(x, m), GC[f"ihfft_{n}_n{m}"]) < 1e-13
         assert _rel(co.hilbert(x), GC[f"hilbert_{n}"]) < 1e-13
+
+
+def test_dct4_half_length_formulation():
+    """The arithmetic of the fused type-IV kernel (TM_FAST_DCT4 in fft_tile.cuh; experimental, SFC_DCT4_FUSED=1), emulated
+    with numpy exactly as the kernel indexes it, against the literal sums: tables pre[j] = exp(-i pi (4j+1)/(4N)),
+    post[k] = exp(-i pi k / N); load z[j] = (x[2j], x[N-1-2j]) (swapped for the sine transform) * pre[j]; store
+    X[2k] = Re(y) * scale, X[N-1-2k] = -/+ Im(y) * scale; scales as in api_ext.cu trig_axis."""
+    rng = np.random.default_rng(12)
+    for n in (8, 128, 1024):
+        L = n // 2
+        j = np.arange(L)
+        pre = np.exp(-1j * np.pi * (4 * j + 1) / (4 * n))
+        post = np.exp(-1j * np.pi * j / n)
+        x = rng.standard_normal(n)
+
+        def kernel(v, sine, scale):
+            ev, od = v[2 * j], v[n - 1 - 2 * j]
+            z = ((od + 1j * ev) if sine else (ev + 1j * od)) * pre
+            y = np.fft.fft(z) * post
+            out = np.empty(n)
+            out[2 * j] = y.real * scale
+            out[n - 1 - 2 * j] = y.imag * (scale if sine else -scale)
+            return out
+
+        for ortho in (False, True):
+            norm = "ortho" if ortho else None
+            nn = float(n)
+            sc = {("c", False): np.sqrt(2 / nn) if ortho else 1.0,
+                  ("c", True): np.sqrt(nn / 2) * np.sqrt(2 / nn) if ortho else 2 / nn,
+                  ("s", False): np.sqrt(2 / nn) if ortho else 2.0,
+                  ("s", True): 2 * np.sqrt(nn / 2) if ortho else 1.0}
+            assert np.allclose(kernel(x, False, sc[("c", False)]), co.dct(x, 4, norm), rtol=0, atol=1e-12 * n)
+            assert np.allclose(kernel(x, False, sc[("c", True)]), co.idct(x, 4, norm), rtol=0, atol=1e-12 * n)
+            assert np.allclose(kernel(x, True, sc[("s", False)]), co.dst(x, 4, norm), rtol=0, atol=1e-12 * n)
+            assert np.allclose(kernel(x, True, sc[("s", True)]), co.idst(x, 4, norm), rtol=0, atol=1e-12 * n)

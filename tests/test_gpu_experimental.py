@@ -1,0 +1,42 @@
+"""GPU parity checks for code paths that were written after a round's GPU budget was spent and are therefore OFF by default.
+Skipped unless SFC_TEST_EXPERIMENTAL=1; each case runs in its own process because the knobs are read once per process.
+
+  SFC_DCT4_FUSED=1   TM_FAST_DCT4: DCT-IV / DST-IV rows in one kernel on the n/2-point complex transform (fft_tile.cuh)
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SFC_TEST_EXPERIMENTAL") != "1", reason="experimental paths: set SFC_TEST_EXPERIMENTAL=1")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+DCT4 = r'''
+import numpy as np, sys
+sys.path.insert(0, %r)
+import scirs_b200 as sb
+from oracle import consumers_oracle as co
+rng = np.random.default_rng(4)
+worst = 0.0
+for n in (128, 256, 1024, 4096, 8192, 16384):
+    for rows in (1, 64, 96):
+        x = rng.standard_normal((rows, n))
+        for norm in (None, "ortho"):
+            for name, fn, ofn in (("dct", sb.dctn, co.dctn), ("idct", sb.idctn, co.idctn), ("dst", sb.dstn, co.dstn), ("idst", sb.idstn, co.idstn)):
+                got = fn(x, 4, norm, [1])
+                ref = ofn(x[: min(rows, 4)], 4, norm, [1]) if n > 4096 else ofn(x, 4, norm, [1])
+                g = got[: ref.shape[0]]
+                e = np.linalg.norm(g - ref) / np.linalg.norm(ref)
+                worst = max(worst, e)
+                assert e <= (1e-12 if n <= 4096 else 3e-12), (name, n, rows, norm, e)
+print("dct4 fused parity ok, worst rel-L2", worst)
+''' % ROOT
+
+
+def test_dct4_fused_kernel(build_artifacts):
+    env = dict(os.environ, SFC_DCT4_FUSED="1")
+    r = subprocess.run([sys.executable, "-c", DCT4], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "parity ok" in r.stdout
