@@ -98,7 +98,7 @@ typedef struct sfc_desc {
     /* C2C over ONE axis, with SFC_DESC_AXIS_LEN: the input array holds axis_in_len elements along that
      * axis (zero-padded / cropped to shape[axis] on load) and the output array axis_out_len (cropped on
      * store); 0 = shape[axis].  What the reference does with `x.resize(n)` / `[..n]` slices around its
-     * transforms (dct.rs, hfft/*.rs, spectrogram.rs:287-300) without the extra copies. */
+     * transforms (dct.rs, the hfft module, spectrogram.rs:287-300) without the extra copies. */
     int64_t axis_in_len, axis_out_len;
     /* with SFC_DESC_AUX_MUL: device tables (complex, plan precision) multiplied into the data on the way
      * in (aux_in[j], j = input index along the axis, axis_in_len entries) and on the way out
