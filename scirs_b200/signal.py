@@ -25,6 +25,7 @@ from __future__ import annotations
 
 from collections import deque
 from dataclasses import dataclass
+from itertools import islice
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -466,7 +467,7 @@ class StreamingStft:
         L = self.config.frame_length
         if len(self._buf) < L:
             return None
-        frame = np.fromiter((self._buf[i] for i in range(L)), dtype=np.float64, count=L) * self.window
+        frame = np.fromiter(islice(self._buf, L), dtype=np.float64, count=L) * self.window
         for _ in range(min(self.config.hop_length, len(self._buf))):
             self._buf.popleft()
         self.frames_generated += 1
@@ -543,7 +544,7 @@ class StreamingStft:
         while len(self._buf) >= hop:
             frame = np.zeros(L)
             avail = min(len(self._buf), L)
-            frame[:avail] = [self._buf[i] for i in range(avail)]
+            frame[:avail] = list(islice(self._buf, avail))
             frames.append(frame * self.window)
             for _ in range(min(hop, len(self._buf))):
                 self._buf.popleft()
