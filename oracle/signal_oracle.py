@@ -729,3 +729,80 @@ def wigner_ville(signal, analytic=True, zero_padding=True, time_window=None, fre
     # wvd.rs:79-90, 192-229
     a = hilbert(signal) if analytic else np.asarray(signal, dtype=np.float64).astype(np.complex128)
     return cross_wvd(a, a, zero_padding, time_window, freq_window).real
+
+
+# ---- higher_order.rs: the remaining estimators ----------------------------------------------------
+
+def _wfft(signal, nfft, window):
+    s = np.asarray(signal, dtype=np.float64)
+    if window is not None:
+        s = s * np.array(signal_window(window, s.size, True))
+    return base.fft(s, nfft)
+
+
+def trispectrum(signal, nfft, window=None) -> np.ndarray:  # higher_order.rs:638-684
+    X = _wfft(signal, nfft, window)
+    nb = nfft // 2 + 1
+    out = np.zeros((nb, nb))
+    for i in range(nb):
+        for j in range(nb):
+            out[i, j] = abs(X[i] * X[j] * np.conj(X[i]) * np.conj(X[j]))
+    return out
+
+
+def biamplitude(signal, nfft, window=None) -> np.ndarray:  # higher_order.rs:698-745
+    X = _wfft(signal, nfft, window)
+    nb = nfft // 2 + 1
+    out = np.zeros((nb, nb))
+    for i in range(nb):
+        for j in range(nb):
+            k = (i + j) % nfft
+            if k < nb:
+                out[i, j] = abs(X[i]) * abs(X[j]) * abs(X[k])
+    return out
+
+
+def cumulative_bispectrum(signal, nfft, window=None):  # higher_order.rs:762-804
+    mag = np.abs(welch_bispectrum(signal, nfft, window))
+    nb = mag.shape[0]
+    bandwidth = np.linspace(1.0, float(nb // 2), 10)
+    out = np.zeros(10)
+    for i, bw in enumerate(bandwidth):
+        b = _round(bw)
+        if b > 0:
+            tot, cnt = 0.0, 0
+            for i1 in range(min(b, nb)):
+                for i2 in range(min(b, nb)):
+                    tot += mag[i1, i2]
+                    cnt += 1
+            if cnt > 0:
+                out[i] = tot / cnt
+    return out, bandwidth
+
+
+def skewness_spectrum(signal, nfft, window=None) -> np.ndarray:  # higher_order.rs:818-852
+    B = welch_bispectrum(signal, nfft, window)
+    P = power_spectrum(signal, nfft, window)
+    nb = nfft // 2 + 1
+    out = np.zeros(nb)
+    for i in range(nb):
+        if P[i] > 1e-10:
+            out[i] = abs(B[i, i]) / P[i] ** 1.5
+    return out
+
+
+def detect_phase_coupling(signal, nfft, window=None, fs=1.0, threshold=None):  # higher_order.rs:868-912
+    thresh = 0.5 if threshold is None else threshold
+    b = bicoherence(signal, nfft, window, None, fs)
+    axis = np.linspace(0.0, fs / 2.0, nfft // 2 + 1)
+    peaks = []
+    for i in range(1, b.shape[0] - 1):
+        for j in range(1, b.shape[1] - 1):
+            v = b[i, j]
+            if v > thresh:
+                nbrs = [b[i - 1, j], b[i + 1, j], b[i, j - 1], b[i, j + 1], b[i - 1, j - 1], b[i + 1, j + 1],
+                        b[i - 1, j + 1], b[i + 1, j - 1]]
+                if all(v >= q for q in nbrs):
+                    peaks.append((axis[i], axis[j], v))
+    peaks.sort(key=lambda p: -p[2])
+    return peaks

@@ -967,6 +967,75 @@ def bicoherence(signal, nfft: int, window: Optional[str] = None, n_segments: Opt
     return out, (f1, f2)
 
 
+def _windowed_fft(signal, nfft: int, window: Optional[str]) -> np.ndarray:
+    """``apply_window`` + ``compute_fft`` (higher_order.rs:433-461)."""
+    s = np.asarray(signal, dtype=np.float64).reshape(-1)
+    if window is not None:
+        s = s * signal_window(window, s.size, True)
+    return fft(s, nfft)
+
+
+def trispectrum(signal, nfft: int, window: Optional[str] = None, fs: float = 1.0) -> np.ndarray:
+    """higher_order.rs:638-684: the slice |X(f1) X(f2) X*(f1) X*(f2)|."""
+    X = _windowed_fft(signal, nfft, window)[: nfft // 2 + 1]
+    return np.abs((X[:, None] * X[None, :]) * np.conj(X)[:, None] * np.conj(X)[None, :])
+
+
+def biamplitude(signal, nfft: int, window: Optional[str] = None, fs: float = 1.0
+                ) -> Tuple[np.ndarray, Tuple[np.ndarray, np.ndarray]]:
+    """higher_order.rs:698-745: |X(f1)| |X(f2)| |X(f1+f2)| where f1+f2 stays below Nyquist."""
+    X = _windowed_fft(signal, nfft, window)
+    nb = nfft // 2 + 1
+    mag = np.abs(X)
+    i = np.arange(nb)
+    k = (i[:, None] + i[None, :]) % nfft
+    out = np.where(k < nb, mag[:nb, None] * mag[None, :nb] * mag[np.minimum(k, nfft - 1)], 0.0)
+    axis = np.linspace(0.0, fs / 2.0, nb)
+    return out, (axis, axis.copy())
+
+
+def cumulative_bispectrum(signal, nfft: int, window: Optional[str] = None, fs: float = 1.0
+                          ) -> Tuple[np.ndarray, np.ndarray]:
+    """higher_order.rs:762-804: mean bispectrum magnitude over the leading bw x bw squares, ten bandwidths."""
+    mag, _, _ = bispectrum(signal, nfft, window, None, fs)
+    nb = mag.shape[0]
+    bandwidth = np.linspace(1.0, float(nb // 2), 10)
+    out = np.zeros(10)
+    for i, bw in enumerate(_round_half_away(bandwidth)):
+        m = int(min(bw, nb))
+        if bw > 0 and m > 0:
+            out[i] = mag[:m, :m].sum() / (m * m)
+    return out, bandwidth
+
+
+def skewness_spectrum(signal, nfft: int, window: Optional[str] = None, fs: float = 1.0) -> Tuple[np.ndarray, np.ndarray]:
+    """higher_order.rs:818-852: |B(f, f)| / P(f)^1.5."""
+    cfg = HigherOrderConfig(fs=fs, nfft=nfft, window=window)
+    B, f1, _ = compute_bispectrum(signal, cfg)
+    P, _ = compute_power_spectrum(signal, cfg)
+    nb = nfft // 2 + 1
+    d = np.abs(np.diagonal(B))[:nb]
+    ok = P[:nb] > 1e-10
+    out = np.zeros(nb)
+    out[ok] = d[ok] / P[:nb][ok] ** 1.5
+    return out, f1
+
+
+def detect_phase_coupling(signal, nfft: int, window: Optional[str] = None, fs: float = 1.0,
+                          threshold: Optional[float] = None) -> List[Tuple[float, float, float]]:
+    """higher_order.rs:868-912: local maxima (8 neighbours) of the bicoherence above ``threshold``, strongest first."""
+    thresh = 0.5 if threshold is None else threshold
+    b, (f1, f2) = bicoherence(signal, nfft, window, None, fs)
+    peaks = []
+    for i in range(1, b.shape[0] - 1):
+        for j in range(1, b.shape[1] - 1):
+            v = b[i, j]
+            if v > thresh and v >= b[i - 1:i + 2, j - 1:j + 2].max():
+                peaks.append((float(f1[i]), float(f2[j]), float(v)))
+    peaks.sort(key=lambda p: -p[2])  # stable, like the reference's sort_by
+    return peaks
+
+
 # ------------------------------------------------------------------------------------------------
 # hilbert.rs
 # ------------------------------------------------------------------------------------------------

@@ -139,6 +139,14 @@ def cases():
     for n, nfft, win, fs in ((300, 64, None, 1.0), (500, 50, "hann", 8.0), (256, 33, "hamming", 2.0)):
         x = _sig(n, n + 24) ** 2
         add(f"bicoherence-{n}", lambda sg, so, x=x, a=(nfft, win, None, fs): ((sg.bicoherence(x, *a)[0],), (so.bicoherence(x, *a),)))
+
+    for n, nfft, win in ((300, 64, "hann"), (200, 50, None)):
+        x = _sig(n, n + 25) ** 2
+        add(f"higher-order-rest-{n}", lambda sg, so, x=x, nfft=nfft, win=win: (
+            (sg.trispectrum(x, nfft, win), sg.biamplitude(x, nfft, win)[0], sg.cumulative_bispectrum(x, nfft, win)[0],
+             sg.cumulative_bispectrum(x, nfft, win)[1], sg.skewness_spectrum(x, nfft, win)[0]),
+            (so.trispectrum(x, nfft, win), so.biamplitude(x, nfft, win), so.cumulative_bispectrum(x, nfft, win)[0],
+             so.cumulative_bispectrum(x, nfft, win)[1], so.skewness_spectrum(x, nfft, win))))
     return out
 
 

@@ -180,3 +180,21 @@ def test_host_errors_and_bookkeeping(host_signal):
     assert len(rt.get_all_spectra()) == 2 and rt.get_spectrum() is None
     rt.reset()
     assert rt.get_statistics().base_statistics.samples_processed == 0
+
+
+def test_phase_coupling_peaks(host_signal):
+    """higher_order.rs:868-912 — discrete output (peak list), so it is compared on the CPU only: quadratic phase coupling
+    between 12 and 20 cycles per 128 samples shows up as a bicoherence peak at that bin pair."""
+    sg = host_signal
+    t = np.arange(1024)
+    x = (np.cos(2 * np.pi * 12 * t / 128 + 0.4) + np.cos(2 * np.pi * 20 * t / 128 + 1.1)
+         + np.cos(2 * np.pi * 32 * t / 128 + 1.5) + 0.05 * np.random.default_rng(3).standard_normal(1024))
+    got = sg.detect_phase_coupling(x, 128, "hann", 1.0, 0.3)
+    ref = so.detect_phase_coupling(x, 128, "hann", 1.0, 0.3)
+    assert len(got) > 0 and abs(len(got) - len(ref)) <= 4  # weak noise peaks can tie differently at rounding level
+    # the strongest peaks are unambiguous: same places (a symmetric pair may swap order), same values
+    assert {(p[0], p[1]) for p in got[:4]} == {(p[0], p[1]) for p in ref[:4]}
+    for a, b in zip(got[:4], ref[:4]):
+        assert abs(a[2] - b[2]) <= 1e-9 * abs(b[2])
+    top = sorted((round(got[0][0] * 128), round(got[0][1] * 128)))
+    assert abs(top[0] - 12) <= 1 and abs(top[1] - 20) <= 1
