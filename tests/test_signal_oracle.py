@@ -198,3 +198,29 @@ def test_phase_coupling_peaks(host_signal):
         assert abs(a[2] - b[2]) <= 1e-9 * abs(b[2])
     top = sorted((round(got[0][0] * 128), round(got[0][1] * 128)))
     assert abs(top[0] - 12) <= 1 and abs(top[1] - 20) <= 1
+
+
+def test_spectral_host_logic_random_parameters(host_signal):
+    """Seeded sweep over odd / tiny / mismatched parameters of the spectral callers (argument handling, segment
+    counts, padding, axis construction) against the literal loops."""
+    sg = host_signal
+    rng = np.random.default_rng(77)
+    wins = ["hann", "hamming", "blackman", "boxcar"]
+    dets = ["constant", "linear", "none"]
+    for _ in range(120):
+        n = int(rng.integers(8, 400))
+        x = rng.standard_normal(n) + 0.01 * np.arange(n)
+        nperseg = int(rng.integers(2, min(n, 96) + 1))
+        noverlap = int(rng.integers(0, nperseg))
+        nfft = nperseg + int(rng.integers(0, 40)) if rng.random() < 0.5 else None
+        fs = float(rng.choice([1.0, 7.5, 100.0]))
+        w, d = str(rng.choice(wins)), str(rng.choice(dets))
+        sc_ = str(rng.choice(["density", "spectrum"]))
+        if nperseg < 3 and w != "boxcar":
+            w = "boxcar"  # the reference's symmetric windows divide by nperseg - 1
+        sc.compare(sg.welch(x, fs, w, nperseg, noverlap, nfft, d, sc_), so.welch(x, fs, w, nperseg, noverlap, nfft, d, sc_), 1e-10)
+        b = str(rng.choice(["zeros", "extend", "none"]))
+        pad = bool(rng.integers(0, 2))
+        sc.compare(sg.stft(x, fs, w, nperseg, noverlap, nfft, d, b, pad), so.stft(x, fs, w, nperseg, noverlap, nfft, d, b, pad), 1e-10)
+        pn = n + int(rng.integers(0, 30)) if rng.random() < 0.5 else None
+        sc.compare(sg.periodogram(x, fs, w if n > 2 else "boxcar", pn, d, sc_), so.periodogram(x, fs, w if n > 2 else "boxcar", pn, d, sc_), 1e-10)
