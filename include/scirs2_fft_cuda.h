@@ -126,7 +126,7 @@ typedef struct sfc_desc {
  * sum_m x[m] sin(pi (m+1)(k+1/2)/n) with the DCT-III weights applied to x[n-1] (dst.rs:484-592); sign flips and index
  * reversals are folded into the kernels' load / store */
 #define SFC_DESC_TRIG_SINE 256
-/* kind SFC_R2C, last axis, f64, power-of-two n: out[k] = scale * sum_i x[i] cos(pi (i+1/2)(k+1/2) / n) (with SFC_DESC_TRIG_SINE:
+/* kind SFC_R2C, ONE axis, f64, power-of-two n: out[k] = scale * sum_i x[i] cos(pi (i+1/2)(k+1/2) / n) (with SFC_DESC_TRIG_SINE:
  * sin) in one kernel on the n/2-point complex transform.  EXPERIMENTAL: not yet run on a GPU; the consumers only use it with
  * the environment variable SFC_DCT4_FUSED=1. */
 #define SFC_DESC_DCT4 512

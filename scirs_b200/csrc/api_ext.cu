@@ -316,8 +316,8 @@ int trig_axis(int kind, int type, bool inverse, bool ortho, int64_t O, int64_t N
         }
         if (perr.code != SFC_ERR_NOT_IMPLEMENTED) return fail(perr.code ? perr.code : SFC_ERR_PLAN, perr.msg);
     }
-    if (fuse_enabled() && dct4_fused_enabled() && type == 4 && I == 1 && is_pow2_i64(N) && N >= 128) {
-        // Type IV rows: one kernel on the N/2-point complex transform.  Every variant is a scaled
+    if (fuse_enabled() && dct4_fused_enabled() && type == 4 && is_pow2_i64(N) && N >= 128) {
+        // Type IV, rows or a strided axis: one kernel on the N/2-point complex transform.  Every variant is a scaled
         // sum_i x[i] cos|sin(pi (i+1/2)(k+1/2) / N): dct.rs:688-720 (1 | sqrt(2/N)), :724-746 (input * 2/N | sqrt(N/2), then the
         // forward sum), dst.rs:630-667 (2 | sqrt(2/N)), :671-702 (input * 1/2 | sqrt(N/2), then the un-normalised sum * 2)
         const double nn = (double)N;
@@ -327,9 +327,10 @@ int trig_axis(int kind, int type, bool inverse, bool ortho, int64_t O, int64_t N
         else sc = !inverse ? (ortho ? std::sqrt(2.0 / nn) : 2.0) : (ortho ? 2.0 * std::sqrt(nn / 2.0) : 1.0);
         sfc_desc dd;
         memset(&dd, 0, sizeof dd);
-        dd.ndim = 2;
+        dd.ndim = 3;
         dd.shape[0] = O;
         dd.shape[1] = N;
+        dd.shape[2] = I;
         dd.naxes = 1;
         dd.axes[0] = 1;
         dd.kind = SFC_R2C;

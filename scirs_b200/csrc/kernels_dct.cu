@@ -13,7 +13,13 @@ void register_kernels_dct(void (*add)(const KernelEntry&)) {
     SFC_ADD_DCT2(double, 1024, 2)
     SFC_ADD_DCT2(double, 4096, 1)
     SFC_ADD_DCT2(double, 8192, 1)
-    // TM_FAST_DCT4 (experimental, SFC_DCT4_FUSED=1): rows only, 32 KiB tiles where they exist
+    // TM_FAST_DCT4 (experimental, SFC_DCT4_FUSED=1): 32 KiB tiles for rows, the wide 64 KiB ones for strided axes
+    SFC_ADD_DCT4(double, 64, 64)
+    SFC_ADD_DCT4(double, 128, 32)
+    SFC_ADD_DCT4(double, 256, 16)
+    SFC_ADD_DCT4(double, 512, 8)
+    SFC_ADD_DCT4(double, 1024, 4)
+    SFC_ADD_DCT4(double, 2048, 2)
     SFC_ADD_DCT4(double, 64, 32)
     SFC_ADD_DCT4(double, 128, 16)
     SFC_ADD_DCT4(double, 256, 8)

@@ -1344,24 +1344,30 @@ struct PlanBuilder {
         return true;
     }
 
-    // DCT-IV / DST-IV of contiguous rows of n reals in one kernel (TM_FAST_DCT4); experimental, see fft_tile.cuh
-    bool add_dct4(int64_t n, int64_t O, ArrayRef src, ArrayRef dst, double scale, bool sine) {
+    // DCT-IV / DST-IV of n reals per lane in one kernel (TM_FAST_DCT4): rows (I == 1) or a strided axis with I adjacent
+    // lanes, addressed exactly like add_dct2.  Experimental, see fft_tile.cuh.
+    bool add_dct4(int64_t n, int64_t O, int64_t I, ArrayRef src, ArrayRef dst, double scale, bool sine) {
         Step s;
         const int L = (int)(n / 2);
+        const bool col = I > 1;
         int cnt = 0;
         const KernelEntry* t = kernel_table(&cnt);
         s.k = nullptr;
-        for (int i = 0; i < cnt; ++i)
-            if (t[i].prec == prec && t[i].L == L && t[i].mode == 7 && (!s.k || t[i].TL < s.k->TL)) s.k = &t[i];
-        if (!s.k || O % s.k->TL != 0 || O > 0xFFFFFFFFLL)
+        for (int i = 0; i < cnt; ++i)  // rows: the narrowest tile (more CTAs per SM); strided lanes: the widest
+            if (t[i].prec == prec && t[i].L == L && t[i].mode == 7 && (!s.k || (col ? t[i].TL > s.k->TL : t[i].TL < s.k->TL)))
+                s.k = &t[i];
+        const int64_t lanes = O * I;
+        if (!s.k || lanes % s.k->TL != 0 || (col && I % s.k->TL != 0) || lanes > 0xFFFFFFFFLL)
             return fail(SFC_ERR_NOT_IMPLEMENTED, "no fused DCT-IV kernel for this length / batch");
+        if (col && (int64_t)s.k->TL * (int64_t)rs < 32)
+            return fail(SFC_ERR_NOT_IMPLEMENTED, "column tiles of the fused DCT-IV kernel would be narrower than a sector");
         s.src = src.role;
         s.dst = dst.role;
         s.src_esize = rs;
         s.dst_esize = rs;
-        set_io(s.p.in, 0, n, 1, 1, n, 1, 0);
-        set_io(s.p.out, 0, n, 1, 1, n, 1, 0);
-        s.p.map_in = s.p.map_out = MAP_ROW;
+        set_io(s.p.in, 0, n * I, 1, I, n, 1, 0);
+        set_io(s.p.out, 0, n * I, 1, I, n, 1, 0);
+        s.p.map_in = s.p.map_out = col ? MAP_COL : MAP_ROW;
         s.p.ld_op = LD_C;
         s.p.st_op = ST_C;
         s.p.flags = F_IN_NOMASK | F_OUT_NOMASK | (sine ? F_TRIG_SINE : 0);
@@ -1373,14 +1379,14 @@ struct PlanBuilder {
         s.p.peer_shift = -1;
         s.p.tw = table_stage_tw(prec, L, err);
         if (!s.p.tw) return false;
-        s.p.nlanes = (uint32_t)O;
-        s.p.inner_count = 1;
-        s.p.tiles_per_batch = (uint32_t)(O / s.k->TL);
+        s.p.nlanes = (uint32_t)lanes;
+        s.p.inner_count = (uint32_t)I;
+        s.p.tiles_per_batch = (uint32_t)(lanes / s.k->TL);
         s.nbatch = 1;
-        dev_bytes += O * n * 2 * (int64_t)rs;
+        dev_bytes += lanes * n * 2 * (int64_t)rs;
         char buf[200];
-        snprintf(buf, sizeof buf, "fused %s-IV rows (half-length complex transform): tile L=%d TL=%d threads=%d smem=%zu lanes=%lld",
-                 sine ? "DST" : "DCT", s.k->L, s.k->TL, s.k->threads, s.k->smem, (long long)O);
+        snprintf(buf, sizeof buf, "fused %s-IV %s (half-length complex transform): tile L=%d TL=%d threads=%d smem=%zu lanes=%lld",
+                 sine ? "DST" : "DCT", col ? "columns" : "rows", s.k->L, s.k->TL, s.k->threads, s.k->smem, (long long)lanes);
         s.desc = buf;
         pl.steps_.push_back(s);
         return true;
@@ -1537,13 +1543,14 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
         const int la = axes.back();
         if (d.flags & SFC_DESC_DCT4) {
             const int64_t n = shape[la];
-            if (axes.size() != 1 || la != (int)shape.size() - 1 || !is_pow2(n) || n < 128 || n / 2 > lmax_for(prec) || prec != PREC_F64) {
-                err = {SFC_ERR_NOT_IMPLEMENTED, "fused DCT-IV needs the last axis, f64, a power-of-two length in 128..16384"};
+            if (axes.size() != 1 || !is_pow2(n) || n < 128 || n / 2 > lmax_for(prec) || prec != PREC_F64) {
+                err = {SFC_ERR_NOT_IMPLEMENTED, "fused DCT-IV needs ONE f64 axis of a power-of-two length in 128..16384"};
                 return nullptr;
             }
             pl.in_elems = pl.out_elems = total;
             pl.in_esize = pl.out_esize = rs;
-            if (!B.add_dct4(n, prod(shape, 0, la), {R_IN, true, n}, {R_OUT, true, n}, d.scale, (d.flags & SFC_DESC_TRIG_SINE) != 0))
+            if (!B.add_dct4(n, prod(shape, 0, la), prod(shape, la + 1, shape.size()), {R_IN, true, n}, {R_OUT, true, n}, d.scale,
+                            (d.flags & SFC_DESC_TRIG_SINE) != 0))
                 return nullptr;
             pl.info.in_bytes = pl.info.out_bytes = total * (int64_t)rs;
             pl.info.algorithmic_bytes = 2 * total * (int64_t)rs;

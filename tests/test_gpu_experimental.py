@@ -31,6 +31,15 @@ for n in (128, 256, 1024, 4096, 8192, 16384):
                 e = np.linalg.norm(g - ref) / np.linalg.norm(ref)
                 worst = max(worst, e)
                 assert e <= (1e-12 if n <= 4096 else 3e-12), (name, n, rows, norm, e)
+# strided axes (column tiles) and all axes of a 3-D array
+for shape, axes in (((256, 64), [0]), ((128, 1024, 8), [1]), ((128, 128, 128), None), ((512, 96), [0, 1])):
+    x = rng.standard_normal(shape)
+    for norm in (None, "ortho"):
+        for name, fn, ofn in (("dct", sb.dctn, co.dctn), ("idst", sb.idstn, co.idstn)):
+            got, ref = fn(x, 4, norm, axes), ofn(x, 4, norm, axes)
+            e = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+            worst = max(worst, e)
+            assert e <= 2e-12, (name, shape, axes, norm, e)
 print("dct4 fused parity ok, worst rel-L2", worst)
 ''' % ROOT
 
