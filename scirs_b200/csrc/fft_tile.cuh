@@ -385,7 +385,7 @@ struct Xch {
 // MIRROR_IN (complex-to-real transforms, same lengths): the radix-8 stage comes FIRST and the thread
 // again owns butterfly i and its mirror, so the Hermitian pre-pass pairs X[k], X[L-k] come straight
 // from the thread's own global loads.
-template <typename T, typename C, int S, bool FIRST, bool MIRROR = false, bool MIRROR_IN = false>
+template <typename T, typename C, int S, bool FIRST, bool MIRROR = false, bool MIRROR_IN = false, bool NOTW1 = false>
 __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__ sm,
                                            const Cx<T>* __restrict__ tw, int tw_, int iw, int tr,
                                            int ir, int grp = 0) {
@@ -405,7 +405,8 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
 #pragma unroll
             for (int r = 0; r < R; ++r) v[r] = a[b + r * NB];
             Dft<R, T>::run(v);
-            if constexpr (SFC_TW_LOAD && S >= 16) apply_twiddle_table<R, T>(v, tw, (iw + b * TPL) & ~(S - 1));
+            if constexpr (NOTW1 && S == 1) {
+            } else if constexpr (SFC_TW_LOAD && S >= 16) apply_twiddle_table<R, T>(v, tw, (iw + b * TPL) & ~(S - 1));
             else apply_twiddle_powers<R, T>(v, tw[(iw + b * TPL) & ~(S - 1)]);
 #pragma unroll
             for (int k = 0; k < R; ++k) a[b + k * NB] = v[k];
@@ -447,7 +448,8 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
             if constexpr (MIRROR_IN && S == 1 && NB == 2) {
                 if (b == 1) ib = iw == 0 ? (L / R) / 2 : (L / R) - iw;  // the mirror butterfly
             }
-            if constexpr (SFC_TW_LOAD && S >= 16) apply_twiddle_table<R, T>(v, tw, ib & ~(S - 1));
+            if constexpr (NOTW1 && S == 1) {
+            } else if constexpr (SFC_TW_LOAD && S >= 16) apply_twiddle_table<R, T>(v, tw, ib & ~(S - 1));
             else apply_twiddle_powers<R, T>(v, tw[ib & ~(S - 1)]);
             Cx<T>* dst = sm + tw_ * C::LP + Xch<C, R, S>::write_base(ib);
 #pragma unroll
@@ -654,6 +656,12 @@ enum TileMode : int {
     //   (-1)^k on the output.  NOT YET RUN ON A GPU (written after the round's GPU budget was spent): the planner only
     //   takes it with SFC_DCT4_FUSED=1, and tests/test_gpu_experimental.py is the parity check to run first.
     TM_FAST_DCT4 = 7,
+    // The middle pass of the three-pass plan for large 2-D transforms (tools/fft2_three_pass_emulation.py):
+    // a strided tile of L = 16*LB points whose stages skip the twiddles after the FIRST radix-16 stage, which makes it the
+    // 16 x LB two-dimensional transform of the blocks e = LB*r_lo + c_hi; output q = k2 + 16*kc1 is multiplied by
+    // aux_out[kc1 * c_rest] (W_C^j) and stored at k2*mid_es + kc1*mid_ls (the two mid_* strides are free here: not a double
+    // kernel).  NOT YET RUN ON A GPU: planner knob SFC_FFT2_TILE2D=1, parity check in tests/test_gpu_experimental.py.
+    TM_FAST_2D = 8,
 };
 
 // ---- TMA / mbarrier primitives (PTX) -----------------------------------------------------------
@@ -1077,6 +1085,8 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
         run_stages<T, C, 1, true, false, true>(a, sm, tw, t0, i0, t1, i1, grp);
     } else if constexpr (MODE == TM_FAST_C2R || MODE == TM_FAST_DCT3) {
         run_stages<T, C, 1, false>(a, sm, tw, t0, i0, t1, i1, grp);
+    } else if constexpr (MODE == TM_FAST_2D) {
+        run_stages<T, C, 1, true, false, false, true>(a, sm, tw, t0, i0, t1, i1, grp);
     } else if constexpr (FAST) {
         run_stages<T, C, 1, true>(a, sm, tw, t0, i0, t1, i1, grp);
     } else {
@@ -1134,7 +1144,21 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
         for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
     }
 
-    if constexpr (MODE == TM_FAST_DCT4) {
+    if constexpr (MODE == TM_FAST_2D) {
+        if constexpr (E == 16 && L >= 32) {
+            // q = i1 + m*TPL = k2 + 16*kc1 (the first stage's output digit is the least significant one)
+            const cx* __restrict__ tw2 = reinterpret_cast<const cx*>(p.aux_out);
+            cx* __restrict__ dst = reinterpret_cast<cx*>(p.out.ptr) + off;
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int q = i1 + m * TPL;
+                const int k2 = q & 15, kc1 = q >> 4;
+                const cx v = cmul(a[m], tw2[(int64_t)kc1 * li]);
+                dst[(int64_t)k2 * p.mid_es + (int64_t)kc1 * p.mid_ls] = {v.x * scale, v.y * scale};
+            }
+        }
+        return;
+    } else if constexpr (MODE == TM_FAST_DCT4) {
         if constexpr (E == 16) {
             constexpr int N = 2 * L;
             T* __restrict__ dst = reinterpret_cast<T*>(p.out.ptr) + off;

@@ -80,4 +80,6 @@ struct KernelInst {
     add(::sfc::KernelInst<T, L, TL, false, 16, 6>::entry());
 // fused DCT-IV / DST-IV rows (one half-length complex transform, twiddles on load and store)
 #define SFC_ADD_DCT4(T, L, TL) add(::sfc::KernelInst<T, L, TL, false, 16, 7>::entry());
+// middle pass of the three-pass 2-D plan (16 x L/16 two-dimensional tile)
+#define SFC_ADD_2D(T, L, TL) add(::sfc::KernelInst<T, L, TL, false, 16, 8>::entry());
 #define SFC_ADD_E(T, L, TL, DBL, E) add(::sfc::KernelInst<T, L, TL, DBL, E>::entry());

@@ -28,5 +28,7 @@ void register_kernels_dct(void (*add)(const KernelEntry&)) {
     SFC_ADD_DCT4(double, 2048, 1)
     SFC_ADD_DCT4(double, 4096, 1)
     SFC_ADD_DCT4(double, 8192, 1)
+    // TM_FAST_2D (experimental, SFC_FFT2_TILE2D=1): 16 x 32 tile on 8 adjacent columns
+    SFC_ADD_2D(double, 512, 8)
 }
 }  // namespace sfc

@@ -561,6 +561,15 @@ static int row_fourstep_len() {
     return v;
 }
 
+// the three-pass plan for large 2-D transforms was written after the round's GPU budget was spent: off until it has run
+static bool fft2_tile2d_enabled() {
+    static int v = [] {
+        const char* e = getenv("SFC_FFT2_TILE2D");
+        return e ? atoi(e) : 0;
+    }();
+    return v != 0;
+}
+
 static int64_t scratch_budget_bytes() {
     static int64_t v = [] {
         const char* e = getenv("SFC_WORK_MB");
@@ -1344,6 +1353,85 @@ struct PlanBuilder {
         return true;
     }
 
+    // Forward 2-D transform of [R][C] complex in THREE passes of small tiles (emulated in
+    // tools/fft2_three_pass_emulation.py): R = A*16, C = LB*256.  Experimental (SFC_FFT2_TILE2D=1).
+    bool add_fft2_three_pass(int64_t R, int64_t C, double scale) {
+        const int64_t LA = 16, A = R / LA, Cb = 256, LB = C / Cb, total = R * C;
+        if (R % LA || C % Cb || !is_pow2(A) || !is_pow2(LB) || A > lmax_for(prec) || LA * LB > lmax_for(prec) || LB < 2)
+            return fail(SFC_ERR_NOT_IMPLEMENTED, "three-pass 2-D plan: unsupported extents");
+        need_ms((size_t)total * cs);
+        need_sa((size_t)total * cs);
+        // pass 1 = four-step pass A of axis 0 with L1 = A, L2 = 16: transforms over the high row digit, W_R^(k1*r_lo) on store
+        const void *lo, *hi;
+        int sh;
+        if (!table_fourstep(prec, R, &lo, &hi, &sh, err)) return false;
+        Step a;
+        a.k = pick_kernel_two_per_sm(prec, (int)A, 0);
+        a.src = R_IN;
+        a.dst = R_MS;
+        a.src_esize = a.dst_esize = cs;
+        set_io(a.p.in, R * C, C, 1, LA * C, R, LA, 1);
+        set_io(a.p.out, R * C, C, 1, LA * C, R, LA, 1);
+        a.p.map_in = a.p.map_out = MAP_COL;
+        a.p.ld_op = LD_C;
+        a.p.st_op = ST_TW;
+        a.p.tw_lo = lo;
+        a.p.tw_hi = hi;
+        a.p.tw_shift = sh;
+        a.p.flags = 0;
+        a.p.scale = 1.0;
+        if (!finish_tile(a, LA * C, C, 1, "2-D three-pass: pass 1 (high row digit + twiddle)")) return false;
+        // pass 2 = the 16 x LB two-dimensional tile: lanes (k1, c_rest), elements e = LB*r_lo + c_hi at stride Cb
+        Step m;
+        int cnt = 0;
+        const KernelEntry* t = kernel_table(&cnt);
+        for (int i = 0; i < cnt; ++i)
+            if (t[i].prec == prec && t[i].L == (int)(LA * LB) && t[i].mode == 8 && (!m.k || t[i].TL > m.k->TL)) m.k = &t[i];
+        if (!m.k || Cb % m.k->TL != 0) return fail(SFC_ERR_NOT_IMPLEMENTED, "three-pass 2-D plan: no 2-D tile kernel for this shape");
+        m.src = R_MS;
+        m.dst = R_SA;
+        m.src_esize = m.dst_esize = cs;
+        set_io(m.p.in, 0, LA * C, 1, Cb, LA * LB, 1, 0);
+        set_io(m.p.out, 0, C, 1, Cb, LA * LB, 1, 0);
+        m.p.mid_es = A * C;  // k2  -> row k1 + A*k2
+        m.p.mid_ls = Cb;     // kc1 -> column kc1*Cb + c_rest
+        m.p.aux_out = table_stage_tw(prec, (int)C, err);  // W_C^j, j < C: the pass-A twiddle of axis 1, W_C^(kc1*c_rest)
+        if (!m.p.aux_out) return false;
+        m.p.map_in = m.p.map_out = MAP_COL;
+        m.p.ld_op = LD_C;
+        m.p.st_op = ST_C;
+        m.p.flags = F_IN_NOMASK | F_OUT_NOMASK;
+        m.p.scale = 1.0;
+        m.p.peer_shift = -1;
+        m.p.tw = table_stage_tw(prec, (int)(LA * LB), err);
+        if (!m.p.tw) return false;
+        m.p.nlanes = (uint32_t)(A * Cb);
+        m.p.inner_count = (uint32_t)Cb;
+        m.p.tiles_per_batch = (uint32_t)(A * Cb / m.k->TL);
+        m.nbatch = 1;
+        char buf[200];
+        snprintf(buf, sizeof buf, "2-D three-pass: pass 2 (16 x %lld two-dimensional tile): tile L=%d TL=%d threads=%d smem=%zu lanes=%lld",
+                 (long long)LB, m.k->L, m.k->TL, m.k->threads, m.k->smem, (long long)(A * Cb));
+        m.desc = buf;
+        pl.steps_.push_back(m);
+        // pass 3 = four-step pass B of axis 1 with L1 = LB, L2 = 256: contiguous row segments, output column kc1 + LB*kc2
+        Step b;
+        b.k = pick_kernel_two_per_sm(prec, (int)Cb, 0);
+        b.src = R_SA;
+        b.dst = R_OUT;
+        b.src_esize = b.dst_esize = cs;
+        set_io(b.p.in, C, Cb, 1, 1, Cb, 1, 0);
+        set_io(b.p.out, C, 1, 1, LB, C, LB, 1);
+        b.p.map_in = MAP_ROW;
+        b.p.map_out = MAP_COL;
+        b.p.ld_op = LD_C;
+        b.p.st_op = ST_C;
+        b.p.flags = 0;
+        b.p.scale = scale;
+        dev_bytes += 6 * total * (int64_t)cs;
+        return finish_tile(b, LB, 1, R, "2-D three-pass: pass 3 (low column digit, transposed store)");
+    }
+
     // DCT-IV / DST-IV of n reals per lane in one kernel (TM_FAST_DCT4): rows (I == 1) or a strided axis with I adjacent
     // lanes, addressed exactly like add_dct2.  Experimental, see fft_tile.cuh.
     bool add_dct4(int64_t n, int64_t O, int64_t I, ArrayRef src, ArrayRef dst, double scale, bool sine) {
@@ -1506,7 +1594,15 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
         if (axes.empty()) {
             ok = B.add_copy({R_IN, real_in, 1}, {R_OUT, false, 1}, shape, shape, d.scale);
         }
-        for (size_t i = 0; ok && i < axes.size(); ++i) {
+        // experimental: one plan for both axes of a large forward 2-D transform
+        const bool three_pass_2d = fft2_tile2d_enabled() && !inv && prec == PREC_F64 && shape.size() == 2 && axes.size() == 2 &&
+                                   axes[0] != axes[1] && shape[0] == 8192 && shape[1] == 8192 && d.flags == 0 && d.scatter_parts <= 1;
+        if (three_pass_2d) {
+            ok = B.add_fft2_three_pass(shape[0], shape[1], d.scale);
+            passes += 2;
+            alg += 2 * 2 * total * (int64_t)cs;
+        }
+        for (size_t i = 0; !three_pass_2d && ok && i < axes.size(); ++i) {
             const int a = axes[i];
             const int64_t n = shape[a], O = prod(shape, 0, a), I = prod(shape, a + 1, shape.size());
             const bool last = (i + 1 == axes.size());

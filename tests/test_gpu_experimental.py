@@ -2,6 +2,7 @@
 Skipped unless SFC_TEST_EXPERIMENTAL=1; each case runs in its own process because the knobs are read once per process.
 
   SFC_DCT4_FUSED=1   TM_FAST_DCT4: DCT-IV / DST-IV rows in one kernel on the n/2-point complex transform (fft_tile.cuh)
+  SFC_FFT2_TILE2D=1  TM_FAST_2D: three-pass plan for fft2 8192 x 8192 (tools/fft2_three_pass_emulation.py)
 """
 import os
 import subprocess
@@ -47,5 +48,31 @@ print("dct4 fused parity ok, worst rel-L2", worst)
 def test_dct4_fused_kernel(build_artifacts):
     env = dict(os.environ, SFC_DCT4_FUSED="1")
     r = subprocess.run([sys.executable, "-c", DCT4], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "parity ok" in r.stdout
+
+
+FFT2 = r'''
+import numpy as np, sys, time
+sys.path.insert(0, %r)
+import scirs_b200 as sb
+rng = np.random.default_rng(5)
+n = 8192
+x = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+p = sb.FftPlan([n, n], [0, 1])
+d = p.describe()
+assert "2-D three-pass" in d, d
+got = p.execute(x).reshape(n, n)
+ref = np.fft.fft2(x)   # an independent transform is enough for a first run; the oracle needs minutes at this size
+e = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+print(d)
+assert e <= 1e-12, e
+print("fft2 three-pass parity ok, rel-L2", e)
+''' % ROOT
+
+
+def test_fft2_three_pass_plan(build_artifacts):
+    env = dict(os.environ, SFC_FFT2_TILE2D="1")
+    r = subprocess.run([sys.executable, "-c", FFT2], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "parity ok" in r.stdout
