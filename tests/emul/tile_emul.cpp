@@ -1,0 +1,56 @@
+// TEST INFRASTRUCTURE ONLY — runs tile_fft_kernel instantiations on the host: one CTA at a time, its threads as OS
+// threads, __syncthreads() as a pthread barrier.  Built by tests/test_kernel_emulation.py into tests/emul/_build/.
+#include <cuda_runtime.h>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+thread_local emul_dim3 threadIdx;
+thread_local emul_dim3 blockIdx;
+emul_dim3 blockDim, gridDim;
+pthread_barrier_t emul_cta_barrier;
+namespace sfc {
+alignas(128) unsigned char smem_raw[232448];  // the kernel's `extern __shared__` array: one CTA runs at a time
+}
+
+#include "fft_tile.cuh"
+
+using namespace sfc;
+
+template <typename T, int L, int TL, bool DBL, int E, int MODE>
+static void run_grid(const PassParams& p, unsigned grid) {
+    using C = TileCfg<T, L, TL, E, 1>;
+    blockDim.x = C::NT;
+    gridDim.x = grid;
+    pthread_barrier_init(&emul_cta_barrier, nullptr, C::NT);
+    for (unsigned b = 0; b < grid; ++b) {
+        std::vector<std::thread> th;
+        th.reserve(C::NT);
+        for (int t = 0; t < C::NT; ++t)
+            th.emplace_back([&p, b, t] {
+                threadIdx.x = (unsigned)t;
+                blockIdx.x = b;
+                tile_fft_kernel<T, L, TL, DBL, E, MODE, 1>(p);
+            });
+        for (auto& x : th) x.join();
+    }
+    pthread_barrier_destroy(&emul_cta_barrier);
+}
+
+// key = L * 1000000 + TL * 1000 + MODE (f64, E = 16)
+extern "C" int emul_run(long long key, const PassParams* p, unsigned grid) {
+#define CASE(L, TL, MODE) \
+    case (long long)(L) * 1000000 + (TL) * 1000 + (MODE): run_grid<double, L, TL, false, 16, MODE>(*p, grid); return 0;
+    switch (key) {
+        CASE(512, 8, 1)
+        CASE(512, 4, 1)
+        CASE(256, 8, 1)
+        CASE(64, 32, 7)
+        CASE(512, 4, 7)
+        CASE(256, 16, 7)
+        CASE(512, 8, 8)
+        CASE(64, 64, 5)
+        default: return -1;
+    }
+}
+extern "C" int emul_sizeof_params() { return (int)sizeof(PassParams); }
