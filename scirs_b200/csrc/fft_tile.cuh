@@ -340,7 +340,11 @@ struct TileCfg {
         if constexpr (GROUPS == 1) {
             __syncthreads();
         } else {
+#ifdef SFC_HOST_EMUL
+            emul_unsupported("named barriers (two thread groups per CTA)");
+#else
             asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(NTG) : "memory");
+#endif
         }
     }
 #ifndef SFC_MINB_F64

@@ -36,7 +36,11 @@ struct KernelInst {
             const unsigned cap = (unsigned)(dev < 64 ? resident[dev] : 296);
             if (grid > cap) grid = cap;
         }
+#ifdef SFC_HOST_EMUL  // tests/emul only: the kernel source run on the host to check index logic without a GPU
+        emul_launch(&tile_fft_kernel<T, L, TL, DBL, EMAX, MODE, GROUPS>, p, grid, C::NT);
+#else
         tile_fft_kernel<T, L, TL, DBL, EMAX, MODE, GROUPS><<<grid, C::NT, SMEM_BYTES, s>>>(p);
+#endif
         return cudaGetLastError();
     }
     static KernelEntry entry() {

@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY — runs tile_fft_kernel instantiations on the host: one CTA at a time, its threads as OS
 // threads, __syncthreads() as a pthread barrier.  Built by tests/test_kernel_emulation.py into tests/emul/_build/.
+#define SFC_HOST_EMUL 1
 #include <cuda_runtime.h>
 #include <cstring>
 #include <thread>
@@ -20,21 +21,7 @@ using namespace sfc;
 template <typename T, int L, int TL, bool DBL, int E, int MODE>
 static void run_grid(const PassParams& p, unsigned grid) {
     using C = TileCfg<T, L, TL, E, 1>;
-    blockDim.x = C::NT;
-    gridDim.x = grid;
-    pthread_barrier_init(&emul_cta_barrier, nullptr, C::NT);
-    for (unsigned b = 0; b < grid; ++b) {
-        std::vector<std::thread> th;
-        th.reserve(C::NT);
-        for (int t = 0; t < C::NT; ++t)
-            th.emplace_back([&p, b, t] {
-                threadIdx.x = (unsigned)t;
-                blockIdx.x = b;
-                tile_fft_kernel<T, L, TL, DBL, E, MODE, 1>(p);
-            });
-        for (auto& x : th) x.join();
-    }
-    pthread_barrier_destroy(&emul_cta_barrier);
+    emul_launch(&tile_fft_kernel<T, L, TL, DBL, E, MODE, 1>, p, grid, C::NT);
 }
 
 // key = L * 1000000 + TL * 1000 + MODE (f64, E = 16)

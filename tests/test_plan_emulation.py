@@ -1,0 +1,132 @@
+"""CPU: the PLANNER (scirs_b200/csrc/plan.cu) and the f64 kernel translation units compiled for the host
+(-DSFC_HOST_EMUL, tests/emul/cuda_runtime.h) and driven through Plan::create / Plan::exec on host arrays.
+
+Purpose: check planner plumbing + kernel index logic of code that has not run on a GPU yet (the fused DCT-IV flavour and
+the three-pass fft2 plan), after showing on GPU-validated plans that the emulation reproduces them.  Test infrastructure
+only — see tests/emul/cuda_runtime.h; the product library is untouched and still has no CPU path.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL = os.path.join(ROOT, "tests", "emul")
+CSRC = os.path.join(ROOT, "scirs_b200", "csrc")
+UNITS = ["plan", "kernels_f64_small", "kernels_f64_mid", "kernels_f64_big", "kernels_f64_real", "kernels_f64_dbl_a",
+         "kernels_f64_dbl_b", "kernels_dct"]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    from scirs_b200 import _lib
+
+    bdir = os.path.join(EMUL, "_build", "obj")
+    os.makedirs(bdir, exist_ok=True)
+    out = os.path.join(EMUL, "_build", "libplan_emul.so")
+    hdrs = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))] + [os.path.join(EMUL, "cuda_runtime.h")]
+    newest_hdr = max(os.path.getmtime(h) for h in hdrs)
+    flags = ["-std=c++17", "-O1", "-fPIC", "-pthread", "-DSFC_HOST_EMUL", "-I" + EMUL, "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]
+    procs, objs = [], []
+    for u in UNITS + ["plan_emul"]:
+        src = os.path.join(EMUL, u + ".cpp") if u == "plan_emul" else os.path.join(CSRC, u + ".cu")
+        obj = os.path.join(bdir, u + ".o")
+        objs.append(obj)
+        if not os.path.exists(obj) or os.path.getmtime(obj) < max(newest_hdr, os.path.getmtime(src)):
+            procs.append(subprocess.Popen(["g++", "-x", "c++"] + flags + ["-c", src, "-o", obj]))
+    for pr in procs:
+        assert pr.wait() == 0, "host compilation of the planner / kernels failed"
+    if procs or not os.path.exists(out):
+        subprocess.run(["g++", "-shared", "-pthread", "-o", out] + objs, check=True)
+    os.environ["SFC_FFT2_TILE2D"] = "1"  # read once by the emulated planner at its first plan
+    lib = C.CDLL(out)
+    lib.emul_plan_run.argtypes = [C.POINTER(_lib.sfc_desc), C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+
+    def run(shape, axes, x, out_arr, kind=_lib.SFC_C2C, inverse=False, scale=1.0, flags=0):
+        d = _lib.sfc_desc()
+        d.ndim = len(shape)
+        for i, s in enumerate(shape):
+            d.shape[i] = s
+        d.naxes = len(axes)
+        for i, a in enumerate(axes):
+            d.axes[i] = a
+        d.kind, d.prec, d.direction, d.flags, d.scale = kind, _lib.SFC_PREC_F64, int(inverse), flags, scale
+        buf = C.create_string_buffer(8192)
+        rc = lib.emul_plan_run(C.byref(d), x.ctypes.data_as(C.c_void_p), out_arr.ctypes.data_as(C.c_void_p), buf, len(buf))
+        return rc, buf.value.decode()
+
+    return run
+
+
+def rel(a, b):
+    return np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel())
+
+
+def test_emulated_planner_reproduces_validated_plans(emul):
+    """Plans whose GPU results are already pinned by tests/test_gpu_parity.py: single-pass rows and columns, a 2-D transform,
+    a four-step row, Bluestein, fused rfft / irfft, the fused DCT-II."""
+    from scirs_b200 import _lib
+    from oracle import consumers_oracle as co
+
+    rng = np.random.default_rng(1)
+    c = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    x = c(8, 1024); y = np.zeros_like(x)
+    rc, d = emul([8, 1024], [1], x, y); assert rc == 0, d
+    assert rel(y, np.fft.fft(x, axis=1)) < 1e-14
+    x = c(256, 24); y = np.zeros_like(x)
+    rc, d = emul([256, 24], [0], x, y, inverse=True, scale=1 / 256); assert rc == 0, d
+    assert rel(y, np.fft.ifft(x, axis=0)) < 1e-14
+    x = c(64, 128); y = np.zeros_like(x)
+    rc, d = emul([64, 128], [0, 1], x, y); assert rc == 0, d
+    assert rel(y, np.fft.fft2(x)) < 1e-14
+    x = c(2, 1 << 15); y = np.zeros_like(x)
+    rc, d = emul([2, 1 << 15], [1], x, y); assert rc == 0 and "four-step" in d, d
+    assert rel(y, np.fft.fft(x, axis=1)) < 1e-14
+    x = c(3, 1000); y = np.zeros_like(x)
+    rc, d = emul([3, 1000], [1], x, y); assert rc == 0, d
+    assert rel(y, np.fft.fft(x, axis=1)) < 1e-13
+    xr = rng.standard_normal((4, 2048)); yh = np.zeros((4, 1025), dtype=np.complex128)
+    rc, d = emul([4, 2048], [1], xr, yh, kind=_lib.SFC_R2C); assert rc == 0, d
+    assert rel(yh, np.fft.rfft(xr, axis=1)) < 1e-14
+    back = np.zeros_like(xr)
+    rc, d = emul([4, 2048], [1], yh, back, kind=_lib.SFC_C2R, scale=1 / 2048); assert rc == 0, d
+    assert rel(back, xr) < 1e-14
+    xd = rng.standard_normal((64, 128)); yd = np.zeros_like(xd)
+    rc, d = emul([64, 128], [1], xd, yd, kind=_lib.SFC_R2C, flags=_lib.SFC_DESC_DCT2); assert rc == 0 and "fused DCT-II" in d, d
+    assert rel(yd, co.dctn(xd, 2, None, [1])) < 1e-13
+
+
+@pytest.mark.parametrize("shape,axis", [((32, 128), 1), ((8, 1024), 1), ((2, 16384), 1), ((256, 64), 0), ((4, 512, 16), 1)])
+def test_fused_dct4_plan(emul, shape, axis):
+    """SFC_DESC_DCT4 through Plan::create -> add_dct4 -> TM_FAST_DCT4, cosine and sine, against the literal sums."""
+    from scirs_b200 import _lib
+    from oracle import consumers_oracle as co
+
+    rng = np.random.default_rng(sum(shape))
+    x = rng.standard_normal(shape)
+    for sine in (False, True):
+        y = np.zeros_like(x)
+        rc, d = emul(list(shape), [axis], x, y, kind=_lib.SFC_R2C, scale=0.5,
+                     flags=_lib.SFC_DESC_DCT4 | (_lib.SFC_DESC_TRIG_SINE if sine else 0))
+        assert rc == 0 and ("fused DST-IV" if sine else "fused DCT-IV") in d, d
+        if shape[axis] <= 4096:
+            ref = 0.5 * (co.dstn(x, 4, None, [axis]) / 2.0 if sine else co.dctn(x, 4, None, [axis]))
+        else:  # the literal O(n^2) sums lose 1e-12 themselves at this length: scipy's type IV is twice the plain sum
+            import scipy.fft as sf
+
+            ref = 0.25 * (sf.dst(x, 4, axis=axis) if sine else sf.dct(x, 4, axis=axis))
+        assert rel(y, ref) < 1e-12
+
+
+def test_fft2_three_pass_plan(emul):
+    """SFC_FFT2_TILE2D=1: Plan::create -> add_fft2_three_pass for 256 x 8192 (the plan takes any power-of-two row count from
+    256 with 8192 columns; 8192 x 8192 runs the same three kernels with a longer first pass)."""
+    rng = np.random.default_rng(2)
+    R, Cn = 256, 8192
+    x = rng.standard_normal((R, Cn)) + 1j * rng.standard_normal((R, Cn))
+    y = np.zeros_like(x)
+    rc, d = emul([R, Cn], [0, 1], x, y, scale=0.125)
+    assert rc == 0 and d.count("2-D three-pass") == 3, d
+    assert rel(y, 0.125 * np.fft.fft2(x)) < 1e-13
