@@ -1353,9 +1353,9 @@ struct PlanBuilder {
         return true;
     }
 
-    // Forward 2-D transform of [R][C] complex in THREE passes of small tiles (emulated in
+    // 2-D transform of [R][C] complex in THREE passes of small tiles (emulated in
     // tools/fft2_three_pass_emulation.py): R = A*16, C = LB*256.  Experimental (SFC_FFT2_TILE2D=1).
-    bool add_fft2_three_pass(int64_t R, int64_t C, double scale) {
+    bool add_fft2_three_pass(int64_t R, int64_t C, double scale, bool inverse) {
         const int64_t LA = 16, A = R / LA, Cb = 256, LB = C / Cb, total = R * C;
         if (R % LA || C % Cb || !is_pow2(A) || !is_pow2(LB) || A > lmax_for(prec) || LA * LB > lmax_for(prec) || LB < 2)
             return fail(SFC_ERR_NOT_IMPLEMENTED, "three-pass 2-D plan: unsupported extents");
@@ -1378,7 +1378,7 @@ struct PlanBuilder {
         a.p.tw_lo = lo;
         a.p.tw_hi = hi;
         a.p.tw_shift = sh;
-        a.p.flags = 0;
+        a.p.flags = inverse ? F_CONJ_LD_PRE : 0;  // the inverse is the forward plan on conjugated data (as everywhere else)
         a.p.scale = 1.0;
         if (!finish_tile(a, LA * C, C, 1, "2-D three-pass: pass 1 (high row digit + twiddle)")) return false;
         // pass 2 = the 16 x LB two-dimensional tile: lanes (k1, c_rest), elements e = LB*r_lo + c_hi at stride Cb
@@ -1426,7 +1426,7 @@ struct PlanBuilder {
         b.p.map_out = MAP_COL;
         b.p.ld_op = LD_C;
         b.p.st_op = ST_C;
-        b.p.flags = 0;
+        b.p.flags = inverse ? F_CONJ_ST_POST : 0;
         b.p.scale = scale;
         dev_bytes += 6 * total * (int64_t)cs;
         return finish_tile(b, LB, 1, R, "2-D three-pass: pass 3 (low column digit, transposed store)");
@@ -1595,11 +1595,11 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
             ok = B.add_copy({R_IN, real_in, 1}, {R_OUT, false, 1}, shape, shape, d.scale);
         }
         // experimental: one plan for both axes of a large forward 2-D transform
-        const bool three_pass_2d = fft2_tile2d_enabled() && !inv && prec == PREC_F64 && shape.size() == 2 && axes.size() == 2 &&
+        const bool three_pass_2d = fft2_tile2d_enabled() && prec == PREC_F64 && shape.size() == 2 && axes.size() == 2 &&
                                    axes[0] != axes[1] && shape[0] >= 256 && is_pow2(shape[0]) && shape[1] == 8192 && d.flags == 0 &&
                                    d.scatter_parts <= 1;
         if (three_pass_2d) {
-            ok = B.add_fft2_three_pass(shape[0], shape[1], d.scale);
+            ok = B.add_fft2_three_pass(shape[0], shape[1], d.scale, inv);
             passes += 2;
             alg += 2 * 2 * total * (int64_t)cs;
         }

@@ -67,7 +67,12 @@ ref = np.fft.fft2(x)   # an independent transform is enough for a first run; the
 e = np.linalg.norm(got - ref) / np.linalg.norm(ref)
 print(d)
 assert e <= 1e-12, e
-print("fft2 three-pass parity ok, rel-L2", e)
+pi = sb.FftPlan([n, n], [0, 1], "c2c", "f64", False, 1.0 / (n * n))
+assert "2-D three-pass" in pi.describe()
+back = pi.execute(got).reshape(n, n)
+e2 = np.linalg.norm(back - x) / np.linalg.norm(x)
+assert e2 <= 1e-12, e2
+print("fft2 three-pass parity ok, rel-L2", e, "round trip", e2)
 ''' % ROOT
 
 

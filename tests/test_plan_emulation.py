@@ -130,3 +130,7 @@ def test_fft2_three_pass_plan(emul):
     rc, d = emul([R, Cn], [0, 1], x, y, scale=0.125)
     assert rc == 0 and d.count("2-D three-pass") == 3, d
     assert rel(y, 0.125 * np.fft.fft2(x)) < 1e-13
+    back = np.zeros_like(x)
+    rc, d = emul([R, Cn], [1, 0], y, back, inverse=True, scale=8.0 / (R * Cn))
+    assert rc == 0 and d.count("2-D three-pass") == 3, d
+    assert rel(back, x) < 1e-13
