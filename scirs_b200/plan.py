@@ -30,7 +30,8 @@ class FftPlan:
                  prec: str = "f64", forward: bool = True, scale: float = 1.0,
                  in_shape: Optional[Sequence[int]] = None, real_input: bool = False, scatter_parts: int = 0,
                  axis_in_len: int = 0, axis_out_len: int = 0, aux_in=None, aux_out=None, real_output: bool = False,
-                 dct2: bool = False, dct2_ortho: bool = False):
+                 dct2: bool = False, dct2_ortho: bool = False, dct3: bool = False, dct4: bool = False,
+                 trig_sine: bool = False, scale_dc: float = 0.0):
         lib = _lib.load()
         shape = [int(s) for s in shape]
         if not 1 <= len(shape) <= _lib.SFC_MAX_DIMS:
@@ -67,6 +68,13 @@ class FftPlan:
             d.flags |= _lib.SFC_DESC_REAL_OUTPUT
         if dct2:  # kind "r2c" over the last axis: fused DCT-II rows, real in / real out (dct.rs:523-559)
             d.flags |= _lib.SFC_DESC_DCT2 | (_lib.SFC_DESC_DCT2_ORTHO0 if dct2_ortho else 0)
+        if dct3:  # fused DCT-III (the inverse packing); scale_dc weighs input 0
+            d.flags |= _lib.SFC_DESC_DCT3
+        if dct4:  # fused DCT-IV on the n/2-point complex transform (experimental: include/scirs2_fft_cuda.h)
+            d.flags |= _lib.SFC_DESC_DCT4
+        if trig_sine:  # the sine twins of dct2 / dct3 / dct4
+            d.flags |= _lib.SFC_DESC_TRIG_SINE
+        d.scale_dc = float(scale_dc)
         self._h = C.c_void_p()
         check(lib.sfc_plan_create(C.byref(self._h), C.byref(d)))
         self._lib = lib
