@@ -40,19 +40,26 @@ __global__ void nd_copy_kernel(const __grid_constant__ CopyParams p) {
     }
 }
 
+// the launch, or (tests/emul only, -DSFC_HOST_EMUL) the same kernel run on the host
+#ifdef SFC_HOST_EMUL
+#define SFC_AUX_LAUNCH(...) emul_launch(&__VA_ARGS__, p, (unsigned)blocks, threads)
+#else
+#define SFC_AUX_LAUNCH(...) __VA_ARGS__<<<(unsigned)blocks, threads, 0, s>>>(p)
+#endif
+
 cudaError_t launch_nd_copy(const CopyParams& p, cudaStream_t s) {
     if (p.total <= 0) return cudaSuccess;
     const int threads = 256;
     int64_t blocks = (p.total + threads - 1) / threads;
     if (blocks > 148 * 32) blocks = 148 * 32;
     if (p.src_f64 && p.dst_f64)
-        nd_copy_kernel<double, double><<<(unsigned)blocks, threads, 0, s>>>(p);
+        SFC_AUX_LAUNCH(nd_copy_kernel<double, double>);
     else if (!p.src_f64 && p.dst_f64)
-        nd_copy_kernel<float, double><<<(unsigned)blocks, threads, 0, s>>>(p);
+        SFC_AUX_LAUNCH(nd_copy_kernel<float, double>);
     else if (p.src_f64 && !p.dst_f64)
-        nd_copy_kernel<double, float><<<(unsigned)blocks, threads, 0, s>>>(p);
+        SFC_AUX_LAUNCH(nd_copy_kernel<double, float>);
     else
-        nd_copy_kernel<float, float><<<(unsigned)blocks, threads, 0, s>>>(p);
+        SFC_AUX_LAUNCH(nd_copy_kernel<float, float>);
     return cudaGetLastError();
 }
 
@@ -111,9 +118,9 @@ cudaError_t launch_herm_fill(const HermParams& p, cudaStream_t s) {
     int64_t blocks = (p.total + threads - 1) / threads;
     if (blocks > 148 * 32) blocks = 148 * 32;
     if (p.f64)
-        herm_fill_kernel<double><<<(unsigned)blocks, threads, 0, s>>>(p);
+        SFC_AUX_LAUNCH(herm_fill_kernel<double>);
     else
-        herm_fill_kernel<float><<<(unsigned)blocks, threads, 0, s>>>(p);
+        SFC_AUX_LAUNCH(herm_fill_kernel<float>);
     return cudaGetLastError();
 }
 

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY — the planner (plan.cu) and the f64 kernel translation units compiled for the host with
 // -DSFC_HOST_EMUL against tests/emul/cuda_runtime.h, plus this driver: create a plan from an sfc_desc, execute it on host
 // arrays, return its description.  Checks planner plumbing and kernel index logic without a GPU (no f32, no TMA-pipelined
-// or two-group flavours, no copy / Hermitian-fill steps: those need PTX or kernels that are not emulated).
+// or two-group flavours: those need PTX that is not emulated).
 #include <cuda_runtime.h>
 #include <memory>
 #include <string>
@@ -17,7 +17,7 @@ namespace sfc {
 alignas(128) unsigned char smem_raw[232448];  // the kernel's `extern __shared__` array: one CTA runs at a time
 
 void set_error(int, const std::string&) {}
-// flavours that are not emulated register nothing; steps that need un-emulated kernels fail
+// flavours that are not emulated register nothing
 void register_kernels_f32_small(void (*)(const KernelEntry&)) {}
 void register_kernels_f32_mid(void (*)(const KernelEntry&)) {}
 void register_kernels_f32_big(void (*)(const KernelEntry&)) {}
@@ -27,8 +27,6 @@ void register_kernels_f32_real(void (*)(const KernelEntry&)) {}
 void register_kernels_e8(void (*)(const KernelEntry&)) {}
 void register_kernels_pipe(void (*)(const KernelEntry&)) {}
 void register_kernels_pipe_dbl(void (*)(const KernelEntry&)) {}
-cudaError_t launch_nd_copy(const CopyParams&, cudaStream_t) { return cudaErrorUnknown; }
-cudaError_t launch_herm_fill(const HermParams&, cudaStream_t) { return cudaErrorUnknown; }
 }  // namespace sfc
 
 extern "C" int emul_plan_run(const sfc_desc* d, const void* in, void* out, char* info, int info_len) {

@@ -15,7 +15,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMUL = os.path.join(ROOT, "tests", "emul")
 CSRC = os.path.join(ROOT, "scirs_b200", "csrc")
-UNITS = ["plan", "kernels_f64_small", "kernels_f64_mid", "kernels_f64_big", "kernels_f64_real", "kernels_f64_dbl_a",
+UNITS = ["plan", "aux_kernels", "kernels_f64_small", "kernels_f64_mid", "kernels_f64_big", "kernels_f64_real", "kernels_f64_dbl_a",
          "kernels_f64_dbl_b", "kernels_dct"]
 
 
@@ -134,3 +134,15 @@ def test_fft2_three_pass_plan(emul):
     rc, d = emul([R, Cn], [1, 0], y, back, inverse=True, scale=8.0 / (R * Cn))
     assert rc == 0 and d.count("2-D three-pass") == 3, d
     assert rel(back, x) < 1e-13
+
+
+def test_seeded_plan_sweep(emul):
+    """40 random plans (c2c forward / inverse, r2c, c2r; 1 to 3 dimensions; power-of-two, Bluestein and tiny extents) through
+    the emulated planner + kernels against numpy (tools/emul_asan_sweep.py, the same sweep that is run under
+    AddressSanitizer by hand)."""
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emul_asan_sweep.py"), "40", "7"], capture_output=True,
+                       text=True, timeout=900, env={k: v for k, v in os.environ.items() if k != "LD_PRELOAD"})
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "40 plans executed" in r.stdout and "MISMATCH" not in r.stdout and "plan refused" not in r.stdout, r.stdout
