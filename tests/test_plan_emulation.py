@@ -146,3 +146,49 @@ def test_seeded_plan_sweep(emul):
                        text=True, timeout=900, env={k: v for k, v in os.environ.items() if k != "LD_PRELOAD"})
     assert r.returncode == 0, r.stdout + r.stderr
     assert "40 plans executed" in r.stdout and "MISMATCH" not in r.stdout and "plan refused" not in r.stdout, r.stdout
+
+
+KNOB_SCRIPT = r"""
+import ctypes as C, os, sys
+sys.path.insert(0, %r)
+import numpy as np
+from scirs_b200 import _lib
+lib = C.CDLL(%r)
+rng = np.random.default_rng(4)
+def run(shape, axes, x, y, kind=_lib.SFC_C2C, inverse=0, scale=1.0):
+    d = _lib.sfc_desc(); d.ndim = len(shape)
+    for i, s in enumerate(shape): d.shape[i] = s
+    d.naxes = len(axes)
+    for i, a in enumerate(axes): d.axes[i] = a
+    d.kind, d.prec, d.direction, d.flags, d.scale = kind, _lib.SFC_PREC_F64, inverse, 0, scale
+    buf = C.create_string_buffer(16384)
+    rc = lib.emul_plan_run(C.byref(d), x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), buf, len(buf))
+    assert rc == 0, buf.value
+    return buf.value.decode()
+for shape in ([2, 1 << 16], [1, 1 << 18]):
+    x = rng.standard_normal(shape) + 1j * rng.standard_normal(shape); y = np.empty_like(x)
+    d = run(shape, [1], x, y)
+    assert WANT in d, d
+    e = np.linalg.norm(y - np.fft.fft(x, axis=1)) / np.linalg.norm(y)
+    back = np.empty_like(x)
+    run(shape, [1], y, back, inverse=1, scale=1.0 / shape[1])
+    e2 = np.linalg.norm(back - x) / np.linalg.norm(x)
+    assert e < 1e-14 and e2 < 1e-14, (shape, e, e2)
+n = 100003
+x = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n)); y = np.empty_like(x)
+d = run([2, n], [1], x, y)
+assert "Bluestein" in d or "chirp" in d, d
+assert np.linalg.norm(y - np.fft.fft(x, axis=1)) / np.linalg.norm(y) < 1e-13
+print("knob plans ok")
+"""
+
+
+@pytest.mark.parametrize("env,want", [({"SFC_THREE_LEVEL_MIN": "16384"}, "three-level"), ({"SFC_THREE_LEVEL_MIN": "0"}, "four-step")])
+def test_long_rows_and_bluestein_through_the_emulation(emul, env, want):
+    """Long rows in both decompositions (the knobs are read once per process, hence the subprocess) and a three-pass
+    Bluestein length, forward and inverse, against numpy."""
+    import sys
+
+    script = (KNOB_SCRIPT % (ROOT, os.path.join(EMUL, "_build", "libplan_emul.so"))).replace("WANT", repr(want))
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=900, env=dict(os.environ, **env))
+    assert r.returncode == 0 and "knob plans ok" in r.stdout, r.stdout + r.stderr
