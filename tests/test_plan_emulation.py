@@ -40,7 +40,8 @@ def emul():
         assert pr.wait() == 0, "host compilation of the planner / kernels failed"
     if procs or not os.path.exists(out):
         subprocess.run(["g++", "-shared", "-pthread", "-o", out] + objs, check=True)
-    os.environ["SFC_FFT2_TILE2D"] = "1"  # read once by the emulated planner at its first plan
+    old_knob = os.environ.get("SFC_FFT2_TILE2D")
+    os.environ["SFC_FFT2_TILE2D"] = "1"  # read once by the emulated planner, at its first 2-D plan
     lib = C.CDLL(out)
     lib.emul_plan_run.argtypes = [C.POINTER(_lib.sfc_desc), C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
 
@@ -57,7 +58,11 @@ def emul():
         rc = lib.emul_plan_run(C.byref(d), x.ctypes.data_as(C.c_void_p), out_arr.ctypes.data_as(C.c_void_p), buf, len(buf))
         return rc, buf.value.decode()
 
-    return run
+    yield run
+    if old_knob is None:
+        os.environ.pop("SFC_FFT2_TILE2D", None)
+    else:
+        os.environ["SFC_FFT2_TILE2D"] = old_knob
 
 
 def rel(a, b):
