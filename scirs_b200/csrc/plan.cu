@@ -1416,7 +1416,13 @@ struct PlanBuilder {
         pl.steps_.push_back(m);
         // pass 3 = four-step pass B of axis 1 with L1 = LB, L2 = 256: contiguous row segments, output column kc1 + LB*kc2
         Step b;
-        b.k = pick_kernel_two_per_sm(prec, (int)Cb, 0);
+        // the narrowest tile that still stores 128-byte segments (8 lanes): 32 KiB, four CTAs per SM
+        b.k = nullptr;
+        for (int i = 0; i < cnt; ++i)
+            if (t[i].prec == prec && t[i].L == (int)Cb && t[i].mode == 0 && t[i].groups == 1 && !t[i].dbl && t[i].E == 16 &&
+                t[i].TL >= 8 && LB % t[i].TL == 0 && (!b.k || t[i].TL < b.k->TL))
+                b.k = &t[i];
+        if (!b.k) b.k = pick_kernel_two_per_sm(prec, (int)Cb, 0);
         b.src = R_SA;
         b.dst = R_OUT;
         b.src_esize = b.dst_esize = cs;
