@@ -45,8 +45,10 @@ def emul():
     lib = C.CDLL(out)
     lib.emul_plan_run.argtypes = [C.POINTER(_lib.sfc_desc), C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
 
-    def run(shape, axes, x, out_arr, kind=_lib.SFC_C2C, inverse=False, scale=1.0, flags=0):
+    def run(shape, axes, x, out_arr, kind=_lib.SFC_C2C, inverse=False, scale=1.0, flags=0, axis_in_len=0, axis_out_len=0,
+            scale_dc=0.0):
         d = _lib.sfc_desc()
+        d.axis_in_len, d.axis_out_len, d.scale_dc = axis_in_len, axis_out_len, scale_dc
         d.ndim = len(shape)
         for i, s in enumerate(shape):
             d.shape[i] = s
@@ -197,3 +199,46 @@ def test_long_rows_and_bluestein_through_the_emulation(emul, env, want):
     script = (KNOB_SCRIPT % (ROOT, os.path.join(EMUL, "_build", "libplan_emul.so"))).replace("WANT", repr(want))
     r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=900, env=dict(os.environ, **env))
     assert r.returncode == 0 and "knob plans ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_consumer_plan_features(emul):
+    """Descriptor features the consumers rely on (api_ext.cu): fused DCT-II / DCT-III and their sine twins on rows and on a
+    strided axis, and a padded / cropped axis (SFC_DESC_AXIS_LEN: zero-padding on load, crop on store)."""
+    from scirs_b200 import _lib
+    from oracle import consumers_oracle as co
+
+    rng = np.random.default_rng(6)
+    for shape, axis in (((64, 256), 1), ((512, 32), 0)):
+        x = rng.standard_normal(shape)
+        n = shape[axis]
+        for sine in (False, True):
+            fl = _lib.SFC_DESC_TRIG_SINE if sine else 0
+            y = np.zeros_like(x)
+            rc, d = emul(list(shape), [axis], x, y, kind=_lib.SFC_R2C, flags=_lib.SFC_DESC_DCT2 | fl)
+            assert rc == 0, d
+            ref = co.dstn(x, 2, None, [axis]) if sine else co.dctn(x, 2, None, [axis])
+            assert rel(y, ref) < 1e-13, (shape, axis, sine)
+            # type III with the scales of api_ext.cu trig_axis: dct3 forward (None) = kernel(scale 1/n, dc 1); dst3 forward = (0.25, dc 2)
+            y = np.zeros_like(x)
+            rc, d = emul(list(shape), [axis], x, y, kind=_lib.SFC_R2C, flags=_lib.SFC_DESC_DCT3 | fl,
+                         scale=0.25 if sine else 1.0 / n, scale_dc=2.0 if sine else 1.0)
+            assert rc == 0, d
+            ref = co.dstn(x, 3, None, [axis]) if sine else co.dctn(x, 3, None, [axis])
+            assert rel(y, ref) < 1e-13, (shape, axis, sine, "III")
+    # 100 input samples zero-padded to a 256-point transform, first 60 bins kept
+    x = rng.standard_normal((6, 100)) + 1j * rng.standard_normal((6, 100))
+    y = np.zeros((6, 60), dtype=np.complex128)
+    rc, d = emul([6, 256], [1], x, y, flags=_lib.SFC_DESC_AXIS_LEN, axis_in_len=100, axis_out_len=60)
+    assert rc == 0, d
+    assert rel(y, np.fft.fft(x, 256, axis=1)[:, :60]) < 1e-14
+    # the same on a strided axis, and with a Bluestein length
+    x = rng.standard_normal((100, 12)) + 1j * rng.standard_normal((100, 12))
+    y = np.zeros((60, 12), dtype=np.complex128)
+    rc, d = emul([256, 12], [0], x, y, flags=_lib.SFC_DESC_AXIS_LEN, axis_in_len=100, axis_out_len=60)
+    assert rc == 0, d
+    assert rel(y, np.fft.fft(x, 256, axis=0)[:60]) < 1e-14
+    x = rng.standard_normal((3, 70)) + 1j * rng.standard_normal((3, 70))
+    y = np.zeros((3, 90), dtype=np.complex128)
+    rc, d = emul([3, 90], [1], x, y, flags=_lib.SFC_DESC_AXIS_LEN, axis_in_len=70, axis_out_len=90)
+    assert rc == 0, d
+    assert rel(y, np.fft.fft(x, 90, axis=1)) < 1e-13
