@@ -41,3 +41,17 @@ extern "C" int emul_plan_run(const sfc_desc* d, const void* in, void* out, char*
     snprintf(info, (size_t)info_len, "%s", rc == 0 ? p->describe().c_str() : es.c_str());
     return rc;
 }
+
+// the slab transpose fused into the store: output block q of the split axis goes to outs[q] (peer memory on the device)
+extern "C" int emul_plan_run_scatter(const sfc_desc* d, const void* in, void* const* outs, int nouts, char* info, int info_len) {
+    sfc::PlanError err{0, ""};
+    std::shared_ptr<sfc::Plan> p = sfc::Plan::create(*d, err);
+    if (!p) {
+        snprintf(info, (size_t)info_len, "%s", err.msg.c_str());
+        return err.code ? err.code : -1;
+    }
+    std::string es;
+    const int rc = p->exec(in, nullptr, nullptr, es, outs, nouts);
+    snprintf(info, (size_t)info_len, "%s", rc == 0 ? p->describe().c_str() : es.c_str());
+    return rc;
+}

@@ -60,6 +60,22 @@ def emul():
         rc = lib.emul_plan_run(C.byref(d), x.ctypes.data_as(C.c_void_p), out_arr.ctypes.data_as(C.c_void_p), buf, len(buf))
         return rc, buf.value.decode()
 
+    def run_scatter(shape, axes, x, outs, parts):
+        d = _lib.sfc_desc()
+        d.ndim = len(shape)
+        for i, s in enumerate(shape):
+            d.shape[i] = s
+        d.naxes = len(axes)
+        for i, a in enumerate(axes):
+            d.axes[i] = a
+        d.kind, d.prec, d.direction, d.flags, d.scale, d.scatter_parts = _lib.SFC_C2C, _lib.SFC_PREC_F64, 0, 0, 1.0, parts
+        ptrs = (C.c_void_p * parts)(*outs)
+        buf = C.create_string_buffer(8192)
+        rc = lib.emul_plan_run_scatter(C.byref(d), x.ctypes.data_as(C.c_void_p), ptrs, parts, buf, len(buf))
+        return rc, buf.value.decode()
+
+    run.scatter = run_scatter
+    lib.emul_plan_run_scatter.argtypes = [C.POINTER(_lib.sfc_desc), C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.c_int]
     yield run
     if old_knob is None:
         os.environ.pop("SFC_FFT2_TILE2D", None)
@@ -242,3 +258,29 @@ def test_consumer_plan_features(emul):
     rc, d = emul([3, 90], [1], x, y, flags=_lib.SFC_DESC_AXIS_LEN, axis_in_len=70, axis_out_len=90)
     assert rc == 0, d
     assert rel(y, np.fft.fft(x, 90, axis=1)) < 1e-13
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_slab_fftn_with_the_transpose_fused_into_the_store(emul, P):
+    """The multi-GPU slab fftn of scirs_b200/distributed.py (SlabFftn, mode "p2p") with the ranks run one after the other on
+    host arrays: axis 2 locally, axis 1 with the scatter store writing block q straight into rank q's receive buffer
+    (peer memory over NVLink on the device), axis 0 on the received [n0][s1][n2] slab."""
+    rng = np.random.default_rng(8)
+    n0, n1, n2 = 16, 64, 32
+    s0, s1 = n0 // P, n1 // P
+    X = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+    recv = [np.zeros((n0, s1, n2), dtype=np.complex128) for _ in range(P)]
+    block = s0 * s1 * n2 * 16
+    for r in range(P):
+        x = np.ascontiguousarray(X[r * s0:(r + 1) * s0])
+        work = np.zeros_like(x)
+        rc, d = emul([s0, n1, n2], [2], x, work)
+        assert rc == 0, d
+        rc, d = emul.scatter([s0, n1, n2], [1], work, [recv[q].ctypes.data + r * block for q in range(P)], P)
+        assert rc == 0, d
+    ref = np.fft.fftn(X)
+    for q in range(P):
+        out = np.zeros_like(recv[q])
+        rc, d = emul([n0, s1, n2], [0], recv[q], out)
+        assert rc == 0, d
+        assert rel(out, ref[:, q * s1:(q + 1) * s1, :]) < 1e-14
