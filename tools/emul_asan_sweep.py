@@ -5,7 +5,7 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from scirs_b200 import _lib
-sub = "asan" if os.environ.get("LD_PRELOAD") else "."
+sub = os.environ.get("EMUL_BUILD", "asan" if os.environ.get("LD_PRELOAD") else ".")
 lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "emul", "_build", sub, "libplan_emul.so"))
 count = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
