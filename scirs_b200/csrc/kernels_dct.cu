@@ -30,5 +30,7 @@ void register_kernels_dct(void (*add)(const KernelEntry&)) {
     SFC_ADD_DCT4(double, 8192, 1)
     // TM_FAST_2D (experimental, SFC_FFT2_TILE2D=1): 16 x 32 tile on 8 adjacent columns
     SFC_ADD_2D(double, 512, 8)
+    SFC_ADD_2D(double, 256, 16)   // 4096 columns: 16 x 16 tile on 16 adjacent columns
+    SFC_ADD_2D(double, 1024, 4)   // 16384 columns: 16 x 64 tile on 4 adjacent columns (64-byte segments)
 }
 }  // namespace sfc

@@ -1602,7 +1602,8 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
         }
         // experimental: one plan for both axes of a large forward 2-D transform
         const bool three_pass_2d = fft2_tile2d_enabled() && prec == PREC_F64 && shape.size() == 2 && axes.size() == 2 &&
-                                   axes[0] != axes[1] && shape[0] >= 256 && is_pow2(shape[0]) && shape[1] == 8192 && d.flags == 0 &&
+                                   axes[0] != axes[1] && shape[0] >= 256 && is_pow2(shape[0]) && (shape[1] == 4096 || shape[1] == 8192 || shape[1] == 16384) &&
+                                   d.flags == 0 &&
                                    d.scatter_parts <= 1;
         if (three_pass_2d) {
             ok = B.add_fft2_three_pass(shape[0], shape[1], d.scale, inv);

@@ -143,11 +143,11 @@ def test_fused_dct4_plan(emul, shape, axis):
         assert rel(y, ref) < 1e-12
 
 
-def test_fft2_three_pass_plan(emul):
-    """SFC_FFT2_TILE2D=1: Plan::create -> add_fft2_three_pass for 256 x 8192 (the plan takes any power-of-two row count from
-    256 with 8192 columns; 8192 x 8192 runs the same three kernels with a longer first pass)."""
+@pytest.mark.parametrize("R,Cn", [(256, 8192), (512, 4096), (256, 16384)])
+def test_fft2_three_pass_plan(emul, R, Cn):
+    """SFC_FFT2_TILE2D=1: Plan::create -> add_fft2_three_pass (the plan takes any power-of-two row count from 256 with 4096,
+    8192 or 16384 columns; 8192 x 8192 runs the same three kernels with a longer first pass)."""
     rng = np.random.default_rng(2)
-    R, Cn = 256, 8192
     x = rng.standard_normal((R, Cn)) + 1j * rng.standard_normal((R, Cn))
     y = np.zeros_like(x)
     rc, d = emul([R, Cn], [0, 1], x, y, scale=0.125)
