@@ -28,9 +28,11 @@ for n in (1024, 4096, 16384):
         except Exception as ex:
             print(name, n, "failed:", str(ex)[:120])
     del x, y
-n = 8192
-x = torch.randn(n * n * 2, device=dev, dtype=torch.float64); y = torch.empty_like(x)
-p = FftPlan([n, n], [0, 1])
-t = timeit(p, x, y); byt = 2 * 2 * 16 * n * n
-print(f"fft2 {n}x{n} SFC_FFT2_TILE2D={os.environ.get('SFC_FFT2_TILE2D', '0')}: {t:7.3f} ms {byt/t/1e6:7.0f} GB/s ({byt/t/1e6/HBM:5.1%} of the two-pass roofline)")
-print(p.describe())
+for n in (4096, 8192, 16384):
+    x = torch.randn(n * n * 2, device=dev, dtype=torch.float64); y = torch.empty_like(x)
+    p = FftPlan([n, n], [0, 1])
+    t = timeit(p, x, y, 3); byt = 2 * 2 * 16 * n * n
+    print(f"fft2 {n}x{n} SFC_FFT2_TILE2D={os.environ.get('SFC_FFT2_TILE2D', '0')}: {t:8.3f} ms {byt/t/1e6:7.0f} GB/s ({byt/t/1e6/HBM:5.1%} of the two-pass roofline)", flush=True)
+    print(p.describe())
+    del x, y, p
+    torch.cuda.empty_cache()
