@@ -144,8 +144,24 @@ void evict_old_entries(PlanCacheImpl& c) {
     }
 }
 
+// device-memory pressure (plan.h): give back the scratch of every cached plan that is idle
+size_t release_cached_scratch(const Plan* except) {
+    PlanCacheImpl& c = cache();
+    std::vector<std::shared_ptr<Plan>> plans;
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        for (auto& kv : c.map) plans.push_back(kv.second.plan);
+    }
+    size_t freed = 0;
+    for (auto& p : plans)
+        if (p.get() != except) freed += p->release_scratch();
+    return freed;
+}
+
 std::shared_ptr<Plan> get_or_create_plan(const sfc_desc& d, PlanError& err) {
     PlanCacheImpl& c = cache();
+    static const bool hooked = (sfc::set_scratch_pressure_hook(&release_cached_scratch), true);
+    (void)hooked;
     {
         std::lock_guard<std::mutex> lk(c.mu);
         if (!c.enabled) {
@@ -265,7 +281,7 @@ extern "C" __attribute__((visibility("default"))) int sfc_exec_device_scatter(sf
 
 extern "C" __attribute__((visibility("default"))) int sfc_dev_malloc(void** d_ptr, size_t bytes) {
     if (!d_ptr) return fail(SFC_ERR_VALUE, "null argument");
-    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 256);
+    cudaError_t e = sfc::alloc_with_relief(d_ptr, bytes ? bytes : 256, nullptr);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
     return SFC_OK;
 }
@@ -315,7 +331,7 @@ int sfc_api::ensure_buf(void** p, size_t* cap, size_t bytes) {
     if (*p) cudaFree(*p);
     *p = nullptr;
     *cap = 0;
-    cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 256));
+    cudaError_t e = sfc::alloc_with_relief(p, std::max<size_t>(bytes, 256), nullptr);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
     *cap = std::max<size_t>(bytes, 256);
     return SFC_OK;

@@ -1805,20 +1805,7 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
     }
     if (!ok) return nullptr;
 
-    if (pl.sa_bytes_) {
-        if (cudaMalloc(&pl.sa_, pl.sa_bytes_) != cudaSuccess) {
-            cudaGetLastError();
-            err = {SFC_ERR_MEMORY, "cudaMalloc failed for plan scratch"};
-            return nullptr;
-        }
-    }
-    if (pl.ms_bytes_) {
-        if (cudaMalloc(&pl.ms_, pl.ms_bytes_) != cudaSuccess) {
-            cudaGetLastError();
-            err = {SFC_ERR_MEMORY, "cudaMalloc failed for plan work area"};
-            return nullptr;
-        }
-    }
+    // scratch (sa_ / ms_) is allocated by the first execution: cached plans that are never run again hold no memory
     pl.info.in_bytes = pl.in_elems * (int64_t)pl.in_esize;
     pl.info.out_bytes = pl.out_elems * (int64_t)pl.out_esize;
     pl.info.scratch_bytes = (int64_t)(pl.sa_bytes_ + pl.ms_bytes_);
@@ -1837,9 +1824,60 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
     return sp;
 }
 
+static size_t (*g_pressure_hook)(const Plan*) = nullptr;
+void set_scratch_pressure_hook(size_t (*hook)(const Plan* except)) { g_pressure_hook = hook; }
+
+cudaError_t alloc_with_relief(void** p, size_t bytes, const Plan* except) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation && g_pressure_hook) {
+        cudaGetLastError();
+        if (g_pressure_hook(except) > 0) e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+    }
+    return e;
+}
+
+bool Plan::ensure_scratch(std::string& es) {
+    if (sa_bytes_ && !sa_ && alloc_with_relief(&sa_, sa_bytes_, this) != cudaSuccess) {
+        es = "cudaMalloc failed for plan scratch";
+        return false;
+    }
+    if (ms_bytes_ && !ms_ && alloc_with_relief(&ms_, ms_bytes_, this) != cudaSuccess) {
+        es = "cudaMalloc failed for plan work area";
+        return false;
+    }
+    if ((sa_bytes_ || ms_bytes_) && !busy_ev_ && cudaEventCreateWithFlags(&busy_ev_, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        es = "cudaEventCreate failed";
+        return false;
+    }
+    return true;
+}
+
+size_t Plan::release_scratch() {
+    std::unique_lock<std::mutex> lk(mu_, std::try_to_lock);
+    if (!lk.owns_lock()) return 0;  // being enqueued right now: leave it alone
+    const size_t freed = scratch_resident();
+    if (!freed) return 0;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (prev != device) cudaSetDevice(device);
+    if (busy_valid_) cudaEventSynchronize(busy_ev_);
+    if (sa_) cudaFree(sa_);
+    if (ms_) cudaFree(ms_);
+    sa_ = ms_ = nullptr;
+    busy_valid_ = false;
+    if (prev != device) cudaSetDevice(prev);
+    return freed;
+}
+
 Plan::~Plan() {
     if (sa_) cudaFree(sa_);
     if (ms_) cudaFree(ms_);
+    if (busy_ev_) cudaEventDestroy(busy_ev_);
     for (cudaEvent_t e : side_done_) cudaEventDestroy(e);
     for (cudaStream_t s : side_) cudaStreamDestroy(s);
     if (fork_ev_) cudaEventDestroy(fork_ev_);
@@ -1923,6 +1961,21 @@ extern "C" __attribute__((visibility("default"))) void sfc_debug_phase_dump(void
 
 int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& es, void* const* scatter, int nscatter) {
     std::lock_guard<std::mutex> lk(mu_);
+    const bool uses_scratch = sa_bytes_ || ms_bytes_;
+    if (uses_scratch) {
+        if (!ensure_scratch(es)) return SFC_ERR_MEMORY;
+        // the previous execution may still be running on another stream over the same scratch: order after it
+        if (busy_valid_ && last_stream_ != stream) cudaStreamWaitEvent(stream, busy_ev_, 0);
+    }
+    struct Mark {  // record the "scratch busy until here" event on every exit path that launched something
+        Plan* pl; cudaStream_t st; bool on;
+        ~Mark() {
+            if (!on) return;
+            cudaEventRecord(pl->busy_ev_, st);
+            pl->busy_valid_ = true;
+            pl->last_stream_ = st;
+        }
+    } mark{this, stream, uses_scratch};
     auto base = [&](int role) -> char* {
         switch (role) {
             case R_IN: return (char*)const_cast<void*>(d_in);

@@ -58,7 +58,9 @@ class Plan {
     static std::shared_ptr<Plan> create(const sfc_desc& d, PlanError& err);
     ~Plan();
 
-    // d_in / d_out are device pointers; not re-entrant (serialised internally)
+    // d_in / d_out are device pointers.  Safe to call from several threads and on several streams at once: launches are
+    // enqueued under the plan's mutex, and an execution on another stream than the previous one first waits (on the
+    // device, through an event) for the previous one, because both use the plan's scratch areas.
     int exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& err, void* const* scatter = nullptr,
              int nscatter = 0);
 
@@ -84,8 +86,24 @@ class Plan {
     std::vector<cudaEvent_t> side_done_;
     cudaEvent_t fork_ev_ = nullptr;
     bool ensure_side_streams(int n, std::string& es);
+    // scratch is allocated on first execution (not at plan creation) and can be given back under memory pressure
+    bool ensure_scratch(std::string& es);
+    cudaEvent_t busy_ev_ = nullptr;      // recorded after the last launch of every execution that touches scratch
+    bool busy_valid_ = false;
+    cudaStream_t last_stream_ = nullptr;
     friend struct PlanBuilder;
+
+   public:
+    // Frees the scratch areas if the plan is idle (no execution being enqueued; waits for the last one to finish on the
+    // device).  Returns the bytes released.  Called for the OTHER cached plans when a device allocation fails.
+    size_t release_scratch();
+    size_t scratch_resident() const { return (sa_ ? sa_bytes_ : 0) + (ms_ ? ms_bytes_ : 0); }
 };
+
+// Device-memory pressure: api.cu installs a hook that walks the plan cache and calls release_scratch() on every plan but
+// `except`; plan.cu and ensure_buf call alloc_with_relief, which retries a failed cudaMalloc once after running it.
+void set_scratch_pressure_hook(size_t (*hook)(const Plan* except));
+cudaError_t alloc_with_relief(void** p, size_t bytes, const Plan* except);
 
 // largest single-tile transform per precision
 inline int lmax_for(int prec) { return prec == PREC_F64 ? 8192 : 16384; }

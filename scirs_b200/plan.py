@@ -82,6 +82,13 @@ class FftPlan:
         info = _lib.sfc_plan_info()
         check(lib.sfc_plan_get_info(self._h, C.byref(info)))
         self.info = {f: getattr(info, f) for f, _ in _lib.sfc_plan_info._fields_}
+        # element types of the in / out arrays, from the descriptor flags (not from byte counts)
+        cplx = np.complex128 if prec == "f64" else np.complex64
+        real = np.float64 if prec == "f64" else np.float32
+        real_in = kind == "r2c" or (kind == "c2c" and real_input)
+        real_out = kind == "c2r" or (kind == "c2c" and real_output) or (kind == "r2c" and (dct2 or dct3 or dct4))
+        self.in_dtype = np.dtype(real if real_in else cplx)
+        self.out_dtype = np.dtype(real if real_out else cplx)
 
     def describe(self) -> str:
         buf = C.create_string_buffer(8192)
@@ -94,15 +101,16 @@ class FftPlan:
 
     def execute(self, x: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Host arrays in/out (H2D + transform + D2H)."""
-        cplx = np.complex128 if self.prec == "f64" else np.complex64
-        real = np.float64 if self.prec == "f64" else np.float32
-        in_dt = real if (self.kind == "r2c" or self.info["in_bytes"] * 2 == self.info["out_bytes"] and self.kind == "c2c") else cplx
-        a = np.ascontiguousarray(x, dtype=in_dt)
+        a = np.ascontiguousarray(x, dtype=self.in_dtype)
         if a.nbytes != self.info["in_bytes"]:
             raise ValueError_(f"input has {a.nbytes} bytes, plan expects {self.info['in_bytes']}")
-        out_dt = real if self.kind == "c2r" else cplx
+        out_dt = self.out_dtype
         if out is None:
-            out = np.empty(self.info["out_bytes"] // np.dtype(out_dt).itemsize, dtype=out_dt)
+            out = np.empty(self.info["out_bytes"] // out_dt.itemsize, dtype=out_dt)
+        elif not isinstance(out, np.ndarray) or out.dtype != out_dt or not out.flags.c_contiguous \
+                or not out.flags.writeable or out.nbytes != self.info["out_bytes"]:
+            # the library writes out_bytes raw bytes: anything else would be overrun or filled with garbage
+            raise ValueError_(f"output must be a writable C-contiguous {out_dt} array of {self.info['out_bytes']} bytes")
         check(self._lib.sfc_exec_host(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
         return out
 
@@ -131,9 +139,14 @@ class FftPlanExecutor:
     def execute(self, input: np.ndarray, output: np.ndarray) -> None:
         if input.size != self.n or output.size != self.n:  # planning.rs:509-517
             raise ValueError_(f"Input size mismatch: expected {self.n}, got {input.size}")
-        self.plan.execute(np.asarray(input, dtype=np.complex128), output)
+        # `&mut [Complex64]` in the reference: anything that is not a contiguous complex128 buffer cannot be written in place
+        if not isinstance(output, np.ndarray) or output.dtype != np.complex128 or not output.flags.c_contiguous:
+            raise ValueError_("output must be a C-contiguous complex128 array")
+        self.plan.execute(np.asarray(input, dtype=np.complex128), output.reshape(-1))
 
     def execute_inplace(self, data: np.ndarray) -> None:
         if data.size != self.n:
             raise ValueError_(f"Input size mismatch: expected {self.n}, got {data.size}")
-        self.plan.execute(np.array(data, dtype=np.complex128), data)
+        if not isinstance(data, np.ndarray) or data.dtype != np.complex128 or not data.flags.c_contiguous:
+            raise ValueError_("data must be a C-contiguous complex128 array")
+        self.plan.execute(np.array(data, dtype=np.complex128), data.reshape(-1))

@@ -63,7 +63,7 @@ inline void emul_launch(K kernel, const P& p, unsigned grid, int nt) {
 
 // ---- the slice of the runtime API plan.cu / kernel_inst.cuh use ----
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorUnknown = 999 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorUnknown = 999 };
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
@@ -94,6 +94,8 @@ inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSu
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 template <class F>
 inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 148; return cudaSuccess; }
