@@ -12,7 +12,9 @@ A "step" is one pass of the hot path over one batch of synthetic input:
                     bluestein_1000003 (configs[3], batch 32)
   The non-default workloads are also timed briefly and reported under "others".
 N > 1 shards the batch across ranks with no data-path collective (weak scaling: every rank owns
-65,536 signals); "others.fftn_512_slab" adds the slab-decomposed 3-D transform with its all-to-all.
+65,536 signals); roofline.others.fftn_{512,1024}_slab add the slab-decomposed 3-D transform (library communicator,
+exchange fused into the FFT stores over NVLink) with its parity against the single-GPU plan.
+A step = R back-to-back executions of the plan (R fixed before the timed region so that the K steps last >= 1 s).
 
 value      = whole-job GFLOP/s (5 N log2 N per transform), inputs resident in HBM, CUDA events on
              the launching stream, barrier + synchronize on both sides, max over ranks.
@@ -49,8 +51,8 @@ WORKLOADS = {
     "fft_2p20": ([64, 1 << 20], [1], "c2c", "f64", True, "fft c128 2^20, batch 64 (configs[0] steady state)"),
     "fft_2p24": ([8, 1 << 24], [1], "c2c", "f64", True, "fft c128 2^24, batch 8 (large-N path: three passes of small tiles)"),
     "fftn_512": ([512, 512, 512], [0, 1, 2], "c2c", "f64", True, "fftn c128 512^3 on one GPU (configs[4])"),
-    "bluestein_1000003": ([32, 1000003], [1], "c2c", "f64", True, "fft c128 N=1,000,003 (prime, Bluestein), batch 32 (configs[3])"),
-    "bluestein_1594323": ([32, 1594323], [1], "c2c", "f64", True, "fft c128 N=3^13 (Bluestein), batch 32 (configs[3])"),
+    "bluestein_1000003": ([256, 1000003], [1], "c2c", "f64", True, "fft c128 N=1,000,003 (prime, Bluestein), batch 256 (configs[3])"),
+    "bluestein_1594323": ([256, 1594323], [1], "c2c", "f64", True, "fft c128 N=3^13 (Bluestein), batch 256 (configs[3])"),
     "fftn_1024": ([1024, 1024, 1024], [0, 1, 2], "c2c", "f64", True, "fftn c128 1024^3 on one GPU (configs[4])"),
 }
 
@@ -196,8 +198,15 @@ def cpu_port_run(workload: str, threads: int, budget_s: float, steps: int = 1):
 
 # ------------------------------------------------------------------ GPU arm
 
+MIN_TIMED_S = 1.0      # the timed region of the headline workload lasts at least this long at every N
+PRELOAD_S = 1.0        # the same kernel runs this long right before it: N = 1 and N = 8 are both SUSTAINED numbers
+OTHER_TIMED_S = 0.25   # timed region of each secondary workload
+
 
 def run_gpu(args):
+    import ctypes as C
+
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -222,6 +231,13 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def alloc(workload):
         shape, axes, kind, prec, fwd, desc = WORKLOADS[workload]
         rt = torch.float64 if prec == "f64" else torch.float32
@@ -238,20 +254,35 @@ def run_gpu(args):
         plan = sb.FftPlan(shape, axes, kind, prec, fwd, scale)
         return plan, din, dout
 
-    def time_workload(workload, steps, warmup, sample_clocks=False):
+    def time_workload(workload, steps, warmup, min_total_s, preload_s=0.0, sample_clocks=False):
+        """A step = `reps` executions of the plan over the resident batch, `reps` chosen (the same on every rank) so
+        that the K timed steps last >= min_total_s; times are reported per step and per execution."""
         plan, din, dout = alloc(workload)
         stream = torch.cuda.current_stream()
+        run = lambda: plan.execute_device(din, dout, stream.cuda_stream)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(3):
+            run()
+        c1.record(stream)
+        torch.cuda.synchronize()
+        t1 = max(max_over_ranks(c0.elapsed_time(c1) / 3.0), 1e-3)  # ms per execution
+        reps = max(1, int(math.ceil(min_total_s * 1e3 / (steps * t1))))
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
-            # nvidia-smi needs ~0.2 s to start: begin before the warm-up, keep the GPU under the same
-            # load for a moment after the timed steps, and report the median over the whole window
             sampler.start()
-            t_end = time.time() + 0.6
-            while time.time() < t_end:
-                plan.execute_device(din, dout, stream.cuda_stream)
-                torch.cuda.synchronize()
+        # sustained state: the same kernel back to back before anything is timed (nvidia-smi also needs ~0.2 s to start)
+        t_end = time.time() + max(preload_s, 0.6 if sampler else 0.0)
+        while time.time() < t_end:
+            for _ in range(8):
+                run()
+            torch.cuda.synchronize()
         for _ in range(warmup):
-            plan.execute_device(din, dout, stream.cuda_stream)
+            for _ in range(reps):
+                run()
         barrier()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -259,7 +290,8 @@ def run_gpu(args):
         t_all0.record(stream)
         for e0, e1 in evs:
             e0.record(stream)
-            plan.execute_device(din, dout, stream.cuda_stream)
+            for _ in range(reps):
+                run()
             e1.record(stream)
         t_all1.record(stream)
         barrier()
@@ -267,84 +299,100 @@ def run_gpu(args):
         if sampler:
             t_end = time.time() + 0.4
             while time.time() < t_end:
-                plan.execute_device(din, dout, stream.cuda_stream)
+                run()
                 torch.cuda.synchronize()
             clocks = sampler.stop()
-        total_ms = t_all0.elapsed_time(t_all1)
+        total_ms = max_over_ranks(t_all0.elapsed_time(t_all1))
         per = [a.elapsed_time(b) for a, b in evs]
-        if world > 1:
-            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
         info = plan.info
         del din, dout
-        return {"ms_per_step": total_ms / steps, "kernel_ms": sum(per) / len(per), "info": info, "plan": plan,
-                "clocks": clocks}
+        return {"ms_per_step": total_ms / steps, "ms_per_exec": total_ms / steps / reps, "kernel_ms": sum(per) / len(per) / reps,
+                "reps": reps, "timed_s": total_ms / 1e3, "info": info, "plan": plan, "clocks": clocks}
 
     def summarize(workload, r):
         shape, axes, kind, prec, fwd, desc = WORKLOADS[workload]
         fl = flops_of(shape, axes, kind)
-        ms = r["ms_per_step"]
+        ms = r["ms_per_exec"]
         alg = r["info"]["algorithmic_bytes"]
-        return {"what": desc, "gflops": fl * world / ms / 1e6, "ms_per_step": ms, "hbm_gbs": alg / r["kernel_ms"] / 1e6,
-                "frac_of_hbm": alg / r["kernel_ms"] / 1e6 / hbm, "launches_per_step": r["info"]["num_launches"],
-                "passes": r["info"]["num_passes"], "dtype": prec}
+        dev_b = r["info"]["device_bytes"]
+        return {"what": desc, "gflops": round(fl * world / ms / 1e6, 1), "ms": round(ms, 4), "hbm_gbs": round(alg / r["kernel_ms"] / 1e6, 1),
+                "frac": round(alg / r["kernel_ms"] / 1e6 / hbm, 4), "launches": r["info"]["num_launches"],
+                "passes": r["info"]["num_passes"], "device_bytes_over_algorithmic": round(dev_b / max(alg, 1), 3), "dtype": prec}
 
     # ---------------- headline workload
     wl = args.workload
     shape, axes, kind, prec, fwd, desc = WORKLOADS[wl]
-    r = time_workload(wl, args.steps, args.warmup, sample_clocks=True)
+    r = time_workload(wl, args.steps, args.warmup, MIN_TIMED_S, PRELOAD_S, sample_clocks=True)
     clocks = r.pop("clocks", None)
     head = summarize(wl, r)
-    launches = r["info"]["num_launches"] * args.steps
+    reps = r["reps"]
+    step_ms = r["ms_per_step"]
+    launches = r["info"]["num_launches"] * args.steps * reps
 
     # roofline of the dominant (here: only) kernel of the step
     alg = r["info"]["algorithmic_bytes"]
-    traffic = None
-    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-    summ = os.path.join(ROOT, "profiles", "r1_ncu_full.json")
-    ncu_key = {"c2c_f64_65536x4096": "r1_full_c2c4096#0", "rfft_f64": "r1_full_rfft4096#0",
-               "irfft_f64": "r1_full_irfft4096#0"}.get(wl)
-    if ncu_key and os.path.exists(summ):
-        try:
-            traffic = json.load(open(summ)).get(ncu_key, {}).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    achieved = alg / r["info"]["num_launches"] / (r["kernel_ms"] / r["info"]["num_launches"]) / 1e6
+    traffic, traffic_src = None, None
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: NOT measurable inside a timed run (needs ncu's replay);
+    # taken from the committed ncu --set full capture of the same kernel and labelled as such
+    for tag in ("r2", "r1"):
+        summ = os.path.join(ROOT, "profiles", f"{tag}_ncu_full.json")
+        ncu_key = {"c2c_f64_65536x4096": f"{tag}_full_c2c4096#0", "rfft_f64": f"{tag}_full_rfft4096#0",
+                   "irfft_f64": f"{tag}_full_irfft4096#0"}.get(wl)
+        if ncu_key and os.path.exists(summ):
+            try:
+                traffic = json.load(open(summ)).get(ncu_key, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+            if traffic:
+                traffic_src = f"profiles/{tag}_ncu_full.json ({ncu_key}: dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full)"
+                break
+    nl = r["info"]["num_launches"]
+    achieved = alg / nl / (r["kernel_ms"] / nl) / 1e6
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
-                "traffic": traffic, "peak_source": hbm_src, "kernel": "sfc::tile_fft_kernel",
-                "algorithmic_bytes_per_launch": alg // r["info"]["num_launches"],
-                "kernel_ms": round(r["kernel_ms"] / r["info"]["num_launches"], 4)}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src, "kernel": "sfc::tile_fft_kernel",
+                "algorithmic_bytes_per_launch": alg // nl, "kernel_ms": round(r["kernel_ms"] / nl, 4),
+                "timed_region_s": round(r["timed_s"], 3), "executions_per_step": reps}
 
     # ---------------- e2e through the C ABI with pinned host buffers
     e2e = None
     try:
-        import numpy as np
-
         plan = r["plan"]
         nin, nout = plan.info["in_bytes"], plan.info["out_bytes"]
         hin = torch.empty(nin, dtype=torch.uint8).pin_memory()
         hout = torch.empty(nout, dtype=torch.uint8).pin_memory()
         rt = np.float64 if prec == "f64" else np.float32
         hin.numpy().view(rt)[:] = np.random.default_rng(7 + rank).standard_normal(nin // np.dtype(rt).itemsize).astype(rt)
-        import ctypes as C
-
-        e_steps = max(2, min(args.steps, 5))
-        for _ in range(1):
+        # the PCIe roofline of this call, measured here: pinned H2D and D2H of the same sizes running at the same time
+        dscr_in = torch.empty(nin, dtype=torch.uint8, device=dev)
+        dscr_out = torch.empty(nout, dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        pcie_s = None
+        for it in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s1):
+                dscr_in.copy_(hin, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hout.copy_(dscr_out, non_blocking=True)
+            torch.cuda.synchronize()
+            pcie_s = time.perf_counter() - t0
+        pcie_s = max_over_ranks(pcie_s)
+        del dscr_in, dscr_out
+        e_steps = max(3, min(args.steps, 5))
+        for _ in range(2):
             sb.error.check(lib.sfc_exec_host(plan._h, C.c_void_p(hin.data_ptr()), C.c_void_p(hout.data_ptr())))
         barrier()
         t0 = time.perf_counter()
         for _ in range(e_steps):
             sb.error.check(lib.sfc_exec_host(plan._h, C.c_void_p(hin.data_ptr()), C.c_void_p(hout.data_ptr())))
         barrier()
-        dt = (time.perf_counter() - t0) / e_steps
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks((time.perf_counter() - t0) / e_steps)
         e2e = {"value": round(flops_of(shape, axes, kind) * world / dt / 1e9, 2), "unit": "GFLOP/s",
                "h2d_bytes_per_step": int(nin), "d2h_bytes_per_step": int(nout), "ms_per_step": round(dt * 1e3, 3),
-               "api": "sfc_exec_host (C ABI, pinned host buffers)", "steps": e_steps}
+               "api": "sfc_exec_host (C ABI, pinned host buffers, 16-chunk H2D / kernel / D2H pipeline)", "steps": e_steps,
+               "pcie_duplex_copy_ms": round(pcie_s * 1e3, 3),
+               "pcie_duplex_gbs": round((nin + nout) / pcie_s / 1e9, 1),
+               "pcie_frac": round(pcie_s / dt, 4)}
         del hin, hout
     except Exception as ex:  # keep the line printable; say why
         e2e = {"value": None, "unit": "GFLOP/s", "error": str(ex)[:200]}
@@ -355,67 +403,151 @@ def run_gpu(args):
         del r
         torch.cuda.empty_cache()
         for name in WORKLOADS:
-            if name == wl:
+            if name == wl or (world > 1 and name in ("fftn_1024",)):
                 continue
             try:
-                rr = time_workload(name, 5, 3)
-                others[name] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in summarize(name, rr).items()}
+                rr = time_workload(name, 5, 3, OTHER_TIMED_S)
+                others[name] = summarize(name, rr)
                 del rr
                 torch.cuda.empty_cache()
             except Exception as ex:
                 others[name] = {"error": str(ex)[:160]}
         if world == 1:
+            # BASELINE configs[0] as written: ONE 2^20 transform (batch 1).  Device-resident latency of back-to-back
+            # executions, of a CUDA graph of the plan's launches, and the host call sb.fft (H2D + D2H of 16 MiB each, plan
+            # cache hit) — floor: 67.1 MB of algorithmic traffic = 10.2 us at the HBM peak
+            try:
+                n = 1 << 20
+                plan = sb.FftPlan([1, n], [1])
+                x = torch.randn(2 * n, dtype=torch.float64, device=dev)
+                y = torch.empty_like(x)
+                st = torch.cuda.Stream()
+                with torch.cuda.stream(st):
+                    for _ in range(20):
+                        plan.execute_device(x, y, st.cuda_stream)
+                    st.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(st)
+                    for _ in range(200):
+                        plan.execute_device(x, y, st.cuda_stream)
+                    e1.record(st)
+                    st.synchronize()
+                    stream_us = e0.elapsed_time(e1) / 200 * 1e3
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=st):
+                        for _ in range(10):
+                            plan.execute_device(x, y, st.cuda_stream)
+                    g.replay()
+                    st.synchronize()
+                    e0.record(st)
+                    for _ in range(20):
+                        g.replay()
+                    e1.record(st)
+                    st.synchronize()
+                    graph_us = e0.elapsed_time(e1) / 200 * 1e3
+                hx = np.random.default_rng(1).standard_normal(n) + 1j * np.random.default_rng(2).standard_normal(n)
+                for _ in range(3):
+                    sb.fft(hx)
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    sb.fft(hx)
+                host_us = (time.perf_counter() - t0) / 20 * 1e6
+                others["fft_2p20_batch1"] = {"what": "fft c128 2^20, batch 1 (configs[0] as written): latency per transform",
+                                             "device_us": round(stream_us, 2), "device_graph_us": round(graph_us, 2),
+                                             "host_call_us": round(host_us, 1), "floor_us": round(2 * 2 * 16 * n / hbm / 1e3, 2),
+                                             "frac": round(2 * 2 * 16 * n / hbm / 1e3 / graph_us, 4), "passes": 2, "dtype": "f64"}
+                del x, y, plan, g
+            except Exception as ex:
+                others["fft_2p20_batch1"] = {"error": str(ex)[:160]}
             # batched DCT-II (dct.rs:523-559) as ONE fused kernel per row (Makhoul packing on the
             # n/2-point transform); algorithmic bytes = n reals in + n reals out per row
-            try:
-                import numpy as np
-
-                B, n = 65536, 4096
-                plan = sb.FftPlan([B, n], [1], "r2c", "f64", True, 1.0, dct2=True)
-                x = torch.randn(B * n, dtype=torch.float64, device=dev)
-                y = torch.empty_like(x)
-                st = torch.cuda.current_stream()
-                for _ in range(3):
-                    plan.execute_device(x, y, st.cuda_stream)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(st)
-                for _ in range(5):
-                    plan.execute_device(x, y, st.cuda_stream)
-                e1.record(st)
-                torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1) / 5
-                byt = 2 * 8 * B * n
-                others["dct2_f64"] = {"what": "batched DCT-II f64, 65,536 x 4096 (SURVEY 8f rank 1; one fused kernel on the n/2-point packed transform)",
-                                      "ms_per_step": round(ms, 4), "hbm_gbs": round(byt / ms / 1e6, 1),
-                                      "frac_of_hbm": round(byt / ms / 1e6 / hbm, 4), "launches_per_step": 1, "dtype": "f64"}
-                del x, y, plan
-                torch.cuda.empty_cache()
-            except Exception as ex:
-                others["dct2_f64"] = {"error": str(ex)[:160]}
+            for nm, kw in (("dct2_f64", dict(dct2=True)), ("dct4_f64", dict(dct4=True))):
+                try:
+                    B, n = 65536, 4096
+                    plan = sb.FftPlan([B, n], [1], "r2c", "f64", True, 1.0, **kw)
+                    x = torch.randn(B * n, dtype=torch.float64, device=dev)
+                    y = torch.empty_like(x)
+                    st = torch.cuda.current_stream()
+                    for _ in range(3):
+                        plan.execute_device(x, y, st.cuda_stream)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(st)
+                    for _ in range(50):
+                        plan.execute_device(x, y, st.cuda_stream)
+                    e1.record(st)
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / 50
+                    byt = 2 * 8 * B * n
+                    others[nm] = {"what": f"batched DCT-{'II' if nm[3] == '2' else 'IV'} f64, 65,536 x 4096 (SURVEY 8f rank 1; one fused kernel on the n/2-point transform)",
+                                  "ms": round(ms, 4), "hbm_gbs": round(byt / ms / 1e6, 1), "frac": round(byt / ms / 1e6 / hbm, 4),
+                                  "launches": 1, "dtype": "f64"}
+                    del x, y, plan
+                    torch.cuda.empty_cache()
+                except Exception as ex:
+                    others[nm] = {"error": str(ex)[:160]}
         if world > 1:
-            try:
-                from scirs_b200.distributed import bench_slab_fftn
+            # BASELINE configs[4]: slab-decomposed fftn through the library's own communicator (sfc_comm_* / sfc_dist_*:
+            # no torch / NCCL in the data path), parity against the single-GPU plan computed outside the timed region
+            from scirs_b200.distributed import bench_slab_fftn
 
-                others["fftn_512_slab"] = bench_slab_fftn(512, steps=5, warmup=3)
-            except Exception as ex:
-                others["fftn_512_slab"] = {"error": str(ex)[:200]}
+            for n3, lay in ((512, "transposed"), (512, "natural"), (1024, "transposed")):
+                key = f"fftn_{n3}_slab" + ("" if lay == "transposed" else "_natural")
+                try:
+                    others[key] = bench_slab_fftn(n3, steps=10, warmup=3, layout=lay, min_seconds=0.25)
+                except Exception as ex:
+                    others[key] = {"error": str(ex)[:300]}
+                torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, sample, dt, th = cpu_port_run(wl, 1, 12.0)
         cpu = {"value": round(v, 3), "unit": "GFLOP/s", "cores": th, "kind": "port", "sample": sample,
                "seconds": round(dt, 2)}
+        try:  # an independent strong-CPU yardstick: scipy's pocketfft on every host core
+            import scipy.fft as sf
+
+            nthr = os.cpu_count() or 1
+            rows = 8192
+            xs = np.random.default_rng(3).standard_normal((rows, shape[-1])) + 1j * np.random.default_rng(4).standard_normal((rows, shape[-1]))
+            sf.fft(xs, axis=1, workers=nthr)
+            t0 = time.perf_counter()
+            nrep = 0
+            while time.perf_counter() - t0 < 3.0:
+                sf.fft(xs, axis=1, workers=nthr)
+                nrep += 1
+            dtp = (time.perf_counter() - t0) / nrep
+            cpu["pocketfft"] = {"value": round(flops_of([rows, shape[-1]], [1], "c2c") / dtp / 1e9, 2), "unit": "GFLOP/s", "cores": nthr,
+                                "sample": f"scipy.fft.fft (pocketfft) on {rows} x {shape[-1]} c128, workers={nthr}"}
+        except Exception as ex:
+            cpu["pocketfft"] = {"error": str(ex)[:120]}
 
     if rank == 0:
+        # the driver keeps `roofline` whole and drops unknown top-level keys: every secondary figure the review needs is
+        # mirrored there in compact form
+        compact = {}
+        for k, v in others.items():
+            if "error" in v:
+                compact[k] = {"error": v["error"][:80]}
+            elif "nvlink_frac_of_900" in v:
+                compact[k] = {"ms": v["ms_per_step"], "parity_rel_l2": v["parity_rel_l2"], "nvlink_frac": v["nvlink_frac_of_900"],
+                              "exchange_ms": v["exchange_ms"], "stage_ms": v["stage_ms"], "gflops": v["gflops"]}
+            elif "device_us" in v:
+                compact[k] = {kk: v[kk] for kk in ("device_us", "device_graph_us", "host_call_us", "floor_us", "frac")}
+            else:
+                compact[k] = {kk: v[kk] for kk in ("ms", "frac", "passes", "launches", "gflops") if kk in v}
+        roofline["others"] = compact
         line = {
             "metric": "batched f64 c2c FFT GFLOP/s (5 N log2 N)" if kind == "c2c" else "batched FFT GFLOP/s (2.5 N log2 N, real)",
             "value": round(head["gflops"], 2), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(head["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": prec, "data": "synthetic",
             "config": {"workload": wl, "what": desc, "per_gpu_shape": shape, "axes": axes, "sharding": "batch split, no collective",
-                       "l2": "inputs (>= 2 GB) larger than the 126 MB L2; no flush needed"},
+                       "step": f"{reps} executions of the plan over the resident 65,536 x 4096 batch ({reps * shape[0]} transforms per GPU per step)",
+                       "ms_per_execution": head["ms"],
+                       "l2": "inputs (>= 2 GB) larger than the 126 MB L2; no flush needed",
+                       "preload": f"{PRELOAD_S} s of the same kernel right before the timed region (sustained clocks at every N)"},
             "hbm_gbs": round(head["hbm_gbs"] * world, 1), "roofline": roofline, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches, "cpu_baseline": cpu, "others": others,
+            "gpu_launches": launches, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

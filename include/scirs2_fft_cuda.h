@@ -21,7 +21,7 @@ extern "C" {
 #endif
 
 #define SFC_MAX_DIMS 8
-#define SFC_ABI_VERSION 1
+#define SFC_ABI_VERSION 2
 
 /* FFTError variants, scirs2-fft/src/error.rs:7-46 */
 typedef enum sfc_status {
@@ -95,6 +95,10 @@ typedef struct sfc_desc {
      * the slab transpose of a distributed fftn fused into the FFT store (distributed.rs:232-268) */
     int32_t scatter_parts;
     int32_t reserved;
+    /* with scatter_parts > 1: element pitch of the split axis inside every destination block (0 = the inner
+     * extent, i.e. dense [outer][n/parts][inner] blocks).  A larger pitch lets block q land inside a bigger array
+     * of the destination rank (the second exchange of a natural-layout slab fftn). */
+    int64_t scatter_pitch;
     /* C2C over ONE axis, with SFC_DESC_AXIS_LEN: the input array holds axis_in_len elements along that
      * axis (zero-padded / cropped to shape[axis] on load) and the output array axis_out_len (cropped on
      * store); 0 = shape[axis].  What the reference does with `x.resize(n)` / `[..n]` slices around its
@@ -171,6 +175,95 @@ int sfc_ipc_get_handle(const void* d_ptr, void* handle_out);   /* SFC_IPC_HANDLE
 int sfc_ipc_open_handle(const void* handle, void** d_ptr_out); /* maps a peer allocation */
 int sfc_ipc_close_handle(void* d_ptr);
 int sfc_stream_synchronize(void* stream);
+
+
+/* ================================================================ multi-GPU (SURVEY 8e / 8b last row)
+ * Replaces `trait Communicator` + `DistributedFFT` of scirs2-fft/src/distributed.rs:76-103, 115-362 (whose
+ * exchange is a mock, :232-268, 765-769) for the GPUs of ONE node (an NVLink / NVSwitch domain).  Nothing here
+ * needs Python, torch or NCCL: ranks find each other through a POSIX shared-memory segment, map each other's
+ * device buffers with CUDA IPC, and synchronise ON THE DEVICE through flags in that mapped memory
+ * (st.release.sys / ld.acquire.sys), so an exchange is stores over NVLink by the FFT kernel itself plus two
+ * one-block kernels.  Two ways to drive it:
+ *   - one process per GPU ("rank" mode, the launch model of the benchmark): every rank calls
+ *     sfc_comm_init_rank with the same job-unique `name`;
+ *   - one process driving several GPUs ("local" mode, what a plain Rust program calling fftn() wants):
+ *     sfc_comm_init_local; the *_multi / *_host entry points then take the data of all GPUs at once. */
+#define SFC_MAX_GPUS 16
+typedef struct sfc_comm sfc_comm;
+/* ngpu <= 0: every visible device; devices == NULL: 0 .. ngpu-1.  Enables peer access between them. */
+int sfc_comm_init_local(sfc_comm** out, int32_t ngpu, const int32_t* devices);
+/* Collective over the `world` processes of a node; `name`: [A-Za-z0-9_.-]{1,64}, unique to this job (e.g. launcher
+ * pid + start time).  `device` is the CUDA device this rank drives.  Times out (SFC_ERR_COMMUNICATION) after
+ * SFC_COMM_TIMEOUT_MS (default 60000) if a rank never shows up. */
+int sfc_comm_init_rank(sfc_comm** out, const char* name, int32_t rank, int32_t world, int32_t device);
+int sfc_comm_destroy(sfc_comm* comm);
+int sfc_comm_size(const sfc_comm* comm);  /* Communicator::size, distributed.rs:99 */
+int sfc_comm_rank(const sfc_comm* comm);  /* Communicator::rank, :102 (local mode: 0) */
+int sfc_comm_barrier(sfc_comm* comm);     /* Communicator::barrier, :96 — host-side */
+/* host-side all-gather of `bytes` per rank (out: world * bytes); a no-op copy in local mode */
+int sfc_comm_allgather(sfc_comm* comm, const void* in, void* out, size_t bytes);
+/* Symmetric device allocation (collective, same `bytes` on every rank): the buffer of every rank is mapped into
+ * every other rank, so distributed plans can store straight into it.  rank mode: *d_ptr = this rank's buffer;
+ * local mode: d_ptr receives ngpu pointers. */
+int sfc_comm_alloc(sfc_comm* comm, size_t bytes, void** d_ptr);
+int sfc_comm_free(sfc_comm* comm, void* d_ptr);  /* collective; local mode: the first pointer */
+
+/* DecompositionStrategy, distributed.rs:18-29 */
+typedef enum sfc_decomposition {
+    SFC_DECOMP_REPLICATED = 0,  /* every GPU runs the whole plan on its own data (replicas only) */
+    SFC_DECOMP_BATCH_SPLIT = 1, /* axis 0 is a pure batch axis: contiguous split, no exchange */
+    SFC_DECOMP_SLAB = 2         /* 3-D c2c: axis-0 slabs, FFT axes 2 and 1, exchange, FFT axis 0 (distributed.rs:356-362) */
+} sfc_decomposition;
+typedef enum sfc_slab_layout {
+    SFC_SLAB_TRANSPOSED = 0, /* output stays axis-1-distributed: rank r holds out[:, r*n1/P:(r+1)*n1/P, :] */
+    SFC_SLAB_NATURAL = 1     /* a second exchange (fused into the axis-0 FFT store) restores axis-0 slabs: a true fftn */
+} sfc_slab_layout;
+
+/* `base.shape` is the GLOBAL shape; ngpu is the communicator's size (sfc_desc{.., ngpu, decomposition}). */
+typedef struct sfc_dist_desc {
+    sfc_desc base;
+    int32_t decomposition; /* sfc_decomposition */
+    int32_t layout;        /* sfc_slab_layout (SLAB only) */
+    int32_t chunks;        /* SLAB: pieces the exchange is pipelined in (0 = library default) */
+    int32_t reserved;
+} sfc_dist_desc;
+
+typedef struct sfc_dist_info {
+    int32_t world, rank;                   /* rank of the first GPU this process drives */
+    int32_t decomposition, layout, chunks;
+    int32_t reserved;
+    int64_t local_in_elems, local_out_elems; /* per GPU, in elements of the in / out type */
+    int64_t local_in_shape[SFC_MAX_DIMS], local_out_shape[SFC_MAX_DIMS];
+    int64_t exchange_bytes_sent;           /* per GPU per exchange, to OTHER GPUs: (P-1)/P of the local slab */
+    int32_t num_exchanges;                 /* 0 batch split, 1 transposed, 2 natural */
+    int32_t num_launches;                  /* kernel launches per GPU per execution */
+    int64_t algorithmic_bytes;             /* per GPU */
+    double nominal_flops;                  /* whole transform */
+} sfc_dist_info;
+
+typedef struct sfc_dist_plan sfc_dist_plan;
+int sfc_dist_plan_create(sfc_dist_plan** out, sfc_comm* comm, const sfc_dist_desc* desc); /* collective */
+int sfc_dist_plan_destroy(sfc_dist_plan* plan);                                           /* collective */
+int sfc_dist_plan_get_info(const sfc_dist_plan* plan, sfc_dist_info* info);
+/* Stage timing of the SLAB pipeline on this process' first GPU (CUDA events between the stages of every later
+ * execution): sfc_dist_plan_stage_ms returns the number of stages written, in order — FFT axis 2 | FFT axis 1 +
+ * scatter | signal + wait | FFT axis 0 (+ scatter) | [natural: signal + wait 2 and copy-out]. */
+int sfc_dist_plan_profile(sfc_dist_plan* plan, int32_t enable);
+int sfc_dist_plan_stage_ms(sfc_dist_plan* plan, double* ms, int32_t cap);
+/* rank mode: this rank's slab / batch share, device pointers, caller's stream.  The call only enqueues work. */
+int sfc_dist_exec_device(sfc_dist_plan* plan, const void* d_in, void* d_out, void* stream);
+/* local mode: one pointer per GPU (in communicator order); streams == NULL: library streams, one per GPU.
+ * Only enqueues; sfc_dist_synchronize waits for every GPU. */
+int sfc_dist_exec_device_multi(sfc_dist_plan* plan, const void* const* d_in, void* const* d_out, void* const* streams);
+int sfc_dist_synchronize(sfc_dist_plan* plan);
+/* Host buffers, H2D + transform + D2H.  local mode: the WHOLE global array in C order (output in natural layout
+ * whatever `layout` says); every GPU copies over its own PCIe link.  rank mode: this rank's share. */
+int sfc_dist_exec_host(sfc_dist_plan* plan, const void* h_in, void* h_out);
+/* The free functions sfc_fftn / sfc_ifftn (3-D complex, every axis, power-of-two extents divisible by the GPU
+ * count) and sfc_execute_batch run over `ngpu` GPUs of this process from now on (0 or 1: single GPU, the default;
+ * < 0: all visible).  This is how `use scirs2_fft_cuda as scirs2_fft` reaches the whole box without new arguments. */
+int sfc_set_num_gpus(int32_t ngpu);
+int sfc_get_num_gpus(void);
 
 /* --------------------------------------------------------------- plan cache
  * plan_cache.rs:28-235 — 128 entries, 1 h TTL, LRU, hit/miss counters. */

@@ -53,6 +53,7 @@ class sfc_desc(C.Structure):
         ("in_shape", C.c_int64 * SFC_MAX_DIMS),
         ("scatter_parts", C.c_int32),
         ("reserved", C.c_int32),
+        ("scatter_pitch", C.c_int64),
         ("axis_in_len", C.c_int64),
         ("axis_out_len", C.c_int64),
         ("aux_in", C.c_void_p),
@@ -84,6 +85,41 @@ class sfc_cache_stats(C.Structure):
     ]
 
 
+SFC_MAX_GPUS = 16
+SFC_DECOMP_REPLICATED, SFC_DECOMP_BATCH_SPLIT, SFC_DECOMP_SLAB = 0, 1, 2
+SFC_SLAB_TRANSPOSED, SFC_SLAB_NATURAL = 0, 1
+
+
+class sfc_dist_desc(C.Structure):
+    _fields_ = [
+        ("base", sfc_desc),
+        ("decomposition", C.c_int32),
+        ("layout", C.c_int32),
+        ("chunks", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class sfc_dist_info(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32),
+        ("rank", C.c_int32),
+        ("decomposition", C.c_int32),
+        ("layout", C.c_int32),
+        ("chunks", C.c_int32),
+        ("reserved", C.c_int32),
+        ("local_in_elems", C.c_int64),
+        ("local_out_elems", C.c_int64),
+        ("local_in_shape", C.c_int64 * SFC_MAX_DIMS),
+        ("local_out_shape", C.c_int64 * SFC_MAX_DIMS),
+        ("exchange_bytes_sent", C.c_int64),
+        ("num_exchanges", C.c_int32),
+        ("num_launches", C.c_int32),
+        ("algorithmic_bytes", C.c_int64),
+        ("nominal_flops", C.c_double),
+    ]
+
+
 LIB_NAME = "libscirs2_fft_cuda.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
 
@@ -111,6 +147,26 @@ SIGNATURES = {
     "sfc_ipc_open_handle": (_int, [_vp, C.POINTER(_vp)]),
     "sfc_ipc_close_handle": (_int, [_vp]),
     "sfc_stream_synchronize": (_int, [_vp]),
+    "sfc_comm_init_local": (_int, [C.POINTER(_vp), _i32, _pi32]),
+    "sfc_comm_init_rank": (_int, [C.POINTER(_vp), _str, _i32, _i32, _i32]),
+    "sfc_comm_destroy": (_int, [_vp]),
+    "sfc_comm_size": (_int, [_vp]),
+    "sfc_comm_rank": (_int, [_vp]),
+    "sfc_comm_barrier": (_int, [_vp]),
+    "sfc_comm_allgather": (_int, [_vp, _vp, _vp, C.c_size_t]),
+    "sfc_comm_alloc": (_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "sfc_comm_free": (_int, [_vp, _vp]),
+    "sfc_dist_plan_create": (_int, [C.POINTER(_vp), _vp, C.POINTER(sfc_dist_desc)]),
+    "sfc_dist_plan_destroy": (_int, [_vp]),
+    "sfc_dist_plan_get_info": (_int, [_vp, C.POINTER(sfc_dist_info)]),
+    "sfc_dist_plan_profile": (_int, [_vp, _i32]),
+    "sfc_dist_plan_stage_ms": (_int, [_vp, _pd, _i32]),
+    "sfc_dist_exec_device": (_int, [_vp, _vp, _vp, _vp]),
+    "sfc_dist_exec_device_multi": (_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "sfc_dist_synchronize": (_int, [_vp]),
+    "sfc_dist_exec_host": (_int, [_vp, _vp, _vp]),
+    "sfc_set_num_gpus": (_int, [_i32]),
+    "sfc_get_num_gpus": (_int, []),
     "sfc_cache_get_stats": (_int, [C.POINTER(sfc_cache_stats)]),
     "sfc_cache_set_enabled": (_int, [_int]),
     "sfc_cache_is_enabled": (_int, []),

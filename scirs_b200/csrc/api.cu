@@ -105,6 +105,7 @@ CacheKey make_key(const sfc_desc& d) {
     k.flags = d.flags;
     k.scale = d.scale;
     k.scatter_parts = d.scatter_parts;
+    k.scatter_pitch = d.scatter_parts > 1 ? d.scatter_pitch : 0;
     if (d.flags & SFC_DESC_AXIS_LEN) {
         k.axis_in_len = d.axis_in_len;
         k.axis_out_len = d.axis_out_len;
@@ -811,6 +812,12 @@ int fftn_common(const void* x, int32_t ndim, const int64_t* in_shape, int dtype,
         return SFC_OK;
     }
     if (!out || out_cap < vprod(tsh)) return fail(SFC_ERR_VALUE, "output buffer too small");
+    if (ndim == 3 && dtype == SFC_C128 && ish == tsh && ax.size() == 3 && ax[0] != ax[1] && ax[0] != ax[2] && ax[1] != ax[2]) {
+        // sfc_set_num_gpus(P > 1): slab decomposition over the GPUs of this process (dist.cu)
+        bool handled = false;
+        rc = multi_fftn_host(x, tsh.data(), ax.data(), inverse, scale, out, &handled);
+        if (rc != SFC_OK || handled) return rc;
+    }
     rc = run_c2c_host(x, ish, dtype, tsh, ax, inverse, scale, &d_res);
     if (rc != SFC_OK) return rc;
     return download(out, d_res, (size_t)vprod(tsh) * 16);
@@ -1191,6 +1198,11 @@ extern "C" __attribute__((visibility("default"))) int sfc_execute_batch(const do
     d.prec = SFC_PREC_F64;
     d.direction = inverse ? SFC_INVERSE : SFC_FORWARD;
     d.scale = 1.0;  // FftPlanExecutor::execute is unnormalised in both directions (planning.rs:501-550)
+    {
+        bool handled = false;  // sfc_set_num_gpus(P > 1): contiguous batch split over the GPUs of this process
+        rc = multi_batch_host(d, inputs, outputs, &handled);
+        if (rc != SFC_OK || handled) return rc;
+    }
     sfc_plan* h = nullptr;
     if ((rc = sfc_plan_create(&h, &d)) != SFC_OK) return rc;
     rc = sfc_exec_host(h, inputs, outputs);

@@ -99,4 +99,8 @@ int run_c2c_host(const void* x, const std::vector<int64_t>& in_shape, int dtype,
                  const std::vector<int>& axes, bool inverse, double scale, void** d_res);
 int download(void* h, const void* d, size_t bytes);    // D2H on the workspace stream + synchronize
 
+// dist.cu: the free functions over several GPUs of this process (sfc_set_num_gpus); *handled says whether they ran
+int multi_fftn_host(const void* x, const int64_t* shape3, const int* axes3, bool inverse, double scale, double* out, bool* handled);
+int multi_batch_host(const sfc_desc& d, const void* in, void* out, bool* handled);
+
 }  // namespace sfc_api

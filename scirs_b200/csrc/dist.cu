@@ -1,0 +1,1172 @@
+// dist.cu — multi-GPU behind the C ABI: communicator, symmetric device memory and the distributed plans
+// (batch split; slab-decomposed 3-D transforms whose transposes are fused into the FFT stores).
+//
+// Replaces `trait Communicator` (scirs2-fft/src/distributed.rs:85-103) and the slab path of `DistributedFFT`
+// (:115-362; its exchange is a mock, :232-268, 765-769).  No Python, no torch, no NCCL in here:
+//   * rendezvous of the processes of a node: a POSIX shared-memory segment (sequence-numbered all-gather slots);
+//   * data path: every rank's receive window is mapped into every other rank (CUDA IPC, or plain peer access when
+//     one process drives all GPUs); the axis-1 FFT kernel stores block q of its output straight into rank q's
+//     window over NVLink (PassParams::peer_out, fft_tile.cuh) — FFT pass and all-to-all are ONE kernel;
+//   * synchronisation: per-source flags in the same mapped memory, written with st.release.sys by a one-block
+//     kernel after the scatter and polled with ld.acquire.sys by a one-block kernel in front of the next pass.
+//     Everything is stream-ordered; the host never blocks inside an execution.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "api_internal.h"
+#include "plan.h"
+
+using namespace sfc;
+using namespace sfc_api;
+
+#define SFC_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+// ------------------------------------------------------------------ device-side flags
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct FlagPtrs {
+    unsigned long long* p[SFC_MAX_GPUS];
+};
+
+// after this rank's scatter kernel: tell every destination that its block has landed (stream order puts the
+// stores of the previous kernel before the fence; release at system scope publishes them to the peer GPU)
+__global__ void dist_signal_kernel(FlagPtrs flags, int world, unsigned long long epoch) {
+    const int q = threadIdx.x;
+    if (q < world) {
+        __threadfence_system();
+        st_release_sys(flags.p[q], epoch);
+    }
+}
+
+// in front of the pass that consumes the receive window: wait until every source has signalled this epoch.
+// Bounded: a rank that died must not hang the GPU — after timeout_ns the kernel gives up and raises *status.
+__global__ void dist_wait_kernel(const unsigned long long* flags, int world, unsigned long long epoch,
+                                 unsigned long long timeout_ns, int* status) {
+    const int q = threadIdx.x;
+    if (q < world) {
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(flags + q) < epoch) {
+            if (global_ns() - t0 > timeout_ns) {
+                *status = 1 + q;
+                __threadfence_system();
+                break;
+            }
+            __nanosleep(20);
+        }
+    }
+}
+
+double env_ms(const char* name, double dflt) {
+    const char* e = getenv(name);
+    return e ? atof(e) : dflt;
+}
+
+// ------------------------------------------------------------------ shared-memory rendezvous (rank mode)
+
+constexpr uint32_t SHM_MAGIC = 0x53464332u;  // "SFC2"
+constexpr size_t SLOT_BYTES = 256;
+
+struct ShmSeg {
+    std::atomic<uint32_t> magic;
+    std::atomic<uint32_t> world;
+    std::atomic<uint32_t> attached;
+    uint32_t pad;
+    std::atomic<uint64_t> seq[2][SFC_MAX_GPUS];
+    unsigned char slot[2][SFC_MAX_GPUS][SLOT_BYTES];
+};
+
+}  // namespace
+
+// one GPU driven by this process
+struct RankCtx {
+    int rank = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;  // library stream (host executions, *_multi without caller streams)
+    int* status_h = nullptr;        // pinned + mapped: raised by a wait kernel that timed out
+    int* status_d = nullptr;
+};
+
+struct SymAlloc {
+    size_t bytes = 0;
+    std::vector<void*> base;                // [local rank] this process' own buffers
+    std::vector<std::vector<void*>> peer;   // [local rank][global rank] address usable from that local rank's device
+};
+
+struct sfc_comm {
+    bool local_mode = true;
+    int world = 1;
+    std::vector<RankCtx> ranks;  // local mode: world entries; rank mode: one
+    // rank mode
+    std::string shm_name;
+    ShmSeg* shm = nullptr;
+    uint64_t gen = 0;
+    double timeout_ms = 60000.0;
+    std::vector<std::unique_ptr<SymAlloc>> allocs;
+    int live_plans = 0;
+    bool host_only = false;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+bool name_ok(const char* n) {
+    if (!n || !*n) return false;
+    size_t len = 0;
+    for (const char* c = n; *c; ++c, ++len) {
+        const bool ok = (*c >= 'a' && *c <= 'z') || (*c >= 'A' && *c <= 'Z') || (*c >= '0' && *c <= '9') || *c == '_' ||
+                        *c == '.' || *c == '-';
+        if (!ok) return false;
+    }
+    return len <= 64;
+}
+
+// all-gather of <= SLOT_BYTES per rank through the shared segment.  Generation g uses slot set g & 1; a rank can
+// only reach generation g+2 after every rank published g+1, i.e. after every rank finished reading g.
+int shm_allgather_small(sfc_comm* c, const void* in, void* out, size_t bytes) {
+    if (bytes > SLOT_BYTES) return fail(SFC_ERR_VALUE, "internal: shm slot overflow");
+    ShmSeg* s = c->shm;
+    const int r = c->ranks[0].rank;
+    const int set = (int)(c->gen & 1);
+    const uint64_t want = c->gen + 1;
+    memcpy(s->slot[set][r], in, bytes);
+    s->seq[set][r].store(want, std::memory_order_release);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int q = 0; q < c->world; ++q) {
+        int spins = 0;
+        while (s->seq[set][q].load(std::memory_order_acquire) != want) {
+            if (++spins > 200) {
+                std::this_thread::sleep_for(std::chrono::microseconds(50));
+                const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                if (ms > c->timeout_ms) {
+                    char b[128];
+                    snprintf(b, sizeof b, "rank %d did not reach the rendezvous within %.0f ms", q, c->timeout_ms);
+                    return fail(SFC_ERR_COMMUNICATION, b);
+                }
+            }
+        }
+        memcpy((char*)out + (size_t)q * bytes, s->slot[set][q], bytes);
+    }
+    c->gen += 1;
+    return SFC_OK;
+}
+
+int comm_allgather(sfc_comm* c, const void* in, void* out, size_t bytes) {
+    if (c->local_mode || c->world == 1) {
+        if (out != in) memcpy(out, in, bytes);
+        return SFC_OK;
+    }
+    for (size_t off = 0; off < bytes || off == 0; off += SLOT_BYTES) {
+        const size_t n = std::min(SLOT_BYTES, bytes - off);
+        std::vector<unsigned char> tmp((size_t)c->world * n);
+        int rc = shm_allgather_small(c, (const char*)in + off, tmp.data(), n);
+        if (rc != SFC_OK) return rc;
+        for (int q = 0; q < c->world; ++q) memcpy((char*)out + (size_t)q * bytes + off, tmp.data() + (size_t)q * n, n);
+        if (bytes == 0) break;
+    }
+    return SFC_OK;
+}
+
+// collective agreement on success: every rank learns whether any rank failed
+int comm_all_ok(sfc_comm* c, int my_rc) {
+    if (c->local_mode || c->world == 1) return my_rc;
+    int32_t mine = my_rc;
+    std::vector<int32_t> all(c->world);
+    const std::string keep = sfc_last_error();
+    int rc = comm_allgather(c, &mine, all.data(), sizeof mine);
+    if (rc != SFC_OK) return rc;
+    if (my_rc != SFC_OK) return fail(my_rc, keep);
+    for (int q = 0; q < c->world; ++q)
+        if (all[q] != SFC_OK) {
+            char b[96];
+            snprintf(b, sizeof b, "rank %d failed (status %d) in a collective call", q, all[q]);
+            return fail(all[q], b);
+        }
+    return SFC_OK;
+}
+
+int init_rank_ctx(RankCtx& rc) {
+    DeviceGuard g(rc.device);
+    cudaError_t e = cudaStreamCreateWithFlags(&rc.stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+    e = cudaHostAlloc((void**)&rc.status_h, sizeof(int), cudaHostAllocMapped);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+    *rc.status_h = 0;
+    e = cudaHostGetDevicePointer((void**)&rc.status_d, rc.status_h, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
+    return SFC_OK;
+}
+
+SymAlloc* find_alloc(sfc_comm* c, const void* p, int lr, size_t* off) {
+    for (auto& a : c->allocs) {
+        const char* b = (const char*)a->base[lr];
+        if ((const char*)p >= b && (const char*)p < b + a->bytes) {
+            *off = (size_t)((const char*)p - b);
+            return a.get();
+        }
+    }
+    return nullptr;
+}
+
+int sym_alloc(sfc_comm* c, size_t bytes, SymAlloc** out) {
+    auto a = std::make_unique<SymAlloc>();
+    a->bytes = std::max<size_t>(bytes, 256);
+    const int nl = (int)c->ranks.size();
+    a->base.assign(nl, nullptr);
+    a->peer.assign(nl, std::vector<void*>(c->world, nullptr));
+    int rc = SFC_OK;
+    for (int lr = 0; lr < nl && rc == SFC_OK; ++lr) {
+        DeviceGuard g(c->ranks[lr].device);
+        cudaError_t e = alloc_with_relief(&a->base[lr], a->bytes, nullptr);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc (symmetric buffer)");
+    }
+    if (c->local_mode) {
+        if (rc == SFC_OK)
+            for (int lr = 0; lr < nl; ++lr)
+                for (int q = 0; q < c->world; ++q) a->peer[lr][q] = a->base[q];  // UVA + peer access
+    } else {
+        cudaIpcMemHandle_t mine;
+        memset(&mine, 0, sizeof mine);
+        if (rc == SFC_OK && c->world > 1) {
+            cudaError_t e = cudaIpcGetMemHandle(&mine, a->base[0]);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaIpcGetMemHandle");
+        }
+        rc = comm_all_ok(c, rc);
+        if (rc == SFC_OK) {
+            std::vector<cudaIpcMemHandle_t> all(c->world);
+            rc = comm_allgather(c, &mine, all.data(), sizeof mine);
+            const int me = c->ranks[0].rank;
+            for (int q = 0; q < c->world && rc == SFC_OK; ++q) {
+                if (q == me) {
+                    a->peer[0][q] = a->base[0];
+                } else {
+                    cudaError_t e = cudaIpcOpenMemHandle(&a->peer[0][q], all[q], cudaIpcMemLazyEnablePeerAccess);
+                    if (e != cudaSuccess) {
+                        cudaGetLastError();
+                        rc = fail(SFC_ERR_COMMUNICATION, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+                    }
+                }
+            }
+            rc = comm_all_ok(c, rc);
+        }
+    }
+    if (rc != SFC_OK) {
+        for (int lr = 0; lr < nl; ++lr)
+            if (a->base[lr]) {
+                DeviceGuard g(c->ranks[lr].device);
+                cudaFree(a->base[lr]);
+            }
+        return rc;
+    }
+    *out = a.get();
+    c->allocs.push_back(std::move(a));
+    return SFC_OK;
+}
+
+int sym_free(sfc_comm* c, SymAlloc* a) {
+    // nobody may still be storing into a buffer that is about to go away
+    for (auto& r : c->ranks) {
+        DeviceGuard g(r.device);
+        cudaDeviceSynchronize();
+    }
+    int rc = SFC_OK;
+    if (!c->local_mode && c->world > 1) {
+        int32_t token = 0;
+        std::vector<int32_t> all(c->world);
+        rc = comm_allgather(c, &token, all.data(), sizeof token);  // barrier
+        const int me = c->ranks[0].rank;
+        for (int q = 0; q < c->world; ++q)
+            if (q != me && a->peer[0][q]) cudaIpcCloseMemHandle(a->peer[0][q]);
+        if (rc == SFC_OK) rc = comm_allgather(c, &token, all.data(), sizeof token);  // everybody unmapped: now free
+    }
+    for (size_t lr = 0; lr < a->base.size(); ++lr) {
+        DeviceGuard g(c->ranks[lr].device);
+        cudaFree(a->base[lr]);
+    }
+    for (size_t i = 0; i < c->allocs.size(); ++i)
+        if (c->allocs[i].get() == a) {
+            c->allocs.erase(c->allocs.begin() + (long)i);
+            break;
+        }
+    return rc;
+}
+
+}  // namespace
+
+// ====================================================================== communicator entry points
+
+SFC_EXPORT int sfc_comm_init_local(sfc_comm** out, int32_t ngpu, const int32_t* devices) {
+    if (!out) return fail(SFC_ERR_VALUE, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SFC_ERR_BACKEND, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (ngpu <= 0) ngpu = ndev;
+    if (ngpu > SFC_MAX_GPUS) return fail(SFC_ERR_VALUE, "at most 16 GPUs per communicator");
+    auto c = std::make_unique<sfc_comm>();
+    c->local_mode = true;
+    c->world = ngpu;
+    c->timeout_ms = env_ms("SFC_COMM_TIMEOUT_MS", 60000.0);
+    for (int i = 0; i < ngpu; ++i) {
+        const int d = devices ? devices[i] : i;
+        if (d < 0 || d >= ndev) return fail(SFC_ERR_VALUE, "device index out of range");
+        for (int j = 0; j < i; ++j)
+            if (c->ranks[j].device == d) return fail(SFC_ERR_VALUE, "a device may appear only once in a communicator");
+        RankCtx r;
+        r.rank = i;
+        r.device = d;
+        c->ranks.push_back(r);
+    }
+    for (auto& r : c->ranks) {
+        int rc = init_rank_ctx(r);
+        if (rc != SFC_OK) return rc;
+        DeviceGuard g(r.device);
+        for (auto& o : c->ranks) {
+            if (o.device == r.device) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, r.device, o.device);
+            if (!can) return fail(SFC_ERR_COMMUNICATION, "the GPUs of this communicator cannot access each other's memory");
+            cudaError_t e = cudaDeviceEnablePeerAccess(o.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+            cudaGetLastError();
+        }
+    }
+    *out = c.release();
+    return SFC_OK;
+}
+
+SFC_EXPORT int sfc_comm_init_rank(sfc_comm** out, const char* name, int32_t rank, int32_t world, int32_t device) {
+    if (!out) return fail(SFC_ERR_VALUE, "null argument");
+    *out = nullptr;
+    if (world < 1 || world > SFC_MAX_GPUS) return fail(SFC_ERR_VALUE, "world size must be in 1..16");
+    if (rank < 0 || rank >= world) return fail(SFC_ERR_VALUE, "rank out of range");
+    if (!name_ok(name)) return fail(SFC_ERR_VALUE, "communicator name must match [A-Za-z0-9_.-]{1,64}");
+    // device < 0: a host-only communicator (rendezvous, barrier, all-gather; no device memory, no plans) — what the
+    // CPU tests of the rendezvous protocol use
+    const bool host_only = device < 0;
+    if (!host_only) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            return fail(SFC_ERR_BACKEND, "no CUDA device available (this library has no CPU fallback)");
+        }
+        if (device >= ndev) return fail(SFC_ERR_VALUE, "device index out of range");
+    }
+    auto c = std::make_unique<sfc_comm>();
+    c->local_mode = false;
+    c->host_only = host_only;
+    c->world = world;
+    c->timeout_ms = env_ms("SFC_COMM_TIMEOUT_MS", 60000.0);
+    RankCtx r;
+    r.rank = rank;
+    r.device = device;
+    c->ranks.push_back(r);
+    int rc = SFC_OK;
+    if (!host_only) {
+        cudaError_t ce = cudaSetDevice(device);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
+        rc = init_rank_ctx(c->ranks[0]);
+        if (rc != SFC_OK) return rc;
+    }
+    if (world > 1) {
+        c->shm_name = std::string("/sfc_") + name;
+        // whoever comes first creates the segment (ftruncate zero-fills it); `magic` is published last
+        int fd = shm_open(c->shm_name.c_str(), O_CREAT | O_RDWR, 0600);
+        if (fd < 0) return fail(SFC_ERR_COMMUNICATION, std::string("shm_open failed for ") + c->shm_name);
+        if (ftruncate(fd, (off_t)sizeof(ShmSeg)) != 0) {
+            close(fd);
+            return fail(SFC_ERR_COMMUNICATION, "ftruncate failed for the rendezvous segment");
+        }
+        void* m = mmap(nullptr, sizeof(ShmSeg), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        if (m == MAP_FAILED) return fail(SFC_ERR_COMMUNICATION, "mmap failed for the rendezvous segment");
+        c->shm = reinterpret_cast<ShmSeg*>(m);
+        uint32_t expect = 0;
+        if (c->shm->magic.compare_exchange_strong(expect, SHM_MAGIC)) c->shm->world.store((uint32_t)world);
+        const auto t0 = std::chrono::steady_clock::now();
+        while (c->shm->world.load() == 0) {
+            std::this_thread::sleep_for(std::chrono::microseconds(50));
+            if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() > c->timeout_ms)
+                return fail(SFC_ERR_COMMUNICATION, "rendezvous segment was never initialised");
+        }
+        if (c->shm->world.load() != (uint32_t)world)
+            return fail(SFC_ERR_COMMUNICATION, "ranks disagree on the world size (or a stale segment with this name exists)");
+        c->shm->attached.fetch_add(1);
+        // first collective doubles as the attach barrier; after it nobody needs the NAME any more
+        int32_t tok = rank;
+        std::vector<int32_t> all(world);
+        rc = comm_allgather(c.get(), &tok, all.data(), sizeof tok);
+        if (rc != SFC_OK) {
+            shm_unlink(c->shm_name.c_str());
+            return rc;
+        }
+        if (rank == 0) shm_unlink(c->shm_name.c_str());
+    }
+    *out = c.release();
+    return SFC_OK;
+}
+
+SFC_EXPORT int sfc_comm_destroy(sfc_comm* c) {
+    if (!c) return SFC_OK;
+    while (!c->allocs.empty()) sym_free(c, c->allocs.back().get());
+    for (auto& r : c->ranks) {
+        if (c->host_only) break;
+        DeviceGuard g(r.device);
+        if (r.stream) cudaStreamDestroy(r.stream);
+        if (r.status_h) cudaFreeHost(r.status_h);
+    }
+    if (c->shm) munmap(c->shm, sizeof(ShmSeg));
+    delete c;
+    return SFC_OK;
+}
+
+SFC_EXPORT int sfc_comm_size(const sfc_comm* c) { return c ? c->world : 0; }
+SFC_EXPORT int sfc_comm_rank(const sfc_comm* c) { return c ? c->ranks[0].rank : -1; }
+
+SFC_EXPORT int sfc_comm_barrier(sfc_comm* c) {
+    if (!c) return fail(SFC_ERR_VALUE, "null argument");
+    int32_t tok = 0;
+    std::vector<int32_t> all(c->world);
+    return comm_allgather(c, &tok, all.data(), sizeof tok);
+}
+
+SFC_EXPORT int sfc_comm_allgather(sfc_comm* c, const void* in, void* out, size_t bytes) {
+    if (!c || !in || !out) return fail(SFC_ERR_VALUE, "null argument");
+    return comm_allgather(c, in, out, bytes);
+}
+
+SFC_EXPORT int sfc_comm_alloc(sfc_comm* c, size_t bytes, void** d_ptr) {
+    if (!c || !d_ptr) return fail(SFC_ERR_VALUE, "null argument");
+    if (c->host_only) return fail(SFC_ERR_BACKEND, "host-only communicator (no CUDA device; this library has no CPU fallback)");
+    SymAlloc* a = nullptr;
+    int rc = sym_alloc(c, bytes, &a);
+    if (rc != SFC_OK) return rc;
+    for (size_t lr = 0; lr < a->base.size(); ++lr) d_ptr[lr] = a->base[lr];
+    return SFC_OK;
+}
+
+SFC_EXPORT int sfc_comm_free(sfc_comm* c, void* d_ptr) {
+    if (!c || !d_ptr) return fail(SFC_ERR_VALUE, "null argument");
+    for (auto& a : c->allocs)
+        if (a->base[0] == d_ptr) return sym_free(c, a.get());
+    return fail(SFC_ERR_VALUE, "pointer was not returned by sfc_comm_alloc");
+}
+
+// ====================================================================== distributed plans
+
+namespace {
+
+struct DistRank {
+    std::shared_ptr<Plan> a, b, c;  // slab: axis 2 | axis 1 + scatter | axis 0 (+ scatter for the natural layout)
+    std::shared_ptr<Plan> whole;    // slab on a single GPU
+    sfc_plan* handle = nullptr;     // batch split / replicated: an ordinary plan handle on this GPU (pipelined host path)
+    void* work = nullptr;           // [s0][n1][n2] between passes A and B
+    std::vector<cudaEvent_t> ev;
+    // host executions
+    void *h_in_dev = nullptr, *h_out_dev = nullptr;
+};
+
+}  // namespace
+
+struct sfc_dist_plan {
+    sfc_comm* comm = nullptr;
+    sfc_dist_desc desc{};
+    sfc_dist_info info{};
+    std::vector<DistRank> r;
+    int64_t n0 = 0, n1 = 0, n2 = 0, s0 = 0, s1 = 0;
+    size_t cs = 16;
+    size_t block_bytes = 0, recv_bytes = 0;
+    SymAlloc* recv = nullptr;   // 2 x [P][s0][s1][n2]: exchange-1 window, double buffered
+    SymAlloc* flags = nullptr;  // [2 exchanges][SFC_MAX_GPUS] epochs
+    SymAlloc* win2 = nullptr;   // natural layout, outputs that are not symmetric allocations: [s0][n1][n2]
+    uint64_t epoch = 0;
+    double timeout_ns = 20e9;
+    bool profile = false;  // record an event after every stage of GPU 0 (sfc_dist_plan_profile)
+    int nmarks = 0;
+    // batch split
+    std::vector<int64_t> b_start, b_count;
+    size_t in_row_bytes = 0, out_row_bytes = 0;
+};
+
+namespace {
+
+int make_plan(const sfc_desc& d, std::shared_ptr<Plan>& out) {
+    PlanError err{0, ""};
+    // distributed plans own their sub-plans (no sharing through the cache: each GPU needs its own scratch and tables)
+    out = Plan::create(d, err);
+    if (!out) return fail(err.code ? err.code : SFC_ERR_PLAN, err.msg);
+    std::string es;
+    const int rc = out->prepare(es);  // no device allocation later, in the middle of a multi-GPU enqueue
+    if (rc != 0) return fail(rc, es);
+    return SFC_OK;
+}
+
+sfc_desc c2c_desc(const sfc_dist_desc& dd, std::initializer_list<int64_t> shape, int axis, double scale, int parts,
+                  int64_t pitch) {
+    sfc_desc d;
+    memset(&d, 0, sizeof d);
+    d.ndim = (int)shape.size();
+    int i = 0;
+    for (int64_t s : shape) d.shape[i++] = s;
+    d.naxes = 1;
+    d.axes[0] = axis;
+    d.kind = SFC_C2C;
+    d.prec = dd.base.prec;
+    d.direction = dd.base.direction;
+    d.scale = scale;
+    d.scatter_parts = parts;
+    d.scatter_pitch = pitch;
+    return d;
+}
+
+int build_slab(sfc_dist_plan* p) {
+    sfc_comm* c = p->comm;
+    const sfc_desc& b = p->desc.base;
+    const int P = c->world;
+    if (b.kind != SFC_C2C || b.ndim != 3) return fail(SFC_ERR_NOT_IMPLEMENTED, "slab decomposition: 3-D complex transforms only");
+    if (b.naxes != 3) return fail(SFC_ERR_NOT_IMPLEMENTED, "slab decomposition transforms all three axes");
+    bool seen[3] = {false, false, false};
+    for (int i = 0; i < 3; ++i) {
+        if (b.axes[i] < 0 || b.axes[i] > 2 || seen[b.axes[i]]) return fail(SFC_ERR_VALUE, "axes must be a permutation of (0, 1, 2)");
+        seen[b.axes[i]] = true;
+    }
+    if (b.flags != 0) return fail(SFC_ERR_NOT_IMPLEMENTED, "slab decomposition takes plain complex arrays (no descriptor flags)");
+    p->n0 = b.shape[0];
+    p->n1 = b.shape[1];
+    p->n2 = b.shape[2];
+    if (p->n0 <= 0 || p->n1 <= 0 || p->n2 <= 0) return fail(SFC_ERR_VALUE, "shape entries must be positive");
+    // distributed.rs:356-362 splits with ceil(); the fused scatter needs equal power-of-two blocks
+    if (p->n0 % P || p->n1 % P) return fail(SFC_ERR_VALUE, "slab decomposition needs n0 and n1 divisible by the number of GPUs");
+    p->s0 = p->n0 / P;
+    p->s1 = p->n1 / P;
+    p->cs = b.prec == SFC_PREC_F64 ? 16 : 8;
+    const bool natural = p->desc.layout == SFC_SLAB_NATURAL;
+    p->block_bytes = (size_t)(p->s0 * p->s1 * p->n2) * p->cs;
+    p->recv_bytes = p->block_bytes * (size_t)P;
+    p->timeout_ns = env_ms("SFC_EXCHANGE_TIMEOUT_MS", 20000.0) * 1e6;
+    const double scale = b.scale == 0.0 ? 1.0 : b.scale;
+    p->r.resize(c->ranks.size());
+    int rc = SFC_OK;
+    for (size_t lr = 0; lr < c->ranks.size() && rc == SFC_OK; ++lr) {
+        DeviceGuard g(c->ranks[lr].device);
+        DistRank& dr = p->r[lr];
+        if (P == 1) {
+            sfc_desc d = b;
+            d.scale = scale;
+            rc = make_plan(d, dr.whole);
+            continue;
+        }
+        rc = make_plan(c2c_desc(p->desc, {p->s0, p->n1, p->n2}, 2, 1.0, 0, 0), dr.a);
+        if (rc == SFC_OK) rc = make_plan(c2c_desc(p->desc, {p->s0, p->n1, p->n2}, 1, 1.0, P, 0), dr.b);
+        if (rc == SFC_OK)
+            rc = make_plan(c2c_desc(p->desc, {p->n0, p->s1, p->n2}, 0, scale, natural ? P : 0, natural ? p->n1 * p->n2 : 0), dr.c);
+        if (rc == SFC_OK) {
+            cudaError_t e = alloc_with_relief(&dr.work, p->recv_bytes, nullptr);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc (slab work buffer)");
+        }
+    }
+    rc = comm_all_ok(c, rc);
+    if (rc != SFC_OK || P == 1) return rc;
+    rc = sym_alloc(c, 2 * p->recv_bytes, &p->recv);
+    if (rc != SFC_OK) return rc;
+    rc = sym_alloc(c, 4096, &p->flags);
+    if (rc != SFC_OK) return rc;
+    for (size_t lr = 0; lr < c->ranks.size(); ++lr) {
+        DeviceGuard g(c->ranks[lr].device);
+        cudaMemset(p->flags->base[lr], 0, 4096);
+        cudaDeviceSynchronize();
+    }
+    return sfc_comm_barrier(c);  // nobody signals before every flag page is zero
+}
+
+int build_batch(sfc_dist_plan* p) {
+    sfc_comm* c = p->comm;
+    const sfc_desc& b = p->desc.base;
+    const int P = c->world;
+    const bool split = p->desc.decomposition == SFC_DECOMP_BATCH_SPLIT;
+    if (split) {
+        if (b.ndim < 2) return fail(SFC_ERR_VALUE, "batch split needs a leading batch axis");
+        for (int i = 0; i < b.naxes; ++i)
+            if (b.axes[i] == 0) return fail(SFC_ERR_VALUE, "batch split: axis 0 must not be transformed");
+        if (b.scatter_parts > 1) return fail(SFC_ERR_VALUE, "batch split plans cannot scatter");
+    }
+    p->b_start.assign(P, 0);
+    p->b_count.assign(P, split ? 0 : b.shape[0]);
+    if (split) {
+        // contiguous split, rank g gets [g*ceil(B/P), ...) — the reference's slab arithmetic (distributed.rs:356-362)
+        const int64_t per = (b.shape[0] + P - 1) / P;
+        for (int q = 0; q < P; ++q) {
+            p->b_start[q] = std::min<int64_t>((int64_t)q * per, b.shape[0]);
+            p->b_count[q] = std::max<int64_t>(0, std::min<int64_t>(per, b.shape[0] - p->b_start[q]));
+        }
+    }
+    p->r.resize(c->ranks.size());
+    int rc = SFC_OK;
+    for (size_t lr = 0; lr < c->ranks.size() && rc == SFC_OK; ++lr) {
+        DeviceGuard g(c->ranks[lr].device);
+        const int q = c->ranks[lr].rank;
+        if (p->b_count[q] == 0) continue;
+        sfc_desc d = b;
+        d.shape[0] = p->b_count[q];
+        if (d.flags & SFC_DESC_CUSTOM_IN_SHAPE) d.in_shape[0] = p->b_count[q];
+        rc = sfc_plan_create(&p->r[lr].handle, &d);
+        if (rc == SFC_OK) {
+            sfc_plan_info pi;
+            sfc_plan_get_info(p->r[lr].handle, &pi);
+            p->in_row_bytes = (size_t)(pi.in_bytes / d.shape[0]);
+            p->out_row_bytes = (size_t)(pi.out_bytes / d.shape[0]);
+        }
+    }
+    return comm_all_ok(c, rc);
+}
+
+void fill_info(sfc_dist_plan* p) {
+    sfc_dist_info& f = p->info;
+    memset(&f, 0, sizeof f);
+    sfc_comm* c = p->comm;
+    const sfc_desc& b = p->desc.base;
+    const int P = c->world;
+    f.world = P;
+    f.rank = c->ranks[0].rank;
+    f.decomposition = p->desc.decomposition;
+    f.layout = p->desc.layout;
+    f.chunks = 1;
+    if (p->desc.decomposition == SFC_DECOMP_SLAB) {
+        const bool natural = p->desc.layout == SFC_SLAB_NATURAL || P == 1;
+        f.local_in_shape[0] = p->s0; f.local_in_shape[1] = p->n1; f.local_in_shape[2] = p->n2;
+        if (natural) { f.local_out_shape[0] = p->s0; f.local_out_shape[1] = p->n1; f.local_out_shape[2] = p->n2; }
+        else { f.local_out_shape[0] = p->n0; f.local_out_shape[1] = p->s1; f.local_out_shape[2] = p->n2; }
+        f.local_in_elems = f.local_out_elems = p->s0 * p->n1 * p->n2;
+        f.num_exchanges = P == 1 ? 0 : (natural ? 2 : 1);
+        f.exchange_bytes_sent = P == 1 ? 0 : (int64_t)(p->block_bytes * (size_t)(P - 1));
+        f.num_launches = P == 1 ? p->r[0].whole->info.num_launches : 3 + 2 * f.num_exchanges + ((natural && P > 1) ? 1 : 0);
+        f.algorithmic_bytes = 3 * 2 * f.local_in_elems * (int64_t)p->cs;
+        const double tot = (double)p->n0 * (double)p->n1 * (double)p->n2;
+        f.nominal_flops = 5.0 * tot * (log2((double)p->n0) + log2((double)p->n1) + log2((double)p->n2));
+    } else {
+        const int q = f.rank;
+        for (int i = 0; i < b.ndim; ++i) f.local_in_shape[i] = f.local_out_shape[i] = b.shape[i];
+        f.local_in_shape[0] = f.local_out_shape[0] = p->b_count[q];
+        if (p->r[0].handle) {
+            sfc_plan_info pi;
+            sfc_plan_get_info(p->r[0].handle, &pi);
+            const int64_t rows = std::max<int64_t>(p->b_count[q], 1);
+            f.num_launches = pi.num_launches;
+            f.algorithmic_bytes = pi.algorithmic_bytes;
+            f.nominal_flops = pi.nominal_flops * (double)b.shape[0] / (double)rows;
+            // element counts: in / out element sizes follow from the kind and precision
+            const int64_t cs = b.prec == SFC_PREC_F64 ? 16 : 8, rs = cs / 2;
+            const bool rin = b.kind == SFC_R2C || (b.flags & SFC_DESC_REAL_INPUT);
+            const bool rout = b.kind == SFC_C2R || (b.flags & (SFC_DESC_REAL_OUTPUT | SFC_DESC_DCT2 | SFC_DESC_DCT3 | SFC_DESC_DCT4));
+            f.local_in_elems = pi.in_bytes / (rin ? rs : cs);
+            f.local_out_elems = pi.out_bytes / (rout ? rs : cs);
+        }
+    }
+}
+
+// the slab pipeline of ONE GPU, enqueued on `st`
+int enqueue_slab(sfc_dist_plan* p, int lr, const void* d_in, void* d_out, cudaStream_t st, uint64_t epoch,
+                 void* const* out_peers /* natural: where rank q's output lives, as seen from this GPU */) {
+    sfc_comm* c = p->comm;
+    const int P = c->world;
+    RankCtx& rk = c->ranks[lr];
+    DistRank& dr = p->r[lr];
+    std::string es;
+    int rc;
+    if (*rk.status_h != 0) {
+        char b[128];
+        snprintf(b, sizeof b, "an earlier exchange timed out waiting for rank %d", *rk.status_h - 1);
+        return fail(SFC_ERR_COMMUNICATION, b);
+    }
+    if (P == 1) {
+        rc = dr.whole->exec(d_in, d_out, st, es);
+        return rc ? fail(rc, es) : SFC_OK;
+    }
+    const int me = rk.rank;
+    int mk = 0;
+    auto mark = [&]() {
+        if (!p->profile || lr != 0) return;
+        if ((int)dr.ev.size() <= mk) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            dr.ev.push_back(e);
+        }
+        cudaEventRecord(dr.ev[mk++], st);
+        p->nmarks = mk;
+    };
+    const size_t buf = (size_t)(epoch & 1) * p->recv_bytes;
+    mark();
+    unsigned long long* myflags = (unsigned long long*)p->flags->base[lr];
+    // pass A: rows of axis 2
+    rc = dr.a->exec(d_in, dr.work, st, es);
+    if (rc) return fail(rc, es);
+    mark();
+    // pass B: axis 1, block q of the output stored straight into rank q's window (slot `me`)
+    void* targets[SFC_MAX_GPUS];
+    for (int q = 0; q < P; ++q) targets[q] = (char*)p->recv->peer[lr][q] + buf + (size_t)me * p->block_bytes;
+    rc = dr.b->exec(dr.work, targets[0], st, es, targets, P);
+    if (rc) return fail(rc, es);
+    mark();
+    FlagPtrs fp;
+    for (int q = 0; q < P; ++q) fp.p[q] = (unsigned long long*)p->flags->peer[lr][q] + me;
+    dist_signal_kernel<<<1, 32, 0, st>>>(fp, P, epoch);
+    dist_wait_kernel<<<1, 32, 0, st>>>(myflags, P, epoch, (unsigned long long)p->timeout_ns, rk.status_d);
+    mark();
+    // pass C: axis 0 over the window [n0][s1][n2] (source rank order == global axis-0 order)
+    const char* win = (const char*)p->recv->base[lr] + buf;
+    if (p->desc.layout != SFC_SLAB_NATURAL) {
+        rc = dr.c->exec(win, d_out, st, es);
+        if (rc) return fail(rc, es);
+        mark();
+    } else {
+        // second exchange fused into the axis-0 store: rows [q*s0, (q+1)*s0) go to rank q at column offset me*s1
+        for (int q = 0; q < P; ++q) targets[q] = (char*)out_peers[q] + (size_t)(me * p->s1 * p->n2) * p->cs;
+        rc = dr.c->exec(win, targets[0], st, es, targets, P);
+        if (rc) return fail(rc, es);
+        mark();
+        for (int q = 0; q < P; ++q) fp.p[q] = (unsigned long long*)p->flags->peer[lr][q] + SFC_MAX_GPUS + me;
+        dist_signal_kernel<<<1, 32, 0, st>>>(fp, P, epoch);
+        dist_wait_kernel<<<1, 32, 0, st>>>(myflags + SFC_MAX_GPUS, P, epoch, (unsigned long long)p->timeout_ns, rk.status_d);
+        if (out_peers[me] != d_out) {
+            cudaError_t e = cudaMemcpyAsync(d_out, out_peers[me], (size_t)(p->s0 * p->n1 * p->n2) * p->cs, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return cuda_fail(e, "copy out of the exchange window");
+        }
+        mark();
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "slab exchange kernels");
+    return SFC_OK;
+}
+
+int ensure_win2(sfc_dist_plan* p) {
+    if (p->win2) return SFC_OK;
+    return sym_alloc(p->comm, (size_t)(p->s0 * p->n1 * p->n2) * p->cs, &p->win2);
+}
+
+}  // namespace
+
+SFC_EXPORT int sfc_dist_plan_create(sfc_dist_plan** out, sfc_comm* comm, const sfc_dist_desc* desc) {
+    if (!out || !comm || !desc) return fail(SFC_ERR_VALUE, "null argument");
+    *out = nullptr;
+    if (comm->host_only) return fail(SFC_ERR_BACKEND, "host-only communicator (no CUDA device; this library has no CPU fallback)");
+    auto p = std::make_unique<sfc_dist_plan>();
+    p->comm = comm;
+    p->desc = *desc;
+    int rc;
+    switch (desc->decomposition) {
+        case SFC_DECOMP_SLAB: rc = build_slab(p.get()); break;
+        case SFC_DECOMP_BATCH_SPLIT:
+        case SFC_DECOMP_REPLICATED: rc = build_batch(p.get()); break;
+        default: rc = fail(SFC_ERR_VALUE, "unknown decomposition");
+    }
+    if (rc != SFC_OK) {
+        const std::string keep = sfc_last_error();
+        sfc_dist_plan_destroy(p.release());
+        return fail(rc, keep);
+    }
+    fill_info(p.get());
+    comm->live_plans += 1;
+    *out = p.release();
+    return SFC_OK;
+}
+
+SFC_EXPORT int sfc_dist_plan_destroy(sfc_dist_plan* p) {
+    if (!p) return SFC_OK;
+    sfc_comm* c = p->comm;
+    for (size_t lr = 0; lr < p->r.size(); ++lr) {
+        DeviceGuard g(c->ranks[lr].device);
+        cudaDeviceSynchronize();
+        DistRank& dr = p->r[lr];
+        if (dr.work) cudaFree(dr.work);
+        if (dr.handle) sfc_plan_destroy(dr.handle);
+        if (dr.h_in_dev) cudaFree(dr.h_in_dev);
+        if (dr.h_out_dev) cudaFree(dr.h_out_dev);
+        for (cudaEvent_t e : dr.ev) cudaEventDestroy(e);
+    }
+    if (p->win2) sym_free(c, p->win2);
+    if (p->flags) sym_free(c, p->flags);
+    if (p->recv) sym_free(c, p->recv);
+    delete p;
+    return SFC_OK;
+}
+
+SFC_EXPORT int sfc_dist_plan_get_info(const sfc_dist_plan* p, sfc_dist_info* info) {
+    if (!p || !info) return fail(SFC_ERR_VALUE, "null argument");
+    *info = p->info;
+    return SFC_OK;
+}
+
+SFC_EXPORT int sfc_dist_plan_profile(sfc_dist_plan* p, int32_t enable) {
+    if (!p) return fail(SFC_ERR_VALUE, "null argument");
+    p->profile = enable != 0;
+    p->nmarks = 0;
+    return SFC_OK;
+}
+
+SFC_EXPORT int sfc_dist_plan_stage_ms(sfc_dist_plan* p, double* ms, int32_t cap) {
+    if (!p || !ms) return fail(SFC_ERR_VALUE, "null argument");
+    if (p->r.empty() || p->nmarks < 2) return 0;
+    DeviceGuard g(p->comm->ranks[0].device);
+    DistRank& dr = p->r[0];
+    cudaError_t e = cudaEventSynchronize(dr.ev[p->nmarks - 1]);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
+    int n = 0;
+    for (int i = 0; i + 1 < p->nmarks && n < cap; ++i, ++n) {
+        float f = 0.f;
+        cudaEventElapsedTime(&f, dr.ev[i], dr.ev[i + 1]);
+        ms[n] = (double)f;
+    }
+    return n;
+}
+
+SFC_EXPORT int sfc_dist_exec_device(sfc_dist_plan* p, const void* d_in, void* d_out, void* stream) {
+    if (!p || !d_in || !d_out) return fail(SFC_ERR_VALUE, "null argument");
+    sfc_comm* c = p->comm;
+    if (c->local_mode && c->world > 1)
+        return fail(SFC_ERR_VALUE, "this communicator drives several GPUs: use sfc_dist_exec_device_multi");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->desc.decomposition != SFC_DECOMP_SLAB) {
+        if (!p->r[0].handle) return SFC_OK;  // this rank's share of the batch is empty
+        return sfc_exec_device(p->r[0].handle, d_in, d_out, stream);
+    }
+    void* peers[SFC_MAX_GPUS] = {};
+    if (p->desc.layout == SFC_SLAB_NATURAL && c->world > 1) {
+        size_t off = 0;
+        SymAlloc* a = find_alloc(c, d_out, 0, &off);
+        if (a && off + (size_t)(p->s0 * p->n1 * p->n2) * p->cs <= a->bytes) {
+            for (int q = 0; q < c->world; ++q) peers[q] = (char*)a->peer[0][q] + off;  // symmetric: same offset everywhere
+        } else {
+            int rc = ensure_win2(p);  // collective on first use: every rank takes the same branch for the same call
+            if (rc != SFC_OK) return rc;
+            for (int q = 0; q < c->world; ++q) peers[q] = p->win2->peer[0][q];
+        }
+    }
+    p->epoch += 1;
+    return enqueue_slab(p, 0, d_in, d_out, st, p->epoch, peers);
+}
+
+SFC_EXPORT int sfc_dist_exec_device_multi(sfc_dist_plan* p, const void* const* d_in, void* const* d_out, void* const* streams) {
+    if (!p || !d_in || !d_out) return fail(SFC_ERR_VALUE, "null argument");
+    sfc_comm* c = p->comm;
+    if (!c->local_mode) return fail(SFC_ERR_VALUE, "one process per GPU: use sfc_dist_exec_device");
+    const int P = c->world;
+    p->epoch += 1;
+    for (int lr = 0; lr < P; ++lr) {
+        if (!d_in[lr] || !d_out[lr]) return fail(SFC_ERR_VALUE, "null device pointer");
+        DeviceGuard g(c->ranks[lr].device);
+        cudaStream_t st = streams ? (cudaStream_t)streams[lr] : c->ranks[lr].stream;
+        int rc;
+        if (p->desc.decomposition != SFC_DECOMP_SLAB) {
+            if (!p->r[lr].handle) continue;
+            rc = sfc_exec_device(p->r[lr].handle, d_in[lr], d_out[lr], (void*)st);
+            if (rc != SFC_OK) return rc;
+        } else {
+            // one address space: every output is reachable from every GPU, the natural layout needs no window
+            rc = enqueue_slab(p, lr, d_in[lr], d_out[lr], st, p->epoch, d_out);
+            if (rc != SFC_OK) return rc;
+        }
+    }
+    return SFC_OK;
+}
+
+SFC_EXPORT int sfc_dist_synchronize(sfc_dist_plan* p) {
+    if (!p) return fail(SFC_ERR_VALUE, "null argument");
+    sfc_comm* c = p->comm;
+    for (auto& r : c->ranks) {
+        DeviceGuard g(r.device);
+        cudaError_t e = cudaStreamSynchronize(r.stream);
+        if (e != cudaSuccess) return cuda_fail(e, "distributed transform execution");
+        if (*r.status_h != 0) {
+            char b[128];
+            snprintf(b, sizeof b, "exchange timed out waiting for rank %d", *r.status_h - 1);
+            return fail(SFC_ERR_COMMUNICATION, b);
+        }
+    }
+    return SFC_OK;
+}
+
+// Host buffers.  Every GPU moves its share over its own PCIe link; copies of different GPUs run concurrently because
+// everything is enqueued asynchronously before the first wait (pinned memory) or from one thread per GPU (pageable).
+SFC_EXPORT int sfc_dist_exec_host(sfc_dist_plan* p, const void* h_in, void* h_out) {
+    if (!p || !h_in || !h_out) return fail(SFC_ERR_VALUE, "null argument");
+    sfc_comm* c = p->comm;
+    const int nl = (int)c->ranks.size();
+    const bool slab = p->desc.decomposition == SFC_DECOMP_SLAB;
+    const int P = c->world;
+    const size_t slab_bytes = slab ? (size_t)(p->s0 * p->n1 * p->n2) * p->cs : 0;
+    std::vector<size_t> in_off(nl, 0), out_off(nl, 0), in_b(nl, 0), out_b(nl, 0);
+    for (int lr = 0; lr < nl; ++lr) {
+        const int q = c->ranks[lr].rank;
+        if (slab) {
+            in_b[lr] = out_b[lr] = slab_bytes;
+            if (c->local_mode) in_off[lr] = out_off[lr] = (size_t)q * slab_bytes;
+        } else {
+            in_b[lr] = (size_t)p->b_count[q] * p->in_row_bytes;
+            out_b[lr] = (size_t)p->b_count[q] * p->out_row_bytes;
+            if (c->local_mode && p->desc.decomposition == SFC_DECOMP_BATCH_SPLIT) {
+                in_off[lr] = (size_t)p->b_start[q] * p->in_row_bytes;
+                out_off[lr] = (size_t)p->b_start[q] * p->out_row_bytes;
+            }
+        }
+    }
+    if (!slab) {
+        // every GPU runs the chunk-pipelined host path of an ordinary plan handle (H2D / kernels / D2H of different
+        // chunks overlap) on its own PCIe link, from its own host thread
+        std::vector<int> rcs(nl, SFC_OK);
+        std::vector<std::string> msgs(nl);
+        auto run = [&](int lr) {
+            if (!p->r[lr].handle || in_b[lr] == 0) return;
+            cudaSetDevice(c->ranks[lr].device);
+            rcs[lr] = sfc_exec_host(p->r[lr].handle, (const char*)h_in + in_off[lr], (char*)h_out + out_off[lr]);
+            if (rcs[lr] != SFC_OK) msgs[lr] = sfc_last_error();
+        };
+        if (nl == 1) {
+            DeviceGuard g(c->ranks[0].device);
+            run(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int lr = 0; lr < nl; ++lr) th.emplace_back(run, lr);
+            for (auto& t : th) t.join();
+        }
+        for (int lr = 0; lr < nl; ++lr)
+            if (rcs[lr] != SFC_OK) return fail(rcs[lr], msgs[lr]);
+        return SFC_OK;
+    }
+    // device staging: outputs of a local-mode natural slab plan are written by peers, plain allocations are fine (UVA)
+    for (int lr = 0; lr < nl; ++lr) {
+        DeviceGuard g(c->ranks[lr].device);
+        DistRank& dr = p->r[lr];
+        if (!dr.h_in_dev && in_b[lr]) {
+            if (alloc_with_relief(&dr.h_in_dev, in_b[lr], nullptr) != cudaSuccess) return fail(SFC_ERR_MEMORY, "cudaMalloc failed (host-exec staging)");
+        }
+        if (!dr.h_out_dev && out_b[lr]) {
+            if (alloc_with_relief(&dr.h_out_dev, out_b[lr], nullptr) != cudaSuccess) return fail(SFC_ERR_MEMORY, "cudaMalloc failed (host-exec staging)");
+        }
+    }
+    // host slab output of a transposed-layout plan would be the transposed slab; the local-mode host entry always
+    // returns the natural array, so transposed plans run their pass C into staging and are copied out strided below
+    const bool natural = slab && (p->desc.layout == SFC_SLAB_NATURAL || P == 1);
+    if (slab && c->local_mode && !natural)
+        return fail(SFC_ERR_VALUE, "sfc_dist_exec_host on several GPUs needs the natural layout (the output is one C-order array)");
+    p->epoch += 1;
+    std::vector<int> rcs(nl, SFC_OK);
+    std::vector<std::string> msgs(nl);
+    std::vector<void*> outs(nl);
+    for (int lr = 0; lr < nl; ++lr) outs[lr] = p->r[lr].h_out_dev;
+    void* peers_rank[SFC_MAX_GPUS] = {};
+    if (slab && !c->local_mode && natural && P > 1) {
+        int rc = ensure_win2(p);
+        if (rc != SFC_OK) return rc;
+        for (int q = 0; q < P; ++q) peers_rank[q] = p->win2->peer[0][q];
+    }
+    auto run = [&](int lr) {
+        cudaSetDevice(c->ranks[lr].device);
+        cudaStream_t st = c->ranks[lr].stream;
+        DistRank& dr = p->r[lr];
+        if (in_b[lr] == 0) return;
+        cudaError_t e = cudaMemcpyAsync(dr.h_in_dev, (const char*)h_in + in_off[lr], in_b[lr], cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { rcs[lr] = SFC_ERR_BACKEND; msgs[lr] = std::string("H2D copy: ") + cudaGetErrorString(e); return; }
+        int rc = enqueue_slab(p, lr, dr.h_in_dev, dr.h_out_dev, st, p->epoch, c->local_mode ? outs.data() : peers_rank);
+        if (rc != SFC_OK) { rcs[lr] = rc; msgs[lr] = sfc_last_error(); return; }
+        e = cudaMemcpyAsync((char*)h_out + out_off[lr], dr.h_out_dev, out_b[lr], cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rcs[lr] = SFC_ERR_BACKEND; msgs[lr] = std::string("D2H copy: ") + cudaGetErrorString(e); }
+    };
+    if (nl == 1) {
+        DeviceGuard g(c->ranks[0].device);
+        run(0);
+    } else {
+        // one host thread per GPU: pageable copies block their caller, and the exchange needs all GPUs in flight
+        std::vector<std::thread> th;
+        for (int lr = 0; lr < nl; ++lr) th.emplace_back(run, lr);
+        for (auto& t : th) t.join();
+    }
+    for (int lr = 0; lr < nl; ++lr)
+        if (rcs[lr] != SFC_OK) return fail(rcs[lr], msgs[lr]);
+    for (auto& r : c->ranks)
+        if (*r.status_h != 0) return fail(SFC_ERR_COMMUNICATION, "exchange timed out waiting for a peer");
+    return SFC_OK;
+}
+
+// ====================================================================== free functions over several GPUs
+
+namespace {
+struct MultiState {
+    std::mutex mu;
+    int ngpu = 1;
+    sfc_comm* comm = nullptr;
+    struct Entry {
+        std::string key;
+        sfc_dist_plan* plan;
+        uint64_t stamp;
+    };
+    std::vector<Entry> plans;
+    uint64_t clock = 0;
+};
+MultiState& multi() {
+    static MultiState m;
+    return m;
+}
+
+// cached distributed plan of the process-wide local communicator (at most 8 shapes, least recently used goes)
+int multi_plan(MultiState& m, const sfc_dist_desc& dd, sfc_dist_plan** out) {
+    if (!m.comm) {
+        int rc = sfc_comm_init_local(&m.comm, m.ngpu, nullptr);
+        if (rc != SFC_OK) return rc;
+    }
+    sfc_dist_desc k;
+    memset(&k, 0, sizeof k);
+    k.base.ndim = dd.base.ndim;
+    for (int i = 0; i < dd.base.ndim; ++i) k.base.shape[i] = dd.base.shape[i];
+    k.base.naxes = dd.base.naxes;
+    for (int i = 0; i < dd.base.naxes; ++i) k.base.axes[i] = dd.base.axes[i];
+    k.base.kind = dd.base.kind;
+    k.base.prec = dd.base.prec;
+    k.base.direction = dd.base.direction;
+    k.base.scale = dd.base.scale;
+    k.decomposition = dd.decomposition;
+    k.layout = dd.layout;
+    const std::string key((const char*)&k, sizeof k);
+    for (auto& e : m.plans)
+        if (e.key == key) {
+            e.stamp = ++m.clock;
+            *out = e.plan;
+            return SFC_OK;
+        }
+    sfc_dist_plan* p = nullptr;
+    int rc = sfc_dist_plan_create(&p, m.comm, &dd);
+    if (rc != SFC_OK) return rc;
+    if (m.plans.size() >= 8) {
+        size_t v = 0;
+        for (size_t i = 1; i < m.plans.size(); ++i)
+            if (m.plans[i].stamp < m.plans[v].stamp) v = i;
+        sfc_dist_plan_destroy(m.plans[v].plan);
+        m.plans.erase(m.plans.begin() + (long)v);
+    }
+    m.plans.push_back({key, p, ++m.clock});
+    *out = p;
+    return SFC_OK;
+}
+}  // namespace
+
+SFC_EXPORT int sfc_set_num_gpus(int32_t ngpu) {
+    MultiState& m = multi();
+    std::lock_guard<std::mutex> lk(m.mu);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+        cudaGetLastError();
+        ndev = 0;
+    }
+    if (ngpu < 0) ngpu = ndev;
+    if (ngpu == 0) ngpu = 1;
+    if (ngpu > 1 && ngpu > ndev) return fail(SFC_ERR_VALUE, "more GPUs requested than visible");
+    if (ngpu > SFC_MAX_GPUS) return fail(SFC_ERR_VALUE, "at most 16 GPUs");
+    if (ngpu != m.ngpu) {
+        for (auto& e : m.plans) sfc_dist_plan_destroy(e.plan);
+        m.plans.clear();
+        if (m.comm) sfc_comm_destroy(m.comm);
+        m.comm = nullptr;
+        m.ngpu = ngpu;
+    }
+    return SFC_OK;
+}
+
+SFC_EXPORT int sfc_get_num_gpus(void) {
+    MultiState& m = multi();
+    std::lock_guard<std::mutex> lk(m.mu);
+    return m.ngpu;
+}
+
+namespace sfc_api {
+
+// fftn / ifftn of a complex f64 volume over all three axes: slab-decomposed over the GPUs of this process when the
+// shape allows it (*handled = true); otherwise the caller continues on one GPU
+int multi_fftn_host(const void* x, const int64_t* shape3, const int* axes3, bool inverse, double scale, double* out, bool* handled) {
+    *handled = false;
+    MultiState& m = multi();
+    std::lock_guard<std::mutex> lk(m.mu);
+    const int P = m.ngpu;
+    if (P <= 1) return SFC_OK;
+    auto pow2 = [](int64_t v) { return v > 0 && (v & (v - 1)) == 0; };
+    if (!pow2(shape3[0]) || !pow2(shape3[1]) || !pow2(shape3[2])) return SFC_OK;
+    if (shape3[0] % P || shape3[1] % P || !pow2(P)) return SFC_OK;
+    if (shape3[0] * shape3[1] * shape3[2] < ((int64_t)1 << 18)) return SFC_OK;  // too small to be worth an exchange
+    sfc_dist_desc dd;
+    memset(&dd, 0, sizeof dd);
+    dd.base.ndim = 3;
+    for (int i = 0; i < 3; ++i) {
+        dd.base.shape[i] = shape3[i];
+        dd.base.axes[i] = axes3[i];
+    }
+    dd.base.naxes = 3;
+    dd.base.kind = SFC_C2C;
+    dd.base.prec = SFC_PREC_F64;
+    dd.base.direction = inverse ? SFC_INVERSE : SFC_FORWARD;
+    dd.base.scale = scale;
+    dd.decomposition = SFC_DECOMP_SLAB;
+    dd.layout = SFC_SLAB_NATURAL;
+    sfc_dist_plan* p = nullptr;
+    int rc = multi_plan(m, dd, &p);
+    if (rc == SFC_ERR_NOT_IMPLEMENTED || rc == SFC_ERR_VALUE || rc == SFC_ERR_PLAN) return SFC_OK;  // shape the slab path does not take
+    if (rc != SFC_OK) return rc;
+    rc = sfc_dist_exec_host(p, x, out);
+    if (rc == SFC_OK) *handled = true;
+    return rc;
+}
+
+// batched plan on host buffers split over the GPUs of this process
+int multi_batch_host(const sfc_desc& d, const void* in, void* out, bool* handled) {
+    *handled = false;
+    MultiState& m = multi();
+    std::lock_guard<std::mutex> lk(m.mu);
+    if (m.ngpu <= 1 || d.shape[0] < 2 * m.ngpu) return SFC_OK;
+    sfc_dist_desc dd;
+    memset(&dd, 0, sizeof dd);
+    dd.base = d;
+    dd.decomposition = SFC_DECOMP_BATCH_SPLIT;
+    sfc_dist_plan* p = nullptr;
+    int rc = multi_plan(m, dd, &p);
+    if (rc != SFC_OK) return rc;
+    rc = sfc_dist_exec_host(p, in, out);
+    if (rc == SFC_OK) *handled = true;
+    return rc;
+}
+
+}  // namespace sfc_api

@@ -594,6 +594,7 @@ struct PlanBuilder {
     PlanError& err;
     int64_t dev_bytes = 0;
     int scatter_parts = 0;  // > 1: the next single-pass axis stores through the scatter table
+    int64_t scatter_pitch = 0;  // element pitch of the split axis inside a destination block (0 = inner extent)
     // SFC_DESC_AUX_MUL: tables multiplied into the next axis on load (indexed by input position) and
     // on store (indexed by output position); power-of-two lengths only
     const void* aux_in = nullptr;
@@ -872,7 +873,9 @@ struct PlanBuilder {
                     return fail(SFC_ERR_VALUE, "scatter needs the split axis length / parts to be a power of two");
                 s.scatter = true;
                 s.p.peer_shift = ilog2_64(blk);
-                set_io(s.p.out, 0, blk * I, 1, I, n, 1, 0);
+                const int64_t pitch = scatter_pitch > 0 ? scatter_pitch : I;
+                if (pitch < I) return fail(SFC_ERR_VALUE, "scatter_pitch must be at least the inner extent");
+                set_io(s.p.out, 0, blk * pitch, 1, pitch, n, 1, 0);
                 if (!finish_tile(s, O * I, I, 1, "single-pass axis + split-axis scatter store")) return false;
                 if (pl.steps_.back().k->mode != 1)
                     return fail(SFC_ERR_NOT_IMPLEMENTED, "scatter store needs full tiles (lanes % tile lanes == 0)");
@@ -1615,6 +1618,7 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
             const int64_t n = shape[a], O = prod(shape, 0, a), I = prod(shape, a + 1, shape.size());
             const bool last = (i + 1 == axes.size());
             B.scatter_parts = (last && d.scatter_parts > 1) ? d.scatter_parts : 0;
+            B.scatter_pitch = B.scatter_parts ? d.scatter_pitch : 0;
             if (B.scatter_parts > 16) {
                 err = {SFC_ERR_VALUE, "scatter_parts must be <= 16"};
                 return nullptr;
@@ -1625,7 +1629,7 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
             }
             // with a scatter the intermediate passes must not touch the caller's outputs: use scratch
             const int mid_role = d.scatter_parts > 1 ? R_SA : R_OUT;
-            if (d.scatter_parts > 1) B.need_sa((size_t)total * cs);
+            if (d.scatter_parts > 1 && axes.size() > 1) B.need_sa((size_t)total * cs);
             ok = B.add_axis(n, O, I, {i == 0 ? R_IN : mid_role, i == 0 && real_in, ax_in ? ax_in : n},
                             {last ? R_OUT : mid_role, false, ax_out ? ax_out : n}, inv, last ? d.scale : 1.0,
                             last && real_out);
@@ -1857,6 +1861,11 @@ bool Plan::ensure_scratch(std::string& es) {
     return true;
 }
 
+int Plan::prepare(std::string& es) {
+    std::lock_guard<std::mutex> lk(mu_);
+    return ensure_scratch(es) ? 0 : (int)SFC_ERR_MEMORY;
+}
+
 size_t Plan::release_scratch() {
     std::unique_lock<std::mutex> lk(mu_, std::try_to_lock);
     if (!lk.owns_lock()) return 0;  // being enqueued right now: leave it alone
@@ -1961,11 +1970,23 @@ extern "C" __attribute__((visibility("default"))) void sfc_debug_phase_dump(void
 
 int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& es, void* const* scatter, int nscatter) {
     std::lock_guard<std::mutex> lk(mu_);
-    const bool uses_scratch = sa_bytes_ || ms_bytes_;
+    bool uses_scratch = sa_bytes_ || ms_bytes_;
     if (uses_scratch) {
-        if (!ensure_scratch(es)) return SFC_ERR_MEMORY;
-        // the previous execution may still be running on another stream over the same scratch: order after it
-        if (busy_valid_ && last_stream_ != stream) cudaStreamWaitEvent(stream, busy_ev_, 0);
+        // stream capture (CUDA graphs): no allocation and no cross-stream event inside a capture — the plan must have run
+        // once before, and replays of the graph are ordered by the stream they are launched on
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (stream && cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cudaGetLastError();
+        if (cap != cudaStreamCaptureStatusNone) {
+            if ((sa_bytes_ && !sa_) || (ms_bytes_ && !ms_)) {
+                es = "execute the plan once before capturing it into a CUDA graph (its scratch is allocated on first use)";
+                return SFC_ERR_VALUE;
+            }
+            uses_scratch = false;
+        } else {
+            if (!ensure_scratch(es)) return SFC_ERR_MEMORY;
+            // the previous execution may still be running on another stream over the same scratch: order after it
+            if (busy_valid_ && last_stream_ != stream) cudaStreamWaitEvent(stream, busy_ev_, 0);
+        }
     }
     struct Mark {  // record the "scratch busy until here" event on every exit path that launched something
         Plan* pl; cudaStream_t st; bool on;

@@ -97,6 +97,9 @@ class Plan {
     // Frees the scratch areas if the plan is idle (no execution being enqueued; waits for the last one to finish on the
     // device).  Returns the bytes released.  Called for the OTHER cached plans when a device allocation fails.
     size_t release_scratch();
+    // Allocates the scratch areas now (what the first execution would do): needed before stream capture, and by callers
+    // that must not hit a device allocation in the middle of a multi-GPU enqueue.
+    int prepare(std::string& es);
     size_t scratch_resident() const { return (sa_ ? sa_bytes_ : 0) + (ms_ ? ms_bytes_ : 0); }
 };
 

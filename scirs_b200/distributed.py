@@ -1,19 +1,23 @@
-"""Multi-GPU paths: one process per GPU, `torch.distributed` for the plumbing.
+"""Multi-GPU paths.  The product is the C library: communicator, symmetric device memory, the
+batch-split and slab-decomposed plans and their device-side rendezvous all live behind `sfc_comm_*` / `sfc_dist_*`
+(include/scirs2_fft_cuda.h, csrc/dist.cu) — no torch, no NCCL in the data path.  This module is the thin mirror of
+that ABI plus the reference-shaped helpers.
 
-Two ways the hot path shards across the 8 GPUs of a node (SURVEY 8e):
+Two ways the hot path shards across the 8 GPUs of a node:
 
 * batched 1-D / 2-D transforms: independent signals -> contiguous batch split, replicated plans,
-  NO data-path collective (`split_batch`).
+  NO data-path collective (`split_batch`, `DistPlan(..., decomposition="batch_split")`).
 * 3-D `fftn`: slab decomposition exactly as the reference sketches it
   (scirs2-fft/src/distributed.rs:356-362: rank r owns planes [r*s, (r+1)*s) of axis 0, s =
-  ceil(n0/P)): local 2-D FFT over axes (2, 1), ONE transpose exchange, local 1-D FFT over axis 0.
+  ceil(n0/P)): local FFTs over axes 2 and 1, ONE transpose exchange, local FFT over axis 0.
   The reference's exchange is a no-op mock (`distributed.rs:232-268, 765-769`); here it is real:
-    - mode "p2p"  : the axis-1 FFT kernel stores every block straight into the destination rank's
-                    receive buffer (CUDA-IPC mapped peer memory, written over NVLink/NVSwitch) —
-                    the FFT pass and the all-to-all are ONE kernel; no pack, no unpack, no NCCL copy.
-    - mode "nccl" : the same kernel scatters into a local send buffer laid out [P][s0][s1][n2],
-                    then `all_to_all_single` over NCCL moves it.
-  Output is left axis-1-distributed ("transposed out": rank r holds out[:, r*s1:(r+1)*s1, :]).
+    - mode "p2p"  : (default, in the library) the axis-1 FFT kernel stores every block straight into the
+                    destination rank's receive window (CUDA-IPC mapped peer memory, written over NVLink/NVSwitch) —
+                    the FFT pass and the all-to-all are ONE kernel; ranks synchronise through device-side flags.
+    - mode "nccl" : (comparison only, Python + torch.distributed) the same kernel scatters into a local send buffer
+                    laid out [P][s0][s1][n2], then `all_to_all_single` over NCCL moves it.
+  layout "transposed": output stays axis-1-distributed (rank r holds out[:, r*s1:(r+1)*s1, :]);
+  layout "natural": a second exchange, fused into the axis-0 FFT store, restores axis-0 slabs (a true `fftn`).
 
 `local_transform` hooks let the CPU (gloo, world_size 2) tests drive the exchange logic with a
 numpy transform; the product path always runs the CUDA library.
@@ -21,7 +25,9 @@ numpy transform; the product path always runs the CUDA library.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Callable, List, Optional, Tuple
+import itertools
+import os
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -50,31 +56,223 @@ def pack_for_exchange(y: np.ndarray, world_size: int) -> np.ndarray:
     return np.ascontiguousarray(y.reshape(s0, world_size, s1, n2).transpose(1, 0, 2, 3))
 
 
+_comm_counter = itertools.count()
+
+
+class Communicator:
+    """`trait Communicator` (distributed.rs:85-103) for the GPUs of one node, implemented inside the library.
+
+    `Communicator.rank_mode(name, rank, world, device)`: one process per GPU (rendezvous over POSIX shared memory).
+    `Communicator.from_env()`: the same, reading RANK / WORLD_SIZE / LOCAL_RANK as torchrun sets them.
+    `Communicator.local(ngpu)`: one process driving several GPUs."""
+
+    def __init__(self, handle, lib):
+        self._h, self._lib = handle, lib
+
+    @classmethod
+    def rank_mode(cls, name: str, rank: int, world: int, device: int) -> "Communicator":
+        lib = _lib.load()
+        h = C.c_void_p()
+        check(lib.sfc_comm_init_rank(C.byref(h), name.encode(), int(rank), int(world), int(device)))
+        obj = cls(h, lib)
+        obj._rank_mode = True
+        return obj
+
+    @classmethod
+    def from_env(cls, device: Optional[int] = None) -> "Communicator":
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        local = int(os.environ.get("LOCAL_RANK", str(rank)))
+        # the ranks of one launch share MASTER_PORT and their parent (the launcher); the counter separates the
+        # communicators one job creates (every rank creates them in the same order)
+        name = f"{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_{next(_comm_counter)}"
+        return cls.rank_mode(os.environ.get("SFC_COMM_NAME", name), rank, world, local if device is None else device)
+
+    @classmethod
+    def local(cls, ngpu: int = 0, devices: Optional[Sequence[int]] = None) -> "Communicator":
+        lib = _lib.load()
+        h = C.c_void_p()
+        dv = None if devices is None else (C.c_int32 * len(devices))(*devices)
+        check(lib.sfc_comm_init_local(C.byref(h), int(ngpu if devices is None else len(devices)), dv))
+        obj = cls(h, lib)
+        obj._rank_mode = False
+        return obj
+
+    def size(self) -> int:
+        return self._lib.sfc_comm_size(self._h)
+
+    def rank(self) -> int:
+        return self._lib.sfc_comm_rank(self._h)
+
+    def barrier(self) -> None:
+        check(self._lib.sfc_comm_barrier(self._h))
+
+    def allgather_bytes(self, blob: bytes) -> List[bytes]:
+        n = len(blob)
+        out = C.create_string_buffer(n * self.size())
+        check(self._lib.sfc_comm_allgather(self._h, blob, out, n))
+        return [out.raw[i * n:(i + 1) * n] for i in range(self.size())]
+
+    def alloc(self, nbytes: int):
+        """Symmetric device allocation (collective): rank mode -> one pointer, local mode -> one per GPU."""
+        n = 1 if self._is_rank_mode() else self.size()
+        ptrs = (C.c_void_p * max(n, 1))()
+        check(self._lib.sfc_comm_alloc(self._h, int(nbytes), ptrs))
+        return ptrs[0] if n == 1 else [ptrs[i] for i in range(n)]
+
+    def free(self, ptr) -> None:
+        check(self._lib.sfc_comm_free(self._h, C.c_void_p(ptr if isinstance(ptr, int) else ptr[0])))
+
+    def _is_rank_mode(self) -> bool:
+        return getattr(self, "_rank_mode", True)
+
+    def close(self) -> None:
+        if self._h is not None and self._h.value:
+            self._lib.sfc_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_DECOMP = {"replicated": _lib.SFC_DECOMP_REPLICATED, "batch_split": _lib.SFC_DECOMP_BATCH_SPLIT, "slab": _lib.SFC_DECOMP_SLAB}
+_LAYOUT = {"transposed": _lib.SFC_SLAB_TRANSPOSED, "natural": _lib.SFC_SLAB_NATURAL}
+
+
+class DistPlan:
+    """`sfc_dist_plan`: a plan over the GPUs of a communicator (DecompositionStrategy, distributed.rs:18-29)."""
+
+    def __init__(self, comm: Communicator, shape: Sequence[int], axes: Optional[Sequence[int]] = None,
+                 decomposition: str = "slab", layout: str = "transposed", kind: str = "c2c", prec: str = "f64",
+                 forward: bool = True, scale: float = 1.0):
+        lib = _lib.load()
+        dd = _lib.sfc_dist_desc()
+        d = dd.base
+        shape = [int(v) for v in shape]
+        axes = list(range(len(shape))) if axes is None else [int(a) for a in axes]
+        d.ndim = len(shape)
+        for i, v in enumerate(shape):
+            d.shape[i] = v
+        d.naxes = len(axes)
+        for i, a in enumerate(axes):
+            d.axes[i] = a
+        d.kind = {"c2c": _lib.SFC_C2C, "r2c": _lib.SFC_R2C, "c2r": _lib.SFC_C2R}[kind]
+        d.prec = _lib.SFC_PREC_F64 if prec == "f64" else _lib.SFC_PREC_F32
+        d.direction = _lib.SFC_FORWARD if forward else _lib.SFC_INVERSE
+        d.scale = float(scale)
+        dd.decomposition = _DECOMP[decomposition]
+        dd.layout = _LAYOUT[layout]
+        self._h = C.c_void_p()
+        check(lib.sfc_dist_plan_create(C.byref(self._h), comm._h, C.byref(dd)))
+        self._lib, self.comm = lib, comm
+        info = _lib.sfc_dist_info()
+        check(lib.sfc_dist_plan_get_info(self._h, C.byref(info)))
+        self.info = {f: (list(getattr(info, f)) if f.endswith("_shape") else getattr(info, f)) for f, _ in _lib.sfc_dist_info._fields_}
+        nd = len(shape)
+        self.local_in_shape = tuple(self.info["local_in_shape"][:nd])
+        self.local_out_shape = tuple(self.info["local_out_shape"][:nd])
+
+    def execute_device(self, d_in, d_out, stream=0) -> None:
+        """rank mode: this rank's share (device pointers or torch CUDA tensors); enqueues only."""
+        from .plan import _dev_ptr
+
+        check(self._lib.sfc_dist_exec_device(self._h, C.c_void_p(_dev_ptr(d_in)), C.c_void_p(_dev_ptr(d_out)),
+                                             C.c_void_p(int(stream))))
+
+    def execute_device_multi(self, d_in: Sequence, d_out: Sequence, streams: Optional[Sequence[int]] = None) -> None:
+        """local mode: one pointer per GPU; enqueues only (`synchronize` waits)."""
+        from .plan import _dev_ptr
+
+        n = len(d_in)
+        a = (C.c_void_p * n)(*[_dev_ptr(t) for t in d_in])
+        b = (C.c_void_p * n)(*[_dev_ptr(t) for t in d_out])
+        s = None if streams is None else (C.c_void_p * n)(*[int(v) for v in streams])
+        check(self._lib.sfc_dist_exec_device_multi(self._h, a, b, s))
+
+    def synchronize(self) -> None:
+        check(self._lib.sfc_dist_synchronize(self._h))
+
+    def profile(self, enable: bool = True) -> None:
+        check(self._lib.sfc_dist_plan_profile(self._h, 1 if enable else 0))
+
+    def stage_ms(self) -> List[float]:
+        buf = (C.c_double * 8)()
+        n = self._lib.sfc_dist_plan_stage_ms(self._h, buf, 8)
+        if n < 0:
+            check(n)
+        return [buf[i] for i in range(n)]
+
+    def execute_host(self, x: np.ndarray, out: np.ndarray) -> np.ndarray:
+        if not (x.flags.c_contiguous and out.flags.c_contiguous and out.flags.writeable):
+            raise ValueError_("host arrays must be C-contiguous")
+        check(self._lib.sfc_dist_exec_host(self._h, x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.sfc_dist_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def set_num_gpus(ngpu: int) -> None:
+    """`sfc_set_num_gpus`: the free functions (`fftn`, `ifftn`, `ParallelExecutor.execute_batch`) of THIS process run
+    over `ngpu` GPUs from now on (slab decomposition / batch split inside the library)."""
+    check(_lib.load().sfc_set_num_gpus(int(ngpu)))
+
+
+def get_num_gpus() -> int:
+    return _lib.load().sfc_get_num_gpus()
+
+
 class SlabFFT3D:
-    """Forward 3-D c2c of an n0 x n1 x n2 volume distributed as axis-0 slabs over the process group."""
+    """3-D c2c of an n0 x n1 x n2 volume distributed as axis-0 slabs, one process per GPU.
+
+    mode "p2p" (default): `sfc_dist_plan` of the library over a `Communicator` — nothing of torch in the data path.
+    mode "nccl": comparison path, the exchange through `torch.distributed.all_to_all_single`.
+    `local_transform`: CPU tests only (numpy transform + gloo exchange)."""
 
     def __init__(self, n0: int, n1: int, n2: int, group=None, mode: str = "p2p", prec: str = "f64",
-                 local_transform: Optional[Callable] = None):
-        import torch.distributed as dist
+                 local_transform: Optional[Callable] = None, comm: Optional[Communicator] = None,
+                 layout: str = "transposed", forward: bool = True, scale: float = 1.0):
+        self.n0, self.n1, self.n2 = n0, n1, n2
+        self.mode, self.prec, self.layout = mode, prec, layout
+        self.local_transform = local_transform
+        self._own_comm = False
+        self.plan = None
+        self._recv = None
+        if mode == "p2p" and local_transform is None:
+            if comm is None:
+                comm = Communicator.from_env()
+                self._own_comm = True
+            self.comm = comm
+            self.P, self.rank = comm.size(), comm.rank()
+        else:
+            import torch.distributed as dist
 
-        self.dist = dist
-        self.group = group
-        self.P = dist.get_world_size(group)
-        self.rank = dist.get_rank(group)
+            self.dist, self.group = dist, group
+            self.P, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if n0 % self.P or n1 % self.P:
             raise ValueError_("slab decomposition needs n0 and n1 divisible by the number of ranks")
-        self.n0, self.n1, self.n2 = n0, n1, n2
         self.s0, self.s1 = n0 // self.P, n1 // self.P
-        self.mode = mode
-        self.prec = prec
-        self.local_transform = local_transform
-        self._peers = None
-        self._recv = None
-        if local_transform is None:
-            self._init_cuda()
+        if local_transform is not None:
+            return
+        if mode == "p2p":
+            self.plan = DistPlan(self.comm, [n0, n1, n2], [0, 1, 2], "slab", layout, "c2c", prec, forward, scale)
+        else:
+            if layout != "transposed" or not forward:
+                raise ValueError_("the NCCL comparison path only does the forward transposed-out transform")
+            self._init_nccl()
 
-    # ------------------------------------------------------------------ CUDA path
-    def _init_cuda(self):
+    # ------------------------------------------------------------------ NCCL comparison path
+    def _init_nccl(self):
         import torch
 
         from .plan import FftPlan
@@ -84,61 +282,31 @@ class SlabFFT3D:
         cplx_bytes = 16 if self.prec == "f64" else 8
         self.block_elems = self.s0 * self.s1 * self.n2
         self.recv_bytes = self.P * self.block_elems * cplx_bytes
-        # pass 1: [s0][n1][n2] FFT over axis 2 (contiguous rows) into a local work buffer
         self.plan_a = FftPlan([self.s0, self.n1, self.n2], [2], "c2c", self.prec, True)
-        # pass 2: FFT over axis 1 whose store scatters the P blocks of axis 1 to their owners
         self.plan_b = FftPlan([self.s0, self.n1, self.n2], [1], "c2c", self.prec, True, 1.0, scatter_parts=self.P)
-        # pass 3: [n0][s1][n2] FFT over axis 0
         self.plan_c = FftPlan([self.n0, self.s1, self.n2], [0], "c2c", self.prec, True)
         self._torch = torch
-        self._calls = 0
-        wk = C.c_void_p()
-        check(lib.sfc_dev_malloc(C.byref(wk), self.P * self.block_elems * cplx_bytes))
-        self._work = wk.value
-        # two receive buffers, used alternately: a rank may start scattering call k+1 into the
-        # other buffer while a slow peer still reads call k's (one rendezvous per call suffices)
-        ptr = C.c_void_p()
-        check(lib.sfc_dev_malloc(C.byref(ptr), 2 * self.recv_bytes))
-        self._recv = ptr.value
-        if self.mode == "p2p":
-            handle = (C.c_ubyte * 64)()
-            check(lib.sfc_ipc_get_handle(C.c_void_p(self._recv), handle))
-            handles: List[Optional[bytes]] = [None] * self.P
-            self.dist.all_gather_object(handles, bytes(handle), group=self.group)
-            self._peers = []
-            for q in range(self.P):
-                if q == self.rank:
-                    self._peers.append(self._recv)
-                else:
-                    p = C.c_void_p()
-                    buf = (C.c_ubyte * 64).from_buffer_copy(handles[q])
-                    check(lib.sfc_ipc_open_handle(buf, C.byref(p)))
-                    self._peers.append(p.value)
-            # block r of every peer's receive buffer is ours to write
-            off = self.rank * self.block_elems * cplx_bytes
-            self._targets = [(C.c_void_p * self.P)(*[p + b * self.recv_bytes + off for p in self._peers])
-                             for b in range(2)]
-        else:
-            s = C.c_void_p()
-            check(lib.sfc_dev_malloc(C.byref(s), self.recv_bytes))
-            self._send = s.value
-            blk = self.block_elems * cplx_bytes
-            self._targets = [(C.c_void_p * self.P)(*[self._send + q * blk for q in range(self.P)])] * 2
-        self._flag = torch.zeros(1, device="cuda")
-
-    def _sync_ranks(self):
-        """Stream-ordered rendezvous: returns (on this stream) only after every rank's earlier
-        kernels on its stream — including their stores into our buffer — have completed."""
-        self.dist.all_reduce(self._flag, group=self.group)
+        bufs = []
+        for _ in range(3):
+            ptr = C.c_void_p()
+            check(lib.sfc_dev_malloc(C.byref(ptr), self.recv_bytes))
+            bufs.append(ptr.value)
+        self._work, self._recv, self._send = bufs
+        blk = self.block_elems * cplx_bytes
+        self._targets = (C.c_void_p * self.P)(*[self._send + q * blk for q in range(self.P)])
 
     def forward_device(self, x_local, out, stream=None, events=None):
-        """x_local: [s0, n1, n2] complex CUDA tensor; out: [n0, s1, n2] complex CUDA tensor.
-        `events` (optional list) receives CUDA events after each stage for a time breakdown."""
+        """x_local: this rank's [s0, n1, n2] slab; out: [n0, s1, n2] (transposed) or [s0, n1, n2] (natural); CUDA
+        tensors or raw device pointers.  Enqueues on `stream` (default: torch's current stream)."""
+        if self.mode == "p2p":
+            if stream is None:
+                import torch
+
+                stream = torch.cuda.current_stream()
+            self.plan.execute_device(x_local, out, getattr(stream, "cuda_stream", stream))
+            return out
         torch = self._torch
         st = torch.cuda.current_stream() if stream is None else stream
-        b = self._calls & 1
-        self._calls += 1
-        recv = self._recv + b * self.recv_bytes
 
         def mark():
             if events is not None:
@@ -149,32 +317,28 @@ class SlabFFT3D:
         mark()
         self.plan_a.execute_device(x_local, self._work, st.cuda_stream)
         mark()
-        check(self.lib.sfc_exec_device_scatter(self.plan_b._h, C.c_void_p(self._work), self._targets[b], self.P,
+        check(self.lib.sfc_exec_device_scatter(self.plan_b._h, C.c_void_p(self._work), self._targets, self.P,
                                                C.c_void_p(st.cuda_stream)))
         mark()
-        if self.mode == "p2p":
-            self._sync_ranks()  # every rank's blocks have landed in our receive buffer
-        else:
-            real_dt = torch.float64 if self.prec == "f64" else torch.float32
-            n = self.P * self.block_elems * 2
-            self.dist.all_to_all_single(_as_tensor(torch, recv, n, real_dt), _as_tensor(torch, self._send, n, real_dt),
+        real_dt = torch.float64 if self.prec == "f64" else torch.float32
+        n = self.P * self.block_elems * 2
+        with torch.cuda.stream(st):  # the collective must be ordered on the stream the plans run on
+            self.dist.all_to_all_single(_as_tensor(torch, self._recv, n, real_dt), _as_tensor(torch, self._send, n, real_dt),
                                         group=self.group)
         mark()
-        self.plan_c.execute_device(recv, out, st.cuda_stream)
+        self.plan_c.execute_device(self._recv, out, st.cuda_stream)
         mark()
         return out
 
     def close(self):
-        if self._recv is not None and self.local_transform is None:
-            lib = self.lib
-            if self._peers:
-                for q, p in enumerate(self._peers):
-                    if q != self.rank:
-                        lib.sfc_ipc_close_handle(C.c_void_p(p))
-            lib.sfc_dev_free(C.c_void_p(self._recv))
-            lib.sfc_dev_free(C.c_void_p(self._work))
-            if self.mode != "p2p":
-                lib.sfc_dev_free(C.c_void_p(self._send))
+        if self.plan is not None:
+            self.plan.close()
+            self.plan = None
+            if self._own_comm:
+                self.comm.close()
+        if self._recv is not None:
+            for p in (self._recv, self._work, self._send):
+                self.lib.sfc_dev_free(C.c_void_p(p))
             self._recv = None
 
     # ------------------------------------------------------------------ host path (tests only)
@@ -225,44 +389,98 @@ def _as_tensor(torch, ptr: int, n: int, dtype):
     return torch.as_tensor(h, device="cuda")
 
 
-def bench_slab_fftn(n: int, steps: int = 5, warmup: int = 3, mode: str = "p2p"):
-    """Timed slab fftn of an n^3 c128 volume over the default process group (used by bench.py)."""
+def bench_slab_fftn(n: int, steps: int = 5, warmup: int = 3, mode: str = "p2p", layout: str = "transposed",
+                    comm: Optional[Communicator] = None, check_parity: bool = True, min_seconds: float = 0.0):
+    """Timed slab fftn of an n^3 c128 volume, one process per GPU (used by bench.py and tests/dist_worker.py).
+
+    mode "p2p": the library path (`sfc_dist_*`); torch only makes the input tensors and the CUDA events.
+    Parity (outside the timed region): every rank builds the WHOLE seeded volume, transforms it with the
+    single-GPU plan on its own GPU and compares its share of the distributed result: `parity_rel_l2` is the max
+    over ranks; above 1e-12 the bench line fails loudly."""
     import torch
     import torch.distributed as dist
 
-    P = dist.get_world_size()
-    f = SlabFFT3D(n, n, n, mode=mode)
-    g = torch.Generator(device="cuda").manual_seed(6 + dist.get_rank())
-    x = torch.view_as_complex(torch.randn(n // P, n, n, 2, dtype=torch.float64, device="cuda", generator=g))
-    out = torch.empty(n, n // P, n, dtype=torch.complex128, device="cuda")
+    P, rank = dist.get_world_size(), dist.get_rank()
+    f = SlabFFT3D(n, n, n, mode=mode, layout=layout, comm=comm)
+    s0, s1 = n // P, n // P
+    st = torch.cuda.current_stream()
+
+    def slab_of(r):
+        g = torch.Generator(device="cuda").manual_seed(6000 + r)
+        return torch.view_as_complex(torch.randn(s0, n, n, 2, dtype=torch.float64, device="cuda", generator=g))
+
+    x = slab_of(rank)
+    out = torch.empty((n, s1, n) if layout == "transposed" else (s0, n, n), dtype=torch.complex128, device="cuda")
     for _ in range(warmup):
         f.forward_device(x, out)
-    dist.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        f.forward_device(x, out)
-    e1.record()
     dist.barrier()
-    torch.cuda.synchronize()
+    reps = steps
+    while True:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            f.forward_device(x, out)
+        e1.record(st)
+        torch.cuda.synchronize()
+        dist.barrier()
+        tm = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        total_ms = float(tm.item())
+        if total_ms >= min_seconds * 1e3 or reps >= 100000:
+            break
+        reps = int(min(100000, max(reps * 2, reps * min_seconds * 1e3 / max(total_ms, 1e-3) * 1.1)))
+    ms = total_ms / reps
     # one more instrumented call for the stage breakdown
-    evs = []
-    f.forward_device(x, out, events=evs)
-    torch.cuda.synchronize()
-    stage = [evs[i].elapsed_time(evs[i + 1]) for i in range(4)]
-    t = torch.tensor([e0.elapsed_time(e1) / steps] + stage, dtype=torch.float64, device="cuda")
+    stage = []
+    if mode == "p2p":
+        f.plan.profile(True)
+        f.forward_device(x, out)
+        torch.cuda.synchronize()
+        stage = f.plan.stage_ms()
+        f.plan.profile(False)
+    else:
+        evs = []
+        f.forward_device(x, out, events=evs)
+        torch.cuda.synchronize()
+        stage = [evs[i].elapsed_time(evs[i + 1]) for i in range(4)]
+    stage = stage + [0.0] * (6 - len(stage))
+    t = torch.tensor(stage[:6], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, t_a, t_b, t_x, t_c = [float(v) for v in t.tolist()]
+    t_a, t_b, t_x, t_c, t_x2, t_cp = [float(v) for v in t.tolist()]
+    parity = None
+    if check_parity:
+        from .plan import FftPlan
+
+        f.forward_device(x, out)
+        torch.cuda.synchronize()
+        full = torch.cat([slab_of(r) for r in range(P)], dim=0)
+        ref = torch.empty_like(full)
+        FftPlan([n, n, n], [0, 1, 2], "c2c", "f64").execute_device(full, ref, st.cuda_stream)
+        torch.cuda.synchronize()
+        want = ref[:, rank * s1:(rank + 1) * s1, :] if layout == "transposed" else ref[rank * s0:(rank + 1) * s0]
+        num = torch.linalg.vector_norm((out - want).reshape(-1))
+        den = torch.linalg.vector_norm(want.reshape(-1))
+        pe = (num / den).reshape(1)
+        dist.all_reduce(pe, op=dist.ReduceOp.MAX)
+        parity = float(pe.item())
+        del full, ref
+        torch.cuda.empty_cache()
+        if not parity <= 1e-12:
+            raise RuntimeError(f"slab fftn {n}^3 on {P} GPUs (mode {mode}, layout {layout}): rel-L2 {parity:.3e} against the "
+                               "single-GPU plan exceeds 1e-12")
     total = float(n) ** 3
     sent = (P - 1) / P * 16.0 * total / P
+    nx = 2 if layout == "natural" else 1
     wire900, wire770 = sent / 900e9 * 1e3, sent / 770e9 * 1e3
-    xchg = t_b + t_x if mode == "p2p" else t_x  # fused FFT+scatter kernel + rendezvous | NCCL all-to-all
+    xchg = t_b + t_x  # fused FFT + scatter kernel + device-side rendezvous | pack kernel + NCCL all-to-all
     res = {
-        "what": f"fftn c128 {n}^3 slab-decomposed over {P} GPUs, mode {mode} (transposed-out layout)",
+        "what": f"fftn c128 {n}^3 slab-decomposed over {P} GPUs, mode {mode}, {layout} layout ({nx} exchange{'s' if nx > 1 else ''})",
         "ms_per_step": round(ms, 4),
+        "steps": reps,
         "gflops": round(5.0 * total * 3 * np.log2(n) / ms / 1e6, 1),
         "scaling": "strong",
+        "parity_rel_l2": parity,
         "stage_ms": {"fft_axis2": round(t_a, 4), "fft_axis1_scatter" if mode == "p2p" else "fft_axis1_pack": round(t_b, 4),
                      "rendezvous" if mode == "p2p" else "nccl_all_to_all": round(t_x, 4), "fft_axis0": round(t_c, 4)},
         "alltoall_bytes_sent_per_gpu": int(sent),
@@ -272,5 +490,7 @@ def bench_slab_fftn(n: int, steps: int = 5, warmup: int = 3, mode: str = "p2p"):
         "nvlink_frac_of_770": round(wire770 / xchg, 4) if xchg > 0 else None,
         "local_hbm_ms_at_measured_peak": round(3 * 2 * 16.0 * total / P / 6553.9e9 * 1e3, 4),
     }
+    if layout == "natural":
+        res["stage_ms"].update({"rendezvous2": round(t_x2, 4), "copy_out": round(t_cp, 4)})
     f.close()
     return res

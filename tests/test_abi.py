@@ -41,15 +41,15 @@ def test_python_binding_covers_header(lib):
     from scirs_b200 import _lib
 
     assert sorted(_lib.SIGNATURES) == header_symbols()
-    assert lib.sfc_abi_version() == 1
+    assert lib.sfc_abi_version() == 2
 
 
 def test_struct_layouts_match_header(lib):
     from scirs_b200 import _lib
 
     # sfc_desc: int32 ndim (+pad) | int64 shape[8] | int32 naxes, axes[8], kind, prec, direction, flags (+pad) | double | int64[8]
-    #           | int32 scatter_parts, reserved | int64 axis_in_len, axis_out_len | void* aux_in, aux_out | double scale_dc
-    assert C.sizeof(_lib.sfc_desc) == 8 + 64 + 4 * 13 + 4 + 8 + 64 + 8 + 16 + 16 + 8
+    #           | int32 scatter_parts, reserved | int64 scatter_pitch | int64 axis_in_len, axis_out_len | void* aux_in, aux_out | double scale_dc
+    assert C.sizeof(_lib.sfc_desc) == 8 + 64 + 4 * 13 + 4 + 8 + 64 + 8 + 8 + 16 + 16 + 8
     assert C.sizeof(_lib.sfc_plan_info) == 8 * 5 + 8 + 4 * 2
     assert C.sizeof(_lib.sfc_cache_stats) == 40
 

@@ -60,7 +60,7 @@ def emul():
         rc = lib.emul_plan_run(C.byref(d), x.ctypes.data_as(C.c_void_p), out_arr.ctypes.data_as(C.c_void_p), buf, len(buf))
         return rc, buf.value.decode()
 
-    def run_scatter(shape, axes, x, outs, parts):
+    def run_scatter(shape, axes, x, outs, parts, pitch=0, inverse=False, scale=1.0):
         d = _lib.sfc_desc()
         d.ndim = len(shape)
         for i, s in enumerate(shape):
@@ -68,7 +68,8 @@ def emul():
         d.naxes = len(axes)
         for i, a in enumerate(axes):
             d.axes[i] = a
-        d.kind, d.prec, d.direction, d.flags, d.scale, d.scatter_parts = _lib.SFC_C2C, _lib.SFC_PREC_F64, 0, 0, 1.0, parts
+        d.kind, d.prec, d.direction, d.flags, d.scale, d.scatter_parts = _lib.SFC_C2C, _lib.SFC_PREC_F64, int(inverse), 0, scale, parts
+        d.scatter_pitch = pitch
         ptrs = (C.c_void_p * parts)(*outs)
         buf = C.create_string_buffer(8192)
         rc = lib.emul_plan_run_scatter(C.byref(d), x.ctypes.data_as(C.c_void_p), ptrs, parts, buf, len(buf))
@@ -284,3 +285,33 @@ def test_slab_fftn_with_the_transpose_fused_into_the_store(emul, P):
         rc, d = emul([n0, s1, n2], [0], recv[q], out)
         assert rc == 0, d
         assert rel(out, ref[:, q * s1:(q + 1) * s1, :]) < 1e-14
+
+
+@pytest.mark.parametrize("P,shape", [(2, (16, 64, 32)), (4, (16, 64, 32)), (2, (32, 16, 64)), (8, (128, 64, 64)), (2, (16, 64, 32)),
+                                     (4, (32, 128, 32)), (2, (64, 64, 64))])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_slab_fftn_natural_layout_second_exchange(emul, P, shape, inverse):
+    """csrc/dist.cu, layout SFC_SLAB_NATURAL, ranks run one after the other on host arrays: the axis-0 pass stores rows
+    [q*s0, (q+1)*s0) straight into rank q's [s0][n1][n2] output at column offset r*s1 (scatter_pitch = n1*n2), which
+    restores axis-0 slabs without a separate transpose — the same plans sfc_dist_plan_create builds."""
+    rng = np.random.default_rng(9)
+    n0, n1, n2 = shape
+    s0, s1 = n0 // P, n1 // P
+    X = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    recv = [np.zeros((n0, s1, n2), dtype=np.complex128) for _ in range(P)]
+    block = s0 * s1 * n2 * 16
+    for r in range(P):
+        x = np.ascontiguousarray(X[r * s0:(r + 1) * s0])
+        work = np.zeros_like(x)
+        rc, d = emul([s0, n1, n2], [2], x, work, inverse=inverse)
+        assert rc == 0, d
+        rc, d = emul.scatter([s0, n1, n2], [1], work, [recv[q].ctypes.data + r * block for q in range(P)], P, inverse=inverse)
+        assert rc == 0, d
+    outs = [np.zeros((s0, n1, n2), dtype=np.complex128) for _ in range(P)]
+    for r in range(P):
+        rc, d = emul.scatter([n0, s1, n2], [0], recv[r], [outs[q].ctypes.data + r * s1 * n2 * 16 for q in range(P)], P,
+                             pitch=n1 * n2, inverse=inverse, scale=0.5)
+        assert rc == 0, d
+    ref = (np.fft.ifftn(X) * X.size if inverse else np.fft.fftn(X)) * 0.5
+    for q in range(P):
+        assert rel(outs[q], ref[q * s0:(q + 1) * s0]) < 1e-14
