@@ -5,6 +5,7 @@
 //! Every function mirrors the reference signature at the cited lines of scirs2-fft/src/.
 pub mod backend;
 pub mod consumers;
+pub mod dist;
 pub mod ffi;
 
 pub use consumers::{dct, dctn, dht, dst, dstn, hfft, hilbert, idct, idctn, idht, idst, idstn, ihfft, DCTType, DSTType};

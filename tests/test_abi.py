@@ -12,6 +12,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "scirs2_fft_cuda.h")
 
 
+def _has_gpu():
+    try:
+        from scirs_b200 import _lib
+
+        return _lib.load().sfc_device_count() > 0
+    except Exception:
+        return False
+
+
 @pytest.fixture(scope="module")
 def lib(build_artifacts):
     from scirs_b200 import _lib
@@ -44,6 +53,23 @@ def test_python_binding_covers_header(lib):
     assert lib.sfc_abi_version() == 2
 
 
+def test_rust_ffi_is_generated_from_the_header():
+    """rust/scirs2-fft-cuda/src/ffi.rs cannot be compiled here (no rustc): it is at least a mechanical image of the header."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "tools", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text = gen.generate()
+    assert open(gen.OUT).read() == text, "ffi.rs is stale: run python tools/gen_rust_ffi.py"
+    rs_fns = set(re.findall(r"pub fn (sfc_[a-z0-9_]+)\(", text))
+    assert sorted(rs_fns) == header_symbols()
+    # every struct the header defines, field for field
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name in re.findall(r"typedef\s+struct\s+(\w+)\s*\{", hdr):
+        assert f"pub struct {name} {{" in text
+
+
 def test_struct_layouts_match_header(lib):
     from scirs_b200 import _lib
 
@@ -52,6 +78,17 @@ def test_struct_layouts_match_header(lib):
     assert C.sizeof(_lib.sfc_desc) == 8 + 64 + 4 * 13 + 4 + 8 + 64 + 8 + 8 + 16 + 16 + 8
     assert C.sizeof(_lib.sfc_plan_info) == 8 * 5 + 8 + 4 * 2
     assert C.sizeof(_lib.sfc_cache_stats) == 40
+    assert C.sizeof(_lib.sfc_dist_desc) == C.sizeof(_lib.sfc_desc) + 16
+    assert C.sizeof(_lib.sfc_dist_info) == 4 * 6 + 8 * 2 + 64 * 2 + 8 + 4 * 2 + 8 + 8
+    # the C compiler's view of the same structs
+    import tempfile
+
+    src = '#include "scirs2_fft_cuda.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(sfc_desc), sizeof(sfc_plan_info), sizeof(sfc_dist_desc), sizeof(sfc_dist_info));return 0;}\n'
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "sz.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.dirname(HEADER), os.path.join(td, "sz.c"), "-o", os.path.join(td, "sz")], check=True)
+        out = subprocess.run([os.path.join(td, "sz")], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v) for v in out] == [C.sizeof(_lib.sfc_desc), C.sizeof(_lib.sfc_plan_info), C.sizeof(_lib.sfc_dist_desc), C.sizeof(_lib.sfc_dist_info)]
 
 
 def test_sm100a_only(lib):
@@ -67,7 +104,7 @@ def test_uses_bulk_async_and_fp64_pipe_not_tensor_cores(lib):
     assert not re.search(r"\b(UTC\w*MMA|HMMA|DMMA)\b", out)
 
 
-@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="CPU-only behaviour")
+@pytest.mark.skipif(_has_gpu(), reason="CPU-only behaviour")
 def test_no_cpu_fallback(lib):
     import scirs_b200 as sb
 

@@ -8,6 +8,15 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _has_gpu():
+    try:
+        from scirs_b200 import _lib
+
+        return _lib.load().sfc_device_count() > 0
+    except Exception:
+        return False
+
+
 def _build(build_artifacts):
     exe = os.path.join(ROOT, "build", "cpp_mirror_test")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
@@ -18,7 +27,7 @@ def _build(build_artifacts):
     return exe
 
 
-@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="CPU-only behaviour")
+@pytest.mark.skipif(_has_gpu(), reason="CPU-only behaviour")
 def test_cpp_mirror_fails_loudly_without_gpu(build_artifacts):
     out = subprocess.run([_build(build_artifacts)], capture_output=True, text=True)
     assert out.returncode == 0 and "BackendError ok" in out.stdout, out.stdout + out.stderr

@@ -55,7 +55,7 @@ def _spawn(world, case, sizes, timeout=900):
     return records
 
 
-@pytest.mark.parametrize("world", _worlds() if os.path.exists("/dev/nvidia0") else [1])
+@pytest.mark.parametrize("world", _worlds())
 def test_slab_and_batch_split_one_process_per_gpu_host_buffers(build_artifacts, world):
     recs = _spawn(world, "host", "64,256")
     worst64 = max(r["rel_l2"] for r in recs if r["prec"] == "f64")
@@ -65,7 +65,7 @@ def test_slab_and_batch_split_one_process_per_gpu_host_buffers(build_artifacts, 
     assert {r["layout"] for r in recs} >= {"transposed", "natural", "batch_split"}
 
 
-@pytest.mark.parametrize("world", _worlds() if os.path.exists("/dev/nvidia0") else [1])
+@pytest.mark.parametrize("world", _worlds())
 def test_slab_one_process_per_gpu_device_buffers_and_symmetric_output(build_artifacts, world):
     recs = _spawn(world, "device", "128,512")
     assert max(r["rel_l2"] for r in recs) <= 1e-12
