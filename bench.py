@@ -102,7 +102,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for l in self.lines:
             f = [t.strip() for t in l.split(",")]
@@ -111,13 +111,16 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 mx = float(f[1])
+                pw.append(float(f[2]))
             except ValueError:
                 continue
             for nme, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+        pw.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons),
+                "power_w": pw[len(pw) // 2] if pw else None}
 
 
 def flops_of(shape, axes, kind):
@@ -270,6 +273,7 @@ def run_gpu(args):
         c1.record(stream)
         torch.cuda.synchronize()
         t1 = max(max_over_ranks(c0.elapsed_time(c1) / 3.0), 1e-3)  # ms per execution
+        burst_ms = c0.elapsed_time(c1) / 3.0  # this rank, before any sustained load: the "kernel timed alone" figure
         reps = max(1, int(math.ceil(min_total_s * 1e3 / (steps * t1))))
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
@@ -307,7 +311,7 @@ def run_gpu(args):
         info = plan.info
         del din, dout
         return {"ms_per_step": total_ms / steps, "ms_per_exec": total_ms / steps / reps, "kernel_ms": sum(per) / len(per) / reps,
-                "reps": reps, "timed_s": total_ms / 1e3, "info": info, "plan": plan, "clocks": clocks}
+                "burst_ms": burst_ms, "reps": reps, "timed_s": total_ms / 1e3, "info": info, "plan": plan, "clocks": clocks}
 
     def summarize(workload, r):
         shape, axes, kind, prec, fwd, desc = WORKLOADS[workload]
@@ -351,7 +355,12 @@ def run_gpu(args):
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src, "kernel": "sfc::tile_fft_kernel",
                 "algorithmic_bytes_per_launch": alg // nl, "kernel_ms": round(r["kernel_ms"] / nl, 4),
-                "timed_region_s": round(r["timed_s"], 3), "executions_per_step": reps}
+                "timed_region_s": round(r["timed_s"], 3), "executions_per_step": reps,
+                # the same kernel timed alone on a cool GPU (3 executions before any sustained load): what a burst measurement
+                # such as MEASURED_PEAKS.json's copy sees; `frac` above is the SUSTAINED figure (power-capped clocks)
+                "burst": {"kernel_ms": round(r["burst_ms"] / nl, 4), "frac": round(alg / r["burst_ms"] / 1e6 / hbm, 4)},
+                "note": "sustained: a plain device copy at 6.54 TB/s already draws 974 W of the 1000 W cap on this part "
+                        "(profiles/r2d_copy_power_tmap.log), so FP64 transform work on top of full-rate HBM traffic lowers the clocks"}
 
     # ---------------- e2e through the C ABI with pinned host buffers
     e2e = None

@@ -13,7 +13,8 @@ from .fft import (fft, ifft, rfft, irfft, fft2, ifft2, fft2_parallel, ifft2_para
                   rfft_simd, irfft_simd, rfft_adaptive, irfft_adaptive, rfft_batch, irfft_batch)
 from .consumers import (DCTType, DSTType, dct, idct, dct2, idct2, dctn, idctn, dst, idst, dst2, idst2, dstn, idstn,
                         dht, idht, dht2, fht, hfft, ihfft, hilbert, get_window, stft, spectrogram, FftMode, fft_inplace,
-                        process_in_chunks, fft2_efficient, fft_streaming, fftn_optimized)
+                        process_in_chunks, fft2_efficient, fft_streaming, fftn_optimized, fftn_memory_efficient,
+                        rfftn_optimized)
 from .czt import CZT, czt, czt_points, zoom_fft
 from . import signal  # the scirs2-signal callers keep their own namespace (their stft / spectrogram differ from scirs2-fft's)
 from .plan import FftPlan, FftPlanExecutor
@@ -26,6 +27,7 @@ from .backend import FftBackend, CudaFftBackend, BackendManager, BackendContext,
 from .context import (WorkerConfig, WorkerPool, WorkerPoolInfo, get_global_pool, set_workers, get_workers, FftContext,
                       FftContextBuilder, fft_context, with_fft_settings, with_backend, with_workers, without_cache)
 from .planning import (PlannerBackend, PlanningStrategy, AdvancedFftPlanner, PlanBuilder, ParallelExecutor,
-                       ParallelPlanner, get_global_planner, plan_ahead_of_time)
+                       ParallelPlanner, get_global_planner, plan_ahead_of_time, AdaptivePlanningConfig, AdaptivePlanner,
+                       AdaptiveExecutor)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

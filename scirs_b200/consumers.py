@@ -356,3 +356,44 @@ def fftn_optimized(x, shape=None, axes: Optional[Sequence[int]] = None) -> np.nd
     out = np.empty(a.shape, dtype=np.complex128)
     check(lib.sfc_fftn_optimized(_ptr(a), a.ndim, sh, ax, 0 if axes is None else len(axes), _ptr(out)))
     return out
+
+
+def fftn_memory_efficient(x, axes: Optional[Sequence[int]] = None, max_memory_gb: float = 0.0) -> np.ndarray:
+    """ndim_optimized.rs:159-211: the same per-axis `fft(&lane, None)` loop as `fftn_optimized`, one axis at a time
+    (`max_memory_gb` is ignored there too).  Axes longer than 2^20 take the reference's "simplified chunking"
+    (:214-249: independent 65,536-point transforms of consecutive chunks, the last chunk padded to a power of two and cut
+    back) — reproduced as written, because that is what a caller of the reference gets."""
+    a = _real(x)
+    ax = list(range(a.ndim)) if axes is None else [int(v) for v in axes]
+    for v in ax:
+        if v < 0 or v >= a.ndim:
+            raise ValueError_(f"Axis {v} is out of bounds for array with {a.ndim} dimensions")
+    if all(a.shape[v] <= 1048576 for v in ax):
+        return fftn_optimized(a, None, ax)
+    from .fft import fftn as _fftn
+
+    res = a.astype(np.complex128)
+    for v in ax:
+        n = res.shape[v]
+        if n <= 1048576:
+            p = 1 << max(n - 1, 0).bit_length()
+            res = np.ascontiguousarray(np.take(_fftn(res, [p if i == v else s for i, s in enumerate(res.shape)], [v]), range(n), axis=v))
+            continue
+        moved = np.moveaxis(res, v, -1)
+        out = np.empty_like(moved)
+        for s0 in range(0, n, 65536):
+            e0 = min(s0 + 65536, n)
+            cl = e0 - s0
+            p = 1 << max(cl - 1, 0).bit_length()
+            chunk = np.ascontiguousarray(moved[..., s0:e0])
+            out[..., s0:e0] = _fftn(chunk, list(chunk.shape[:-1]) + [p], [chunk.ndim - 1])[..., :cl]
+        res = np.ascontiguousarray(np.moveaxis(out, -1, v))
+    return res
+
+
+def rfftn_optimized(x, shape=None, axes: Optional[Sequence[int]] = None) -> np.ndarray:
+    """ndim_optimized.rs:252-301.  The reference is a placeholder there (its real transform is computed and dropped, the
+    result array stays zero); this is the transform that code sets out to compute: the complex spectrum of the real input
+    over `axes` (every axis by default), in an array of the input's shape, through the same per-axis
+    `fft(&lane, None)` semantics as `fftn_optimized`."""
+    return fftn_optimized(x, shape, axes)

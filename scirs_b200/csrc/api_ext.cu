@@ -37,11 +37,12 @@ bool fuse_enabled() {
     return v != 0;
 }
 
-// the fused type-IV kernel (TM_FAST_DCT4) was written after the round's GPU budget was spent: off until it has been run
+// the fused type-IV kernel (TM_FAST_DCT4): measured 63-66 % of its roofline against 12 % for the 2n-point formulation
+// (profiles/r2a_first_run.log), parity <= 1e-12 (tests/test_gpu_experimental.py); on by default since round 2
 bool dct4_fused_enabled() {
     static int v = [] {
         const char* e = getenv("SFC_DCT4_FUSED");
-        return e ? atoi(e) : 0;
+        return e ? atoi(e) : 1;
     }();
     return v != 0;
 }

@@ -389,10 +389,20 @@ struct Xch {
 // MIRROR_IN (complex-to-real transforms, same lengths): the radix-8 stage comes FIRST and the thread
 // again owns butterfly i and its mirror, so the Hermitian pre-pass pairs X[k], X[L-k] come straight
 // from the thread's own global loads.
-template <typename T, typename C, int S, bool FIRST, bool MIRROR = false, bool MIRROR_IN = false, bool NOTW1 = false>
+// what the late-prefetch flavour does once the exchange buffer is idle (after the last exchange has been read)
+struct LateIssue {
+    const PassParams* p;
+    uint32_t next_blk;
+    uint32_t bar;
+    uint32_t land;
+};
+template <typename T, int L, int TL>
+__device__ __forceinline__ void late_issue(const LateIssue& h);
+
+template <typename T, typename C, int S, bool FIRST, bool MIRROR = false, bool MIRROR_IN = false, bool NOTW1 = false, bool HOOK = false>
 __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__ sm,
                                            const Cx<T>* __restrict__ tw, int tw_, int iw, int tr,
-                                           int ir, int grp = 0) {
+                                           int ir, int grp = 0, const LateIssue* hook = nullptr) {
     constexpr int L = C::L, E = C::E, TPL = C::TPL;
     constexpr int REM = 1 << (ilog2(L) % ilog2(E));  // the one radix smaller than E (1 = none)
     constexpr int R = MIRROR_IN ? ((S == 1 && REM > 1) ? REM : E) : ((L / S >= E) ? E : (L / S));
@@ -479,7 +489,13 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
 #pragma unroll
             for (int m = 0; m < E; ++m) a[m] = src[Xch<C, R, S>::read_off(m)];
         }
-        run_stages<T, C, S * R, false, MIRROR, MIRROR_IN>(a, sm, tw, tr, ir, tr, ir, grp);
+        if constexpr (HOOK && SN * RN == L) {
+            // the stage that follows is the last one and never touches shared memory again: once every thread holds its
+            // elements the buffer is free for the next tile's data
+            C::sync(grp);
+            late_issue<T, C::L, C::TL>(*hook);
+        }
+        run_stages<T, C, S * R, false, MIRROR, MIRROR_IN, false, HOOK>(a, sm, tw, tr, ir, tr, ir, grp, hook);
     }
 }
 
@@ -666,6 +682,13 @@ enum TileMode : int {
     // aux_out[kc1 * c_rest] (W_C^j) and stored at k2*mid_es + kc1*mid_ls (the two mid_* strides are free here: not a double
     // kernel).  NOT YET RUN ON A GPU: planner knob SFC_FFT2_TILE2D=1, parity check in tests/test_gpu_experimental.py.
     TM_FAST_2D = 8,
+    // TM_FAST_C2C made persistent with a LATE prefetch that costs no shared memory: once the last exchange of a tile has
+    // been read back into registers the exchange buffer is idle for the rest of the tile (last radix stage, store
+    // operators, stores), so the TMA unit lands the NEXT tile in it (cp.async.bulk + mbarrier) during that time.  The
+    // next tile then starts with its data already on chip: the global-load latency of every tile but the first hides
+    // behind the previous tile's tail, with the full-size exchange buffer and the same number of CTAs per SM as the
+    // plain flavour.  Contiguous-row tiles (1-D bulk copies) and, through a tensor map, strided column tiles.
+    TM_PIPE_LATE = 9,
 };
 
 // ---- TMA / mbarrier primitives (PTX) -----------------------------------------------------------
@@ -694,6 +717,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  : "memory");
 }
 
+// one box of a 4-D tiled tensor map -> shared memory, completion on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+
 // blockIdx-level index -> (tile, batch)
 __device__ __forceinline__ void decode_block(const PassParams& p, uint32_t blk, uint32_t& tile, uint32_t& batch) {
     if (p.nbatch_fast) {
@@ -716,7 +747,19 @@ __device__ __forceinline__ void pipe_issue(const PassParams& p, uint32_t blk, ui
     if (lane_id == 0) mbar_expect_tx(bar, (uint32_t)(TL * L * sizeof(Cx<T>)));
     __syncwarp();
     const Cx<T>* base = reinterpret_cast<const Cx<T>*>(p.in.ptr) + (int64_t)batch * p.in.batch_stride;
-    if (p.map_in == MAP_COL) {
+    if (p.map_in == MAP_COL && (p.flags & F_TMAP_IN)) {
+        // strided tile through the tensor map: boxes of [tmap_box_rows elements][TL lanes], dense in shared memory
+        const uint32_t lane0 = tile * TL;
+        int c0 = (int)lane0, c2 = 0;
+        if (p.tmap_split) {
+            const uint32_t lo = lane0 / p.inner_count;
+            c0 = (int)(lane0 - lo * p.inner_count);
+            c2 = (int)lo;
+        }
+        const int rows = p.tmap_box_rows;
+        for (int r = lane_id * rows; r < L; r += 32 * rows)
+            tma_load_4d(land + (uint32_t)(r * TL * sizeof(Cx<T>)), p.tmap_in, 2 * c0, r, c2, (int)batch, bar);
+    } else if (p.map_in == MAP_COL) {
         // element rows of TL adjacent lanes: L copies of TL * sizeof(cx) bytes
         const uint32_t lane0 = tile * TL;
         const uint32_t lo = lane0 / p.inner_count, li = lane0 - lo * p.inner_count;
@@ -732,6 +775,14 @@ __device__ __forceinline__ void pipe_issue(const PassParams& p, uint32_t blk, ui
             const Cx<T>* src = base + (int64_t)lo * p.in.outer_stride + (int64_t)li * p.in.inner_stride;
             bulk_g2s(land + (uint32_t)(t * L * sizeof(Cx<T>)), src, (uint32_t)(L * sizeof(Cx<T>)), bar);
         }
+    }
+}
+
+template <typename T, int L, int TL>
+__device__ __forceinline__ void late_issue(const LateIssue& h) {
+    if (threadIdx.x < 32 && h.next_blk < h.p->total_tiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the buffer before the async-proxy writes
+        pipe_issue<T, L, TL>(*h.p, h.next_blk, h.land, h.bar);
     }
 }
 
@@ -766,6 +817,7 @@ template <typename T, int L, int TL, bool DOUBLE, int EMAX, int MODE, int GROUPS
 __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t blk, Cx<T>* sm, const Cx<T>* land,
                                           uint32_t bar, uint32_t parity, uint32_t next_blk, uint32_t bar_next) {
     constexpr bool PIPE = MODE == TM_PIPE_C2C;
+    constexpr bool LATE = MODE == TM_PIPE_LATE;  // data of this tile was landed in the exchange buffer during the previous tile's tail
     constexpr bool GP = PIPE && GROUPS == 2;  // group-pipelined: each thread group walks over its own tiles of TLG lanes
     using C = TileCfg<T, L, TL, EMAX, GROUPS, PIPE && GROUPS == 1>;
     constexpr int LT = GP ? C::TLG : TL;      // lanes per scheduled tile
@@ -930,6 +982,24 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
                     a[m] = cmul(sine ? cx{od, ev} : cx{ev, od}, pre[j]);
                 }
             }
+        } else if constexpr (LATE) {
+            mbar_wait(bar, parity);
+            const cx* src = (p.map_in == MAP_COL) ? land + (i0 * TL + t0) : land + (t0 * L + i0);
+            const int step = (p.map_in == MAP_COL) ? TPL * TL : TPL;
+#pragma unroll
+            for (int m = 0; m < E; ++m) a[m] = src[m * step];
+            // (the barrier that frees the buffer for the first exchange is the one run_stages<FIRST = false> starts with)
+            if (p.flags & F_CONJ_LD_PRE) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
+            }
+            if (p.ld_op == LD_C_MUL && (p.flags & F_CHIRP_GEN)) {
+                chirp_apply<T, E>(a, p, (int64_t)i0 * p.in.pos_es + pos0, (int64_t)TPL * p.in.pos_es, p.chirp_q_in);
+            } else if (p.ld_op == LD_C_MUL) {
+                const cx* __restrict__ aux = reinterpret_cast<const cx*>(p.aux_in);
+#pragma unroll
+                for (int m = 0; m < E; ++m) a[m] = cmul(a[m], aux[(int64_t)(i0 + m * TPL) * p.in.pos_es + pos0]);
+            }
         } else if constexpr (PIPE) {
             // the tile was landed in shared memory by the TMA unit while the previous one was transformed
             mbar_wait(bar, parity);
@@ -1091,6 +1161,10 @@ __device__ __forceinline__ void tile_body(const PassParams& p, const uint32_t bl
         run_stages<T, C, 1, false>(a, sm, tw, t0, i0, t1, i1, grp);
     } else if constexpr (MODE == TM_FAST_2D) {
         run_stages<T, C, 1, true, false, false, true>(a, sm, tw, t0, i0, t1, i1, grp);
+    } else if constexpr (LATE) {
+        static_assert(!DOUBLE && C::E < C::L && GROUPS == 1, "late prefetch: plain multi-stage complex tiles");
+        const LateIssue hook{&p, next_blk, bar_next, smem_u32(sm)};
+        run_stages<T, C, 1, false, false, false, false, true>(a, sm, tw, t0, i0, t1, i1, grp, &hook);
     } else if constexpr (FAST) {
         run_stages<T, C, 1, true>(a, sm, tw, t0, i0, t1, i1, grp);
     } else {
@@ -1408,7 +1482,16 @@ __global__ void __launch_bounds__(TileCfg<T, L, TL, EMAX, GROUPS>::NT, TileCfg<T
 tile_fft_kernel(const __grid_constant__ PassParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Cx<T>* sm = reinterpret_cast<Cx<T>*>(smem_raw);
-    if constexpr (MODE != TM_PIPE_C2C) {
+    if constexpr (MODE == TM_PIPE_LATE) {
+        using C = TileCfg<T, L, TL, EMAX, GROUPS, false>;
+        const uint32_t bar = smem_u32(smem_raw + C::SMEM);  // one mbarrier behind the exchange buffer
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x < 32 && blockIdx.x < p.total_tiles) pipe_issue<T, L, TL>(p, blockIdx.x, smem_u32(sm), bar);
+        uint32_t parity = 0;
+        for (uint32_t blk = blockIdx.x; blk < p.total_tiles; blk += gridDim.x, parity ^= 1u)
+            tile_body<T, L, TL, DOUBLE, EMAX, MODE, GROUPS>(p, blk, sm, sm, bar, parity, blk + gridDim.x, bar);
+    } else if constexpr (MODE != TM_PIPE_C2C) {
         tile_body<T, L, TL, DOUBLE, EMAX, MODE, GROUPS>(p, blockIdx.x, sm, nullptr, 0u, 0u, 0u, 0u);
     } else if constexpr (GROUPS == 1) {
         using C = TileCfg<T, L, TL, EMAX, GROUPS, true>;

@@ -9,7 +9,9 @@ template <typename T, int L, int TL, bool DBL, int EMAX = 16, int MODE = 0, int 
 struct KernelInst {
     using C = TileCfg<T, L, TL, EMAX, GROUPS, MODE == TM_PIPE_C2C && GROUPS == 1>;
     static constexpr bool GP = MODE == TM_PIPE_C2C && GROUPS == 2;
-    static constexpr size_t SMEM_BYTES = GP ? C::SMEM_GP : C::SMEM;
+    static constexpr bool LATE = MODE == TM_PIPE_LATE;
+    static constexpr bool PERSISTENT = MODE == TM_PIPE_C2C || LATE;
+    static constexpr size_t SMEM_BYTES = GP ? C::SMEM_GP : (LATE ? C::SMEM + 16 : C::SMEM);
     static cudaError_t launch(const PassParams& p0, unsigned grid, cudaStream_t s) {
         PassParams p = p0;
         static bool configured[64] = {};
@@ -22,7 +24,7 @@ struct KernelInst {
             if (e != cudaSuccess) return e;
             configured[dev] = true;
         }
-        if (MODE == TM_PIPE_C2C) {
+        if (PERSISTENT) {
             // persistent: as many CTAs as can be resident (2 per SM), each walking over its share of the tiles
             static int resident[64] = {};
             if (dev < 64 && !resident[dev]) {
@@ -86,4 +88,6 @@ struct KernelInst {
 #define SFC_ADD_DCT4(T, L, TL) add(::sfc::KernelInst<T, L, TL, false, 16, 7>::entry());
 // middle pass of the three-pass 2-D plan (16 x L/16 two-dimensional tile)
 #define SFC_ADD_2D(T, L, TL) add(::sfc::KernelInst<T, L, TL, false, 16, 8>::entry());
+// persistent flavour with the late prefetch into the idle exchange buffer (no extra shared memory)
+#define SFC_ADD_PIPE_LATE(T, L, TL) add(::sfc::KernelInst<T, L, TL, false, 16, 9>::entry());
 #define SFC_ADD_E(T, L, TL, DBL, E) add(::sfc::KernelInst<T, L, TL, DBL, E>::entry());

@@ -54,7 +54,10 @@ enum PassFlags : uint32_t {
     // inter-pass twiddle applied on the way IN (W^(e * lane_outer) from ld_tw_*; conjugated with F_LD_TW_CONJ):
     // the inverse half of the three-level Bluestein, whose twiddle index is (element, lane) of the NEXT pass
     F_LD_TW = 1u << 12,
-    F_LD_TW_CONJ = 1u << 13,     // LD_*_MUL / ST_MUL: generate the Bluestein chirp in registers instead of reading aux_*    // likewise for stores       // store only the real part into a real array (irfftn, rfft.rs:722)
+    F_LD_TW_CONJ = 1u << 13,
+    // late-prefetch flavour, strided (column) tiles: the tile is landed by ONE-to-FEW cp.async.bulk.tensor copies through
+    // the tensor map tmap_in (a 4-D view [batch][outer][element][lane] of the input array) instead of per-row bulk copies
+    F_TMAP_IN = 1u << 14,     // LD_*_MUL / ST_MUL: generate the Bluestein chirp in registers instead of reading aux_*    // likewise for stores       // store only the real part into a real array (irfftn, rfft.rs:722)
 };
 
 struct IoDesc {
@@ -106,6 +109,12 @@ struct PassParams {
     // peer_shift < 0 = off.  The pointers may be peer-GPU memory mapped over NVLink.
     int32_t peer_shift;
     void* peer_out[16];
+    // F_TMAP_IN: CUtensorMap (opaque, 128 bytes, 64-byte aligned) encoded by Plan::exec for the input pointer of this launch;
+    // dims (fastest first) = [2 * lanes-contiguous][L elements][outer][batch] in units of the real type
+    alignas(64) unsigned char tmap_in[128];
+    int32_t tmap_box_rows;   // elements of the transform axis per box (min(L, 256)); L / tmap_box_rows copies per tile
+    int32_t tmap_split;      // 0: lanes are contiguous over the whole batch (coordinate 0 = first lane of the tile);
+                             // 1: coordinate 0 = lane inside its outer group, coordinate 2 = the outer index
 #ifdef SFC_PHASE_TIMING
     unsigned long long* dbg;   // developer build only: per-launch phase clock sums (thread 0 of every CTA)
 #endif

@@ -9,6 +9,9 @@
 #include <cstring>
 #include <map>
 #include <tuple>
+#ifndef SFC_HOST_EMUL
+#include <cuda.h>  // CUtensorMap + enums only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked
+#endif
 
 namespace sfc {
 
@@ -502,6 +505,28 @@ static int64_t gpipe_min_tiles() {
     }();
     return v;
 }
+// late-prefetch persistent flavour (TM_PIPE_LATE).  Measured on B200 (profiles/r2c_sustained_ab.log, r2d_copy_power_tmap.log):
+//   contiguous rows (1-D bulk copies): c2c 65,536 x 4096 79.3 % -> 75.3 % sustained, 8192-point rows 58.6 % -> 55.6 %,
+//   2048-point rows 85.2 % -> 82.9 %: the extra shared-memory read of the landed tile costs more than the hidden latency;
+//   strided tiles through a tensor map (UTMALDG): 512 x 8 tiles (128 B segments) lose (fftn 512^3 91.7 % -> 83.5 %), the
+//   1024 x 4 tiles of the four-step path (64 B segments, where per-thread loads are least efficient) gain (2^20 x 64:
+//   75.0 % -> 78.1 %).
+// 0 off | 1 row tiles <= 64 KiB | 2 + 128 KiB row tiles | 3 + every strided tile | 4 (default) only the narrow strided tiles
+// (<= 64 B segments) and multi-row tiles of multi-pass (four-step) plans.
+static int pipe_late_enabled() {
+    static int v = [] {
+        const char* e = getenv("SFC_PIPE_LATE");
+        return e ? atoi(e) : 4;
+    }();
+    return v;
+}
+static int64_t pipe_late_min_tiles() {
+    static int64_t v = [] {
+        const char* e = getenv("SFC_PIPE_LATE_MIN_TILES");
+        return e ? atoll(e) : 4 * 148;  // two tiles for each of the 296 resident CTAs, or prefetching never pays
+    }();
+    return v;
+}
 static bool pipe_big_enabled() {
     static int v = [] {
         const char* e = getenv("SFC_PIPE_BIG");
@@ -687,11 +712,41 @@ struct PlanBuilder {
                         break;
                     }
             }
+            // late-prefetch persistent flavour: contiguous complex rows, no masks; the next tile lands in the idle exchange buffer
+            // (knob value 1: tiles up to 64 KiB; 2: the 128 KiB row tiles too, instead of the split-exchange pipelined flavour)
+            const int plv = pipe_late_enabled();
+            const bool narrow = s.k->TL * (int)cs <= 64 && s.k->L * s.k->TL * (int)cs == 65536;  // the 64 KiB tiles with <= 64 B segments
+            if (mode == 1 && s.k->mode == 1 && plv && !s.k->dbl && (s.p.flags & F_IN_NOMASK) &&
+                (plv == 2 || plv == 3 || s.k->L * s.k->TL * (int)cs <= 65536) &&
+                (s.p.ld_op == LD_C || s.p.ld_op == LD_C_MUL) && !(s.p.flags & F_STAGE_IN) &&
+                tiles * nbatch * std::max<int64_t>(s.batch_mult, 1) >= pipe_late_min_tiles()) {
+                const bool rows_ok = s.p.map_in == MAP_ROW && s.p.in.elem_stride == 1 &&
+                                     (plv <= 3 || (narrow && s.group >= 0 && s.k->TL >= 2));
+                // strided tiles: TL adjacent lanes must be adjacent in memory -> one tensor-map box per <= 256 elements
+                int tm = 0;
+                if (s.p.map_in == MAP_COL && (plv == 3 || (plv == 4 && narrow && s.group >= 0)) && s.k->TL <= 128) {
+                    if ((s.p.inner_count == 1 && s.p.in.outer_stride == 1) ||
+                        (s.p.in.inner_stride == 1 && s.p.in.outer_stride == (int64_t)s.p.inner_count))
+                        tm = 1;
+                    else if (s.p.in.inner_stride == 1 && (int64_t)s.p.inner_count % s.k->TL == 0)
+                        tm = 2;
+                }
+                if (rows_ok || tm) {
+                    const KernelEntry* f = flavour_of(s.k, 9);
+                    if (f) {
+                        s.k = f;
+                        if (!rows_ok) {
+                            s.tmap = tm;
+                            s.p.flags |= F_TMAP_IN;
+                        }
+                    }
+                }
+            }
             // persistent TMA-pipelined flavour: unmasked complex loads of tiles whose TL lanes are adjacent in
             // memory (16-byte aligned bulk copies), and enough tiles for every resident CTA to pipeline a few
             // 128 KiB row tiles (one CTA per SM: nothing else overlaps its loads) always take it when they can
             const bool big_row = s.k->L * s.k->TL * (int)cs > 65536 && s.p.map_in == MAP_ROW && pipe_big_enabled();
-            if (mode == 1 && s.k->mode == 1 && (pipe_enabled() || big_row) && (s.p.flags & F_IN_NOMASK) &&
+            if (mode == 1 && s.k->mode == 1 && (pipe_enabled() || (big_row && pipe_late_enabled() < 2)) && (s.p.flags & F_IN_NOMASK) &&
                 (s.p.ld_op == LD_C || s.p.ld_op == LD_C_MUL) && prec == PREC_F64) {
                 const bool rows_ok = s.p.map_in == MAP_ROW && s.p.in.elem_stride == 1;
                 const bool cols_ok = pipe_enabled() == 1 && s.p.map_in == MAP_COL &&
@@ -722,7 +777,7 @@ struct PlanBuilder {
         snprintf(buf, sizeof buf, "%s: tile L=%d TL=%d%s%s threads=%d smem=%zu lanes=%lld batches=%lld map=%s->%s", what,
                  s.k->L, s.k->TL, s.k->dbl ? " fwd*tab*inv" : "",
                  s.k->groups > 1 ? (s.k->mode == 4 ? " group-pipelined" : (s.k->mode ? " fast 2-groups" : " generic 2-groups"))
-                                  : (s.k->mode == 0 ? " generic" : (s.k->mode == 1 ? " fast" : (s.k->mode == 2 ? " fast-r2c" : (s.k->mode == 3 ? " fast-c2r" : (s.k->groups == 2 ? " group-pipelined" : " pipelined"))))), s.k->threads, s.k->smem, (long long)nlanes,
+                                  : (s.k->mode == 0 ? " generic" : (s.k->mode == 1 ? " fast" : (s.k->mode == 2 ? " fast-r2c" : (s.k->mode == 3 ? " fast-c2r" : (s.k->mode == 9 ? " late-prefetch" : (s.k->groups == 2 ? " group-pipelined" : " pipelined")))))), s.k->threads, s.k->smem, (long long)nlanes,
                  (long long)nbatch, s.p.map_in == MAP_ROW ? "row" : "col", s.p.map_out == MAP_ROW ? "row" : "col");
         s.desc = buf;
         pl.steps_.push_back(s);
@@ -1968,6 +2023,61 @@ extern "C" __attribute__((visibility("default"))) void sfc_debug_phase_dump(void
 }
 #endif
 
+// 4-D tiled tensor map over the input of a strided pass: [batch][outer][element of the axis][2 * contiguous lanes] in units of
+// the real type; one box = [rows][TL lanes].  Encoded per launch (the base pointer is a launch argument); ~1 us on the host.
+static bool encode_tile_map(PassParams& p, const KernelEntry* k, int mode, int64_t nbatch, std::string& es) {
+#ifdef SFC_HOST_EMUL
+    (void)p; (void)k; (void)mode; (void)nbatch;
+    es = "tensor maps are not emulated";
+    return false;
+#else
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) {
+            cudaGetLastError();
+            return (EncodeFn) nullptr;
+        }
+        return (EncodeFn)f;
+    }();
+    if (!fn) {
+        es = "cuTensorMapEncodeTiled is not available from this driver";
+        return false;
+    }
+    const bool f64 = k->prec == PREC_F64;
+    const uint64_t cs = f64 ? 16 : 8;
+    const uint64_t C = mode == 1 ? p.nlanes : p.inner_count;
+    const uint64_t NO = mode == 1 ? 1 : p.nlanes / p.inner_count;
+    cuuint64_t dims[4] = {2 * C, (cuuint64_t)k->L, NO, (cuuint64_t)std::max<int64_t>(nbatch, 1)};
+    cuuint64_t str[3];
+    str[0] = (cuuint64_t)p.in.elem_stride * cs;
+    str[1] = NO > 1 ? (cuuint64_t)p.in.outer_stride * cs : str[0] * dims[1];
+    str[2] = dims[3] > 1 ? (cuuint64_t)p.in.batch_stride * cs : str[1] * dims[2];
+    const cuuint32_t rows = (cuuint32_t)std::min(k->L, 256);
+    cuuint32_t box[4] = {(cuuint32_t)(2 * k->TL), rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMap m;
+    const CUresult r = fn(&m, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.in.ptr, dims, str, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[160];
+        snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu x %llu", (int)r, (unsigned long long)dims[0],
+                 (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3]);
+        es = b;
+        return false;
+    }
+    static_assert(sizeof(CUtensorMap) == sizeof(p.tmap_in), "tensor map size");
+    memcpy(p.tmap_in, &m, sizeof m);
+    p.tmap_box_rows = (int32_t)rows;
+    p.tmap_split = mode == 2 ? 1 : 0;
+    return true;
+#endif
+}
+
 int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& es, void* const* scatter, int nscatter) {
     std::lock_guard<std::mutex> lk(mu_);
     bool uses_scratch = sa_bytes_ || ms_bytes_;
@@ -2047,6 +2157,7 @@ int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& 
 #ifdef SFC_PHASE_TIMING
             p.dbg = getenv("SFC_PHASE_DBG") ? dbg_slot(s.desc) : nullptr;
 #endif
+            if (s.tmap && !encode_tile_map(p, s.k, s.tmap, s.nbatch, es)) return SFC_ERR_BACKEND;
             cudaError_t e = s.k->launch(p, (unsigned)grid, stream);
             if (e != cudaSuccess) return fail(e, s);
             ++i;
@@ -2092,6 +2203,7 @@ int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& 
 #ifdef SFC_PHASE_TIMING
                 p.dbg = getenv("SFC_PHASE_DBG") ? dbg_slot(t.desc) : nullptr;
 #endif
+                if (t.tmap && !encode_tile_map(p, t.k, t.tmap, nb * t.batch_mult, es)) return SFC_ERR_BACKEND;
                 cudaError_t e = t.k->launch(p, (unsigned)grid, st);
                 if (e != cudaSuccess) return fail(e, t);
             }

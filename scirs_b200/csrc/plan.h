@@ -34,6 +34,7 @@ struct Step {
     int group = -1;                          // steps sharing a group are chunk-looped together
     bool batch_fastest = false;              // CTA order: batch index fastest (table reuse in L2)
     bool scatter = false;                    // store through the caller's per-block pointer table
+    int tmap = 0;                            // late-prefetch column tiles: 1 = lanes contiguous over the batch, 2 = per outer group
     int64_t nbatch = 1;                      // batches (blockIdx-level outer index)
     int64_t batch_mult = 1;                  // grouped steps: blockIdx-level batches per group batch (three-level inner passes)
     std::string desc;

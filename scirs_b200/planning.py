@@ -144,3 +144,106 @@ class ParallelPlanner:
 
     def clear_cache(self) -> None:
         self._planner.clear_cache()
+
+
+# ------------------------------------------------------------------ planning_adaptive.rs
+
+
+class AdaptivePlanningConfig:
+    """planning_adaptive.rs:13-45"""
+
+    def __init__(self, enabled: bool = True, min_samples: int = 5, evaluation_interval: float = 10.0,
+                 max_strategy_switches: int = 3, enable_backend_switching: bool = True, improvement_threshold: float = 1.1):
+        self.enabled = enabled
+        self.min_samples = min_samples
+        self.evaluation_interval = evaluation_interval  # seconds (a Duration in the reference)
+        self.max_strategy_switches = max_strategy_switches
+        self.enable_backend_switching = enable_backend_switching
+        self.improvement_threshold = improvement_threshold
+
+
+class _StrategyMetrics:
+    """planning_adaptive.rs:48-86: total / count / integer-nanosecond average"""
+
+    def __init__(self):
+        self.total_ns, self.count, self.avg_ns = 0, 0, 0
+
+    def record(self, seconds: float) -> None:
+        self.total_ns += int(round(seconds * 1e9))
+        self.count += 1
+        self.avg_ns = self.total_ns // self.count
+
+
+class AdaptivePlanner:
+    """planning_adaptive.rs:86-252: records execution times per `PlanningStrategy` and switches to a strategy whose
+    average beats the current one by `improvement_threshold`, at most `max_strategy_switches` times.  The plan itself is
+    the library's cached GPU plan whatever the strategy (the strategies differ in where the HOST looks for a plan first)."""
+
+    def __init__(self, size: Sequence[int], forward: bool = True, config: Optional[AdaptivePlanningConfig] = None):
+        self.size = [int(s) for s in size]
+        self.forward = bool(forward)
+        self.config = config or AdaptivePlanningConfig()
+        self._strategy = PlanningStrategy.CacheFirst  # :131 "Start with a reasonable default"
+        self._backend = PlannerBackend.CUDA
+        self._metrics = {s: _StrategyMetrics() for s in PlanningStrategy}
+        self._last_switch = time.monotonic()
+        self._switches = 0
+        self._plan: Optional[FftPlanExecutor] = None
+
+    def current_strategy(self) -> PlanningStrategy:
+        return self._strategy
+
+    def current_backend(self) -> PlannerBackend:
+        return self._backend
+
+    def get_plan(self) -> FftPlanExecutor:
+        """:153-172"""
+        if self._plan is None:
+            self._plan = AdvancedFftPlanner().plan_fft(self.size, self.forward, self._backend)
+        return self._plan
+
+    def record_execution(self, execution_time: float) -> None:
+        """:175-199 (seconds)"""
+        if not self.config.enabled:
+            return
+        m = self._metrics[self._strategy]
+        m.record(execution_time)
+        if (m.count >= self.config.min_samples and time.monotonic() - self._last_switch >= self.config.evaluation_interval
+                and self._switches < self.config.max_strategy_switches):
+            self._evaluate_strategies()
+
+    def _evaluate_strategies(self) -> None:
+        """:202-238"""
+        best, best_ns = self._strategy, self._metrics[self._strategy].avg_ns
+        for strat, m in self._metrics.items():
+            if m.count == 0 or m.avg_ns == 0:
+                continue
+            if best_ns / m.avg_ns > self.config.improvement_threshold:
+                best, best_ns = strat, m.avg_ns
+        if best != self._strategy:
+            self._strategy = best
+            self._last_switch = time.monotonic()
+            self._switches += 1
+            self._plan = None
+
+    def get_statistics(self):
+        """:241-250: {strategy: (average seconds, count)}"""
+        return {s: (m.avg_ns * 1e-9, m.count) for s, m in self._metrics.items()}
+
+
+class AdaptiveExecutor:
+    """planning_adaptive.rs:254-316"""
+
+    def __init__(self, size: Sequence[int], forward: bool = True, config: Optional[AdaptivePlanningConfig] = None):
+        self._planner = AdaptivePlanner(size, forward, config)
+
+    def execute(self, input: np.ndarray, output: np.ndarray) -> None:
+        t0 = time.perf_counter()
+        self._planner.get_plan().execute(input, output)
+        self._planner.record_execution(time.perf_counter() - t0)
+
+    def current_strategy(self) -> PlanningStrategy:
+        return self._planner.current_strategy()
+
+    def get_statistics(self):
+        return self._planner.get_statistics()

@@ -40,7 +40,39 @@ KNOBS = [
     {"SFC_WORK_MB": "1"},                                                # many rounds through a tiny work area
     {"SFC_BLUE3_MIN": "32768", "SFC_THREE_LEVEL_MIN": "32768"},          # five-pass Bluestein, three-level rows
     {"SFC_GPIPE": "1", "SFC_GPIPE_MIN_TILES": "1"},                      # group-pipelined flavour on every eligible row pass
+    {"SFC_PIPE_LATE": "2", "SFC_PIPE_LATE_MIN_TILES": "1"},              # late-prefetch persistent flavour on every eligible row pass
 ]
+
+
+def test_late_prefetch_flavour(build_artifacts):
+    """TM_PIPE_LATE: persistent CTAs, the next tile lands in the idle exchange buffer (cp.async.bulk + mbarrier) during the
+    tail of the current one.  Every compiled shape, tile counts that are not multiples of the grid, both directions."""
+    code = r'''
+import numpy as np
+from scirs_b200 import FftPlan
+rng = np.random.default_rng(15)
+def rel(a, b): return np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel())
+for prec, n, rows, tol in (("f64", 4096, 1111, 1e-12), ("f64", 4096, 7, 1e-12), ("f64", 8192, 613, 1e-12), ("f64", 2048, 1402, 1e-12),
+                           ("f64", 2048, 1401, 1e-12), ("f32", 8192, 901, 1e-5)):
+    a = rng.standard_normal((rows, n)) + 1j * rng.standard_normal((rows, n))
+    if prec == "f32":
+        a = a.astype(np.complex64)
+    for fwd in (True, False):
+        p = FftPlan([rows, n], [1], "c2c", prec, fwd, 0.5)
+        d = p.describe()
+        assert "late-prefetch" in d, d
+        got = p.execute(a).reshape(rows, n)
+        ref = (np.fft.fft(a.astype(np.complex128), axis=1) if fwd else np.fft.ifft(a.astype(np.complex128), axis=1) * n) * 0.5
+        e = rel(got.astype(np.complex128), ref)
+        assert e < tol, (prec, n, rows, fwd, e)
+        got2 = p.execute(a).reshape(rows, n)   # a second launch of the persistent kernel (fresh mbarrier phase)
+        assert np.array_equal(got, got2)
+print("late prefetch ok")
+'''
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SFC_PIPE_LATE="2", SFC_PIPE_LATE_MIN_TILES="1"),
+                       capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0 and "late prefetch ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
 
 
 @pytest.mark.parametrize("env", KNOBS, ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()) or "defaults")
