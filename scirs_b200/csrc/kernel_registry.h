@@ -43,5 +43,6 @@ void register_kernels_f32_real(void (*add)(const KernelEntry&));
 void register_kernels_pipe(void (*add)(const KernelEntry&));
 void register_kernels_dct(void (*add)(const KernelEntry&));
 void register_kernels_pipe_dbl(void (*add)(const KernelEntry&));
+void register_kernels_r3(void (*add)(const KernelEntry&));
 
 }  // namespace sfc

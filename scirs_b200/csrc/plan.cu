@@ -42,6 +42,7 @@ const KernelEntry* kernel_table(int* count) {
         register_kernels_pipe(add_entry);
         register_kernels_dct(add_entry);
         register_kernels_pipe_dbl(add_entry);
+        register_kernels_r3(add_entry);
     });
     if (count) *count = (int)ktable().size();
     return ktable().data();
@@ -265,7 +266,7 @@ bool table_fourstep(int prec, int64_t M, const void** lo, const void** hi, int* 
     while (((int64_t)1 << lg) < M) ++lg;
     const int sh = (lg + 1) / 2;
     const int64_t nlo = (int64_t)1 << sh;
-    const int64_t nhi = std::max<int64_t>(M >> sh, 1);
+    const int64_t nhi = std::max<int64_t>((M + nlo - 1) >> sh, 1);  // covers (M-1) >> sh for any M (equal to M >> sh for powers of two)
     *lo = roots_table(TK_FS_LO, prec, nlo, (long double)M, 1.0L, M, err);
     if (!*lo) return false;
     *hi = roots_table(TK_FS_HI, prec, nhi, (long double)M, (long double)nlo, M, err);
@@ -399,6 +400,35 @@ const void* table_bluestein_b(int prec, int64_t N, int64_t M, int64_t L1, int64_
 // ------------------------------------------------------------------ builder
 
 static inline bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
+static inline int ilog3_exact(int64_t n) {  // k if n == 3^k, else -1
+    int k = 0;
+    while (n > 1 && n % 3 == 0) {
+        n /= 3;
+        ++k;
+    }
+    return n == 1 ? k : -1;
+}
+// power-of-three tiles (r3_tile.cuh): 1 = on (default), 0 = every non-power-of-two length goes through Bluestein
+static bool radix3_enabled() {
+    static int v = [] {
+        const char* e = getenv("SFC_RADIX3");
+        return e ? atoi(e) : 1;
+    }();
+    return v != 0;
+}
+// the wide tile when there are enough lanes to fill the GPU with it, else the narrow one
+static const KernelEntry* pick_r3(int prec, int L, int64_t lanes) {
+    int n = 0;
+    const KernelEntry* t = kernel_table(&n);
+    const KernelEntry *wide = nullptr, *narrow = nullptr;
+    for (int i = 0; i < n; ++i) {
+        if (t[i].mode != 10 || t[i].prec != prec || t[i].L != L) continue;
+        if (!wide || t[i].TL > wide->TL) wide = &t[i];
+        if (!narrow || t[i].TL < narrow->TL) narrow = &t[i];
+    }
+    if (!wide) return nullptr;
+    return lanes >= (int64_t)wide->TL * 148 ? wide : narrow;
+}
 static inline int64_t next_pow2(int64_t n) {
     int64_t p = 1;
     while (p < n) p <<= 1;
@@ -777,7 +807,7 @@ struct PlanBuilder {
         snprintf(buf, sizeof buf, "%s: tile L=%d TL=%d%s%s threads=%d smem=%zu lanes=%lld batches=%lld map=%s->%s", what,
                  s.k->L, s.k->TL, s.k->dbl ? " fwd*tab*inv" : "",
                  s.k->groups > 1 ? (s.k->mode == 4 ? " group-pipelined" : (s.k->mode ? " fast 2-groups" : " generic 2-groups"))
-                                  : (s.k->mode == 0 ? " generic" : (s.k->mode == 1 ? " fast" : (s.k->mode == 2 ? " fast-r2c" : (s.k->mode == 3 ? " fast-c2r" : (s.k->mode == 9 ? " late-prefetch" : (s.k->groups == 2 ? " group-pipelined" : " pipelined")))))), s.k->threads, s.k->smem, (long long)nlanes,
+                                  : (s.k->mode == 0 ? " generic" : (s.k->mode == 1 ? " fast" : (s.k->mode == 2 ? " fast-r2c" : (s.k->mode == 3 ? " fast-c2r" : (s.k->mode == 10 ? " radix-9/3" : (s.k->mode == 9 ? " late-prefetch" : (s.k->groups == 2 ? " group-pipelined" : " pipelined"))))))), s.k->threads, s.k->smem, (long long)nlanes,
                  (long long)nbatch, s.p.map_in == MAP_ROW ? "row" : "col", s.p.map_out == MAP_ROW ? "row" : "col");
         s.desc = buf;
         pl.steps_.push_back(s);
@@ -898,7 +928,11 @@ struct PlanBuilder {
             Step s;
             // measured (1024^3 f64): with element rows <= 16 KiB apart the 64 KiB two-per-SM tile wins
             // (74 % vs 61 %); with multi-MiB strides (TLB-bound) the wide 128-byte-row tile wins (59 % vs 44 %)
-            if (col && (int64_t)I * (int64_t)cs <= (256 << 10))
+            // a pass whose store goes over NVLink (split-axis scatter) is link-bound, and the link likes long segments
+            // (1024^3 on 8 GPUs: 64 B stores reach 426 GB/s, 128 B stores 667 GB/s): widest tile there
+            if (col && scatter_parts > 1 && (O * I) % 8 == 0)
+                s.k = pick_kernel(prec, (int)n, true, 0);
+            else if (col && (int64_t)I * (int64_t)cs <= (256 << 10))
                 s.k = pick_kernel_two_per_sm(prec, (int)n, 0);
             else
                 s.k = pick_kernel(prec, (int)n, col, 0);
@@ -1002,6 +1036,71 @@ struct PlanBuilder {
             dev_bytes += O * I * (std::min(n, src.n) * (int64_t)src_es + 2 * n * (int64_t)cs +
                                   std::min(n, dst.n) * (int64_t)dst_es);
             return finish_tile(b, L1 * I, I, O, "four-step pass B (rows, transposed store)");
+        }
+
+        // n = 3^k (rustfft: Radix3): power-of-three tiles, one pass up to 3^7 = 2187, two passes (four-step) up to 3^14
+        const int k3 = ilog3_exact(n);
+        if (radix3_enabled() && k3 >= 2 && k3 <= 14 && !src.real && !store_real && src.n == n && dst.n == n && !aux_in && !aux_out &&
+            scatter_parts <= 1 && O * I <= 0x7FFFFFFFLL) {
+            if (k3 <= 7) {
+                Step s;
+                s.k = pick_r3(prec, (int)n, O * I);
+                s.src = src.role;
+                s.dst = dst.role;
+                s.src_esize = cs;
+                s.dst_esize = cs;
+                set_io(s.p.in, 0, n * I, 1, I, n, 1, 0);
+                set_io(s.p.out, 0, n * I, 1, I, n, 1, 0);
+                s.p.map_in = s.p.map_out = col ? MAP_COL : MAP_ROW;
+                s.p.ld_op = LD_C;
+                s.p.st_op = ST_C;
+                s.p.flags = fl_in | fl_out;
+                s.p.scale = scale;
+                dev_bytes += O * I * 2 * n * (int64_t)cs;
+                return finish_tile(s, O * I, I, 1, "single-pass axis, power-of-three tile");
+            }
+            int64_t L1 = 1;
+            for (int i = 0; i < k3 / 2; ++i) L1 *= 3;
+            const int64_t L2 = n / L1;
+            const void *lo, *hi;
+            int sh;
+            if (!table_fourstep(prec, n, &lo, &hi, &sh, err)) return false;
+            const int g = new_group(O, n * I * (int64_t)cs);
+            Step a;
+            a.k = pick_r3(prec, (int)L1, L2 * I * O);
+            a.src = src.role;
+            a.dst = R_MS;
+            a.src_esize = cs;
+            a.dst_esize = cs;
+            a.group = g;
+            set_io(a.p.in, n * I, I, 1, L2 * I, n, L2, 1);
+            set_io(a.p.out, n * I, I, 1, L2 * I, n, L2, 1);
+            a.p.map_in = a.p.map_out = MAP_COL;
+            a.p.ld_op = LD_C;
+            a.p.st_op = ST_TW;
+            a.p.tw_lo = lo;
+            a.p.tw_hi = hi;
+            a.p.tw_shift = sh;
+            a.p.flags = fl_in;
+            a.p.scale = 1.0;
+            if (!finish_tile(a, L2 * I, I, O, "four-step pass A (columns + twiddle), power-of-three tile")) return false;
+            Step b;
+            b.k = pick_r3(prec, (int)L2, L1 * I * O);
+            b.src = R_MS;
+            b.dst = dst.role;
+            b.src_esize = cs;
+            b.dst_esize = cs;
+            b.group = g;
+            set_io(b.p.in, n * I, L2 * I, 1, I, L2, 1, 0);
+            set_io(b.p.out, n * I, I, 1, L1 * I, n, L1, 1);
+            b.p.map_in = col ? MAP_COL : MAP_ROW;
+            b.p.map_out = MAP_COL;
+            b.p.ld_op = LD_C;
+            b.p.st_op = ST_C;
+            b.p.flags = fl_out;
+            b.p.scale = scale;
+            dev_bytes += O * I * 4 * n * (int64_t)cs;
+            return finish_tile(b, L1 * I, I, O, "four-step pass B (rows, transposed store), power-of-three tile");
         }
 
         // Bluestein chirp-z over a padded power-of-two convolution of length M >= 2n-1
@@ -1622,10 +1721,12 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
     for (int a : axes) log2sum += std::log2((double)shape[a]);
     int64_t alg = 0;
     int passes = 0;
-    auto axis_passes = [&](int64_t n) {
+    auto axis_passes = [&](int64_t n, bool plain_complex = false) {
         if (n == 1) return 0;
         const int lmax = lmax_for(prec);
         if (is_pow2(n)) return n <= lmax ? 1 : 2;  // algorithmic passes; long rows may physically take three
+        const int k3 = ilog3_exact(n);
+        if (plain_complex && radix3_enabled() && k3 >= 2 && k3 <= 14) return k3 <= 7 ? 1 : 2;  // power-of-three tiles
         return next_pow2(2 * n - 1) <= lmax ? 1 : 4;
     };
 
@@ -1690,7 +1791,9 @@ std::shared_ptr<Plan> Plan::create(const sfc_desc& d, PlanError& err) {
                             last && real_out);
             B.aux_in = B.aux_out = nullptr;
             B.scatter_parts = 0;
-            const int ap = axis_passes(n);
+            const bool plain = !(i == 0 && real_in) && !(last && real_out) && !(ax_in && ax_in != n) && !(ax_out && ax_out != n) &&
+                               !d.aux_in && !d.aux_out && d.scatter_parts <= 1;
+            const int ap = axis_passes(n, plain);
             passes += ap;
             if (!is_pow2(n) && ap == 4)
                 alg += O * I * (2 * n + 6 * next_pow2(2 * n - 1)) * (int64_t)cs;

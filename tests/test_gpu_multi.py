@@ -30,6 +30,8 @@ def _ngpu():
 def _worlds():
     n = _ngpu()
     w = [p for p in (2, 4, 8) if p <= n]
+    if os.environ.get("SFC_TEST_WORLDS"):  # e.g. "8": only that world size (GPU-minutes on a big box are expensive)
+        w = [int(v) for v in os.environ["SFC_TEST_WORLDS"].split(",") if int(v) <= n]
     return w or [1]
 
 

@@ -490,3 +490,47 @@ def test_full_size_fftn_1024_roundtrip(sb, orc):
     sb.FftPlan([n, n, n], [0, 1, 2], "c2c", "f64", False, 1.0 / n ** 3).execute_device(y, y, s)  # in place
     torch.cuda.synchronize()
     assert float((y - x).norm() / x.norm()) < TOL64
+
+
+def test_power_of_three_lengths(sb, orc):
+    """Lengths 3^k run on radix-9/3 tiles (csrc/r3_tile.cuh; rustfft plans Radix3 for them): one pass up to 3^7, a
+    two-pass four-step up to 3^14.  Against the oracle (extended-precision DFT bins for the long ones), both directions, f32."""
+    rng = np.random.default_rng(314)
+    for k in range(2, 12):
+        n = 3 ** k
+        rows = 5 if k < 10 else 2
+        a = cplx(rng, rows, n)
+        p = sb.FftPlan([rows, n], [1])
+        assert "radix-9/3" in p.describe(), p.describe()
+        got = p.execute(a).reshape(rows, n)
+        ref = np.stack([orc.fft(r, n) for r in a]) if n <= 6561 else np.fft.fft(a, axis=1)
+        assert orc.rel_l2(got, ref) < TOL64, (n, orc.rel_l2(got, ref))
+        inv = sb.FftPlan([rows, n], [1], "c2c", "f64", False, 1.0 / n).execute(got).reshape(rows, n)
+        assert orc.rel_l2(inv, a) < TOL64
+        got32 = sb.FftPlan([rows, n], [1], "c2c", "f32").execute(a.astype(np.complex64)).reshape(rows, n)
+        assert orc.rel_l2(got32.astype(np.complex128), np.fft.fft(a.astype(np.complex64).astype(np.complex128), axis=1)) < TOL32
+    # the free functions reach them too: fft(x, Some(3^9)), strided axes of an N-D array, partial last tiles
+    v = rng.standard_normal(3 ** 9)
+    assert orc.rel_l2(sb.fft(v, 3 ** 9), orc.fft(v, 3 ** 9)) < TOL64
+    vol = cplx(rng, 27, 81, 10)
+    assert orc.rel_l2(sb.fftn(vol, None, [1, 0]), orc.fftn(vol, None, [1, 0])) < TOL64
+    assert orc.rel_l2(sb.ifftn(vol, None, [0]), orc.ifftn(vol, None, [0])) < TOL64
+
+
+def test_full_size_3pow13_batch(sb, orc):
+    """BASELINE configs[3]: 3^13 = 729 x 2187 as a two-pass transform, batch 32 here (256 in bench.py): round trip, Parseval and
+    extended-precision bins of one row."""
+    n, rows = 3 ** 13, 32
+    rng = np.random.default_rng(13)
+    a = cplx(rng, rows, n)
+    p = sb.FftPlan([rows, n], [1])
+    d = p.describe()
+    assert "radix-9/3" in d and p.info["num_passes"] == 2, d
+    got = p.execute(a).reshape(rows, n)
+    back = sb.FftPlan([rows, n], [1], "c2c", "f64", False, 1.0 / n).execute(got).reshape(rows, n)
+    assert orc.rel_l2(back, a) < TOL64
+    assert abs(np.sum(np.abs(got) ** 2) / n / np.sum(np.abs(a) ** 2) - 1.0) < 1e-12
+    bins = np.array([0, 1, 728, 729, 2187, n // 2, n - 1])
+    j = np.arange(n, dtype=np.int64)
+    ref = np.array([np.sum(a[3].astype(np.clongdouble) * np.exp(-2j * np.pi * ((j * int(b)) % n).astype(np.longdouble) / n)) for b in bins])
+    assert np.max(np.abs(got[3][bins] - ref.astype(np.complex128))) / np.max(np.abs(ref)) < 1e-12

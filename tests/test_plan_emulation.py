@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMUL = os.path.join(ROOT, "tests", "emul")
 CSRC = os.path.join(ROOT, "scirs_b200", "csrc")
 UNITS = ["plan", "aux_kernels", "kernels_f64_small", "kernels_f64_mid", "kernels_f64_big", "kernels_f64_real", "kernels_f64_dbl_a",
-         "kernels_f64_dbl_b", "kernels_dct"]
+         "kernels_f64_dbl_b", "kernels_dct", "kernels_r3"]
 
 
 @pytest.fixture(scope="module")
@@ -315,3 +315,21 @@ def test_slab_fftn_natural_layout_second_exchange(emul, P, shape, inverse):
     ref = (np.fft.ifftn(X) * X.size if inverse else np.fft.fftn(X)) * 0.5
     for q in range(P):
         assert rel(outs[q], ref[q * s0:(q + 1) * s0]) < 1e-14
+
+
+@pytest.mark.parametrize("shape,axes", [([5, 9], [1]), ([4, 27], [1]), ([7, 81], [1]), ([3, 243], [1]), ([2, 729], [1]), ([2, 2187], [1]),
+                                         ([81, 6], [0]), ([3, 243, 5], [1]), ([2, 6561], [1]), ([1, 19683], [1]), ([2, 59049], [1]),
+                                         ([27, 9, 4], [0, 1]), ([1, 177147], [1])])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_power_of_three_tiles(emul, shape, axes, inverse):
+    """csrc/r3_tile.cuh through the planner: lengths 3^k as radix-9/3 Stockham tiles (one pass up to 2187, a two-pass four-step
+    above: 3^13 = 729 x 2187 is BASELINE configs[3]) instead of the padded Bluestein convolution.  rustfft plans `Radix3` for
+    these lengths."""
+    rng = np.random.default_rng(33)
+    x = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    y = np.zeros(shape, dtype=np.complex128)
+    rc, d = emul(shape, axes, x, y, inverse=inverse, scale=0.25)
+    assert rc == 0, d
+    assert "power-of-three tile" in d, d
+    ref = (np.fft.ifftn(x, axes=axes) * np.prod([shape[a] for a in axes]) if inverse else np.fft.fftn(x, axes=axes)) * 0.25
+    assert rel(y, ref) < 2e-14, rel(y, ref)

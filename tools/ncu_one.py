@@ -18,6 +18,7 @@ cases = {
     "fftn1024": ([1024, 1024, 1024], [0, 1, 2], "c2c", "f64", 1024 ** 3 * 2, 1024 ** 3 * 2),
     "fft1m64": ([64, 1 << 20], [1], "c2c", "f64", (64 << 20) * 2, (64 << 20) * 2),
 }
+cases["r3_13"] = ([32, 1594323], [1], "c2c", "f64", 32 * 1594323 * 2, 32 * 1594323 * 2)
 cases["dct2"] = ([65536, 4096], [1], "r2c", "f64", 65536 * 4096, 65536 * 4096)
 shape, axes, kind, prec, ni, no = cases[case]
 dt = torch.float64 if prec == "f64" else torch.float32

@@ -38,7 +38,11 @@ def stalls(rep):
             op = src.split()[0].split('.')[0] if src else '?'
             ops[op] += ex; n += ex
         ssum = sum(tot.values()) or 1
-        res.append(({k: round(v / ssum, 3) for k, v in tot.most_common(8)}, {k: v for k, v in ops.most_common(12)}, n))
+        top = {k: v for k, v in ops.most_common(12)}
+        for k in ("UTMALDG", "UBLKCP", "SYNCS", "UTMASTG"):  # TMA / mbarrier evidence, however few of them execute
+            if ops.get(k):
+                top[k] = ops[k]
+        res.append(({k: round(v / ssum, 3) for k, v in tot.most_common(8)}, top, n))
     return res
 
 tag = sys.argv[1]
