@@ -52,7 +52,7 @@ WORKLOADS = {
     "fft_2p24": ([8, 1 << 24], [1], "c2c", "f64", True, "fft c128 2^24, batch 8 (large-N path: three passes of small tiles)"),
     "fftn_512": ([512, 512, 512], [0, 1, 2], "c2c", "f64", True, "fftn c128 512^3 on one GPU (configs[4])"),
     "bluestein_1000003": ([256, 1000003], [1], "c2c", "f64", True, "fft c128 N=1,000,003 (prime, Bluestein), batch 256 (configs[3])"),
-    "bluestein_1594323": ([256, 1594323], [1], "c2c", "f64", True, "fft c128 N=3^13 (Bluestein), batch 256 (configs[3])"),
+    "bluestein_1594323": ([256, 1594323], [1], "c2c", "f64", True, "fft c128 N=3^13 = 729 x 2187 (radix-9/3 four-step; was Bluestein in round 1), batch 256 (configs[3])"),
     "fftn_1024": ([1024, 1024, 1024], [0, 1, 2], "c2c", "f64", True, "fftn c128 1024^3 on one GPU (configs[4])"),
 }
 

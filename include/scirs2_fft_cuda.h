@@ -278,6 +278,15 @@ int sfc_cache_is_enabled(void);                  /* PlanCache::is_enabled  :62-6
 int sfc_cache_clear(void);                       /* PlanCache::clear       :66-71  */
 int sfc_cache_configure(uint64_t max_entries, double max_age_seconds); /* with_config :47-54 */
 
+/* ---------------------------------------------------------- planner options
+ * The GPU planner's tile / pass choices (SFC_PIPE_LATE, SFC_BLUE_L1, SFC_THREE_LEVEL_MIN, SFC_COL_TL,
+ * SFC_RADIX3, ...) default to measured-best settings and can be given in the environment; these two calls override them at
+ * run time so that a tuner can time variants of one plan inside a process and persist the winner per (GPU, shape, dtype)
+ * the way auto_tuning.rs:188-229 does for its algorithm variants.  Setting an option empties the plan cache.
+ * value == NULL removes the override.  sfc_planner_get_option returns the length written (0 = unset). */
+int sfc_planner_set_option(const char* name, const char* value);
+int sfc_planner_get_option(const char* name, char* buf, size_t cap);
+
 /* ------------------------------------------------- drop-in free functions
  * Reference semantics (including its SciPy-divergent quirks) with
  * HOST buffers.  `n`/shape arguments use -1 / NULL for the reference's `None`.

@@ -340,4 +340,68 @@ class BackendManager {
 };
 inline BackendManager& get_backend_manager() { static BackendManager m; return m; }
 
+// ---------------------------------------------------------------- distributed.rs:18-103, 115-362
+// `trait Communicator` for the GPUs of one node and the slab-decomposed 3-D transform, both inside the library.
+enum class DecompositionStrategy { Replicated = SFC_DECOMP_REPLICATED, BatchSplit = SFC_DECOMP_BATCH_SPLIT, Slab = SFC_DECOMP_SLAB };
+enum class SlabLayout { Transposed = SFC_SLAB_TRANSPOSED, Natural = SFC_SLAB_NATURAL };
+
+class Communicator {
+   public:
+    // one process per GPU: every rank passes the same job-unique name
+    static Communicator rank(const std::string& name, int rank, int world, int device) {
+        sfc_comm* h = nullptr;
+        check(sfc_comm_init_rank(&h, name.c_str(), rank, world, device));
+        return Communicator(h);
+    }
+    // one process driving ngpu GPUs (0 = all visible)
+    static Communicator local(int ngpu = 0) {
+        sfc_comm* h = nullptr;
+        check(sfc_comm_init_local(&h, ngpu, nullptr));
+        return Communicator(h);
+    }
+    Communicator(Communicator&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    Communicator(const Communicator&) = delete;
+    ~Communicator() { if (h_) sfc_comm_destroy(h_); }
+    int size() const { return sfc_comm_size(h_); }   // Communicator::size, distributed.rs:99
+    int rank() const { return sfc_comm_rank(h_); }   // Communicator::rank, :102
+    void barrier() const { check(sfc_comm_barrier(h_)); }  // Communicator::barrier, :96
+    sfc_comm* handle() const { return h_; }
+
+   private:
+    explicit Communicator(sfc_comm* h) : h_(h) {}
+    sfc_comm* h_;
+};
+
+// DistributedFFT::distributed_fft (distributed.rs:115-163) for 3-D complex volumes
+class DistributedFFT {
+   public:
+    DistributedFFT(const Communicator& comm, const std::vector<int64_t>& shape, bool inverse = false,
+                   SlabLayout layout = SlabLayout::Natural, double scale = 1.0) {
+        if (shape.size() != 3) throw FFTError(FFTError::Value, "slab decomposition: 3-D complex transforms only");
+        sfc_dist_desc d{};
+        d.base.ndim = 3;
+        d.base.naxes = 3;
+        for (int i = 0; i < 3; ++i) { d.base.shape[i] = shape[(size_t)i]; d.base.axes[i] = i; }
+        d.base.kind = SFC_C2C;
+        d.base.prec = SFC_PREC_F64;
+        d.base.direction = inverse ? SFC_INVERSE : SFC_FORWARD;
+        d.base.scale = scale;
+        d.decomposition = SFC_DECOMP_SLAB;
+        d.layout = (int)layout;
+        check(sfc_dist_plan_create(&h_, comm.handle(), &d));
+        check(sfc_dist_plan_get_info(h_, &info));
+    }
+    DistributedFFT(const DistributedFFT&) = delete;
+    ~DistributedFFT() { if (h_) sfc_dist_plan_destroy(h_); }
+    // host buffers: local mode = the whole C-order volume, rank mode = this rank's slab in and its share out
+    void execute(const Complex64* in, Complex64* out) const { check(sfc_dist_exec_host(h_, in, out)); }
+    sfc_dist_info info{};
+
+   private:
+    sfc_dist_plan* h_ = nullptr;
+};
+
+// fftn / ifftn / execute_batch of THIS process run over ngpu GPUs from now on (-1: all visible, 1: back to one)
+inline void set_num_gpus(int ngpu) { check(sfc_set_num_gpus(ngpu)); }
+
 }  // namespace scirs2_fft_cuda

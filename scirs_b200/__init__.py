@@ -21,7 +21,7 @@ from .plan import FftPlan, FftPlanExecutor
 from .plan_serialization import (PlanInfo, PlanMetrics, PlanDatabaseStats, PlanSerializationManager,
                                  create_and_time_plan)
 from .auto_tuning import (AutoTuner, AutoTuneConfig, BenchmarkResult, FftVariant, SizeRange, SizeStep, SystemInfo,
-                          TuningDatabase)
+                          TuningDatabase, GpuPlanTuner)
 from .plan_cache import PlanCache, CacheStats, get_global_cache
 from .backend import FftBackend, CudaFftBackend, BackendManager, BackendContext, get_backend_manager
 from .context import (WorkerConfig, WorkerPool, WorkerPoolInfo, get_global_pool, set_workers, get_workers, FftContext,

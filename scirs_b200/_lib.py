@@ -172,6 +172,8 @@ SIGNATURES = {
     "sfc_cache_is_enabled": (_int, []),
     "sfc_cache_clear": (_int, []),
     "sfc_cache_configure": (_int, [C.c_uint64, _dbl]),
+    "sfc_planner_set_option": (_int, [_str, _str]),
+    "sfc_planner_get_option": (_int, [_str, C.c_char_p, C.c_size_t]),
     "sfc_fft": (_int, [_vp, _i64, _int, _i64, _vp, _i64, _pi64]),
     "sfc_ifft": (_int, [_vp, _i64, _int, _i64, _vp, _i64, _pi64]),
     "sfc_rfft": (_int, [_vp, _i64, _int, _i64, _vp, _i64, _pi64]),

@@ -274,3 +274,138 @@ class AutoTuner:
         buf[: a.size] = a
         buf = buf[:n] if n <= a.size else buf  # the reference only ever pads (buffer.len() < actual_size)
         return np.asarray(self._run_variant(np.ascontiguousarray(buf), self.get_best_variant(n, forward), forward))
+
+
+# ------------------------------------------------------------------ GPU planner tuning (round 2)
+
+
+class GpuPlanTuner:
+    """Times the GPU planner's variants of ONE plan on the device and persists the winner — the reference's
+    `AutoTuner::run_benchmarks` / `TuningDatabase` idea (auto_tuning.rs:188-229, 409-470) applied to what actually varies here:
+    tile shapes, pass counts and the TMA flavours (the `SFC_*` options of DESIGN.md section 11), not CPU algorithm variants.
+
+    Options are switched at run time through `sfc_planner_set_option` (no new process per variant).  The database is JSON
+    next to the reference's own (`database_path`), keyed by `arch|kind|prec|shape|axes|direction`; `plan()` builds a plan
+    under the stored options, so `plan_ahead_of_time`-style warm-up gets the tuned tiles.
+    """
+
+    def __init__(self, database_path: str = ".fft_gpu_tuning_db.json", repetitions: int = 20, warmup: int = 3):
+        self.database_path = database_path
+        self.repetitions, self.warmup = int(repetitions), int(warmup)
+        self.entries: Dict[str, dict] = {}
+        self.arch_id = f"{platform.machine()}-sm_100a"
+        if os.path.exists(database_path):
+            self.load()
+
+    # -- persistence
+    def load(self) -> None:
+        try:
+            d = json.load(open(self.database_path))
+        except (OSError, ValueError) as ex:
+            raise IOError_(f"cannot read {self.database_path}: {ex}")
+        if d.get("arch_id") == self.arch_id:  # winners of another GPU generation do not transfer
+            self.entries = dict(d.get("entries", {}))
+
+    def save(self) -> None:
+        try:
+            json.dump({"arch_id": self.arch_id, "entries": self.entries}, open(self.database_path, "w"), indent=1, sort_keys=True)
+        except OSError as ex:
+            raise IOError_(f"cannot write {self.database_path}: {ex}")
+
+    # -- candidates
+    @staticmethod
+    def key(shape, axes, kind, prec, forward) -> str:
+        return "|".join(["sm_100a", kind, prec, "x".join(str(int(s)) for s in shape), ",".join(str(int(a)) for a in axes),
+                         "fwd" if forward else "inv"])
+
+    @staticmethod
+    def candidates(shape: Sequence[int], axes: Sequence[int]) -> List[Dict[str, str]]:
+        """Option sets worth timing for this geometry ({} = the library defaults, always first)."""
+        cands: List[Dict[str, str]] = [{}]
+        last = len(shape) - 1
+        for a in axes:
+            n = int(shape[a])
+            pow2 = n & (n - 1) == 0
+            if pow2 and a == last and n >= 2048:          # contiguous rows: persistent late-prefetch flavour
+                cands += [{"SFC_PIPE_LATE": "2"}]
+            if pow2 and a == last and n > 8192:           # multi-pass rows: two passes of big tiles / three of small ones, TMA on or off
+                cands += [{"SFC_PIPE_LATE": "0"}, {"SFC_PIPE_LATE": "3"}, {"SFC_THREE_LEVEL_MIN": str(n)},
+                          {"SFC_THREE_LEVEL_MIN": str(1 << 40)}]
+            if pow2 and a != last:                        # strided axis: tensor-map tiles, narrower tiles
+                cands += [{"SFC_PIPE_LATE": "3"}, {"SFC_COL_SMEM_KB": "40"}]
+            if not pow2 and n > 4096:                     # Bluestein: first factor of the padded length
+                cands += [{"SFC_BLUE_L1": v} for v in ("256", "512", "2048")]
+        out, seen = [], set()
+        for c in cands:
+            t = tuple(sorted(c.items()))
+            if t not in seen:
+                seen.add(t)
+                out.append(c)
+        return out
+
+    # -- measurement
+    def _time(self, shape, axes, kind, prec, forward, options: Dict[str, str]) -> float:
+        import torch
+
+        from . import _lib
+        from .error import check
+        from .plan import FftPlan
+
+        lib = _lib.load()
+        for k, v in options.items():
+            check(lib.sfc_planner_set_option(k.encode(), v.encode()))
+        try:
+            plan = FftPlan(shape, axes, kind, prec, forward)
+            rt = torch.float64 if prec == "f64" else torch.float32
+            x = torch.randn(plan.info["in_bytes"] // (8 if prec == "f64" else 4), dtype=rt, device="cuda")
+            y = torch.empty(plan.info["out_bytes"] // (8 if prec == "f64" else 4), dtype=rt, device="cuda")
+            st = torch.cuda.current_stream()
+            for _ in range(self.warmup):
+                plan.execute_device(x, y, st.cuda_stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(self.repetitions):
+                plan.execute_device(x, y, st.cuda_stream)
+            e1.record(st)
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / self.repetitions
+        finally:
+            for k in options:
+                lib.sfc_planner_set_option(k.encode(), None)
+
+    def tune(self, shape: Sequence[int], axes: Optional[Sequence[int]] = None, kind: str = "c2c", prec: str = "f64",
+             forward: bool = True) -> dict:
+        shape = [int(s) for s in shape]
+        axes = list(range(len(shape))) if axes is None else [int(a) for a in axes]
+        results = []
+        for opts in self.candidates(shape, axes):
+            try:
+                results.append((self._time(shape, axes, kind, prec, forward, opts), opts))
+            except Exception as ex:  # an option set the planner refuses for this shape is simply not a candidate
+                results.append((float("inf"), dict(opts, error=str(ex)[:80])))
+        best_ms, best = min(results, key=lambda r: r[0])
+        entry = {"options": best, "ms": round(best_ms, 5), "default_ms": round(results[0][0], 5),
+                 "candidates": [{"options": o, "ms": (None if math.isinf(t) else round(t, 5))} for t, o in results]}
+        self.entries[self.key(shape, axes, kind, prec, forward)] = entry
+        return entry
+
+    def options_for(self, shape, axes=None, kind="c2c", prec="f64", forward=True) -> Dict[str, str]:
+        axes = list(range(len(shape))) if axes is None else list(axes)
+        e = self.entries.get(self.key(shape, axes, kind, prec, forward))
+        return dict(e["options"]) if e else {}
+
+    def plan(self, shape, axes=None, kind="c2c", prec="f64", forward=True, scale: float = 1.0):
+        """A plan built under the tuned options of this geometry (library defaults if it was never tuned)."""
+        from . import _lib
+        from .error import check
+        from .plan import FftPlan
+
+        lib = _lib.load()
+        opts = self.options_for(shape, axes, kind, prec, forward)
+        for k, v in opts.items():
+            check(lib.sfc_planner_set_option(k.encode(), v.encode()))
+        try:
+            return FftPlan(shape, axes, kind, prec, forward, scale)
+        finally:
+            for k in opts:
+                lib.sfc_planner_set_option(k.encode(), None)

@@ -473,6 +473,27 @@ extern "C" __attribute__((visibility("default"))) int sfc_cache_configure(uint64
     return SFC_OK;
 }
 
+// ---------------------------------------------------------- planner options
+
+extern "C" __attribute__((visibility("default"))) int sfc_planner_set_option(const char* name, const char* value) {
+    if (!name || strncmp(name, "SFC_", 4) != 0 || strlen(name) > 64) return fail(SFC_ERR_VALUE, "option names start with SFC_");
+    sfc::planner_set_option(name, value);
+    // cached plans were built under the old options
+    PlanCacheImpl& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.map.clear();
+    return SFC_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sfc_planner_get_option(const char* name, char* buf, size_t cap) {
+    if (!name || !buf || cap == 0) return fail(SFC_ERR_VALUE, "null argument");
+    const std::string v = sfc::planner_get_option(name);
+    const size_t n = std::min(cap - 1, v.size());
+    memcpy(buf, v.data(), n);
+    buf[n] = 0;
+    return (int)n;
+}
+
 // ====================================================== drop-in free functions
 
 namespace sfc_api {

@@ -17,6 +17,35 @@ namespace sfc {
 
 // ------------------------------------------------------------ kernel table
 
+// ---- planner options: environment variables that can be overridden at run time (sfc_planner_set_option), so that a tuner
+// can time variants of a plan inside one process and persist the winners (auto_tuning.rs:188-229)
+static std::mutex g_knob_mu;
+static std::map<std::string, std::string>& knob_overrides() {
+    static std::map<std::string, std::string> m;
+    return m;
+}
+static thread_local std::string g_knob_tmp;
+static const char* knob_env(const char* name) {
+    {
+        std::lock_guard<std::mutex> lk(g_knob_mu);
+        auto it = knob_overrides().find(name);
+        if (it != knob_overrides().end()) {
+            g_knob_tmp = it->second;
+            return g_knob_tmp.c_str();
+        }
+    }
+    return getenv(name);
+}
+void planner_set_option(const char* name, const char* value) {
+    std::lock_guard<std::mutex> lk(g_knob_mu);
+    if (value) knob_overrides()[name] = value;
+    else knob_overrides().erase(name);
+}
+std::string planner_get_option(const char* name) {
+    const char* v = knob_env(name);
+    return v ? std::string(v) : std::string();
+}
+
 static std::vector<KernelEntry>& ktable() {
     static std::vector<KernelEntry> v;
     return v;
@@ -69,8 +98,8 @@ static const KernelEntry* flavour_of(const KernelEntry* k, int mode) {
 }
 
 static bool fast_enabled() {
-    static int v = [] {
-        const char* e = getenv("SFC_FAST");
+    const int v = [] {
+        const char* e = knob_env("SFC_FAST");
         return e ? atoi(e) : 1;
     }();
     return v != 0;
@@ -79,16 +108,16 @@ static bool fast_enabled() {
 // ROW tiles want few lanes per CTA (small tiles, more CTAs per SM); COL tiles want
 // many adjacent lanes (>= 128 B contiguous per element row).
 static int groups_mode() {
-    static int v = [] {
-        const char* e = getenv("SFC_GROUPS");
+    const int v = [] {
+        const char* e = knob_env("SFC_GROUPS");
         return e ? atoi(e) : 0;  // measured on B200: two named-barrier groups per CTA are slower (1024^3: 69% -> 61%)
     }();
     return v;
 }
 
 static int col_tl_cap() {
-    static int v = [] {
-        const char* e = getenv("SFC_COL_TL");
+    const int v = [] {
+        const char* e = knob_env("SFC_COL_TL");
         return e ? atoi(e) : 0;
     }();
     return v;
@@ -97,15 +126,15 @@ static int col_tl_cap() {
 // column tiles of internal passes: widest tile whose exchange buffer stays under this many KiB (100 = two 64 KiB
 // tiles per SM, 40 = four 32 KiB tiles per SM)
 static int col_smem_cap_kb() {
-    static int v = [] {
-        const char* e = getenv("SFC_COL_SMEM_KB");
+    const int v = [] {
+        const char* e = knob_env("SFC_COL_SMEM_KB");
         return e ? atoi(e) : 100;
     }();
     return v;
 }
 static int forced_e() {
-    static int v = [] {
-        const char* e = getenv("SFC_FORCE_E");
+    const int v = [] {
+        const char* e = knob_env("SFC_FORCE_E");
         return e ? atoi(e) : 0;
     }();
     return v;
@@ -291,8 +320,8 @@ bool table_chirp_roots(int64_t N, const void** lo, const void** hi, int* shift, 
 }
 
 static bool chirp_gen_enabled() {
-    static int v = [] {
-        const char* e = getenv("SFC_CHIRP_GEN");
+    const int v = [] {
+        const char* e = knob_env("SFC_CHIRP_GEN");
         return e ? atoi(e) : 1;
     }();
     return v != 0;
@@ -410,24 +439,33 @@ static inline int ilog3_exact(int64_t n) {  // k if n == 3^k, else -1
 }
 // power-of-three tiles (r3_tile.cuh): 1 = on (default), 0 = every non-power-of-two length goes through Bluestein
 static bool radix3_enabled() {
-    static int v = [] {
-        const char* e = getenv("SFC_RADIX3");
+    const int v = [] {
+        const char* e = knob_env("SFC_RADIX3");
         return e ? atoi(e) : 1;
     }();
     return v != 0;
 }
-// the wide tile when there are enough lanes to fill the GPU with it, else the narrow one
-static const KernelEntry* pick_r3(int prec, int L, int64_t lanes) {
+// rows: the 243-thread tile (three CTAs per SM); strided passes: the 486-thread tile with twice the lanes (longer segments).
+// Measured (profiles/r2g_r3_tiles_latency_tmap.log): contiguous 729-point rows 61.9 % (729 x 9 lanes) -> 77.0 % (729 x 3),
+// 2187-point rows 54.1 % -> 67.6 %; in the strided passes of 3^13 narrower tiles lose.
+static const KernelEntry* pick_r3(int prec, int L, bool strided) {
     int n = 0;
     const KernelEntry* t = kernel_table(&n);
-    const KernelEntry *wide = nullptr, *narrow = nullptr;
+    {   // experiment knob: SFC_R3_TL_<L>=<lanes per tile>
+        char nm[32];
+        snprintf(nm, sizeof nm, "SFC_R3_TL_%d", L);
+        const char* e = knob_env(nm);
+        if (e)
+            for (int i = 0; i < n; ++i)
+                if (t[i].mode == 10 && t[i].prec == prec && t[i].L == L && t[i].TL == atoi(e)) return &t[i];
+    }
+    const KernelEntry* best = nullptr;
+    const int want = strided ? 486 : 243;
     for (int i = 0; i < n; ++i) {
         if (t[i].mode != 10 || t[i].prec != prec || t[i].L != L) continue;
-        if (!wide || t[i].TL > wide->TL) wide = &t[i];
-        if (!narrow || t[i].TL < narrow->TL) narrow = &t[i];
+        if (!best || std::abs(t[i].threads - want) < std::abs(best->threads - want)) best = &t[i];
     }
-    if (!wide) return nullptr;
-    return lanes >= (int64_t)wide->TL * 148 ? wide : narrow;
+    return best;
 }
 static inline int64_t next_pow2(int64_t n) {
     int64_t p = 1;
@@ -441,8 +479,8 @@ static inline int ilog2_64(int64_t n) {
 }
 
 static int col_single_limit(int prec) {
-    static int v = [] {
-        const char* e = getenv("SFC_COL_SINGLE_MAX");
+    const int v = [] {
+        const char* e = knob_env("SFC_COL_SINGLE_MAX");
         return e ? atoi(e) : 0;
     }();
     if (v > 0) return v;
@@ -451,8 +489,8 @@ static int col_single_limit(int prec) {
 
 // row length that is transformed as two half-length lanes (0 = never); SFC_ROW_SPLIT overrides
 static int row_split_len(int prec) {
-    static int v = [] {
-        const char* e = getenv("SFC_ROW_SPLIT");
+    const int v = [] {
+        const char* e = knob_env("SFC_ROW_SPLIT");
         return e ? atoi(e) : -1;
     }();
     if (v >= 0) return v;
@@ -464,8 +502,8 @@ static int row_split_len(int prec) {
 // bytes of work area so that pass k+1 reads what pass k wrote out of the 126 MB L2, and `ways`
 // rounds run concurrently on side streams to keep every SM busy.  0 = off.
 static int64_t l2_chunk_bytes() {
-    static int64_t v = [] {
-        const char* e = getenv("SFC_L2_CHUNK_MB");
+    const int64_t v = [] {
+        const char* e = knob_env("SFC_L2_CHUNK_MB");
         // measured on B200 (2^20 x 64 four-step, Bluestein 1,000,003 x 32): no gain from L2-resident
         // rounds (75.6 % either way / 56 % vs 61 %) — the 64 KiB-tile passes are SM-bound, not DRAM-bound
         int64_t mb = e ? atoll(e) : 0;
@@ -474,23 +512,23 @@ static int64_t l2_chunk_bytes() {
     return v;
 }
 static int l2_ways() {
-    static int v = [] {
-        const char* e = getenv("SFC_L2_WAYS");
+    const int v = [] {
+        const char* e = knob_env("SFC_L2_WAYS");
         int w = e ? atoi(e) : 3;
         return std::max(1, std::min(w, 16));
     }();
     return v;
 }
 static int64_t l2_max_batch_bytes() {
-    static int64_t v = [] {
-        const char* e = getenv("SFC_L2_MAXB_MB");
+    const int64_t v = [] {
+        const char* e = knob_env("SFC_L2_MAXB_MB");
         return e ? (atoll(e) << 20) : l2_chunk_bytes();
     }();
     return v;
 }
 static int64_t l2_total_bytes() {
-    static int64_t v = [] {
-        const char* e = getenv("SFC_L2_TOTAL_MB");
+    const int64_t v = [] {
+        const char* e = knob_env("SFC_L2_TOTAL_MB");
         int64_t mb = e ? atoll(e) : 72;
         return mb << 20;
     }();
@@ -501,19 +539,19 @@ static int64_t l2_total_bytes() {
 // 53 -> 73 %; L = 2, 4 (32..64 B rows, already coalesced) lose 3-14 points; L = 32 / 64 (which also exchange through
 // the buffer) 69 -> 69 % / 89 -> 73 %: staged for 8 <= L <= 16 only
 static int stage_io_max_len() {
-    static int v = [] {
-        const char* e = getenv("SFC_STAGE_IO");
+    const int v = [] {
+        const char* e = knob_env("SFC_STAGE_IO");
         return e ? atoi(e) : 16;
     }();
     return v;
 }
 static int pipe_enabled() {  // 0 off, 1 row and column tiles, 2 row tiles only
-    static int v = [] {
+    const int v = [] {
         // measured on B200 (profiles/README.md): the half-size split exchange that makes room for the landing
         // buffer costs more (FFT phase 4.7k -> 6.6k cycles per 4096-point tile) than the hidden load latency
         // gains (c2c 92 % -> 88 %, Bluestein 59 % -> 57 %); per-row bulk copies for column tiles are far too
         // slow (60 cycles each).  Kept selectable for the next round's tensor-map variant.
-        const char* e = getenv("SFC_PIPE");
+        const char* e = knob_env("SFC_PIPE");
         return e ? atoi(e) : 0;
     }();
     return v;
@@ -522,15 +560,15 @@ static int pipe_enabled() {  // 0 off, 1 row and column tiles, 2 row tiles only
 // landing buffer per SM (shared memory has no room for two next to two full-size exchange buffers) only 64 KiB of loads are
 // in flight per SM, less than the two independent CTAs of the plain flavour keep in flight.  Off.
 static bool gpipe_enabled() {
-    static int v = [] {
-        const char* e = getenv("SFC_GPIPE");
+    const int v = [] {
+        const char* e = knob_env("SFC_GPIPE");
         return e ? atoi(e) : 0;
     }();
     return v != 0;
 }
 static int64_t gpipe_min_tiles() {
-    static int64_t v = [] {
-        const char* e = getenv("SFC_GPIPE_MIN_TILES");
+    const int64_t v = [] {
+        const char* e = knob_env("SFC_GPIPE_MIN_TILES");
         return e ? atoll(e) : 8 * 148;  // four tiles for each group of each of the 148 persistent CTAs
     }();
     return v;
@@ -544,43 +582,43 @@ static int64_t gpipe_min_tiles() {
 // 0 off | 1 row tiles <= 64 KiB | 2 + 128 KiB row tiles | 3 + every strided tile | 4 (default) only the narrow strided tiles
 // (<= 64 B segments) and multi-row tiles of multi-pass (four-step) plans.
 static int pipe_late_enabled() {
-    static int v = [] {
-        const char* e = getenv("SFC_PIPE_LATE");
+    const int v = [] {
+        const char* e = knob_env("SFC_PIPE_LATE");
         return e ? atoi(e) : 4;
     }();
     return v;
 }
 static int64_t pipe_late_min_tiles() {
-    static int64_t v = [] {
-        const char* e = getenv("SFC_PIPE_LATE_MIN_TILES");
+    const int64_t v = [] {
+        const char* e = knob_env("SFC_PIPE_LATE_MIN_TILES");
         return e ? atoll(e) : 4 * 148;  // two tiles for each of the 296 resident CTAs, or prefetching never pays
     }();
     return v;
 }
 static bool pipe_big_enabled() {
-    static int v = [] {
-        const char* e = getenv("SFC_PIPE_BIG");
+    const int v = [] {
+        const char* e = knob_env("SFC_PIPE_BIG");
         return e ? atoi(e) : 1;
     }();
     return v != 0;
 }
 static int64_t pipe_min_tiles() {
-    static int64_t v = [] {
-        const char* e = getenv("SFC_PIPE_MIN_TILES");
+    const int64_t v = [] {
+        const char* e = knob_env("SFC_PIPE_MIN_TILES");
         return e ? atoll(e) : 1184;  // 4 tiles for each of the 296 resident CTAs
     }();
     return v;
 }
 static int tile_group_log2() {
-    static int v = [] {
-        const char* e = getenv("SFC_TILE_GROUP_LOG2");
+    const int v = [] {
+        const char* e = knob_env("SFC_TILE_GROUP_LOG2");
         return e ? std::max(0, std::min(atoi(e), 10)) : 3;  // table-driven Bluestein 57 % -> 61 %; neutral with generated chirps
     }();
     return v;
 }
 static int blue_l1_cap() {
-    static int v = [] {
-        const char* e = getenv("SFC_BLUE_L1");
+    const int v = [] {
+        const char* e = knob_env("SFC_BLUE_L1");
         return e ? atoi(e) : 1024;
     }();
     return v;
@@ -591,8 +629,8 @@ static int blue_l1_cap() {
 // 2048..8192-point column tiles of the two-pass form have 16..32 B rows and one CTA per SM); 2^20 / 2^21 are faster
 // in two passes (7.7 / 7.5 vs 6.9 / 7.2).
 static int64_t three_level_min() {
-    static int64_t v = [] {
-        const char* e = getenv("SFC_THREE_LEVEL_MIN");
+    const int64_t v = [] {
+        const char* e = knob_env("SFC_THREE_LEVEL_MIN");
         return e ? atoll(e) : (int64_t)1 << 22;
     }();
     return v;
@@ -602,15 +640,15 @@ static int64_t three_level_min() {
 // and 32 x 3^13: 3.54 -> 4.00 ms — with chirp generation, twiddles and the fused transform pair the small-tile passes
 // are SM-bound too (4.7 TB/s average), so the two extra passes cost more than they save: off.
 static int64_t blue3_min() {
-    static int64_t v = [] {
-        const char* e = getenv("SFC_BLUE3_MIN");
+    const int64_t v = [] {
+        const char* e = knob_env("SFC_BLUE3_MIN");
         return e ? atoll(e) : 0;
     }();
     return v;
 }
 static int row_fourstep_len() {
-    static int v = [] {
-        const char* e = getenv("SFC_ROW_FOURSTEP");
+    const int v = [] {
+        const char* e = knob_env("SFC_ROW_FOURSTEP");
         return e ? atoi(e) : 0;
     }();
     return v;
@@ -618,16 +656,16 @@ static int row_fourstep_len() {
 
 // the three-pass plan for large 2-D transforms was written after the round's GPU budget was spent: off until it has run
 static bool fft2_tile2d_enabled() {
-    static int v = [] {
-        const char* e = getenv("SFC_FFT2_TILE2D");
+    const int v = [] {
+        const char* e = knob_env("SFC_FFT2_TILE2D");
         return e ? atoi(e) : 0;
     }();
     return v != 0;
 }
 
 static int64_t scratch_budget_bytes() {
-    static int64_t v = [] {
-        const char* e = getenv("SFC_WORK_MB");
+    const int64_t v = [] {
+        const char* e = knob_env("SFC_WORK_MB");
         int64_t mb = e ? atoll(e) : 2048;
         if (mb < 1) mb = 1;
         return mb << 20;
@@ -1044,7 +1082,7 @@ struct PlanBuilder {
             scatter_parts <= 1 && O * I <= 0x7FFFFFFFLL) {
             if (k3 <= 7) {
                 Step s;
-                s.k = pick_r3(prec, (int)n, O * I);
+                s.k = pick_r3(prec, (int)n, col);
                 s.src = src.role;
                 s.dst = dst.role;
                 s.src_esize = cs;
@@ -1067,7 +1105,7 @@ struct PlanBuilder {
             if (!table_fourstep(prec, n, &lo, &hi, &sh, err)) return false;
             const int g = new_group(O, n * I * (int64_t)cs);
             Step a;
-            a.k = pick_r3(prec, (int)L1, L2 * I * O);
+            a.k = pick_r3(prec, (int)L1, true);
             a.src = src.role;
             a.dst = R_MS;
             a.src_esize = cs;
@@ -1085,7 +1123,7 @@ struct PlanBuilder {
             a.p.scale = 1.0;
             if (!finish_tile(a, L2 * I, I, O, "four-step pass A (columns + twiddle), power-of-three tile")) return false;
             Step b;
-            b.k = pick_r3(prec, (int)L2, L1 * I * O);
+            b.k = pick_r3(prec, (int)L2, true);  // its transposed store is the strided side
             b.src = R_MS;
             b.dst = dst.role;
             b.src_esize = cs;
@@ -1273,7 +1311,7 @@ struct PlanBuilder {
         // the fused row pass B is fastest on 4096-point rows (one 64 KiB tile, no spills): L2 = 4096 whenever that
         // leaves >= 64-point columns (measured: M = 2^21 61.8 % with 512 x 4096 vs 59.1 % with 1024 x 2048)
         int64_t L1 = std::min<int64_t>((int64_t)1 << (lg / 2), blue_l1_cap());
-        if (!getenv("SFC_BLUE_L1") && prec == PREC_F64 && M / 4096 >= 64 && M / 4096 <= 1024) L1 = M / 4096;
+        if (!knob_env("SFC_BLUE_L1") && prec == PREC_F64 && M / 4096 >= 64 && M / 4096 <= 1024) L1 = M / 4096;
         int64_t L2 = M / L1;
         if (L2 > lmax) {
             L2 = lmax;
@@ -2258,7 +2296,7 @@ int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& 
                 return SFC_ERR_VALUE;
             }
 #ifdef SFC_PHASE_TIMING
-            p.dbg = getenv("SFC_PHASE_DBG") ? dbg_slot(s.desc) : nullptr;
+            p.dbg = knob_env("SFC_PHASE_DBG") ? dbg_slot(s.desc) : nullptr;
 #endif
             if (s.tmap && !encode_tile_map(p, s.k, s.tmap, s.nbatch, es)) return SFC_ERR_BACKEND;
             cudaError_t e = s.k->launch(p, (unsigned)grid, stream);
@@ -2304,7 +2342,7 @@ int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& 
                     return SFC_ERR_VALUE;
                 }
 #ifdef SFC_PHASE_TIMING
-                p.dbg = getenv("SFC_PHASE_DBG") ? dbg_slot(t.desc) : nullptr;
+                p.dbg = knob_env("SFC_PHASE_DBG") ? dbg_slot(t.desc) : nullptr;
 #endif
                 if (t.tmap && !encode_tile_map(p, t.k, t.tmap, nb * t.batch_mult, es)) return SFC_ERR_BACKEND;
                 cudaError_t e = t.k->launch(p, (unsigned)grid, st);

@@ -123,4 +123,8 @@ const void* table_bluestein_b(int prec, int64_t N, int64_t M, int64_t L1, int64_
 
 void set_error(int code, const std::string& msg);
 
+// planner options (the SFC_* knobs of DESIGN.md section 11): a run-time override takes precedence over the environment
+void planner_set_option(const char* name, const char* value);  // value == nullptr: back to the environment / default
+std::string planner_get_option(const char* name);
+
 }  // namespace sfc

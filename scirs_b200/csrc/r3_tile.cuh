@@ -70,8 +70,13 @@ struct R3Cfg {
     static constexpr int L = L_, TL = TL_, E = 9;
     static constexpr int TPL = L / 9;
     static constexpr int NT = TPL * TL;
-    static constexpr int LP = L + 1;  // L is odd: an even pitch keeps consecutive lanes on different 16-byte bank groups
+    // lane pitch in 16-byte slots: L = 3^k is 1 or 3 mod 8, so with the pitch L itself the lane-fastest (column) mapping puts
+    // eight consecutive lanes on eight different bank groups (r2: L + 1 measured 45 % conflicting wavefronts)
+    static constexpr int LP = L;
     static constexpr size_t SMEM = (size_t)TL * LP * sizeof(Cx<T>);
+    // resident CTAs the register allocator leaves room for: three 243-thread tiles (35 KiB) or two 486-thread tiles (70 KiB)
+    // per SM — the first cut ran ONE 729-thread CTA per SM (70 registers) at 44 % of its roofline
+    static constexpr int MINB = NT <= 256 ? 3 : (NT <= 512 ? 2 : 1);
     static_assert(L % 9 == 0 && NT <= 1024, "L must be a multiple of 9 and the tile at most 1024 threads");
 };
 
@@ -127,7 +132,7 @@ __device__ __forceinline__ void r3_stages(Cx<T> (&a)[9], Cx<T>* __restrict__ sm,
 }
 
 template <typename T, int L, int TL>
-__global__ void __launch_bounds__(R3Cfg<T, L, TL>::NT) r3_tile_kernel(const __grid_constant__ PassParams p) {
+__global__ void __launch_bounds__(R3Cfg<T, L, TL>::NT, R3Cfg<T, L, TL>::MINB) r3_tile_kernel(const __grid_constant__ PassParams p) {
     using C = R3Cfg<T, L, TL>;
     using cx = Cx<T>;
     constexpr int E = 9, TPL = C::TPL;

@@ -62,6 +62,16 @@ int main() {
         for (int k = 0; k < 32; ++k) REQUIRE(std::abs(psd[k] - (k == 4 ? 0.25 : 0.0)) < 1e-12);
         try { welch_psd(tone, 1.0, box, 0, 64, "bogus"); return 1; } catch (const FFTError& e) { REQUIRE(e.kind == FFTError::Value); }
     }
+    {  // distributed.rs mirror on however many GPUs are visible (one: the degenerate slab plan)
+        auto comm = Communicator::local(1);
+        REQUIRE(comm.size() == 1 && comm.rank() == 0);
+        DistributedFFT dplan(comm, {8, 16, 4});
+        std::vector<Complex64> vin(8 * 16 * 4, Complex64(0.0, 0.0)), vout(vin.size());
+        vin[0] = 1.0;  // impulse -> all ones
+        dplan.execute(vin.data(), vout.data());
+        for (auto& c : vout) REQUIRE(std::abs(c - Complex64(1.0, 0.0)) < 1e-12);
+        REQUIRE(dplan.info.world == 1 && dplan.info.num_exchanges == 0);
+    }
     std::puts("cpp mirror ok");
     return 0;
 }

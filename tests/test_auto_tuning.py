@@ -57,3 +57,52 @@ def test_benchmarks_and_optimal_fft_on_gpu(tmp_path, build_artifacts):
     x = np.random.default_rng(1).standard_normal(100) + 0j
     assert np.allclose(t.run_optimal_fft(x, 128, True), np.fft.fft(x, 128), atol=1e-10)
     assert np.allclose(t.run_optimal_fft(x, None, False), np.fft.ifft(x) * 100, atol=1e-10)  # unnormalised inverse
+
+
+def test_gpu_plan_tuner_candidates_and_database(tmp_path):
+    """The GPU planner tuner (round 2): candidate option sets per geometry and the JSON database — no GPU needed."""
+    from scirs_b200.auto_tuning import GpuPlanTuner
+
+    c = GpuPlanTuner.candidates([64, 1 << 20], [1])
+    assert c[0] == {} and {"SFC_THREE_LEVEL_MIN": str(1 << 20)} in c and {"SFC_PIPE_LATE": "3"} in c
+    assert {"SFC_BLUE_L1": "512"} in GpuPlanTuner.candidates([32, 1000003], [1])
+    assert GpuPlanTuner.candidates([512, 512, 512], [0])[1:] == [{"SFC_PIPE_LATE": "3"}, {"SFC_COL_SMEM_KB": "40"}]
+    db = str(tmp_path / "gpu_db.json")
+    t = GpuPlanTuner(db)
+    key = t.key([64, 1 << 20], [1], "c2c", "f64", True)
+    t.entries[key] = {"options": {"SFC_PIPE_LATE": "3"}, "ms": 0.8, "default_ms": 0.9, "candidates": []}
+    t.save()
+    t2 = GpuPlanTuner(db)
+    assert t2.options_for([64, 1 << 20], [1]) == {"SFC_PIPE_LATE": "3"} and t2.options_for([8, 8], [1]) == {}
+
+
+def test_planner_options_round_trip():
+    import ctypes as C
+
+    from scirs_b200 import _lib
+
+    lib = _lib.load()
+    buf = C.create_string_buffer(64)
+    assert lib.sfc_planner_get_option(b"SFC_TEST_OPTION_X", buf, 64) == 0
+    assert lib.sfc_planner_set_option(b"SFC_TEST_OPTION_X", b"17") == 0
+    assert lib.sfc_planner_get_option(b"SFC_TEST_OPTION_X", buf, 64) == 2 and buf.value == b"17"
+    assert lib.sfc_planner_set_option(b"SFC_TEST_OPTION_X", None) == 0
+    assert lib.sfc_planner_get_option(b"SFC_TEST_OPTION_X", buf, 64) == 0
+    assert lib.sfc_planner_set_option(b"PATH", b"1") == _lib.SFC_ERR_VALUE
+
+
+@pytest.mark.gpu
+def test_gpu_plan_tuner_on_device(tmp_path):
+    import numpy as np
+
+    from scirs_b200.auto_tuning import GpuPlanTuner
+
+    t = GpuPlanTuner(str(tmp_path / "db.json"), repetitions=5, warmup=2)
+    e = t.tune([8, 1 << 17], [1])
+    assert e["ms"] <= e["default_ms"] + 1e-9 and len(e["candidates"]) >= 4
+    t.save()
+    p = GpuPlanTuner(str(tmp_path / "db.json")).plan([8, 1 << 17], [1])
+    x = np.random.default_rng(0).standard_normal((8, 1 << 17)) + 0j
+    got = p.execute(x).reshape(8, -1)
+    ref = np.fft.fft(x, axis=1)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-12

@@ -52,6 +52,8 @@ for rep in sys.argv[2:]:
     name = os.path.basename(rep).replace('.ncu-rep', '')
     rows, units = raw(rep)
     st = stalls(rep)
+    if rows and len(st) > len(rows) and len(st) % len(rows) == 0:  # the source page lists every kernel once per view (SASS, PTX, ...)
+        st = st[::len(st) // len(rows)]
     for i, d in enumerate(rows):
         k = d['Kernel Name']
         m = {key: d.get(key) for key in KEYS if key in d}
