@@ -283,7 +283,7 @@ __device__ __forceinline__ void apply_twiddle_powers(Cx<T> (&v)[R], Cx<T> w1) {
 
 // v[k] *= W_L^(base*k) read straight from the stage table, for stages whose stride S is >= 16: all threads of a
 // half warp then share `base`, every load touches one or two addresses (L1 broadcast), and the 53-instruction FP64
-// product tree above is saved.  Measured (tools/exp31.sh, 65536 x 4096): 1.5% SLOWER for f64 c2c (91.5% against 93.0%
+// product tree above is saved.  Measured (tools/r1_experiments/exp31.sh, 65536 x 4096): 1.5% SLOWER for f64 c2c (91.5% against 93.0%
 // of the HBM peak) and 3% slower for f64 rfft -- the 15 extra L1 loads per butterfly cost more issue slots next to the
 // tile's own global loads than the FP64 tree does.  Off; -DSFC_TW_LOAD=1 builds it.
 #ifndef SFC_TW_LOAD

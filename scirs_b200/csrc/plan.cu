@@ -814,7 +814,7 @@ struct PlanBuilder {
             // memory (16-byte aligned bulk copies), and enough tiles for every resident CTA to pipeline a few
             // 128 KiB row tiles (one CTA per SM: nothing else overlaps its loads) always take it when they can
             const bool big_row = s.k->L * s.k->TL * (int)cs > 65536 && s.p.map_in == MAP_ROW && pipe_big_enabled();
-            if (mode == 1 && s.k->mode == 1 && (pipe_enabled() || (big_row && pipe_late_enabled() < 2)) && (s.p.flags & F_IN_NOMASK) &&
+            if (mode == 1 && s.k->mode == 1 && (pipe_enabled() || (big_row && plv != 2 && plv != 3)) && (s.p.flags & F_IN_NOMASK) &&
                 (s.p.ld_op == LD_C || s.p.ld_op == LD_C_MUL) && prec == PREC_F64) {
                 const bool rows_ok = s.p.map_in == MAP_ROW && s.p.in.elem_stride == 1;
                 const bool cols_ok = pipe_enabled() == 1 && s.p.map_in == MAP_COL &&
