@@ -35,7 +35,10 @@ class PassParams(C.Structure):  # pass_params.h, field for field
                 ("ld_tw_lo", C.c_void_p), ("ld_tw_hi", C.c_void_p), ("ld_tw_shift", C.c_int32), ("rtw", C.c_void_p),
                 ("chirp_lo", C.c_void_p), ("chirp_hi", C.c_void_p), ("chirp_shift", C.c_int32), ("chirp_mod", C.c_uint64),
                 ("chirp_q_in", C.c_double * 2), ("chirp_q_out", C.c_double * 2), ("scale", C.c_double),
-                ("scale_dc", C.c_double), ("peer_shift", C.c_int32), ("peer_out", C.c_void_p * 16)]
+                ("scale_dc", C.c_double), ("peer_shift", C.c_int32), ("peer_out", C.c_void_p * 16),
+                # alignas(64) CUtensorMap of the tensor-map tiles (never used by the host emulation), then the struct's tail padding
+                ("_pad_tmap", C.c_uint8 * 8), ("tmap_in", C.c_uint8 * 128), ("tmap_box_rows", C.c_int32),
+                ("tmap_split", C.c_int32), ("_pad_tail", C.c_uint8 * 56)]
 
 
 @pytest.fixture(scope="module")
