@@ -70,10 +70,25 @@ struct R3Cfg {
     static constexpr int L = L_, TL = TL_, E = 9;
     static constexpr int TPL = L / 9;
     static constexpr int NT = TPL * TL;
-    // lane pitch in 16-byte slots: L = 3^k is 1 or 3 mod 8, so with the pitch L itself the lane-fastest (column) mapping puts
-    // eight consecutive lanes on eight different bank groups (r2: L + 1 measured 45 % conflicting wavefronts)
-    static constexpr int LP = L;
-    static constexpr size_t SMEM = (size_t)TL * LP * sizeof(Cx<T>);
+    // Exchange layout in slots of one complex element.  A warp-wide 128-bit access is served in groups of eight threads and
+    // costs one wavefront per group only when the eight slots differ modulo 8 (ncu source page of the round-2 tiles: every
+    // LDS/STS of a strided tile at exactly twice its ideal wavefronts with the plain pitch L).  Every access of the stages
+    // is "lane base + i + constant" modulo 8 (9^k = 1 mod 8), so the lane bases decide:
+    //   * lane-fastest (column) mapping, tid = TL*i + t: base(t) = r(t) mod 8 with r(t) = (TL mod 8) * t for odd TL
+    //     (residue = TL * tid, a bijection on eight consecutive tids) and r(t) = (TL/2 mod 8) * (t >> 1) + 4 * (t & 1) for
+    //     even TL (found by exhaustive search over the tiles in use, tools/bank_sim_r3.py);
+    //   * butterfly-fastest (row) mapping: base(t) = t * L mod 8, the residues simply continue across a lane boundary.
+    // f32 tiles (64-bit accesses, sixteen threads per wavefront) keep the plain pitch.
+    static constexpr bool PADDED = sizeof(T) == 8;
+    static constexpr int LP = PADDED ? (L + 7) / 8 * 8 : L;
+    static __device__ __forceinline__ int lane_base(int t, bool col) {
+        if constexpr (!PADDED) return t * LP;
+        else {
+            const int r = col ? ((TL & 1) ? (TL & 7) * t : ((TL / 2) & 7) * (t >> 1) + 4 * (t & 1)) : t * L;
+            return t * LP + (r & 7);
+        }
+    }
+    static constexpr size_t SMEM = ((size_t)TL * LP + (PADDED ? 8 : 0)) * sizeof(Cx<T>);
     // resident CTAs the register allocator leaves room for: three 243-thread tiles (35 KiB) or two 486-thread tiles (70 KiB)
     // per SM — the first cut ran ONE 729-thread CTA per SM (70 registers) at 44 % of its roofline
     static constexpr int MINB = NT <= 256 ? 3 : (NT <= 512 ? 2 : 1);
@@ -81,8 +96,8 @@ struct R3Cfg {
 };
 
 template <typename T, typename C, int S>
-__device__ __forceinline__ void r3_stages(Cx<T> (&a)[9], Cx<T>* __restrict__ sm, const Cx<T>* __restrict__ tw, int tw_, int iw,
-                                          int tr, int ir) {
+__device__ __forceinline__ void r3_stages(Cx<T> (&a)[9], Cx<T>* __restrict__ sm, const Cx<T>* __restrict__ tw, int bw, int iw,
+                                          int br, int ir) {  // bw / br: lane base (slots) of the writing / reading mapping
     constexpr int L = C::L, TPL = C::TPL;
     constexpr int R = (L / S >= 9) ? 9 : (L / S);  // 9, or a trailing 3
     static_assert(R == 9 || R == 3, "L must be a power of three");
@@ -117,17 +132,17 @@ __device__ __forceinline__ void r3_stages(Cx<T> (&a)[9], Cx<T>* __restrict__ sm,
                 v[7] = cmul(v[7], cmul(w4, w3));
                 v[8] = cmul(v[8], csqr(w4));
             }
-            Cx<T>* dst = sm + tw_ * C::LP + q + R * base;
+            Cx<T>* dst = sm + bw + q + R * base;
 #pragma unroll
             for (int k = 0; k < R; ++k) dst[k * S] = v[k];
         }
     }
     if constexpr (!LAST) {
         __syncthreads();
-        const Cx<T>* src = sm + tr * C::LP + ir;
+        const Cx<T>* src = sm + br + ir;
 #pragma unroll
         for (int m = 0; m < 9; ++m) a[m] = src[m * TPL];
-        r3_stages<T, C, S * R>(a, sm, tw, tr, ir, tr, ir);
+        r3_stages<T, C, S * R>(a, sm, tw, br, ir, br, ir);
     }
 }
 
@@ -161,15 +176,19 @@ __global__ void __launch_bounds__(R3Cfg<T, L, TL>::NT, R3Cfg<T, L, TL>::MINB) r3
             for (int m = 0; m < E; ++m) a[m].y = -a[m].y;
         }
     }
-    r3_stages<T, C, 1>(a, sm, reinterpret_cast<const cx*>(p.tw), t0, i0, t1, i1);
+    // column-friendly lane bases when both mappings are lane-fastest, or one of them is and the lanes are long enough that
+    // the butterfly-fastest accesses rarely straddle two lanes (tools/bank_sim_r3.py prints every case)
+    const bool col = (p.map_in == MAP_COL && p.map_out == MAP_COL) || ((p.map_in == MAP_COL || p.map_out == MAP_COL) && L >= 243);
+    const int b0 = C::lane_base(t0, col), b1 = C::lane_base(t1, col);
+    r3_stages<T, C, 1>(a, sm, reinterpret_cast<const cx*>(p.tw), b0, i0, b1, i1);
     if constexpr (C::L == 9) {
         if (p.map_in != p.map_out) {  // single-stage tiles never pass through shared memory: remap explicitly
             __syncthreads();
 #pragma unroll
-            for (int m = 0; m < E; ++m) sm[t0 * C::LP + m] = a[m];
+            for (int m = 0; m < E; ++m) sm[b0 + m] = a[m];
             __syncthreads();
 #pragma unroll
-            for (int m = 0; m < E; ++m) a[m] = sm[t1 * C::LP + m];
+            for (int m = 0; m < E; ++m) a[m] = sm[b1 + m];
         }
     }
     const uint32_t lane = tile * TL + (uint32_t)t1;
