@@ -539,7 +539,8 @@ def run_gpu(args):
                 compact[k] = {"error": v["error"][:80]}
             elif "nvlink_frac_of_900" in v:
                 compact[k] = {"ms": v["ms_per_step"], "parity_rel_l2": v["parity_rel_l2"], "nvlink_frac": v["nvlink_frac_of_900"],
-                              "exchange_ms": v["exchange_ms"], "stage_ms": v["stage_ms"], "gflops": v["gflops"]}
+                              "exchange_ms": v["exchange_ms"], "stage_ms": v["stage_ms"], "gflops": v["gflops"],
+                              "pipelined": v.get("pipelined")}
             elif "device_us" in v:
                 compact[k] = {kk: v[kk] for kk in ("device_us", "device_graph_us", "host_call_us", "floor_us", "frac")}
             else:

@@ -224,7 +224,10 @@ typedef struct sfc_dist_desc {
     sfc_desc base;
     int32_t decomposition; /* sfc_decomposition */
     int32_t layout;        /* sfc_slab_layout (SLAB only) */
-    int32_t chunks;        /* SLAB: pieces the exchange is pipelined in (0 = library default) */
+    int32_t chunks;        /* SLAB: column blocks of the last axis the exchange is pipelined in: the axis-0 pass of block j
+                            * runs while block j+1 is scattered over NVLink (0 = library default: 1 = off, or SFC_SLAB_CHUNKS
+                            * — measured on 2 x B200 the overlap returns nothing; lowered to what the
+                            * tiles of both passes allow, see sfc_dist_info.chunks) */
     int32_t reserved;
 } sfc_dist_desc;
 
@@ -247,7 +250,9 @@ int sfc_dist_plan_destroy(sfc_dist_plan* plan);                                 
 int sfc_dist_plan_get_info(const sfc_dist_plan* plan, sfc_dist_info* info);
 /* Stage timing of the SLAB pipeline on this process' first GPU (CUDA events between the stages of every later
  * execution): sfc_dist_plan_stage_ms returns the number of stages written, in order — FFT axis 2 | FFT axis 1 +
- * scatter | signal + wait | FFT axis 0 (+ scatter) | [natural: signal + wait 2 and copy-out]. */
+ * scatter | signal + wait | FFT axis 0 (+ scatter) | [natural: signal + wait 2 and copy-out].  A pipelined plan
+ * (sfc_dist_info.chunks > 1) reports three: FFT axis 2 | the scatter passes of all column blocks (the axis-0 passes
+ * overlap them on a side stream) | what is left of the axis-0 passes after the last scatter. */
 int sfc_dist_plan_profile(sfc_dist_plan* plan, int32_t enable);
 int sfc_dist_plan_stage_ms(sfc_dist_plan* plan, double* ms, int32_t cap);
 /* rank mode: this rank's slab / batch share, device pointers, caller's stream.  The call only enqueues work. */

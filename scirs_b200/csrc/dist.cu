@@ -84,6 +84,11 @@ __global__ void dist_wait_kernel(const unsigned long long* flags, int world, uns
     }
 }
 
+bool slab_side_priority() {
+    const char* e = getenv("SFC_SLAB_SIDE_PRIORITY");
+    return e ? atoi(e) != 0 : true;
+}
+
 double env_ms(const char* name, double dflt) {
     const char* e = getenv(name);
     return e ? atof(e) : dflt;
@@ -493,12 +498,17 @@ SFC_EXPORT int sfc_comm_free(sfc_comm* c, void* d_ptr) {
 
 namespace {
 
+constexpr int MAX_CHUNKS = 8;
+
 struct DistRank {
     std::shared_ptr<Plan> a, b, c;  // slab: axis 2 | axis 1 + scatter | axis 0 (+ scatter for the natural layout)
     std::shared_ptr<Plan> whole;    // slab on a single GPU
     sfc_plan* handle = nullptr;     // batch split / replicated: an ordinary plan handle on this GPU (pipelined host path)
     void* work = nullptr;           // [s0][n1][n2] between passes A and B
     std::vector<cudaEvent_t> ev;
+    // pipelined exchange: the axis-0 pass of column block j runs on `side` while the scatter of block j+1 runs on the caller's stream
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // host executions
     void *h_in_dev = nullptr, *h_out_dev = nullptr;
 };
@@ -514,7 +524,8 @@ struct sfc_dist_plan {
     size_t cs = 16;
     size_t block_bytes = 0, recv_bytes = 0;
     SymAlloc* recv = nullptr;   // 2 x [P][s0][s1][n2]: exchange-1 window, double buffered
-    SymAlloc* flags = nullptr;  // [2 exchanges][SFC_MAX_GPUS] epochs
+    SymAlloc* flags = nullptr;  // [2 exchanges][MAX_CHUNKS][SFC_MAX_GPUS] epochs
+    int chunks = 1;             // column blocks of n2 the first exchange is pipelined in (1 = one scatter, one wait)
     SymAlloc* win2 = nullptr;   // natural layout, outputs that are not symmetric allocations: [s0][n1][n2]
     uint64_t epoch = 0;
     double timeout_ns = 20e9;
@@ -604,6 +615,42 @@ int build_slab(sfc_dist_plan* p) {
     }
     rc = comm_all_ok(c, rc);
     if (rc != SFC_OK || P == 1) return rc;
+    // Pipelined exchange: passes B and C run window by window over `chunks` column blocks of n2 (Plan::exec with an
+    // ExecWindow), so the axis-0 pass of block j overlaps the NVLink scatter of block j+1.  The block count must suit the
+    // tiles of both passes on every rank: everybody proposes, the minimum wins.
+    // Measured on 2 x B200 (profiles/r2n_slab_pipelined.log): parity identical, but the time is conserved — 512^3: 1.481 ms
+    // with one block, 1.507 / 1.537 / 1.596 ms with 2 / 4 / 8; 1024^3: 13.05 / 13.05 / 13.11 / 13.18 ms — whatever the
+    // side stream's priority.  The scatter kernel is bound by the remote stores its SMs can keep in flight, so every SM slot
+    // the axis-0 pass takes slows it down by as much as the overlap hides.  Off by default (1 block); asking for more
+    // (sfc_dist_desc.chunks, SFC_SLAB_CHUNKS) stays available and tested.
+    {
+        const char* e = getenv("SFC_SLAB_CHUNKS");
+        int want = p->desc.chunks > 0 ? p->desc.chunks : (e ? atoi(e) : 1);
+        want = std::max(1, std::min(want, MAX_CHUNKS));
+        int k = 1;
+        while (k * 2 <= want) k *= 2;
+        for (size_t lr = 0; lr < c->ranks.size(); ++lr)
+            while (k > 1 && !(p->r[lr].b->window_ok(p->n2, k) && p->r[lr].c->window_ok(p->n2, k))) k /= 2;
+        int all[SFC_MAX_GPUS] = {};
+        rc = comm_allgather(c, &k, all, sizeof(int));
+        if (rc != SFC_OK) return rc;
+        for (int q = 0; q < P; ++q) k = std::min(k, std::max(all[q], 1));
+        p->chunks = k;
+        if (k > 1) {
+            for (size_t lr = 0; lr < c->ranks.size(); ++lr) {
+                DeviceGuard g(c->ranks[lr].device);
+                DistRank& dr = p->r[lr];
+                // highest priority: a block of the axis-0 pass that has become ready takes the SM slots the (link-bound)
+                // scatter CTAs of the next block free up, instead of queueing behind all of them
+                int prio_lo = 0, prio_hi = 0;
+                cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+                cudaError_t ce = cudaStreamCreateWithPriority(&dr.side, cudaStreamNonBlocking, slab_side_priority() ? prio_hi : prio_lo);
+                if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&dr.ev_fork, cudaEventDisableTiming);
+                if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&dr.ev_join, cudaEventDisableTiming);
+                if (ce != cudaSuccess) return cuda_fail(ce, "side stream of the pipelined exchange");
+            }
+        }
+    }
     rc = sym_alloc(c, 2 * p->recv_bytes, &p->recv);
     if (rc != SFC_OK) return rc;
     rc = sym_alloc(c, 4096, &p->flags);
@@ -667,7 +714,7 @@ void fill_info(sfc_dist_plan* p) {
     f.rank = c->ranks[0].rank;
     f.decomposition = p->desc.decomposition;
     f.layout = p->desc.layout;
-    f.chunks = 1;
+    f.chunks = p->desc.decomposition == SFC_DECOMP_SLAB ? p->chunks : 1;
     if (p->desc.decomposition == SFC_DECOMP_SLAB) {
         const bool natural = p->desc.layout == SFC_SLAB_NATURAL || P == 1;
         f.local_in_shape[0] = p->s0; f.local_in_shape[1] = p->n1; f.local_in_shape[2] = p->n2;
@@ -676,7 +723,8 @@ void fill_info(sfc_dist_plan* p) {
         f.local_in_elems = f.local_out_elems = p->s0 * p->n1 * p->n2;
         f.num_exchanges = P == 1 ? 0 : (natural ? 2 : 1);
         f.exchange_bytes_sent = P == 1 ? 0 : (int64_t)(p->block_bytes * (size_t)(P - 1));
-        f.num_launches = P == 1 ? p->r[0].whole->info.num_launches : 3 + 2 * f.num_exchanges + ((natural && P > 1) ? 1 : 0);
+        // A | chunks x (B window, signal, wait, C window) | natural: signal, wait, copy-out
+        f.num_launches = P == 1 ? p->r[0].whole->info.num_launches : 1 + 4 * p->chunks + ((natural && P > 1) ? 3 : 0);
         f.algorithmic_bytes = 3 * 2 * f.local_in_elems * (int64_t)p->cs;
         const double tot = (double)p->n0 * (double)p->n1 * (double)p->n2;
         f.nominal_flops = 5.0 * tot * (log2((double)p->n0) + log2((double)p->n1) + log2((double)p->n2));
@@ -740,36 +788,51 @@ int enqueue_slab(sfc_dist_plan* p, int lr, const void* d_in, void* d_out, cudaSt
     mark();
     // pass B: axis 1, block q of the output stored straight into rank q's window (slot `me`)
     void* targets[SFC_MAX_GPUS];
+    void* ctargets[SFC_MAX_GPUS];
     for (int q = 0; q < P; ++q) targets[q] = (char*)p->recv->peer[lr][q] + buf + (size_t)me * p->block_bytes;
-    rc = dr.b->exec(dr.work, targets[0], st, es, targets, P);
-    if (rc) return fail(rc, es);
-    mark();
-    FlagPtrs fp;
-    for (int q = 0; q < P; ++q) fp.p[q] = (unsigned long long*)p->flags->peer[lr][q] + me;
-    dist_signal_kernel<<<1, 32, 0, st>>>(fp, P, epoch);
-    dist_wait_kernel<<<1, 32, 0, st>>>(myflags, P, epoch, (unsigned long long)p->timeout_ns, rk.status_d);
-    mark();
-    // pass C: axis 0 over the window [n0][s1][n2] (source rank order == global axis-0 order)
     const char* win = (const char*)p->recv->base[lr] + buf;
-    if (p->desc.layout != SFC_SLAB_NATURAL) {
-        rc = dr.c->exec(win, d_out, st, es);
+    const bool natural = p->desc.layout == SFC_SLAB_NATURAL;
+    // second exchange fused into the axis-0 store: rows [q*s0, (q+1)*s0) go to rank q at column offset me*s1
+    if (natural)
+        for (int q = 0; q < P; ++q) ctargets[q] = (char*)out_peers[q] + (size_t)(me * p->s1 * p->n2) * p->cs;
+    FlagPtrs fp;
+    const int K = p->chunks;
+    // pass C (axis 0) consumes the window [n0][s1][n2] (source rank order == global axis-0 order); with K > 1 it runs on
+    // the side stream, block j as soon as every source has signalled block j, while this stream scatters block j+1
+    cudaStream_t cst = K > 1 ? dr.side : st;
+    if (K > 1) {
+        cudaEventRecord(dr.ev_fork, st);  // the side stream writes d_out: after everything enqueued on `st` so far
+        cudaStreamWaitEvent(dr.side, dr.ev_fork, 0);
+    }
+    for (int j = 0; j < K; ++j) {
+        const ExecWindow w{p->n2, j, K};
+        rc = dr.b->exec(dr.work, targets[0], st, es, targets, P, K > 1 ? &w : nullptr);
         if (rc) return fail(rc, es);
-        mark();
-    } else {
-        // second exchange fused into the axis-0 store: rows [q*s0, (q+1)*s0) go to rank q at column offset me*s1
-        for (int q = 0; q < P; ++q) targets[q] = (char*)out_peers[q] + (size_t)(me * p->s1 * p->n2) * p->cs;
-        rc = dr.c->exec(win, targets[0], st, es, targets, P);
-        if (rc) return fail(rc, es);
-        mark();
-        for (int q = 0; q < P; ++q) fp.p[q] = (unsigned long long*)p->flags->peer[lr][q] + SFC_MAX_GPUS + me;
+        if (K == 1) mark();
+        for (int q = 0; q < P; ++q) fp.p[q] = (unsigned long long*)p->flags->peer[lr][q] + j * SFC_MAX_GPUS + me;
         dist_signal_kernel<<<1, 32, 0, st>>>(fp, P, epoch);
-        dist_wait_kernel<<<1, 32, 0, st>>>(myflags + SFC_MAX_GPUS, P, epoch, (unsigned long long)p->timeout_ns, rk.status_d);
+        dist_wait_kernel<<<1, 32, 0, cst>>>(myflags + j * SFC_MAX_GPUS, P, epoch, (unsigned long long)p->timeout_ns, rk.status_d);
+        if (K == 1) mark();
+        if (!natural) rc = dr.c->exec(win, d_out, cst, es, nullptr, 0, K > 1 ? &w : nullptr);
+        else rc = dr.c->exec(win, ctargets[0], cst, es, ctargets, P, K > 1 ? &w : nullptr);
+        if (rc) return fail(rc, es);
+    }
+    if (K > 1) mark();  // end of the scatter passes on the caller's stream
+    if (natural) {
+        for (int q = 0; q < P; ++q) fp.p[q] = (unsigned long long*)p->flags->peer[lr][q] + MAX_CHUNKS * SFC_MAX_GPUS + me;
+        if (K == 1) mark();
+        dist_signal_kernel<<<1, 32, 0, cst>>>(fp, P, epoch);
+        dist_wait_kernel<<<1, 32, 0, cst>>>(myflags + MAX_CHUNKS * SFC_MAX_GPUS, P, epoch, (unsigned long long)p->timeout_ns, rk.status_d);
         if (out_peers[me] != d_out) {
-            cudaError_t e = cudaMemcpyAsync(d_out, out_peers[me], (size_t)(p->s0 * p->n1 * p->n2) * p->cs, cudaMemcpyDeviceToDevice, st);
+            cudaError_t e = cudaMemcpyAsync(d_out, out_peers[me], (size_t)(p->s0 * p->n1 * p->n2) * p->cs, cudaMemcpyDeviceToDevice, cst);
             if (e != cudaSuccess) return cuda_fail(e, "copy out of the exchange window");
         }
-        mark();
     }
+    if (K > 1) {
+        cudaEventRecord(dr.ev_join, dr.side);
+        cudaStreamWaitEvent(st, dr.ev_join, 0);
+    }
+    mark();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "slab exchange kernels");
     return SFC_OK;
@@ -819,6 +882,9 @@ SFC_EXPORT int sfc_dist_plan_destroy(sfc_dist_plan* p) {
         if (dr.h_in_dev) cudaFree(dr.h_in_dev);
         if (dr.h_out_dev) cudaFree(dr.h_out_dev);
         for (cudaEvent_t e : dr.ev) cudaEventDestroy(e);
+        if (dr.ev_fork) cudaEventDestroy(dr.ev_fork);
+        if (dr.ev_join) cudaEventDestroy(dr.ev_join);
+        if (dr.side) cudaStreamDestroy(dr.side);
     }
     if (p->win2) sym_free(c, p->win2);
     if (p->flags) sym_free(c, p->flags);

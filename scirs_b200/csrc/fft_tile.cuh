@@ -732,6 +732,10 @@ __device__ __forceinline__ void decode_block(const PassParams& p, uint32_t blk, 
         const uint32_t th = blk / per, r = blk - th * per;
         batch = r >> p.tile_group_shift;
         tile = (th << p.tile_group_shift) + (r & ((1u << p.tile_group_shift) - 1u));
+    } else if (p.win_len) {
+        const uint32_t row = blk / p.win_len;
+        tile = row * p.win_row_tiles + p.win_first + (blk - row * p.win_len);
+        batch = 0;
     } else {
         tile = blk % p.tiles_per_batch;
         batch = blk / p.tiles_per_batch;

@@ -115,6 +115,11 @@ struct PassParams {
     int32_t tmap_box_rows;   // elements of the transform axis per box (min(L, 256)); L / tmap_box_rows copies per tile
     int32_t tmap_split;      // 0: lanes are contiguous over the whole batch (coordinate 0 = first lane of the tile);
                              // 1: coordinate 0 = lane inside its outer group, coordinate 2 = the outer index
+    // Tile window (single-launch plans, set per execution by Plan::exec): the lanes form rows of win_row_tiles tiles and
+    // this launch only takes tiles [win_first, win_first + win_len) of every row — CTA blk works on tile
+    // (blk / win_len) * win_row_tiles + win_first + blk % win_len.  win_len == 0 = off.  Lets the pipelined slab exchange
+    // run the strided passes chunk by chunk over column blocks of the SAME dense arrays (dist.cu).
+    uint32_t win_row_tiles, win_first, win_len;
 #ifdef SFC_PHASE_TIMING
     unsigned long long* dbg;   // developer build only: per-launch phase clock sums (thread 0 of every CTA)
 #endif

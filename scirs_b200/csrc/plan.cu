@@ -2219,8 +2219,22 @@ static bool encode_tile_map(PassParams& p, const KernelEntry* k, int mode, int64
 #endif
 }
 
-int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& es, void* const* scatter, int nscatter) {
+bool Plan::window_ok(int64_t row_lanes, int nwin) const {
+    if (steps_.size() != 1 || nwin < 1 || row_lanes < 1) return false;
+    const Step& s = steps_[0];
+    if (s.kind != K_TILE || s.group >= 0 || s.nbatch != 1 || s.tmap || !s.k || s.p.nbatch_fast) return false;
+    if (row_lanes % s.k->TL) return false;
+    const int64_t row_tiles = row_lanes / s.k->TL;
+    return (int64_t)s.p.nlanes % row_lanes == 0 && row_tiles % nwin == 0 && (int64_t)s.p.tiles_per_batch * s.k->TL == (int64_t)s.p.nlanes;
+}
+
+int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& es, void* const* scatter, int nscatter,
+               const ExecWindow* win) {
     std::lock_guard<std::mutex> lk(mu_);
+    if (win && (!window_ok(win->row_lanes, win->count) || win->index < 0 || win->index >= win->count)) {
+        es = "this plan cannot be executed over a window of its lanes";
+        return SFC_ERR_VALUE;
+    }
     bool uses_scratch = sa_bytes_ || ms_bytes_;
     if (uses_scratch) {
         // stream capture (CUDA graphs): no allocation and no cross-stream event inside a capture — the plan must have run
@@ -2290,7 +2304,13 @@ int Plan::exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& 
                 }
                 for (int q = 0; q < nscatter; ++q) p.peer_out[q] = scatter[q];
             }
-            const uint64_t grid = (uint64_t)p.tiles_per_batch * (uint64_t)s.nbatch;
+            uint64_t grid = (uint64_t)p.tiles_per_batch * (uint64_t)s.nbatch;
+            if (win) {
+                p.win_row_tiles = (uint32_t)(win->row_lanes / s.k->TL);
+                p.win_len = p.win_row_tiles / (uint32_t)win->count;
+                p.win_first = p.win_len * (uint32_t)win->index;
+                grid /= (uint64_t)win->count;
+            }
             if (grid == 0 || grid > 0x7FFFFFFFULL) {
                 es = "grid too large";
                 return SFC_ERR_VALUE;

@@ -49,6 +49,12 @@ struct Group {
     size_t slice_bytes = 0;  // work-area bytes per round
 };
 
+// Execute only column block `index` of `count` of every row of `row_lanes` adjacent lanes (PassParams::win_*).
+struct ExecWindow {
+    int64_t row_lanes;
+    int index, count;
+};
+
 struct PlanError {
     int code;
     std::string msg;
@@ -63,7 +69,10 @@ class Plan {
     // enqueued under the plan's mutex, and an execution on another stream than the previous one first waits (on the
     // device, through an event) for the previous one, because both use the plan's scratch areas.
     int exec(const void* d_in, void* d_out, cudaStream_t stream, std::string& err, void* const* scatter = nullptr,
-             int nscatter = 0);
+             int nscatter = 0, const struct ExecWindow* win = nullptr);
+    // true when exec() accepts a window of `nwin` column blocks over rows of `row_lanes` lanes (one tile-kernel launch,
+    // no scratch, no batch loop, tiles that divide the blocks)
+    bool window_ok(int64_t row_lanes, int nwin) const;
 
     sfc_desc desc{};
     sfc_plan_info info{};

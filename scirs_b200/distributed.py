@@ -146,7 +146,7 @@ class DistPlan:
 
     def __init__(self, comm: Communicator, shape: Sequence[int], axes: Optional[Sequence[int]] = None,
                  decomposition: str = "slab", layout: str = "transposed", kind: str = "c2c", prec: str = "f64",
-                 forward: bool = True, scale: float = 1.0):
+                 forward: bool = True, scale: float = 1.0, chunks: int = 0):
         lib = _lib.load()
         dd = _lib.sfc_dist_desc()
         d = dd.base
@@ -164,6 +164,7 @@ class DistPlan:
         d.scale = float(scale)
         dd.decomposition = _DECOMP[decomposition]
         dd.layout = _LAYOUT[layout]
+        dd.chunks = int(chunks)  # slab: column blocks the first exchange is pipelined in (0 = library default, 1 = off)
         self._h = C.c_void_p()
         check(lib.sfc_dist_plan_create(C.byref(self._h), comm._h, C.byref(dd)))
         self._lib, self.comm = lib, comm
@@ -241,7 +242,7 @@ class SlabFFT3D:
 
     def __init__(self, n0: int, n1: int, n2: int, group=None, mode: str = "p2p", prec: str = "f64",
                  local_transform: Optional[Callable] = None, comm: Optional[Communicator] = None,
-                 layout: str = "transposed", forward: bool = True, scale: float = 1.0):
+                 layout: str = "transposed", forward: bool = True, scale: float = 1.0, chunks: int = 0):
         self.n0, self.n1, self.n2 = n0, n1, n2
         self.mode, self.prec, self.layout = mode, prec, layout
         self.local_transform = local_transform
@@ -265,7 +266,7 @@ class SlabFFT3D:
         if local_transform is not None:
             return
         if mode == "p2p":
-            self.plan = DistPlan(self.comm, [n0, n1, n2], [0, 1, 2], "slab", layout, "c2c", prec, forward, scale)
+            self.plan = DistPlan(self.comm, [n0, n1, n2], [0, 1, 2], "slab", layout, "c2c", prec, forward, scale, chunks)
         else:
             if layout != "transposed" or not forward:
                 raise ValueError_("the NCCL comparison path only does the forward transposed-out transform")
@@ -390,10 +391,12 @@ def _as_tensor(torch, ptr: int, n: int, dtype):
 
 
 def bench_slab_fftn(n: int, steps: int = 5, warmup: int = 3, mode: str = "p2p", layout: str = "transposed",
-                    comm: Optional[Communicator] = None, check_parity: bool = True, min_seconds: float = 0.0):
+                    comm: Optional[Communicator] = None, check_parity: bool = True, min_seconds: float = 0.0, chunks: int = 0):
     """Timed slab fftn of an n^3 c128 volume, one process per GPU (used by bench.py and tests/dist_worker.py).
 
     mode "p2p": the library path (`sfc_dist_*`); torch only makes the input tensors and the CUDA events.
+    `chunks`: column blocks the exchange is pipelined in (0 = library default); when the plan is pipelined, an unpipelined
+    twin (chunks = 1) is timed beside it: its stages do not overlap, so its breakdown says what every stage costs.
     Parity (outside the timed region): every rank builds the WHOLE seeded volume, transforms it with the
     single-GPU plan on its own GPU and compares its share of the distributed result: `parity_rel_l2` is the max
     over ranks; above 1e-12 the bench line fails loudly."""
@@ -401,7 +404,7 @@ def bench_slab_fftn(n: int, steps: int = 5, warmup: int = 3, mode: str = "p2p", 
     import torch.distributed as dist
 
     P, rank = dist.get_world_size(), dist.get_rank()
-    f = SlabFFT3D(n, n, n, mode=mode, layout=layout, comm=comm)
+    f = SlabFFT3D(n, n, n, mode=mode, layout=layout, comm=comm, chunks=chunks)
     s0, s1 = n // P, n // P
     st = torch.cuda.current_stream()
 
@@ -411,43 +414,62 @@ def bench_slab_fftn(n: int, steps: int = 5, warmup: int = 3, mode: str = "p2p", 
 
     x = slab_of(rank)
     out = torch.empty((n, s1, n) if layout == "transposed" else (s0, n, n), dtype=torch.complex128, device="cuda")
-    for _ in range(warmup):
-        f.forward_device(x, out)
-    torch.cuda.synchronize()
-    dist.barrier()
-    reps = steps
-    while True:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(st)
-        for _ in range(reps):
-            f.forward_device(x, out)
-        e1.record(st)
+
+    def timed(obj, min_s):
+        for _ in range(warmup):
+            obj.forward_device(x, out)
         torch.cuda.synchronize()
         dist.barrier()
-        tm = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        total_ms = float(tm.item())
-        if total_ms >= min_seconds * 1e3 or reps >= 100000:
-            break
-        reps = int(min(100000, max(reps * 2, reps * min_seconds * 1e3 / max(total_ms, 1e-3) * 1.1)))
-    ms = total_ms / reps
-    # one more instrumented call for the stage breakdown
-    stage = []
-    if mode == "p2p":
-        f.plan.profile(True)
-        f.forward_device(x, out)
-        torch.cuda.synchronize()
-        stage = f.plan.stage_ms()
-        f.plan.profile(False)
+        reps = steps
+        while True:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(reps):
+                obj.forward_device(x, out)
+            e1.record(st)
+            torch.cuda.synchronize()
+            dist.barrier()
+            tm = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            total_ms = float(tm.item())
+            if total_ms >= min_s * 1e3 or reps >= 100000:
+                break
+            reps = int(min(100000, max(reps * 2, reps * min_s * 1e3 / max(total_ms, 1e-3) * 1.1)))
+        return total_ms / reps, reps
+
+    def stages_of(obj):  # one more instrumented call, max over ranks per stage
+        if mode == "p2p":
+            obj.plan.profile(True)
+            obj.forward_device(x, out)
+            torch.cuda.synchronize()
+            stage = obj.plan.stage_ms()
+            obj.plan.profile(False)
+        else:
+            evs = []
+            obj.forward_device(x, out, events=evs)
+            torch.cuda.synchronize()
+            stage = [evs[i].elapsed_time(evs[i + 1]) for i in range(4)]
+        stage = stage + [0.0] * (6 - len(stage))
+        t = torch.tensor(stage[:6], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    ms, reps = timed(f, min_seconds)
+    nchunks = int(f.plan.info["chunks"]) if mode == "p2p" else 1
+    pipelined = None
+    if nchunks > 1:
+        # pipelined plan: FFT axis 2 | scatter passes of all column blocks (the axis-0 passes overlap them on a side
+        # stream) | what is left of the axis-0 passes after the last scatter
+        pa, pb, ptail = stages_of(f)[:3]
+        pipelined = {"chunks": nchunks, "ms_per_step": round(ms, 4),
+                     "stage_ms": {"fft_axis2": round(pa, 4), "fft_axis1_scatter_blocks": round(pb, 4), "fft_axis0_tail": round(ptail, 4)}}
+        g = SlabFFT3D(n, n, n, mode=mode, layout=layout, comm=f.comm, chunks=1)
+        ms_un, _ = timed(g, min(min_seconds, 0.25))
+        t_a, t_b, t_x, t_c, t_x2, t_cp = stages_of(g)
+        g.close()
+        pipelined["unpipelined_ms_per_step"] = round(ms_un, 4)
     else:
-        evs = []
-        f.forward_device(x, out, events=evs)
-        torch.cuda.synchronize()
-        stage = [evs[i].elapsed_time(evs[i + 1]) for i in range(4)]
-    stage = stage + [0.0] * (6 - len(stage))
-    t = torch.tensor(stage[:6], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_a, t_b, t_x, t_c, t_x2, t_cp = [float(v) for v in t.tolist()]
+        t_a, t_b, t_x, t_c, t_x2, t_cp = stages_of(f)
     parity = None
     if check_parity:
         from .plan import FftPlan
@@ -481,6 +503,7 @@ def bench_slab_fftn(n: int, steps: int = 5, warmup: int = 3, mode: str = "p2p", 
         "gflops": round(5.0 * total * 3 * np.log2(n) / ms / 1e6, 1),
         "scaling": "strong",
         "parity_rel_l2": parity,
+        "pipelined": pipelined,
         "stage_ms": {"fft_axis2": round(t_a, 4), "fft_axis1_scatter" if mode == "p2p" else "fft_axis1_pack": round(t_b, 4),
                      "rendezvous" if mode == "p2p" else "nccl_all_to_all": round(t_x, 4), "fft_axis0": round(t_c, 4)},
         "alltoall_bytes_sent_per_gpu": int(sent),

@@ -109,8 +109,13 @@ def case_device(comm, rank, P, sizes):
         sb.FftPlan([n, n, n], [0, 1, 2], "c2c", "f64").execute_device(full, ref, torch.cuda.current_stream().cuda_stream)
         mine = full[rank * s0:(rank + 1) * s0].contiguous()
         side = torch.cuda.Stream()
-        for layout in ("transposed", "natural"):
-            plan = DistPlan(comm, shape, [0, 1, 2], "slab", layout)
+        # chunks: 0 = library default (one scatter + one wait), 4 / 2 / 8 = pipelined exchange over that many column
+        # blocks of n2 (8 = the most the flag page holds)
+        for layout, chunks in (("transposed", 0), ("natural", 0), ("transposed", 4), ("natural", 4), ("transposed", 8), ("natural", 2)):
+            plan = DistPlan(comm, shape, [0, 1, 2], "slab", layout, chunks=chunks)
+            assert 1 <= plan.info["chunks"] <= max(chunks, 1), plan.info
+            if P > 1 and n >= 512 and chunks:
+                assert plan.info["chunks"] == chunks, plan.info  # BASELINE configs[4] sizes take every block count
             want = ref[:, rank * s1:(rank + 1) * s1, :] if layout == "transposed" else ref[rank * s0:(rank + 1) * s0]
             outs = {"plain": torch.empty(plan.local_out_shape, dtype=torch.complex128, device="cuda")}
             sym = None
@@ -133,7 +138,7 @@ def case_device(comm, rank, P, sizes):
                         got = out
                     worst = max(worst, float((got - want).norm() / want.norm()))
                 ok = emit(ok, rank=rank, case="device", shape=list(shape), layout=layout + ":" + kind, dir="fwd", prec="f64",
-                          rel_l2=worst, ok=bool(worst <= 1e-12))
+                          chunks=int(plan.info["chunks"]), rel_l2=worst, ok=bool(worst <= 1e-12))
             comm.barrier()
             if sym is not None:
                 comm.free(sym)

@@ -55,3 +55,30 @@ extern "C" int emul_plan_run_scatter(const sfc_desc* d, const void* in, void* co
     snprintf(info, (size_t)info_len, "%s", rc == 0 ? p->describe().c_str() : es.c_str());
     return rc;
 }
+
+// the same plan executed window by window (column blocks of every row of `row_lanes` lanes, last block first): the union of
+// the windows must give what one full execution gives.  nouts == 0: plain output `out`; otherwise the scatter table.
+extern "C" int emul_plan_run_windows(const sfc_desc* d, const void* in, void* out, void* const* outs, int nouts, long long row_lanes,
+                                     int nwin, char* info, int info_len) {
+    sfc::PlanError err{0, ""};
+    std::shared_ptr<sfc::Plan> p = sfc::Plan::create(*d, err);
+    if (!p) {
+        snprintf(info, (size_t)info_len, "%s", err.msg.c_str());
+        return err.code ? err.code : -1;
+    }
+    if (!p->window_ok(row_lanes, nwin)) {
+        snprintf(info, (size_t)info_len, "window_ok() refused: %s", p->describe().c_str());
+        return -2;
+    }
+    std::string es;
+    for (int w = nwin - 1; w >= 0; --w) {
+        sfc::ExecWindow win{row_lanes, w, nwin};
+        const int rc = nouts ? p->exec(in, nullptr, nullptr, es, outs, nouts, &win) : p->exec(in, out, nullptr, es, nullptr, 0, &win);
+        if (rc != 0) {
+            snprintf(info, (size_t)info_len, "%s", es.c_str());
+            return rc;
+        }
+    }
+    snprintf(info, (size_t)info_len, "%s", p->describe().c_str());
+    return 0;
+}

@@ -38,7 +38,8 @@ class PassParams(C.Structure):  # pass_params.h, field for field
                 ("scale_dc", C.c_double), ("peer_shift", C.c_int32), ("peer_out", C.c_void_p * 16),
                 # alignas(64) CUtensorMap of the tensor-map tiles (never used by the host emulation), then the struct's tail padding
                 ("_pad_tmap", C.c_uint8 * 8), ("tmap_in", C.c_uint8 * 128), ("tmap_box_rows", C.c_int32),
-                ("tmap_split", C.c_int32), ("_pad_tail", C.c_uint8 * 56)]
+                ("tmap_split", C.c_int32), ("win_row_tiles", C.c_uint32), ("win_first", C.c_uint32), ("win_len", C.c_uint32),
+                ("_pad_tail", C.c_uint8 * 44)]
 
 
 @pytest.fixture(scope="module")

@@ -75,7 +75,27 @@ def emul():
         rc = lib.emul_plan_run_scatter(C.byref(d), x.ctypes.data_as(C.c_void_p), ptrs, parts, buf, len(buf))
         return rc, buf.value.decode()
 
+    def run_windows(shape, axes, x, out_arr, outs, parts, row_lanes, nwin, pitch=0, inverse=False, scale=1.0):
+        d = _lib.sfc_desc()
+        d.ndim = len(shape)
+        for i, s in enumerate(shape):
+            d.shape[i] = s
+        d.naxes = len(axes)
+        for i, a in enumerate(axes):
+            d.axes[i] = a
+        d.kind, d.prec, d.direction, d.flags, d.scale, d.scatter_parts = _lib.SFC_C2C, _lib.SFC_PREC_F64, int(inverse), 0, scale, parts
+        d.scatter_pitch = pitch
+        ptrs = (C.c_void_p * max(parts, 1))(*outs) if parts else None
+        buf = C.create_string_buffer(8192)
+        rc = lib.emul_plan_run_windows(C.byref(d), x.ctypes.data_as(C.c_void_p),
+                                       out_arr.ctypes.data_as(C.c_void_p) if out_arr is not None else None, ptrs, parts,
+                                       row_lanes, nwin, buf, len(buf))
+        return rc, buf.value.decode()
+
     run.scatter = run_scatter
+    run.windows = run_windows
+    lib.emul_plan_run_windows.argtypes = [C.POINTER(_lib.sfc_desc), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_longlong,
+                                          C.c_int, C.c_char_p, C.c_int]
     lib.emul_plan_run_scatter.argtypes = [C.POINTER(_lib.sfc_desc), C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.c_int]
     yield run
     if old_knob is None:
@@ -315,6 +335,42 @@ def test_slab_fftn_natural_layout_second_exchange(emul, P, shape, inverse):
     ref = (np.fft.ifftn(X) * X.size if inverse else np.fft.fftn(X)) * 0.5
     for q in range(P):
         assert rel(outs[q], ref[q * s0:(q + 1) * s0]) < 1e-14
+
+
+@pytest.mark.parametrize("P,shape,nwin", [(2, (128, 128, 64), 2), (2, (256, 128, 128), 4), (4, (256, 256, 64), 4)])
+@pytest.mark.parametrize("natural", [False, True])
+def test_slab_fftn_column_windows(emul, P, shape, nwin, natural):
+    """csrc/dist.cu, pipelined exchange: the axis-1 scatter pass and the axis-0 pass executed window by window over column blocks of
+    n2 (Plan::exec with an ExecWindow, PassParams::win_*), on the same dense arrays — block j of pass C only needs block j of
+    every peer's pass B, which is what lets the device overlap them.  Ranks and windows run one after the other here."""
+    rng = np.random.default_rng(10)
+    n0, n1, n2 = shape
+    s0, s1 = n0 // P, n1 // P
+    X = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    recv = [np.zeros((n0, s1, n2), dtype=np.complex128) for _ in range(P)]
+    block = s0 * s1 * n2 * 16
+    for r in range(P):
+        x = np.ascontiguousarray(X[r * s0:(r + 1) * s0])
+        work = np.zeros_like(x)
+        rc, d = emul([s0, n1, n2], [2], x, work)
+        assert rc == 0, d
+        rc, d = emul.windows([s0, n1, n2], [1], work, None, [recv[q].ctypes.data + r * block for q in range(P)], P, n2, nwin)
+        assert rc == 0, d
+    ref = np.fft.fftn(X) * 0.5
+    if not natural:
+        for q in range(P):
+            out = np.zeros_like(recv[q])
+            rc, d = emul.windows([n0, s1, n2], [0], recv[q], out, [], 0, n2, nwin, scale=0.5)
+            assert rc == 0, d
+            assert rel(out, ref[:, q * s1:(q + 1) * s1, :]) < 1e-14
+    else:
+        outs = [np.zeros((s0, n1, n2), dtype=np.complex128) for _ in range(P)]
+        for r in range(P):
+            rc, d = emul.windows([n0, s1, n2], [0], recv[r], None, [outs[q].ctypes.data + r * s1 * n2 * 16 for q in range(P)], P, n2, nwin,
+                                 pitch=n1 * n2, scale=0.5)
+            assert rc == 0, d
+        for q in range(P):
+            assert rel(outs[q], ref[q * s0:(q + 1) * s0]) < 1e-14
 
 
 @pytest.mark.parametrize("shape,axes", [([5, 9], [1]), ([4, 27], [1]), ([7, 81], [1]), ([3, 243], [1]), ([2, 729], [1]), ([2, 2187], [1]),
