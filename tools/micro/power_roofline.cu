@@ -1,0 +1,160 @@
+// power_roofline.cu — what bandwidth can ANY kernel sustain on this part when it moves HBM-rate data AND executes the FP64
+// / shared-memory work of an FFT tile?  A streaming kernel with the tile kernel's shape (256 threads, 16 complex points per
+// thread, 16 B loads / stores at a 256-element stride) does K FP64 instructions per point on independent chains and S
+// shared-memory exchanges (STS.128, barrier, LDS.128 of another thread's slot), nothing else.  The 4096-point c2c tile
+// executes 694 FP64 instructions per 16 points = 43 per point and 2 exchanges.  Sustained: 1.5 s preload, >= 1 s timed,
+// SM clock and power sampled over NVML meanwhile.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o power_roofline power_roofline.cu -ldl
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <chrono>
+#include <thread>
+#include <atomic>
+#include <dlfcn.h>
+#include <cuda_runtime.h>
+
+template <int K, int S, bool ADD, int NT = 256, int MINB = 2, bool PERSIST = false, int MODE = 0>
+__global__ void __launch_bounds__(NT, MINB) stream_kernel(const double2* __restrict__ in, double2* __restrict__ out, double a, double b,
+                                                          unsigned ntiles) {
+    extern __shared__ __align__(128) double2 sm[];
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const size_t base = (size_t)tile * (16 * NT) + threadIdx.x;
+    double2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = in[base + m * NT];
+#pragma unroll
+    for (int s = 0; s <= S; ++s) {
+        constexpr int KS = K / (S + 1);
+#pragma unroll
+        for (int k = 0; k < KS / 2; ++k) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                if (ADD) { v[m].x = v[m].x + b; v[m].y = v[m].y + a; }
+                else { v[m].x = fma(v[m].x, a, b); v[m].y = fma(v[m].y, a, b); }
+            }
+        }
+        if (s < S && MODE == 1) {
+            // warp-local exchange: same traffic, no CTA-wide barrier (a warp's 512 slots are its own)
+            double2* w = sm + (threadIdx.x >> 5) * (17 * 32);
+            const int l = threadIdx.x & 31;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) w[17 * l + m] = v[m];
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = w[l + 34 * m];
+            __syncwarp();
+        } else if (s < S && MODE == 2) {
+            // half the data: real parts only, 8-byte slots
+            double* h = reinterpret_cast<double*>(sm);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) h[17 * threadIdx.x + m] = v[m].x;
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m].x = h[threadIdx.x + (NT + NT / 16) * m];
+            __syncthreads();
+        } else if (s < S && MODE == 3) {
+            if (a == 123.456) sm[threadIdx.x] = v[0];  // shared memory allocated, never touched
+        } else if (s < S) {
+            // padded exchange like the tile kernel's: thread t writes slots 17 t + m, reads t + 272 m (another thread's data)
+#pragma unroll
+            for (int m = 0; m < 16; ++m) sm[17 * threadIdx.x + m] = v[m];
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = sm[threadIdx.x + (NT + NT / 16) * m];
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) out[base + m * NT] = v[m];
+    if (!PERSIST) break;
+  }
+}
+
+// random payload: constant data toggles no wires and draws far less power (first cut: zeros copied at 6.8 TB/s for 761 W)
+__global__ void fill_random(double2* p, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long z = i * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        unsigned long long w = z * 0xD6E8FEB86659FD93ull; w ^= w >> 32;
+        p[i] = make_double2((double)(long long)z * (1.0 / 9223372036854775808.0), (double)(long long)w * (1.0 / 9223372036854775808.0));
+    }
+}
+
+typedef int (*nvml_fn)(...);
+struct Nvml {
+    void* h = nullptr; void* dev = nullptr;
+    int (*init)() = nullptr; int (*get)(unsigned, void**) = nullptr; int (*clk)(void*, int, unsigned*) = nullptr; int (*pwr)(void*, unsigned*) = nullptr;
+    bool ok = false;
+    Nvml() {
+        h = dlopen("libnvidia-ml.so.1", RTLD_NOW);
+        if (!h) return;
+        init = (int (*)())dlsym(h, "nvmlInit_v2");
+        get = (int (*)(unsigned, void**))dlsym(h, "nvmlDeviceGetHandleByIndex_v2");
+        clk = (int (*)(void*, int, unsigned*))dlsym(h, "nvmlDeviceGetClockInfo");
+        pwr = (int (*)(void*, unsigned*))dlsym(h, "nvmlDeviceGetPowerUsage");
+        ok = init && get && clk && pwr && init() == 0 && get(0, &dev) == 0;
+    }
+};
+
+template <int K, int S, bool ADD, int NT = 256, int MINB = 2, bool PERSIST = false, int MODE = 0>
+void run(const char* name, const double2* in, double2* out, size_t n, Nvml& nv) {
+    const unsigned ntiles = (unsigned)(n / (16 * NT));
+    const unsigned grid = PERSIST ? 148 * MINB : ntiles;
+    const size_t smem = S ? (size_t)(17 * NT + 16) * 16 : 0;
+    cudaFuncSetAttribute(stream_kernel<K, S, ADD, NT, MINB, PERSIST, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto launch = [&]() { stream_kernel<K, S, ADD, NT, MINB, PERSIST, MODE><<<grid, NT, smem>>>(in, out, 0.9173, 0.3391, ntiles); };
+    auto t0 = std::chrono::steady_clock::now();
+    while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < 1.5) {
+        for (int i = 0; i < 16; ++i) launch();
+        cudaDeviceSynchronize();
+    }
+    std::atomic<bool> stop{false};
+    std::vector<unsigned> clk, pw;
+    std::thread th([&]() {
+        while (!stop && nv.ok) {
+            unsigned c = 0, p = 0;
+            if (nv.clk(nv.dev, 1 /* SM */, &c) == 0 && nv.pwr(nv.dev, &p) == 0) { clk.push_back(c); pw.push_back(p); }
+            std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        }
+    });
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int reps = 800;
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i) launch();
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    stop = true; th.join();
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+    std::sort(clk.begin(), clk.end()); std::sort(pw.begin(), pw.end());
+    const double gbs = 2.0 * n * 16 / ms / 1e6;
+    printf("%-44s %7.4f ms  %7.1f GB/s  %5.1f%% of 6553.9   sm %4u MHz  %4u W   (%s)\n", name, ms, gbs, gbs / 65.539,
+           clk.empty() ? 0 : clk[clk.size() / 2], pw.empty() ? 0 : pw[pw.size() / 2] / 1000, cudaGetErrorString(cudaGetLastError()));
+    fflush(stdout);
+}
+
+int main() {
+    const size_t n = (size_t)65536 * 4096;  // complex points: 4 GiB in, 4 GiB out (the headline batch)
+    double2 *in, *out;
+    if (cudaMalloc(&in, n * 16) != cudaSuccess || cudaMalloc(&out, n * 16) != cudaSuccess) { printf("alloc failed\n"); return 1; }
+    fill_random<<<148 * 8, 256>>>(in, n);
+    cudaDeviceSynchronize();
+    Nvml nv;
+    printf("streaming kernel, 65,536 x 4096 complex f64 (8.59 GB per launch), random payload, sustained; NVML %s\n", nv.ok ? "ok" : "unavailable");
+    run<0, 0, false>("copy (0 FP64 / point, no exchange)", in, out, n, nv);
+    run<0, 2, false, 256, 2, false, 3>("copy, 70 KiB of shared memory allocated, unused", in, out, n, nv);
+    run<0, 2, false>("0 FP64 / point, 2 exchanges", in, out, n, nv);
+    run<0, 2, false, 256, 2, false, 1>("0 FP64, 2 warp-local exchanges (no CTA barrier)", in, out, n, nv);
+    run<0, 2, false, 256, 2, false, 2>("0 FP64, 2 exchanges of half the data", in, out, n, nv);
+    run<42, 0, false>("42 DFMA / point", in, out, n, nv);
+    run<42, 2, false>("42 DFMA / point, 2 exchanges (the 4096 tile)", in, out, n, nv);
+    run<42, 2, false, 256, 2, false, 1>("42 DFMA, 2 warp-local exchanges", in, out, n, nv);
+    run<42, 2, false, 256, 2, false, 2>("42 DFMA, 2 exchanges of half the data", in, out, n, nv);
+    run<42, 2, false, 256, 2, false, 3>("42 DFMA, shared memory allocated, no exchange", in, out, n, nv);
+    run<42, 2, false, 128, 4, false>("42 DFMA, 2 exchanges, 128-thread tiles x 4 / SM", in, out, n, nv);
+    run<42, 2, false, 128, 4, false, 1>("42 DFMA, 2 warp-local exchanges, 128 x 4 / SM", in, out, n, nv);
+    return 0;
+}
