@@ -286,6 +286,9 @@ __device__ __forceinline__ void apply_twiddle_powers(Cx<T> (&v)[R], Cx<T> w1) {
 // product tree above is saved.  Measured (tools/r1_experiments/exp31.sh, 65536 x 4096): 1.5% SLOWER for f64 c2c (91.5% against 93.0%
 // of the HBM peak) and 3% slower for f64 rfft -- the 15 extra L1 loads per butterfly cost more issue slots next to the
 // tile's own global loads than the FP64 tree does.  Off; -DSFC_TW_LOAD=1 builds it.
+#ifndef SFC_INPLACE_MID
+#define SFC_INPLACE_MID 1
+#endif
 #ifndef SFC_TW_LOAD
 #define SFC_TW_LOAD 0
 #endif
@@ -408,7 +411,18 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
     constexpr int R = MIRROR_IN ? ((S == 1 && REM > 1) ? REM : E) : ((L / S >= E) ? E : (L / S));
     constexpr bool LAST = (S * R == L);
     constexpr int NB = E / R;  // butterflies per thread in this stage
-    if constexpr (!LAST && !FIRST) C::sync(grp);  // previous readers done before we overwrite
+    // Middle stage of the three-stage tiles (L = R1 * 16 * R3; R1 = 16, or 8 in the complex-to-real flavour) done IN PLACE: output
+    // k goes back to the slot input k came from, which only this thread reads or writes, so the barrier that protects the
+    // exchange buffer against overwriting (one of the three barriers of a tile) is not needed; the last stage then reads through
+    // the permuted positions:  Stockham element q + S k + 16 S h  ->  in-place element q + S h + (L / 16) k   (S = R1).
+    // The streaming proxy of the tile (tools/micro/power_roofline.cu) puts ~3 points of the HBM roofline on every CTA-wide
+    // barrier; measured on the tiles (profiles/r2r_inplace_mid.log): 4096-point c2c 78.7 -> 81.2 %, 2048 84.4 -> 86.1 %.
+    // Real flavours (65,536 x 4096, sustained, profiles/r2s_inplace_real.log): complex-to-real f64 85.9 -> 87.4 % (kept), f32
+    // 79.1 -> 77.7 % (off); real-to-complex with the mirrored last stage f64 84.9 -> 83.6 % (a 12-byte spill; off), f32 +0.5.
+    constexpr bool MID_INPLACE = SFC_INPLACE_MID && !HOOK && !C::SPLIT && E == 16 && R == 16 && !LAST && S > 1 &&
+                                 (SFC_INPLACE_MID > 1 || (!MIRROR && (!MIRROR_IN || sizeof(T) == 8))) &&
+                                 (MIRROR_IN ? S == 8 : S == 16) && L / (S * R) >= 2 && L / (S * R) <= 16;
+    if constexpr (!LAST && !FIRST && !MID_INPLACE) C::sync(grp);  // previous readers done before we overwrite
     if constexpr (C::SPLIT && !LAST) {
         // half-size exchange buffer: real parts first, imaginary parts second (outputs parked in a[] meanwhile)
         static_assert(!MIRROR && !MIRROR_IN, "split exchange is for the plain complex flavours");
@@ -465,12 +479,41 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
             if constexpr (NOTW1 && S == 1) {
             } else if constexpr (SFC_TW_LOAD && S >= 16) apply_twiddle_table<R, T>(v, tw, ib & ~(S - 1));
             else apply_twiddle_powers<R, T>(v, tw[ib & ~(S - 1)]);
-            Cx<T>* dst = sm + tw_ * C::LP + Xch<C, R, S>::write_base(ib);
+            if constexpr (MID_INPLACE) {
+                using X1 = Xch<C, S, 1>;  // the layout the first stage wrote and this thread just read through
+                Cx<T>* dst = sm + tw_ * C::LP + X1::read_base(iw);
 #pragma unroll
-            for (int k = 0; k < R; ++k) dst[k * S] = v[k];
+                for (int k = 0; k < R; ++k) dst[X1::read_off(k)] = v[k];
+            } else {
+                Cx<T>* dst = sm + tw_ * C::LP + Xch<C, R, S>::write_base(ib);
+#pragma unroll
+                for (int k = 0; k < R; ++k) dst[k * S] = v[k];
+            }
         }
     }
-    if constexpr (!LAST) {
+    if constexpr (MID_INPLACE) {
+        C::sync(grp);
+        constexpr int RN = L / (S * R);        // radix of the last stage
+        constexpr int KP = TPL + TPL / S;      // slot distance of consecutive k (one pad slot per S elements)
+        constexpr int LS = ilog2(S);
+        const Cx<T>* lane = sm + tr * C::LP;
+        // slot of Stockham element ib + 16 S r (ib < 16 S): (ib mod S) + KP (ib div S) + (S + 1) r
+        const int b0 = (ir & (S - 1)) + KP * (ir >> LS);
+        if constexpr (MIRROR && E / RN == 2) {
+            // butterfly 0 = ir, butterfly 1 = its mirror (16 S - ir, or 8 S for ir = 0)
+            const int j2 = ir == 0 ? (S * R) / 2 : S * R - ir;
+            const int b1 = (j2 & (S - 1)) + KP * (j2 >> LS);
+#pragma unroll
+            for (int r = 0; r < RN; ++r) {
+                a[2 * r] = lane[b0 + (S + 1) * r];
+                a[2 * r + 1] = lane[b1 + (S + 1) * r];
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; ++m) a[m] = lane[b0 + (S + 1) * ((RN * m) >> 4) + KP * ((RN * m) & 15)];
+        }
+        run_stages<T, C, S * R, false, MIRROR, MIRROR_IN, false, HOOK>(a, sm, tw, tr, ir, tr, ir, grp, hook);
+    } else if constexpr (!LAST) {
         C::sync(grp);
         const Cx<T>* src = sm + tr * C::LP + Xch<C, R, S>::read_base(ir);
         constexpr int SN = S * R;                                  // stride of the next stage
