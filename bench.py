@@ -359,8 +359,10 @@ def run_gpu(args):
                 # the same kernel timed alone on a cool GPU (3 executions before any sustained load): what a burst measurement
                 # such as MEASURED_PEAKS.json's copy sees; `frac` above is the SUSTAINED figure (power-capped clocks)
                 "burst": {"kernel_ms": round(r["burst_ms"] / nl, 4), "frac": round(alg / r["burst_ms"] / 1e6 / hbm, 4)},
-                "note": "sustained: a plain device copy at 6.54 TB/s already draws 974 W of the 1000 W cap on this part "
-                        "(profiles/r2d_copy_power_tmap.log), so FP64 transform work on top of full-rate HBM traffic lowers the clocks"}
+                "note": "sustained, at the 1000 W cap (a plain copy of random data already draws ~975-995 W at 6.5-6.8 TB/s). A synthetic "
+                        "streaming kernel with this tile's shape (same loads / stores, 42 FP64 instructions per point, two CTA-wide "
+                        "shared-memory exchanges) sustains 83-84 % of the peak on this part, the same kernel without the exchanges 104 % "
+                        "(profiles/r2q_power_roofline.log): the exchange barriers, not the FP64 work, set the ceiling of this design"}
 
     # ---------------- e2e through the C ABI with pinned host buffers
     e2e = None

@@ -18,6 +18,10 @@
 
 namespace sfc {
 
+#ifndef SFC_R3_INPLACE_MID
+#define SFC_R3_INPLACE_MID 0
+#endif
+
 template <typename T>
 __device__ __forceinline__ void dft3(Cx<T>& a0, Cx<T>& a1, Cx<T>& a2) {
     constexpr T S3 = (T)0.86602540378443864676372317075294L;  // sin(pi/3)
@@ -103,7 +107,13 @@ __device__ __forceinline__ void r3_stages(Cx<T> (&a)[9], Cx<T>* __restrict__ sm,
     static_assert(R == 9 || R == 3, "L must be a power of three");
     constexpr bool LAST = (S * R == L);
     constexpr int NB = 9 / R;
-    if constexpr (!LAST && S > 1) __syncthreads();  // readers of the previous exchange are done
+    // a middle stage followed by the last one writes IN PLACE (output k into the slot input k came from, touched by this
+    // thread only): no barrier against overwriting the previous exchange; the last stage reads through the permutation
+    //   Stockham element q + S k + 9 S h  ->  in-place element q + S h + (L / 9) k      (same scheme as fft_tile.cuh)
+    // Measured (profiles/r2t_final_single_gpu.log): no gain on these tiles (3^13 x 256 7.20 -> 7.22 ms, 729-point rows 75.8 ->
+    // 73.6 %): off, -DSFC_R3_INPLACE_MID=1 builds it.
+    constexpr bool MID_INPLACE = SFC_R3_INPLACE_MID && R == 9 && !LAST && S > 1 && L >= 729 && (L / (S * 9) == 3 || L / (S * 9) == 9);  // 243: the permuted reads straddle bank groups (tools/bank_sim_r3.py)
+    if constexpr (!LAST && S > 1 && !MID_INPLACE) __syncthreads();  // readers of the previous exchange are done
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         Cx<T> v[R];
@@ -132,12 +142,25 @@ __device__ __forceinline__ void r3_stages(Cx<T> (&a)[9], Cx<T>* __restrict__ sm,
                 v[7] = cmul(v[7], cmul(w4, w3));
                 v[8] = cmul(v[8], csqr(w4));
             }
-            Cx<T>* dst = sm + bw + q + R * base;
+            if constexpr (MID_INPLACE) {
+                Cx<T>* dst = sm + bw + iw;
 #pragma unroll
-            for (int k = 0; k < R; ++k) dst[k * S] = v[k];
+                for (int k = 0; k < R; ++k) dst[k * TPL] = v[k];
+            } else {
+                Cx<T>* dst = sm + bw + q + R * base;
+#pragma unroll
+                for (int k = 0; k < R; ++k) dst[k * S] = v[k];
+            }
         }
     }
-    if constexpr (!LAST) {
+    if constexpr (MID_INPLACE) {
+        __syncthreads();
+        constexpr int RN = L / (S * 9);  // radix of the last stage
+        const Cx<T>* src = sm + br + (ir % S) + TPL * (ir / S);
+#pragma unroll
+        for (int m = 0; m < 9; ++m) a[m] = src[S * ((RN * m) / 9) + TPL * ((RN * m) % 9)];
+        r3_stages<T, C, S * R>(a, sm, tw, br, ir, br, ir);
+    } else if constexpr (!LAST) {
         __syncthreads();
         const Cx<T>* src = sm + br + ir;
 #pragma unroll

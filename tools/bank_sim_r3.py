@@ -4,6 +4,7 @@ Model (matches the ncu source page of the round-2 tiles, where every LDS.128 / S
 its ideal wavefronts): a warp-wide 128-bit access is served in groups of eight consecutive threads, one wavefront per group
 when the eight 16-byte slots differ modulo 8.  Prints, per registered tile and thread mapping, wavefronts / ideal over every
 access of every stage, for the plain pitch L (round 2, first cut) and for lane_base()."""
+INPLACE = False  # the kernel default
 TILES = [(9, 243), (9, 486), (27, 81), (27, 162), (81, 27), (81, 54), (243, 9), (243, 18), (729, 3), (729, 6), (2187, 1), (2187, 2), (2187, 3)]
 
 
@@ -20,14 +21,24 @@ def mapping(mode, tid, TL, TPL):
 
 
 def stage_accesses(L):
-    """yields (kind, f) with f(i) -> slot offsets inside a lane for butterfly index i (one list entry per instruction)"""
-    S = 1
+    """yields (kind, f) with f(i) -> slot offsets inside a lane for butterfly index i (one list entry per instruction); the
+    middle stage in front of the last one works in place for L >= 729 with INPLACE (r3_stages, -DSFC_R3_INPLACE_MID=1)"""
     TPL = L // 9
+    stages, S = [], 1
     while True:
         R = 9 if L // S >= 9 else L // S
         if S * R == L:
-            return
+            break
+        stages.append((S, R))
+        S *= R
+    for idx, (S, R) in enumerate(stages):
+        RN = L // (S * R)
+        inplace = INPLACE and R == 9 and S > 1 and L >= 729 and idx == len(stages) - 1 and RN in (3, 9)
         NB = 9 // R
+        if inplace:
+            yield "write in place S=%d" % S, (lambda i: [i + k * TPL for k in range(9)])
+            yield "read permuted", (lambda i, S=S, RN=RN: [(i % S) + TPL * (i // S) + S * ((RN * m) // 9) + TPL * ((RN * m) % 9) for m in range(9)])
+            continue
 
         def wr(i, S=S, R=R, NB=NB):
             out = []
@@ -38,7 +49,6 @@ def stage_accesses(L):
             return out
         yield "write S=%d" % S, wr
         yield "read after S=%d" % S, lambda i: [i + m * TPL for m in range(9)]
-        S *= R
 
 
 def wavefronts(L, TL, wmode, rmode, layout):

@@ -16,12 +16,14 @@
 #include <dlfcn.h>
 #include <cuda_runtime.h>
 
-template <int K, int S, bool ADD, int NT = 256, int MINB = 2, bool PERSIST = false, int MODE = 0>
+template <int K, int S, bool ADD, int NT = 256, int MINB = 2, bool PERSIST = false, int MODE = 0, int PF = 0>
 __global__ void __launch_bounds__(NT, MINB) stream_kernel(const double2* __restrict__ in, double2* __restrict__ out, double a, double b,
                                                           unsigned ntiles) {
     extern __shared__ __align__(128) double2 sm[];
   for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const size_t base = (size_t)tile * (16 * NT) + threadIdx.x;
+    if (PF > 0 && threadIdx.x == 0 && tile + PF < ntiles)  // pull the tile some CTA will need PF tiles from now into L2
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in + (size_t)(tile + PF) * (16 * NT)), "r"(16 * NT * 16) : "memory");
     double2 v[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) v[m] = in[base + m * NT];
@@ -99,13 +101,13 @@ struct Nvml {
     }
 };
 
-template <int K, int S, bool ADD, int NT = 256, int MINB = 2, bool PERSIST = false, int MODE = 0>
+template <int K, int S, bool ADD, int NT = 256, int MINB = 2, bool PERSIST = false, int MODE = 0, int PF = 0>
 void run(const char* name, const double2* in, double2* out, size_t n, Nvml& nv) {
     const unsigned ntiles = (unsigned)(n / (16 * NT));
     const unsigned grid = PERSIST ? 148 * MINB : ntiles;
     const size_t smem = S ? (size_t)(17 * NT + 16) * 16 : 0;
-    cudaFuncSetAttribute(stream_kernel<K, S, ADD, NT, MINB, PERSIST, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    auto launch = [&]() { stream_kernel<K, S, ADD, NT, MINB, PERSIST, MODE><<<grid, NT, smem>>>(in, out, 0.9173, 0.3391, ntiles); };
+    cudaFuncSetAttribute(stream_kernel<K, S, ADD, NT, MINB, PERSIST, MODE, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto launch = [&]() { stream_kernel<K, S, ADD, NT, MINB, PERSIST, MODE, PF><<<grid, NT, smem>>>(in, out, 0.9173, 0.3391, ntiles); };
     auto t0 = std::chrono::steady_clock::now();
     while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < 1.5) {
         for (int i = 0; i < 16; ++i) launch();
@@ -145,16 +147,16 @@ int main() {
     Nvml nv;
     printf("streaming kernel, 65,536 x 4096 complex f64 (8.59 GB per launch), random payload, sustained; NVML %s\n", nv.ok ? "ok" : "unavailable");
     run<0, 0, false>("copy (0 FP64 / point, no exchange)", in, out, n, nv);
-    run<0, 2, false, 256, 2, false, 3>("copy, 70 KiB of shared memory allocated, unused", in, out, n, nv);
-    run<0, 2, false>("0 FP64 / point, 2 exchanges", in, out, n, nv);
-    run<0, 2, false, 256, 2, false, 1>("0 FP64, 2 warp-local exchanges (no CTA barrier)", in, out, n, nv);
-    run<0, 2, false, 256, 2, false, 2>("0 FP64, 2 exchanges of half the data", in, out, n, nv);
-    run<42, 0, false>("42 DFMA / point", in, out, n, nv);
     run<42, 2, false>("42 DFMA / point, 2 exchanges (the 4096 tile)", in, out, n, nv);
-    run<42, 2, false, 256, 2, false, 1>("42 DFMA, 2 warp-local exchanges", in, out, n, nv);
-    run<42, 2, false, 256, 2, false, 2>("42 DFMA, 2 exchanges of half the data", in, out, n, nv);
-    run<42, 2, false, 256, 2, false, 3>("42 DFMA, shared memory allocated, no exchange", in, out, n, nv);
+    run<42, 2, false, 256, 2, false, 0, 148>("  + L2 prefetch of tile + 148", in, out, n, nv);
+    run<42, 2, false, 256, 2, false, 0, 296>("  + L2 prefetch of tile + 296", in, out, n, nv);
+    run<42, 2, false, 256, 2, false, 0, 592>("  + L2 prefetch of tile + 592", in, out, n, nv);
+    run<42, 2, false, 256, 2, false, 0, 1184>("  + L2 prefetch of tile + 1184", in, out, n, nv);
     run<42, 2, false, 128, 4, false>("42 DFMA, 2 exchanges, 128-thread tiles x 4 / SM", in, out, n, nv);
-    run<42, 2, false, 128, 4, false, 1>("42 DFMA, 2 warp-local exchanges, 128 x 4 / SM", in, out, n, nv);
+    run<42, 2, false, 128, 4, false, 0, 1184>("  + L2 prefetch of tile + 1184", in, out, n, nv);
+    run<42, 3, false, 512, 1, false>("42 DFMA, 3 exchanges, 512-thread tiles (128 KiB)", in, out, n, nv);
+    run<42, 3, false, 512, 1, false, 0, 296>("  + L2 prefetch of tile + 296", in, out, n, nv);
+    run<84, 2, false>("84 DFMA / point, 2 exchanges (two transforms)", in, out, n, nv);
+    run<84, 2, false, 256, 2, false, 0, 592>("  + L2 prefetch of tile + 592", in, out, n, nv);
     return 0;
 }
