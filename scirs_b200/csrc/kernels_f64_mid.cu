@@ -11,5 +11,8 @@ void register_kernels_f64_mid(void (*add)(const KernelEntry&)) {
     SFC_ADD(double, 2048, 2, false)
     SFC_ADD(double, 2048, 1, false)
     SFC_ADD(double, 1024, 2, false)
+    // one thread group (named barrier) per lane: contiguous-row tiles whose lanes are whole warps never synchronise the CTA
+    add(::sfc::KernelInst<double, 512, 4, false, 16, 1, 4>::entry());
+    add(::sfc::KernelInst<double, 1024, 2, false, 16, 1, 2>::entry());
 }
 }  // namespace sfc

@@ -41,6 +41,7 @@ KNOBS = [
     {"SFC_BLUE3_MIN": "32768", "SFC_THREE_LEVEL_MIN": "32768"},          # five-pass Bluestein, three-level rows
     {"SFC_GPIPE": "1", "SFC_GPIPE_MIN_TILES": "1"},                      # group-pipelined flavour on every eligible row pass
     {"SFC_PIPE_LATE": "2", "SFC_PIPE_LATE_MIN_TILES": "1"},              # late-prefetch persistent flavour on every eligible row pass
+    {"SFC_ROW_LANE_GROUPS": "0"},                                        # 512 x 4 / 1024 x 2 row tiles with CTA-wide barriers
 ]
 
 

@@ -85,6 +85,75 @@ __global__ void fill_random(double2* p, size_t n) {
     }
 }
 
+
+// Candidate structure for the 4096-point tile: the row is LANDED in shared memory by one bulk copy (no LSU global loads, no
+// registers), every warp transforms a 512-slot region of its own through two rounds (read 16, compute, write back in place,
+// __syncwarp) — the first two radix-16 stages with the first exchange inside a warp — and only the last exchange synchronises
+// the CTA.  Shared-memory traffic: 3 reads + 2 writes of the tile (5 x 64 KiB) against 2 + 2 today plus the global loads that
+// no longer pass through the LSU.  Access patterns are conflict-free stand-ins (slot bijections), not the real index algebra.
+template <int K, bool ADD>
+__global__ void __launch_bounds__(256, 2) landed_kernel(const double2* __restrict__ in, double2* __restrict__ out, double a, double b,
+                                                        unsigned ntiles) {
+    extern __shared__ __align__(128) double2 sm[];
+    __shared__ __align__(8) unsigned long long bar;
+    const unsigned tile = blockIdx.x;
+    const unsigned sbar = (unsigned)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbar), "r"(65536) : "memory");
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(sm);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + c * 16384),
+                         "l"(in + (size_t)tile * 4096 + c * 1024), "r"(16384), "r"(sbar)
+                         : "memory");
+    }
+    {  // everybody waits for the landing
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(sbar), "r"(0) : "memory");
+    }
+    const int l = threadIdx.x & 31;
+    double2* w = sm + (threadIdx.x >> 5) * 512;  // the warp's own 512 slots
+    double2 v[16];
+    constexpr int KS = K / 3;
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+        // read 16 slots of the warp's region (lane + 32 m: conflict-free), compute, write back to the same slots
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = w[((l + 32 * m) + 7 * round * m) & 511];
+#pragma unroll
+        for (int k = 0; k < KS / 2; ++k)
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                if (ADD) { v[m].x = v[m].x + b; v[m].y = v[m].y + a; }
+                else { v[m].x = fma(v[m].x, a, b); v[m].y = fma(v[m].y, a, b); }
+            }
+#pragma unroll
+        for (int m = 0; m < 16; ++m) w[((l + 32 * m) + 7 * round * m) & 511] = v[m];
+        if (round == 0) __syncwarp();
+    }
+    __syncthreads();
+    // the one CTA-wide exchange: thread t reads slots t + 256 m (other warps' regions), last stage, coalesced stores
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = sm[threadIdx.x + 256 * m];
+#pragma unroll
+    for (int k = 0; k < KS / 2; ++k)
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            if (ADD) { v[m].x = v[m].x + b; v[m].y = v[m].y + a; }
+            else { v[m].x = fma(v[m].x, a, b); v[m].y = fma(v[m].y, a, b); }
+        }
+    const size_t base = (size_t)tile * 4096 + threadIdx.x;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) out[base + m * 256] = v[m];
+}
+
 typedef int (*nvml_fn)(...);
 struct Nvml {
     void* h = nullptr; void* dev = nullptr;
@@ -101,13 +170,27 @@ struct Nvml {
     }
 };
 
+template <typename F>
+void run_launch(const char* name, F launch, size_t n, Nvml& nv);
+
+template <int K, bool ADD>
+void run_landed(const char* name, const double2* in, double2* out, size_t n, Nvml& nv, int smem_kb = 64) {
+    const unsigned ntiles = (unsigned)(n / 4096);
+    cudaFuncSetAttribute(landed_kernel<K, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024);
+    run_launch(name, [&]() { landed_kernel<K, ADD><<<ntiles, 256, smem_kb * 1024>>>(in, out, 0.9173, 0.3391, ntiles); }, n, nv);
+}
+
 template <int K, int S, bool ADD, int NT = 256, int MINB = 2, bool PERSIST = false, int MODE = 0, int PF = 0>
 void run(const char* name, const double2* in, double2* out, size_t n, Nvml& nv) {
     const unsigned ntiles = (unsigned)(n / (16 * NT));
     const unsigned grid = PERSIST ? 148 * MINB : ntiles;
     const size_t smem = S ? (size_t)(17 * NT + 16) * 16 : 0;
     cudaFuncSetAttribute(stream_kernel<K, S, ADD, NT, MINB, PERSIST, MODE, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    auto launch = [&]() { stream_kernel<K, S, ADD, NT, MINB, PERSIST, MODE, PF><<<grid, NT, smem>>>(in, out, 0.9173, 0.3391, ntiles); };
+    run_launch(name, [&]() { stream_kernel<K, S, ADD, NT, MINB, PERSIST, MODE, PF><<<grid, NT, smem>>>(in, out, 0.9173, 0.3391, ntiles); }, n, nv);
+}
+
+template <typename F>
+void run_launch(const char* name, F launch, size_t n, Nvml& nv) {
     auto t0 = std::chrono::steady_clock::now();
     while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < 1.5) {
         for (int i = 0; i < 16; ++i) launch();
@@ -148,15 +231,11 @@ int main() {
     printf("streaming kernel, 65,536 x 4096 complex f64 (8.59 GB per launch), random payload, sustained; NVML %s\n", nv.ok ? "ok" : "unavailable");
     run<0, 0, false>("copy (0 FP64 / point, no exchange)", in, out, n, nv);
     run<42, 2, false>("42 DFMA / point, 2 exchanges (the 4096 tile)", in, out, n, nv);
-    run<42, 2, false, 256, 2, false, 0, 148>("  + L2 prefetch of tile + 148", in, out, n, nv);
-    run<42, 2, false, 256, 2, false, 0, 296>("  + L2 prefetch of tile + 296", in, out, n, nv);
-    run<42, 2, false, 256, 2, false, 0, 592>("  + L2 prefetch of tile + 592", in, out, n, nv);
-    run<42, 2, false, 256, 2, false, 0, 1184>("  + L2 prefetch of tile + 1184", in, out, n, nv);
-    run<42, 2, false, 128, 4, false>("42 DFMA, 2 exchanges, 128-thread tiles x 4 / SM", in, out, n, nv);
-    run<42, 2, false, 128, 4, false, 0, 1184>("  + L2 prefetch of tile + 1184", in, out, n, nv);
-    run<42, 3, false, 512, 1, false>("42 DFMA, 3 exchanges, 512-thread tiles (128 KiB)", in, out, n, nv);
-    run<42, 3, false, 512, 1, false, 0, 296>("  + L2 prefetch of tile + 296", in, out, n, nv);
-    run<84, 2, false>("84 DFMA / point, 2 exchanges (two transforms)", in, out, n, nv);
-    run<84, 2, false, 256, 2, false, 0, 592>("  + L2 prefetch of tile + 592", in, out, n, nv);
+    run<42, 2, false, 256, 2, false, 1>("42 DFMA, 2 warp-local exchanges", in, out, n, nv);
+    run_landed<42, false>("42 DFMA, bulk landing + warp-local + 1 CTA exchange", in, out, n, nv);
+    run_landed<42, false>("  same, 80 KiB of shared memory (two CTAs per SM)", in, out, n, nv, 80);
+    run_landed<42, true>("42 DADD, bulk landing + warp-local + 1 CTA exchange", in, out, n, nv);
+    run_landed<42, true>("  same, 80 KiB of shared memory (two CTAs per SM)", in, out, n, nv, 80);
+    run_landed<0, false>("0 FP64, bulk landing + warp-local + 1 CTA exchange", in, out, n, nv);
     return 0;
 }
