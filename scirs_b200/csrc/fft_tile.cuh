@@ -289,6 +289,9 @@ __device__ __forceinline__ void apply_twiddle_powers(Cx<T> (&v)[R], Cx<T> w1) {
 #ifndef SFC_INPLACE_MID
 #define SFC_INPLACE_MID 1
 #endif
+#ifndef SFC_INPLACE_MID_HOOK  // the in-place middle stage in the late-prefetch (TM_PIPE_LATE) flavour too
+#define SFC_INPLACE_MID_HOOK 1
+#endif
 #ifndef SFC_TW_LOAD
 #define SFC_TW_LOAD 0
 #endif
@@ -419,7 +422,7 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
     // barrier; measured on the tiles (profiles/r2r_inplace_mid.log): 4096-point c2c 78.7 -> 81.2 %, 2048 84.4 -> 86.1 %.
     // Real flavours (65,536 x 4096, sustained, profiles/r2s_inplace_real.log): complex-to-real f64 85.9 -> 87.4 % (kept), f32
     // 79.1 -> 77.7 % (off); real-to-complex with the mirrored last stage f64 84.9 -> 83.6 % (a 12-byte spill; off), f32 +0.5.
-    constexpr bool MID_INPLACE = SFC_INPLACE_MID && !HOOK && !C::SPLIT && E == 16 && R == 16 && !LAST && S > 1 &&
+    constexpr bool MID_INPLACE = SFC_INPLACE_MID && (!HOOK || SFC_INPLACE_MID_HOOK) && !C::SPLIT && E == 16 && R == 16 && !LAST && S > 1 &&
                                  (SFC_INPLACE_MID > 1 || (!MIRROR && (!MIRROR_IN || sizeof(T) == 8))) &&
                                  (MIRROR_IN ? S == 8 : S == 16) && L / (S * R) >= 2 && L / (S * R) <= 16;
     if constexpr (!LAST && !FIRST && !MID_INPLACE) C::sync(grp);  // previous readers done before we overwrite
@@ -511,6 +514,11 @@ __device__ __forceinline__ void run_stages(Cx<T> (&a)[C::E], Cx<T>* __restrict__
         } else {
 #pragma unroll
             for (int m = 0; m < E; ++m) a[m] = lane[b0 + (S + 1) * ((RN * m) >> 4) + KP * ((RN * m) & 15)];
+        }
+        if constexpr (HOOK) {
+            // the last stage never touches shared memory again: the buffer is free for the next tile's data (late prefetch)
+            C::sync(grp);
+            late_issue<T, C::L, C::TL>(*hook);
         }
         run_stages<T, C, S * R, false, MIRROR, MIRROR_IN, false, HOOK>(a, sm, tw, tr, ir, tr, ir, grp, hook);
     } else if constexpr (!LAST) {

@@ -116,15 +116,15 @@ static int groups_mode() {
 }
 
 // one named-barrier group per lane for the contiguous-row tiles whose lanes are whole warps
-static bool row_lane_groups() {
+static int row_lane_groups() {
 #ifdef SFC_HOST_EMUL
-    return false;  // tests/emul has no named barriers: the host emulation keeps the single-group flavour (same arithmetic)
+    return 0;  // tests/emul has no named barriers: the host emulation keeps the single-group flavour (same arithmetic)
 #endif
     const int v = [] {
         const char* e = knob_env("SFC_ROW_LANE_GROUPS");
         return e ? atoi(e) : 1;  // measured (sustained): 512-point rows 93.2 -> 97.8 %, 1024-point rows 92.4 -> 93.6 %
     }();
-    return v != 0;
+    return v;
 }
 
 static int col_tl_cap() {
@@ -781,7 +781,9 @@ struct PlanBuilder {
             }
             // contiguous rows whose lanes are whole warps (512 x 4, 1024 x 2): one named-barrier group per lane, so the exchanges
             // of a row never wait for the other rows of the tile (the streaming proxy: CTA-wide barriers are what costs)
-            if (mode == 1 && s.k->mode == 1 && s.k->groups == 1 && !s.k->dbl && row_lane_groups() && s.p.map_in == MAP_ROW &&
+            // (f32, 16 KiB tiles, six CTAs per SM: 90.9 -> 86.0 % and 90.4 -> 84.8 %, so f64 only unless SFC_ROW_LANE_GROUPS=2)
+            if (mode == 1 && s.k->mode == 1 && s.k->groups == 1 && !s.k->dbl && row_lane_groups() &&
+                (prec == PREC_F64 || row_lane_groups() > 1) && s.p.map_in == MAP_ROW &&
                 s.p.map_out == MAP_ROW && s.k->TL > 1 && !(s.p.flags & (F_STAGE_IN | F_STAGE_OUT)) && !s.scatter) {
                 int cnt = 0;
                 const KernelEntry* t = kernel_table(&cnt);
