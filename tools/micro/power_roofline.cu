@@ -38,7 +38,17 @@ __global__ void __launch_bounds__(NT, MINB) stream_kernel(const double2* __restr
                 else { v[m].x = fma(v[m].x, a, b); v[m].y = fma(v[m].y, a, b); }
             }
         }
-        if (s < S && MODE == 1) {
+        if (s < S && MODE == 5 && s == 1) {
+            // second exchange inside the warp
+            double2* w = sm + (threadIdx.x >> 5) * (17 * 32);
+            const int l = threadIdx.x & 31;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) w[17 * l + m] = v[m];
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = w[l + 34 * m];
+            __syncwarp();
+        } else if (s < S && MODE == 1) {
             // warp-local exchange: same traffic, no CTA-wide barrier (a warp's 512 slots are its own)
             double2* w = sm + (threadIdx.x >> 5) * (17 * 32);
             const int l = threadIdx.x & 31;
@@ -69,8 +79,16 @@ __global__ void __launch_bounds__(NT, MINB) stream_kernel(const double2* __restr
             __syncthreads();
         }
     }
+    if (MODE == 5) {
+        // thread (k0, k1): k0 = (t & 1) + 2 (t >> 5), k1 = (t >> 1) & 15 -> element k0 + 16 k1 + 256 m: 32-byte segments
+        const int t = threadIdx.x;
+        const size_t ob = (size_t)tile * (16 * NT) + ((t & 1) + 2 * (t >> 5)) + 16 * ((t >> 1) & 15);
 #pragma unroll
-    for (int m = 0; m < 16; ++m) out[base + m * NT] = v[m];
+        for (int m = 0; m < 16; ++m) out[ob + m * NT] = v[m];
+    } else {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) out[base + m * NT] = v[m];
+    }
     if (!PERSIST) break;
   }
 }
@@ -232,10 +250,8 @@ int main() {
     run<0, 0, false>("copy (0 FP64 / point, no exchange)", in, out, n, nv);
     run<42, 2, false>("42 DFMA / point, 2 exchanges (the 4096 tile)", in, out, n, nv);
     run<42, 2, false, 256, 2, false, 1>("42 DFMA, 2 warp-local exchanges", in, out, n, nv);
-    run_landed<42, false>("42 DFMA, bulk landing + warp-local + 1 CTA exchange", in, out, n, nv);
-    run_landed<42, false>("  same, 80 KiB of shared memory (two CTAs per SM)", in, out, n, nv, 80);
-    run_landed<42, true>("42 DADD, bulk landing + warp-local + 1 CTA exchange", in, out, n, nv);
-    run_landed<42, true>("  same, 80 KiB of shared memory (two CTAs per SM)", in, out, n, nv, 80);
-    run_landed<0, false>("0 FP64, bulk landing + warp-local + 1 CTA exchange", in, out, n, nv);
+    run<42, 2, false, 256, 2, false, 5>("42 DFMA, CTA exchange + warp-local exchange + 32 B store segments", in, out, n, nv);
+    run<42, 2, true, 256, 2, false, 5>("42 DADD, CTA exchange + warp-local exchange + 32 B store segments", in, out, n, nv);
+    run<42, 2, true>("42 DADD / point, 2 exchanges", in, out, n, nv);
     return 0;
 }
